@@ -1,0 +1,271 @@
+/* nig_b200.h -- C ABI of the B200-native batched IndustrialEnv step path (libnig_b200.so).
+ *
+ * The reference (danieleschmidt/neoRL-industrial-gym) is pure Python and has no FFI layer; its
+ * boundary for this path is the public env API. Each entry point below names the reference
+ * interface it replaces (paths relative to the reference's src/neorl_industrial/). The Python
+ * package neorl_industrial (neorl-industrial-gym_b200/neorl_industrial) binds these with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - Every function returns a nig_status (0 = ok); nig_last_error() gives the thread-local message.
+ *    No exceptions cross the ABI; nothing allocates after nig_create() except the lazily created
+ *    host staging of the *_host calls.
+ *  - "dev" pointers are CUDA device pointers on the env's device; `stream` is a cudaStream_t
+ *    (NULL = legacy default stream). The *_host calls take ordinary host pointers, do the
+ *    host<->device copies themselves (pinned staging, cudaMemcpyAsync) and return synchronised.
+ *  - Device state is SoA fp32: component k of env i lives at state[k * pitch + i];
+ *    pitch = nig_pitch(env) (n_envs rounded up to 128 elements). Every per-env DEVICE array handed to
+ *    nig_step()/nig_rollout() must have capacity >= pitch elements (rows of SoA arrays are
+ *    `pitch` apart); host arrays are exact-size.
+ *  - Envs are identified by a global id = env_id_offset + local index; all random streams are
+ *    keyed by (seed, global id, tick) so a sharded run reproduces the unsharded one bit-for-bit.
+ */
+#ifndef NIG_B200_H
+#define NIG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NIG_API __attribute__((visibility("default")))
+#else
+#define NIG_API
+#endif
+
+#define NIG_ABI_VERSION 1
+#define NIG_MAX_CONSTRAINTS 8
+#define NIG_MAX_STATE_DIM 32
+#define NIG_MAX_ACTION_DIM 8
+#define NIG_MAX_NOISE_DIM 23
+#define NIG_STATS_SLOTS 32
+
+typedef struct nig_env nig_env_t; /* opaque */
+
+typedef enum nig_status {
+    NIG_OK = 0,
+    NIG_ERR_INVALID = 1,     /* bad argument (shape, kind, null pointer, limit) -> Python ValueError   */
+    NIG_ERR_CUDA = 2,        /* CUDA runtime/driver failure                      -> Python RuntimeError */
+    NIG_ERR_NO_DEVICE = 3,   /* no usable sm_100 device: the library never falls back to the CPU        */
+    NIG_ERR_UNSUPPORTED = 4
+} nig_status;
+
+/* utils.make registry (utils.py:26-32); the two "Advanced" ids are not instantiable upstream */
+typedef enum nig_env_kind {
+    NIG_ENV_CHEMICAL_REACTOR = 0, /* environments/chemical_reactor.py */
+    NIG_ENV_POWER_GRID = 1,       /* environments/power_grid.py       */
+    NIG_ENV_ROBOT_ASSEMBLY = 2    /* environments/robot_assembly.py   */
+} nig_env_kind;
+
+/* SafetyConstraint (core/types.py:56-64) as a declarative descriptor.
+ *  BUILTIN : the env's own check_fn number `id` (registration order in the env's __init__)
+ *  BOUND   : lo <= s[si] + coef * a[ai] <= hi on the pre-step state and clipped action (ai < 0: no
+ *            action term) -- the SafetyWrapper temperature/pressure-bound form (README.md:126-139)
+ *  HOSTMASK: bit `id` of the caller-supplied per-env mask says "violated" (lets the Python layer keep
+ *            arbitrary check_fn callables: it evaluates them on the host, the kernel applies them) */
+typedef enum nig_con_kind { NIG_CON_BUILTIN = 0, NIG_CON_BOUND = 1, NIG_CON_HOSTMASK = 2 } nig_con_kind;
+
+typedef struct nig_constraint {
+    int32_t kind;
+    int32_t id;
+    int32_t si;
+    int32_t ai;
+    float coef;
+    float lo;
+    float hi;
+    float penalty;    /* added to the reward when violated (base.py:179-183) */
+    int32_t critical; /* violated -> terminated = true, reward -= 1000 (base.py:195-198) */
+} nig_constraint_t;
+
+typedef struct nig_env_spec {
+    int32_t state_dim;
+    int32_t action_dim;
+    int32_t noise_dim;          /* Gaussian draws per step, in the reference's draw order */
+    int32_t max_episode_steps;  /* 500 reactor (chemical_reactor.py:66), 1000 others (base.py:27) */
+    int32_t n_constraints;
+    int32_t reserved;
+    nig_constraint_t constraints[NIG_MAX_CONSTRAINTS]; /* the built-ins with their penalties */
+} nig_env_spec_t;
+
+typedef struct nig_config {
+    int32_t env_kind;
+    int32_t device;            /* CUDA device ordinal */
+    int64_t n_envs;            /* envs owned by THIS handle (this GPU's shard) */
+    int64_t env_id_offset;     /* global id of local env 0 */
+    uint64_t seed;
+    int32_t max_episode_steps; /* 0 = env default; <= 65535 */
+    int32_t auto_reset;        /* 1: a finished env is re-initialised inside the same step call */
+    int32_t n_constraints;     /* -1 = the env's built-ins */
+    int32_t reserved;
+    nig_constraint_t constraints[NIG_MAX_CONSTRAINTS];
+} nig_config_t;
+
+/* per-step output flag bits */
+enum {
+    NIG_F_TERMINATED = 1,  /* base.py:190 / :196 */
+    NIG_F_TRUNCATED = 2,   /* base.py:191 */
+    NIG_F_CRITICAL = 4,    /* info["critical_shutdown"], base.py:210 */
+    NIG_F_RESET = 8,       /* the env was auto-reset after this transition */
+    NIG_F_INACTIVE = 128   /* env already finished and auto_reset == 0: nothing was stepped */
+};
+
+enum { NIG_LAYOUT_SOA = 0, NIG_LAYOUT_AOS = 1 };
+
+/* One IndustrialEnv.step (base.py:157-213) over all envs of the handle.
+ * SoA arrays are [dim][pitch]; AoS arrays are [n][dim]. NULL = not supplied / not wanted. */
+typedef struct nig_step_io {
+    const float* actions;       /* in : [A][pitch] or [n][A]; clipped to [-1, 1] by the kernel (base.py:167) */
+    const float* noise;         /* in : teacher-forced process noise [NZ][pitch] or [n][NZ]; NULL -> in-kernel Philox */
+    const float* reset_states;  /* in : teacher-forced post-done states [S][pitch] or [n][S]; NULL -> in-kernel draw */
+    const uint8_t* hostmask;    /* in : [n] bits for NIG_CON_HOSTMASK constraints; NULL -> 0 */
+    float* obs;                 /* out: state AFTER the call (post auto-reset): [S][pitch] or [n][S] */
+    float* next_obs;            /* out: s' of the transition (pre auto-reset); same layout as obs */
+    float* reward;              /* out: [n] */
+    uint8_t* flags;             /* out: [n] NIG_F_* bits */
+    uint8_t* viol_mask;         /* out: [n] bit k = constraint k violated on the pre-step state */
+    int32_t action_layout;      /* NIG_LAYOUT_* of actions */
+    int32_t aux_layout;         /* NIG_LAYOUT_* of noise / reset_states / obs / next_obs */
+} nig_step_io_t;
+
+/* fused K-step rollout policies */
+enum {
+    NIG_POLICY_ACTIONS = 0,  /* actions[K][A][pitch] read from HBM (TMA-staged through shared memory) */
+    NIG_POLICY_UNIFORM = 1,  /* a ~ U(-1,1)^A from the in-kernel Philox policy stream (= action_space.sample(),
+                                the reference's timing harness performance_benchmark.py:106-133) */
+    NIG_POLICY_ZERO = 2,
+    NIG_POLICY_PCTRL = 3     /* get_dataset's "PID-like" P-controller mixes (chemical_reactor.py:364-390) */
+};
+
+/* get_dataset policy parameters (chemical_reactor.py:333-390, power_grid.py:216-232,
+ * robot_assembly.py:266-291). Per step, with probability p_ctrl the env's controller
+ * branch is taken, else a ~ U(-uniform_scale, uniform_scale)^A:
+ *   reactor: a_j = gain[j][0]*(T-320)/50 + gain[j][1]*(level-55)/50 + sigma[j]*N(0,1)
+ *   grid   : a_j = gain[j][0]*freq_dev   + gain[j][1]*(sum load - sum gen)/8 + sigma[j]*N(0,1)
+ *   robot  : mode 0: a[0:3] = gain[0][0]*(target-pos), a[3:7] = gain[3][0]*q[3:7]  (expert, :268-277)
+ *            mode 1: a[0:3] = gain[0][0]*(target-pos), a[3:7] ~ U(-sigma[3], sigma[3])  (mixed, :284-287)
+ * store_clip > 0: the dataset stores clip(a, +-store_clip) (reactor 1, robot 2); the env itself always
+ * clips to +-1 (base.py:167). */
+typedef struct nig_policy_params {
+    float p_ctrl;
+    float uniform_scale;
+    float store_clip;
+    int32_t mode;
+    float gain[NIG_MAX_ACTION_DIM][2];
+    float sigma[NIG_MAX_ACTION_DIM];
+} nig_policy_params_t;
+
+enum { NIG_ROLLOUT_USE_TMA = 1 /* stage NIG_POLICY_ACTIONS through cp.async.bulk.tensor */ };
+
+typedef struct nig_rollout {
+    int32_t n_steps;            /* K */
+    int32_t policy;             /* NIG_POLICY_* */
+    int32_t flags;              /* NIG_ROLLOUT_* */
+    int32_t reserved;
+    const float* actions;       /* dev [K][A][pitch] when policy == NIG_POLICY_ACTIONS */
+    const float* noise;         /* dev teacher-forced noise [K][NZ][pitch]; NULL -> in-kernel Philox */
+    nig_policy_params_t pp;
+    float* reward_sum;          /* out dev [n]: sum over the K steps of this call (fp32, step order); NULL ok */
+    int32_t* viol_count;        /* out dev [n]: violations over the K steps; NULL ok */
+    int32_t* done_count;        /* out dev [n]: episodes finished over the K steps; NULL ok */
+} nig_rollout_t;
+
+/* D4RL-layout transition arrays written by the on-device get_dataset (chemical_reactor.py:414-420,
+ * power_grid.py:244-249, robot_assembly.py:303-308). Row-major, episode-contiguous, device pointers
+ * with capacity for `capacity` transitions. next_observations / safety are documented extensions. */
+typedef struct nig_dataset_out {
+    float* observations;        /* [M][S] */
+    float* actions;             /* [M][A] (clipped, as stored by the reference) */
+    float* rewards;             /* [M]    */
+    uint8_t* terminals;         /* [M]    terminated | truncated (reactor); terminated (grid/robot) */
+    uint8_t* timeouts;          /* [M]    all zero (chemical_reactor.py:419); NULL ok */
+    float* next_observations;   /* [M][S] extension; NULL ok */
+    uint8_t* safety;            /* [M]    extension: violation mask of the transition; NULL ok */
+    int64_t capacity;
+} nig_dataset_out_t;
+
+/* stats block: NIG_STATS_SLOTS x 8 bytes on the device; slots < 24 are int64 counters, slots >= 24 are
+ * fp64 sums. Summable across ranks (one NCCL all-reduce). */
+enum {
+    NIG_ST_STEPS = 0, NIG_ST_EPISODES = 1, NIG_ST_TERMINATED = 2, NIG_ST_TRUNCATED = 3,
+    NIG_ST_CRITICAL = 4, NIG_ST_VIOLATIONS = 5, NIG_ST_SUCCESSES = 6 /* episodes with return > 0 */,
+    NIG_ST_EP_LEN_SUM = 7, NIG_ST_CON0 = 8 /* .. NIG_ST_CON0+7 per-constraint violation counts */,
+    NIG_ST_EP_LEN_SQ = 16,
+    NIG_ST_F_RETURN_SUM = 24, NIG_ST_F_RETURN_SQ = 25, NIG_ST_F_REWARD_SUM = 26
+};
+
+NIG_API int nig_abi_version(void);
+NIG_API const char* nig_last_error(void);
+NIG_API int nig_device_count(int* count);
+
+/* env metadata: replaces reading state_dim/action_dim/safety_constraints/max_episode_steps off the
+ * env object (environments/base.py:41-72, chemical_reactor.py:38-69, power_grid.py:53-79,
+ * robot_assembly.py:56-82) */
+NIG_API int nig_env_spec(int env_kind, nig_env_spec_t* out);
+
+/* utils.make (utils.py:12-39) + IndustrialEnv.__init__ (base.py:22-72) for n_envs envs */
+NIG_API int nig_create(const nig_config_t* cfg, nig_env_t** out);
+NIG_API int nig_destroy(nig_env_t* env);
+NIG_API int64_t nig_pitch(const nig_env_t* env);
+NIG_API int64_t nig_num_envs(const nig_env_t* env);
+
+/* add_safety_constraint / remove_safety_constraint (base.py:220-228) and SafetyWrapper (README.md:126-139) */
+NIG_API int nig_set_constraints(nig_env_t* env, const nig_constraint_t* cons, int32_t n);
+
+/* IndustrialEnv.reset (base.py:133-155) + _get_initial_state (chemical_reactor.py:89-107,
+ * power_grid.py:90-110, robot_assembly.py:113-137). mask NULL = all envs; init_states NULL = draw. */
+NIG_API int nig_reset(nig_env_t* env, const uint8_t* mask_dev, const float* init_states_dev, int32_t layout, void* stream);
+NIG_API int nig_reset_host(nig_env_t* env, const uint8_t* mask, const float* init_states_aos, float* obs_aos_out);
+
+/* IndustrialEnv.step (base.py:157-213) incl. _check_safety_constraints (:94-124), _dynamics,
+ * _compute_reward, _is_done of the three envs */
+NIG_API int nig_step(nig_env_t* env, const nig_step_io_t* io, void* stream);
+/* same with HOST pointers (AoS, exact-size): H2D of the inputs, the kernel, D2H of the outputs */
+NIG_API int nig_step_host(nig_env_t* env, const nig_step_io_t* io);
+
+/* K fused steps with state in registers: the `for step: action = policy(obs); env.step(action)` loops of
+ * performance_benchmark.py:106-133, utils.evaluate_with_safety (utils.py:82-125) and get_dataset */
+NIG_API int nig_rollout(nig_env_t* env, const nig_rollout_t* r, void* stream);
+
+/* get_dataset (chemical_reactor.py:324-420): n_episodes episodes of <= n_steps steps each with the given
+ * policy, written episode-contiguously in D4RL layout on the device. Episodes are independent envs with
+ * global ids env_id_offset + [0, n_episodes). *n_written receives the transition count. */
+NIG_API int nig_dataset(nig_env_t* env, int64_t n_episodes, int32_t n_steps, int32_t policy,
+                        const nig_policy_params_t* pp, const nig_dataset_out_t* out, int64_t* n_written, void* stream);
+/* length probe only (pass 1 of nig_dataset): total transitions the same call would write */
+NIG_API int nig_dataset_size(nig_env_t* env, int64_t n_episodes, int32_t n_steps, int32_t policy,
+                             const nig_policy_params_t* pp, int64_t* n_transitions, void* stream);
+
+/* checkpoint / teacher forcing: env.state, env.current_step, env.violation_count (base.py:50-57) */
+NIG_API int nig_get_state(nig_env_t* env, float* state_dev, int32_t layout, int32_t* ep_step_dev, int32_t* ep_viol_dev, uint8_t* done_dev, void* stream);
+NIG_API int nig_set_state(nig_env_t* env, const float* state_dev, int32_t layout, const int32_t* ep_step_dev, const int32_t* ep_viol_dev, const uint8_t* done_dev, void* stream);
+NIG_API int nig_get_state_host(nig_env_t* env, float* state_aos, int32_t* ep_step, int32_t* ep_viol, uint8_t* done);
+NIG_API int nig_set_state_host(nig_env_t* env, const float* state_aos, const int32_t* ep_step, const int32_t* ep_viol, const uint8_t* done);
+/* raw device views (zero-copy wrapping by the host language) */
+NIG_API int nig_state_ptr(nig_env_t* env, float** state_dev_soa, uint32_t** ep_word_dev);
+NIG_API int nig_get_tick(const nig_env_t* env, uint32_t* tick, uint32_t* epoch);
+NIG_API int nig_set_tick(nig_env_t* env, uint32_t tick, uint32_t epoch);
+/* reset(seed=...) made effective (the reference ignores it, base.py:135) */
+NIG_API int nig_set_seed(nig_env_t* env, uint64_t seed);
+
+/* violation / return counters (info["violations"], info["total_violations"], evaluate_with_safety's
+ * aggregates utils.py:128-152). The device block can be all-reduced in place (NCCL sum over int64/fp64). */
+NIG_API int nig_stats_ptr(nig_env_t* env, void** stats_dev);
+NIG_API int nig_read_stats(nig_env_t* env, int64_t* counters24, double* sums8);
+NIG_API int nig_clear_stats(nig_env_t* env, void* stream);
+
+NIG_API int nig_sync(nig_env_t* env);
+/* page-locked host buffers for the *_host calls (the copies are then true async DMA) */
+NIG_API int nig_host_alloc(size_t bytes, void** out);
+NIG_API int nig_host_free(void* p);
+/* kernels launched by this handle since creation (bench.py's gpu_launches claim) */
+NIG_API int64_t nig_launch_count(const nig_env_t* env);
+/* measured-peak probe: issues a dependent-free stream of unfused fp32 add/mul and returns ops per launch */
+NIG_API int nig_fp32_probe(int device, int32_t iters, double* ops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NIG_B200_H */

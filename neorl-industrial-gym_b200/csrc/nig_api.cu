@@ -1,0 +1,653 @@
+// nig_api.cu -- C-ABI of libnig_b200.so (see include/nig_b200.h). Host-side handle management,
+// argument validation, kernel dispatch and the host<->device staging of the *_host entry points.
+// There is no CPU implementation of the step path in this library: without an sm_100 device
+// nig_create() fails with NIG_ERR_NO_DEVICE.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "nig_kernels.cuh"
+
+using namespace nig;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define NIG_CUDA(expr)                                                                                \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(NIG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+const int kS[3] = {Reactor::S, Grid::S, Robot::S};
+const int kA[3] = {Reactor::A, Grid::A, Robot::A};
+const int kNZ[3] = {Reactor::NZ, Grid::NZ, Robot::NZ};
+const int kMaxSteps[3] = {Reactor::MAX_STEPS, Grid::MAX_STEPS, Robot::MAX_STEPS};
+
+void builtin_constraints(int kind, nig_constraint_t* c)
+{
+    // penalties / critical flags in registration order: chemical_reactor.py:38-60, power_grid.py:53-72,
+    // robot_assembly.py:56-75
+    const float pen[3][3] = {{-100.f, -50.f, -25.f}, {-50.f, -30.f, -20.f}, {-100.f, -200.f, -50.f}};
+    for (int k = 0; k < 3; ++k) {
+        c[k] = nig_constraint_t{NIG_CON_BUILTIN, k, 0, -1, 0.f, 0.f, 0.f, pen[kind][k], k < 2 ? 1 : 0};
+    }
+}
+
+bool cons_is_default(int kind, const nig_constraint_t* c, int n)
+{
+    if (n != 3) return false;
+    nig_constraint_t d[3];
+    builtin_constraints(kind, d);
+    for (int k = 0; k < 3; ++k)
+        if (c[k].kind != NIG_CON_BUILTIN || c[k].id != k || c[k].penalty != d[k].penalty || (c[k].critical != 0) != (d[k].critical != 0))
+            return false;
+    return true;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+} // namespace
+
+struct nig_env {
+    nig_config_t cfg;
+    int kind, S, A, NZ;
+    int64_t n, pitch;
+    int max_steps;
+    ConsParams cons;
+    RngKey key;
+    uint32_t tick, epoch;
+    float* state;
+    uint32_t* ep_word;
+    double* ep_return;
+    unsigned long long* stats;
+    cudaStream_t stream;       // internal stream of the *_host calls
+    // device staging of the *_host calls (lazily allocated)
+    float *h_actions, *h_noise, *h_reset, *h_obs, *h_next_obs, *h_reward;
+    uint8_t *h_hostmask, *h_flags, *h_viol, *h_mask;
+    int32_t *h_i32a, *h_i32b;
+    int64_t launches;
+    int step_vec;              // 0 = auto
+    PFN_encodeTiled encode_tiled;
+    int64_t* d_len;            // dataset: per-episode lengths / offsets
+    int64_t d_len_cap;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(T** p, size_t count)
+{
+    if (*p) return NIG_OK;
+    NIG_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    NIG_CUDA(cudaMemset(*p, 0, count * sizeof(T)));
+    return NIG_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+inline unsigned grid_for(int64_t items) { return (unsigned)((items + kThreads - 1) / kThreads); }
+
+template <class Env, int VEC>
+int launch_step_t(nig_env* e, const StepArgs& a, cudaStream_t st)
+{
+    const int64_t threads = (e->pitch + VEC - 1) / VEC;
+    const unsigned g = grid_for(threads);
+    if (e->cons.is_default) step_kernel<Env, VEC, true><<<g, kThreads, 0, st>>>(a);
+    else step_kernel<Env, VEC, false><<<g, kThreads, 0, st>>>(a);
+    e->launches++;
+    NIG_CUDA(cudaGetLastError());
+    return NIG_OK;
+}
+
+int pick_vec(const nig_env* e, bool soa)
+{
+    if (e->step_vec) return e->step_vec;
+    if (!soa) return 1;
+    // enough threads to fill 148 SMs x 2048 threads twice over before widening the per-thread vector
+    const int64_t full = 148LL * 2048;
+    if (e->kind == NIG_ENV_CHEMICAL_REACTOR) return e->pitch >= 8 * full ? 4 : (e->pitch >= 4 * full ? 2 : 1);
+    return 1;   // 32-/24-d states: two envs per thread would need > 250 registers
+}
+
+int launch_step(nig_env* e, const StepArgs& a, cudaStream_t st)
+{
+    const int vec = pick_vec(e, a.action_aos == 0 && a.aux_aos == 0);
+    switch (e->kind) {
+    case NIG_ENV_CHEMICAL_REACTOR:
+        return vec == 4 ? launch_step_t<Reactor, 4>(e, a, st) : vec == 2 ? launch_step_t<Reactor, 2>(e, a, st) : launch_step_t<Reactor, 1>(e, a, st);
+    case NIG_ENV_POWER_GRID:
+        return vec >= 2 ? launch_step_t<Grid, 2>(e, a, st) : launch_step_t<Grid, 1>(e, a, st);
+    default:
+        return vec >= 2 ? launch_step_t<Robot, 2>(e, a, st) : launch_step_t<Robot, 1>(e, a, st);
+    }
+}
+
+template <class Env, int POLICY, bool TMA>
+int launch_rollout_t(nig_env* e, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
+{
+    const unsigned g = grid_for(e->pitch);
+    const size_t smem = TMA ? (size_t)2 * kTmaChunk * Env::A * kThreads * sizeof(float) : 0;
+    if (e->cons.is_default) {
+        if (TMA) NIG_CUDA(cudaFuncSetAttribute(rollout_kernel<Env, true, POLICY, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rollout_kernel<Env, true, POLICY, TMA><<<g, kThreads, smem, st>>>(a, map);
+    } else {
+        if (TMA) NIG_CUDA(cudaFuncSetAttribute(rollout_kernel<Env, false, POLICY, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rollout_kernel<Env, false, POLICY, TMA><<<g, kThreads, smem, st>>>(a, map);
+    }
+    e->launches++;
+    NIG_CUDA(cudaGetLastError());
+    return NIG_OK;
+}
+
+template <class Env>
+int launch_rollout_env(nig_env* e, const RolloutArgs& a, int policy, bool tma, const CUtensorMap& map, cudaStream_t st)
+{
+    switch (policy) {
+    case NIG_POLICY_ACTIONS:
+        return tma ? launch_rollout_t<Env, NIG_POLICY_ACTIONS, true>(e, a, map, st) : launch_rollout_t<Env, NIG_POLICY_ACTIONS, false>(e, a, map, st);
+    case NIG_POLICY_UNIFORM: return launch_rollout_t<Env, NIG_POLICY_UNIFORM, false>(e, a, map, st);
+    case NIG_POLICY_ZERO: return launch_rollout_t<Env, NIG_POLICY_ZERO, false>(e, a, map, st);
+    case NIG_POLICY_PCTRL: return launch_rollout_t<Env, NIG_POLICY_PCTRL, false>(e, a, map, st);
+    default: return fail(NIG_ERR_INVALID, "unknown rollout policy %d", policy);
+    }
+}
+
+int make_action_map(nig_env* e, const float* actions, int n_steps, CUtensorMap* map)
+{
+    if (!e->encode_tiled) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        NIG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(NIG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        e->encode_tiled = (PFN_encodeTiled)fn;
+    }
+    // actions[K][A][pitch] fp32 as a 3-D tensor (x = env, y = action component, z = step); one box = the
+    // kTmaChunk x A x 128 tile a CTA consumes over kTmaChunk steps
+    const cuuint64_t gdim[3] = {(cuuint64_t)e->pitch, (cuuint64_t)e->A, (cuuint64_t)n_steps};
+    const cuuint64_t gstr[2] = {(cuuint64_t)e->pitch * sizeof(float), (cuuint64_t)e->pitch * e->A * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)kThreads, (cuuint32_t)e->A, (cuuint32_t)kTmaChunk};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = e->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)actions, gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(NIG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return NIG_OK;
+}
+
+int validate_constraints(int kind, const nig_constraint_t* c, int n)
+{
+    if (n < 0 || n > NIG_MAX_CONSTRAINTS) return fail(NIG_ERR_INVALID, "n_constraints %d outside [0, %d]", n, NIG_MAX_CONSTRAINTS);
+    for (int k = 0; k < n; ++k) {
+        switch (c[k].kind) {
+        case NIG_CON_BUILTIN:
+            if (c[k].id < 0 || c[k].id > 2) return fail(NIG_ERR_INVALID, "constraint %d: builtin id %d outside [0, 2]", k, c[k].id);
+            break;
+        case NIG_CON_BOUND:
+            if (c[k].si < 0 || c[k].si >= kS[kind]) return fail(NIG_ERR_INVALID, "constraint %d: state index %d outside [0, %d)", k, c[k].si, kS[kind]);
+            if (c[k].ai >= kA[kind]) return fail(NIG_ERR_INVALID, "constraint %d: action index %d outside [-1, %d)", k, c[k].ai, kA[kind]);
+            break;
+        case NIG_CON_HOSTMASK:
+            if (c[k].id < 0 || c[k].id > 7) return fail(NIG_ERR_INVALID, "constraint %d: hostmask bit %d outside [0, 7]", k, c[k].id);
+            break;
+        default: return fail(NIG_ERR_INVALID, "constraint %d: unknown kind %d", k, c[k].kind);
+        }
+    }
+    return NIG_OK;
+}
+
+void set_cons(nig_env* e, const nig_constraint_t* c, int n)
+{
+    memset(&e->cons, 0, sizeof e->cons);
+    e->cons.n = n;
+    for (int k = 0; k < n; ++k) e->cons.c[k] = c[k];
+    e->cons.is_default = cons_is_default(e->kind, c, n) ? 1 : 0;
+}
+
+#define NIG_CHECK_ENV(e)                                                        \
+    if (!(e)) return fail(NIG_ERR_INVALID, "null env handle");                  \
+    DeviceGuard guard_((e)->cfg.device);                                        \
+    if (!guard_.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", (e)->cfg.device)
+
+int state_io(nig_env* e, float* ext_state, int layout, int32_t* st, int32_t* vi, uint8_t* dn, bool to_ext, cudaStream_t s)
+{
+    StateIoArgs a{e->state, e->ep_word, e->n, e->pitch, ext_state, st, vi, dn, e->S, layout == NIG_LAYOUT_AOS ? 1 : 0, to_ext ? 1 : 0};
+    state_io_kernel<<<grid_for(e->n), kThreads, 0, s>>>(a);
+    e->launches++;
+    NIG_CUDA(cudaGetLastError());
+    return NIG_OK;
+}
+
+} // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int nig_abi_version(void) { return NIG_ABI_VERSION; }
+const char* nig_last_error(void) { return g_err; }
+
+int nig_device_count(int* count)
+{
+    if (!count) return fail(NIG_ERR_INVALID, "null count");
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; (void)cudaGetLastError(); return fail(NIG_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *count = n;
+    return NIG_OK;
+}
+
+int nig_env_spec(int kind, nig_env_spec_t* out)
+{
+    if (!out) return fail(NIG_ERR_INVALID, "null spec");
+    if (kind < 0 || kind > 2) return fail(NIG_ERR_INVALID, "unknown env kind %d", kind);
+    memset(out, 0, sizeof *out);
+    out->state_dim = kS[kind];
+    out->action_dim = kA[kind];
+    out->noise_dim = kNZ[kind];
+    out->max_episode_steps = kMaxSteps[kind];
+    out->n_constraints = 3;
+    builtin_constraints(kind, out->constraints);
+    return NIG_OK;
+}
+
+int nig_create(const nig_config_t* cfg, nig_env_t** out)
+{
+    if (!cfg || !out) return fail(NIG_ERR_INVALID, "null config or output pointer");
+    *out = nullptr;
+    if (cfg->env_kind < 0 || cfg->env_kind > 2) return fail(NIG_ERR_INVALID, "unknown env kind %d", cfg->env_kind);
+    if (cfg->n_envs <= 0) return fail(NIG_ERR_INVALID, "n_envs must be positive (got %lld)", (long long)cfg->n_envs);
+    if (cfg->n_envs > (1LL << 31)) return fail(NIG_ERR_INVALID, "n_envs %lld exceeds 2^31", (long long)cfg->n_envs);
+    if (cfg->max_episode_steps < 0 || cfg->max_episode_steps > 65535) return fail(NIG_ERR_INVALID, "max_episode_steps %d outside [0, 65535]", cfg->max_episode_steps);
+    int ndev = 0;
+    if (nig_device_count(&ndev) != NIG_OK || ndev == 0) {
+        char why[256];
+        snprintf(why, sizeof why, "%s", ndev == 0 && g_err[0] ? g_err : "device count is 0");
+        return fail(NIG_ERR_NO_DEVICE, "no CUDA device visible (%s): libnig_b200 has no CPU fallback", why);
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(NIG_ERR_INVALID, "device %d outside [0, %d)", cfg->device, ndev);
+    cudaDeviceProp prop;
+    NIG_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(NIG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", cfg->device, prop.major, prop.minor);
+    DeviceGuard guard(cfg->device);
+    if (!guard.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device);
+
+    nig_env* e = new (std::nothrow) nig_env();
+    if (!e) return fail(NIG_ERR_INVALID, "out of host memory");
+    memset(e, 0, sizeof *e);
+    e->cfg = *cfg;
+    e->kind = cfg->env_kind;
+    e->S = kS[e->kind]; e->A = kA[e->kind]; e->NZ = kNZ[e->kind];
+    e->n = cfg->n_envs;
+    e->pitch = (e->n + 127) / 128 * 128;
+    e->max_steps = cfg->max_episode_steps ? cfg->max_episode_steps : kMaxSteps[e->kind];
+    e->key = RngKey{(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)};
+    if (const char* v = getenv("NIG_STEP_VEC")) e->step_vec = atoi(v);
+    nig_constraint_t def[3];
+    const nig_constraint_t* c = cfg->constraints;
+    int nc = cfg->n_constraints;
+    if (nc < 0) { builtin_constraints(e->kind, def); c = def; nc = 3; }
+    int rc = validate_constraints(e->kind, c, nc);
+    if (rc == NIG_OK) {
+        set_cons(e, c, nc);
+        rc = dev_alloc(&e->state, (size_t)e->S * e->pitch);
+    }
+    if (rc == NIG_OK) rc = dev_alloc(&e->ep_word, (size_t)e->pitch);
+    if (rc == NIG_OK) rc = dev_alloc(&e->ep_return, (size_t)e->pitch);
+    if (rc == NIG_OK) rc = dev_alloc(&e->stats, (size_t)NIG_STATS_SLOTS);
+    if (rc == NIG_OK && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
+        rc = fail(NIG_ERR_CUDA, "cudaStreamCreate failed");
+    if (rc != NIG_OK) { nig_destroy(e); return rc; }
+    *out = e;
+    return NIG_OK;
+}
+
+int nig_destroy(nig_env_t* e)
+{
+    if (!e) return NIG_OK;
+    DeviceGuard guard(e->cfg.device);
+    cudaFree(e->state); cudaFree(e->ep_word); cudaFree(e->ep_return); cudaFree(e->stats);
+    cudaFree(e->h_actions); cudaFree(e->h_noise); cudaFree(e->h_reset); cudaFree(e->h_obs); cudaFree(e->h_next_obs);
+    cudaFree(e->h_reward); cudaFree(e->h_hostmask); cudaFree(e->h_flags); cudaFree(e->h_viol); cudaFree(e->h_mask);
+    cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->d_len);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return NIG_OK;
+}
+
+int64_t nig_pitch(const nig_env_t* e) { return e ? e->pitch : 0; }
+int64_t nig_num_envs(const nig_env_t* e) { return e ? e->n : 0; }
+int64_t nig_launch_count(const nig_env_t* e) { return e ? e->launches : 0; }
+
+int nig_set_constraints(nig_env_t* e, const nig_constraint_t* cons, int32_t n)
+{
+    if (!e) return fail(NIG_ERR_INVALID, "null env handle");
+    if (n > 0 && !cons) return fail(NIG_ERR_INVALID, "null constraint array");
+    const int rc = validate_constraints(e->kind, cons, n);
+    if (rc != NIG_OK) return rc;
+    set_cons(e, cons, n);
+    return NIG_OK;
+}
+
+int nig_reset(nig_env_t* e, const uint8_t* mask, const float* init_states, int32_t layout, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    e->epoch += 1;     // explicit resets draw with a fresh epoch; auto-resets reuse the current one
+    ResetArgs a{e->state, e->ep_word, e->ep_return, e->n, e->pitch, (uint32_t)e->cfg.env_id_offset, e->tick, e->epoch, e->key,
+                mask, init_states, layout == NIG_LAYOUT_AOS ? 1 : 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = grid_for(e->n);
+    switch (e->kind) {
+    case NIG_ENV_CHEMICAL_REACTOR: reset_kernel<Reactor><<<g, kThreads, 0, st>>>(a); break;
+    case NIG_ENV_POWER_GRID: reset_kernel<Grid><<<g, kThreads, 0, st>>>(a); break;
+    default: reset_kernel<Robot><<<g, kThreads, 0, st>>>(a); break;
+    }
+    e->launches++;
+    NIG_CUDA(cudaGetLastError());
+    return NIG_OK;
+}
+
+int nig_reset_host(nig_env_t* e, const uint8_t* mask, const float* init_states_aos, float* obs_aos_out)
+{
+    NIG_CHECK_ENV(e);
+    int rc;
+    const uint8_t* dmask = nullptr;
+    const float* dinit = nullptr;
+    if (mask) {
+        if ((rc = dev_alloc(&e->h_mask, (size_t)e->pitch)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(e->h_mask, mask, (size_t)e->n, cudaMemcpyHostToDevice, e->stream));
+        dmask = e->h_mask;
+    }
+    if (init_states_aos) {
+        if ((rc = dev_alloc(&e->h_reset, (size_t)e->pitch * e->S)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(e->h_reset, init_states_aos, (size_t)e->n * e->S * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        dinit = e->h_reset;
+    }
+    if ((rc = nig_reset(e, dmask, dinit, NIG_LAYOUT_AOS, e->stream)) != NIG_OK) return rc;
+    if (obs_aos_out) {
+        if ((rc = dev_alloc(&e->h_obs, (size_t)e->pitch * e->S)) != NIG_OK) return rc;
+        if ((rc = state_io(e, e->h_obs, NIG_LAYOUT_AOS, nullptr, nullptr, nullptr, true, e->stream)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(obs_aos_out, e->h_obs, (size_t)e->n * e->S * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    }
+    NIG_CUDA(cudaStreamSynchronize(e->stream));
+    return NIG_OK;
+}
+
+int nig_step(nig_env_t* e, const nig_step_io_t* io, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    if (!io || !io->actions) return fail(NIG_ERR_INVALID, "nig_step: null io or actions");
+    if (io->noise && e->NZ == 0) return fail(NIG_ERR_INVALID, "nig_step: env kind %d has no process noise", e->kind);
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.state = e->state; a.ep_word = e->ep_word; a.n = e->n; a.pitch = e->pitch;
+    a.env0 = (uint32_t)e->cfg.env_id_offset; a.tick = e->tick; a.epoch = e->epoch; a.key = e->key;
+    a.max_steps = e->max_steps; a.auto_reset = e->cfg.auto_reset;
+    a.actions = io->actions; a.noise = io->noise; a.reset_states = io->reset_states; a.hostmask = io->hostmask;
+    a.obs = io->obs; a.next_obs = io->next_obs; a.reward = io->reward; a.flags = io->flags; a.viol_mask = io->viol_mask;
+    a.action_aos = io->action_layout == NIG_LAYOUT_AOS; a.aux_aos = io->aux_layout == NIG_LAYOUT_AOS;
+    a.stats = e->stats; a.cons = e->cons;
+    const int rc = launch_step(e, a, (cudaStream_t)stream);
+    if (rc == NIG_OK) e->tick += 1;
+    return rc;
+}
+
+int nig_step_host(nig_env_t* e, const nig_step_io_t* io)
+{
+    NIG_CHECK_ENV(e);
+    if (!io || !io->actions) return fail(NIG_ERR_INVALID, "nig_step_host: null io or actions");
+    if (io->noise && e->NZ == 0) return fail(NIG_ERR_INVALID, "nig_step_host: env kind %d has no process noise", e->kind);
+    int rc;
+    const size_t n = (size_t)e->n, cap = (size_t)e->pitch;
+    nig_step_io_t d;
+    memset(&d, 0, sizeof d);
+    d.action_layout = NIG_LAYOUT_AOS; d.aux_layout = NIG_LAYOUT_AOS;
+    cudaStream_t st = e->stream;
+    if ((rc = dev_alloc(&e->h_actions, cap * e->A)) != NIG_OK) return rc;
+    NIG_CUDA(cudaMemcpyAsync(e->h_actions, io->actions, n * e->A * sizeof(float), cudaMemcpyHostToDevice, st));
+    d.actions = e->h_actions;
+    if (io->noise) {
+        if ((rc = dev_alloc(&e->h_noise, cap * e->NZ)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(e->h_noise, io->noise, n * e->NZ * sizeof(float), cudaMemcpyHostToDevice, st));
+        d.noise = e->h_noise;
+    }
+    if (io->reset_states) {
+        if ((rc = dev_alloc(&e->h_reset, cap * e->S)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(e->h_reset, io->reset_states, n * e->S * sizeof(float), cudaMemcpyHostToDevice, st));
+        d.reset_states = e->h_reset;
+    }
+    if (io->hostmask) {
+        if ((rc = dev_alloc(&e->h_hostmask, cap)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(e->h_hostmask, io->hostmask, n, cudaMemcpyHostToDevice, st));
+        d.hostmask = e->h_hostmask;
+    }
+    if (io->obs) { if ((rc = dev_alloc(&e->h_obs, cap * e->S)) != NIG_OK) return rc; d.obs = e->h_obs; }
+    if (io->next_obs) { if ((rc = dev_alloc(&e->h_next_obs, cap * e->S)) != NIG_OK) return rc; d.next_obs = e->h_next_obs; }
+    if (io->reward) { if ((rc = dev_alloc(&e->h_reward, cap)) != NIG_OK) return rc; d.reward = e->h_reward; }
+    if (io->flags) { if ((rc = dev_alloc(&e->h_flags, cap)) != NIG_OK) return rc; d.flags = e->h_flags; }
+    if (io->viol_mask) { if ((rc = dev_alloc(&e->h_viol, cap)) != NIG_OK) return rc; d.viol_mask = e->h_viol; }
+    if ((rc = nig_step(e, &d, st)) != NIG_OK) return rc;
+    if (io->obs) NIG_CUDA(cudaMemcpyAsync(io->obs, e->h_obs, n * e->S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (io->next_obs) NIG_CUDA(cudaMemcpyAsync(io->next_obs, e->h_next_obs, n * e->S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (io->reward) NIG_CUDA(cudaMemcpyAsync(io->reward, e->h_reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (io->flags) NIG_CUDA(cudaMemcpyAsync(io->flags, e->h_flags, n, cudaMemcpyDeviceToHost, st));
+    if (io->viol_mask) NIG_CUDA(cudaMemcpyAsync(io->viol_mask, e->h_viol, n, cudaMemcpyDeviceToHost, st));
+    NIG_CUDA(cudaStreamSynchronize(st));
+    return NIG_OK;
+}
+
+int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    if (!r) return fail(NIG_ERR_INVALID, "nig_rollout: null descriptor");
+    if (r->n_steps <= 0) return fail(NIG_ERR_INVALID, "nig_rollout: n_steps must be positive (got %d)", r->n_steps);
+    if (r->policy == NIG_POLICY_ACTIONS && !r->actions) return fail(NIG_ERR_INVALID, "nig_rollout: NIG_POLICY_ACTIONS needs an actions tensor");
+    if (r->noise && e->NZ == 0) return fail(NIG_ERR_INVALID, "nig_rollout: env kind %d has no process noise", e->kind);
+    for (int k = 0; k < e->cons.n; ++k)
+        if (e->cons.c[k].kind == NIG_CON_HOSTMASK) return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: host-evaluated constraints cannot run inside a fused rollout");
+    RolloutArgs a;
+    memset(&a, 0, sizeof a);
+    a.state = e->state; a.ep_word = e->ep_word; a.ep_return = e->ep_return; a.n = e->n; a.pitch = e->pitch;
+    a.env0 = (uint32_t)e->cfg.env_id_offset; a.tick = e->tick; a.epoch = e->epoch; a.key = e->key;
+    a.max_steps = e->max_steps; a.auto_reset = e->cfg.auto_reset; a.n_steps = r->n_steps;
+    a.actions = r->actions; a.noise = r->noise; a.pp = r->pp;
+    a.reward_sum = r->reward_sum; a.viol_count = r->viol_count; a.done_count = r->done_count;
+    a.stats = e->stats; a.cons = e->cons;
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
+    const bool tma = r->policy == NIG_POLICY_ACTIONS && (r->flags & NIG_ROLLOUT_USE_TMA);
+    int rc;
+    if (tma && (rc = make_action_map(e, r->actions, r->n_steps, &map)) != NIG_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (e->kind) {
+    case NIG_ENV_CHEMICAL_REACTOR: rc = launch_rollout_env<Reactor>(e, a, r->policy, tma, map, st); break;
+    case NIG_ENV_POWER_GRID: rc = launch_rollout_env<Grid>(e, a, r->policy, tma, map, st); break;
+    default: rc = launch_rollout_env<Robot>(e, a, r->policy, tma, map, st); break;
+    }
+    if (rc == NIG_OK) e->tick += (uint32_t)r->n_steps;
+    return rc;
+}
+
+int nig_dataset(nig_env_t* e, int64_t, int32_t, int32_t, const nig_policy_params_t*, const nig_dataset_out_t*, int64_t*, void*)
+{
+    (void)e;
+    return fail(NIG_ERR_UNSUPPORTED, "nig_dataset: not built yet");
+}
+int nig_dataset_size(nig_env_t* e, int64_t, int32_t, int32_t, const nig_policy_params_t*, int64_t*, void*)
+{
+    (void)e;
+    return fail(NIG_ERR_UNSUPPORTED, "nig_dataset_size: not built yet");
+}
+
+int nig_get_state(nig_env_t* e, float* state_dev, int32_t layout, int32_t* st, int32_t* vi, uint8_t* dn, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    return state_io(e, state_dev, layout, st, vi, dn, true, (cudaStream_t)stream);
+}
+int nig_set_state(nig_env_t* e, const float* state_dev, int32_t layout, const int32_t* st, const int32_t* vi, const uint8_t* dn, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    return state_io(e, const_cast<float*>(state_dev), layout, const_cast<int32_t*>(st), const_cast<int32_t*>(vi), const_cast<uint8_t*>(dn), false, (cudaStream_t)stream);
+}
+
+int nig_get_state_host(nig_env_t* e, float* state_aos, int32_t* st, int32_t* vi, uint8_t* dn)
+{
+    NIG_CHECK_ENV(e);
+    int rc;
+    const size_t n = (size_t)e->n, cap = (size_t)e->pitch;
+    if ((rc = dev_alloc(&e->h_obs, cap * e->S)) != NIG_OK) return rc;
+    if ((rc = dev_alloc(&e->h_i32a, cap)) != NIG_OK) return rc;
+    if ((rc = dev_alloc(&e->h_i32b, cap)) != NIG_OK) return rc;
+    if ((rc = dev_alloc(&e->h_flags, cap)) != NIG_OK) return rc;
+    if ((rc = state_io(e, e->h_obs, NIG_LAYOUT_AOS, e->h_i32a, e->h_i32b, e->h_flags, true, e->stream)) != NIG_OK) return rc;
+    if (state_aos) NIG_CUDA(cudaMemcpyAsync(state_aos, e->h_obs, n * e->S * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    if (st) NIG_CUDA(cudaMemcpyAsync(st, e->h_i32a, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (vi) NIG_CUDA(cudaMemcpyAsync(vi, e->h_i32b, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (dn) NIG_CUDA(cudaMemcpyAsync(dn, e->h_flags, n, cudaMemcpyDeviceToHost, e->stream));
+    NIG_CUDA(cudaStreamSynchronize(e->stream));
+    return NIG_OK;
+}
+
+int nig_set_state_host(nig_env_t* e, const float* state_aos, const int32_t* st, const int32_t* vi, const uint8_t* dn)
+{
+    NIG_CHECK_ENV(e);
+    int rc;
+    const size_t n = (size_t)e->n, cap = (size_t)e->pitch;
+    float* ds = nullptr; int32_t *dst = nullptr, *dvi = nullptr; uint8_t* ddn = nullptr;
+    if (state_aos) {
+        if ((rc = dev_alloc(&e->h_obs, cap * e->S)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(e->h_obs, state_aos, n * e->S * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        ds = e->h_obs;
+    }
+    if (st) {
+        if ((rc = dev_alloc(&e->h_i32a, cap)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(e->h_i32a, st, n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        dst = e->h_i32a;
+    }
+    if (vi) {
+        if ((rc = dev_alloc(&e->h_i32b, cap)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(e->h_i32b, vi, n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        dvi = e->h_i32b;
+    }
+    if (dn) {
+        if ((rc = dev_alloc(&e->h_flags, cap)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(e->h_flags, dn, n, cudaMemcpyHostToDevice, e->stream));
+        ddn = e->h_flags;
+    }
+    if ((rc = state_io(e, ds, NIG_LAYOUT_AOS, dst, dvi, ddn, false, e->stream)) != NIG_OK) return rc;
+    NIG_CUDA(cudaStreamSynchronize(e->stream));
+    return NIG_OK;
+}
+
+int nig_state_ptr(nig_env_t* e, float** state, uint32_t** ep_word)
+{
+    if (!e) return fail(NIG_ERR_INVALID, "null env handle");
+    if (state) *state = e->state;
+    if (ep_word) *ep_word = e->ep_word;
+    return NIG_OK;
+}
+
+int nig_get_tick(const nig_env_t* e, uint32_t* tick, uint32_t* epoch)
+{
+    if (!e) return fail(NIG_ERR_INVALID, "null env handle");
+    if (tick) *tick = e->tick;
+    if (epoch) *epoch = e->epoch;
+    return NIG_OK;
+}
+int nig_set_tick(nig_env_t* e, uint32_t tick, uint32_t epoch)
+{
+    if (!e) return fail(NIG_ERR_INVALID, "null env handle");
+    e->tick = tick; e->epoch = epoch;
+    return NIG_OK;
+}
+
+int nig_set_seed(nig_env_t* e, uint64_t seed)
+{
+    if (!e) return fail(NIG_ERR_INVALID, "null env handle");
+    e->cfg.seed = seed;
+    e->key = RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    return NIG_OK;
+}
+
+int nig_stats_ptr(nig_env_t* e, void** p)
+{
+    if (!e || !p) return fail(NIG_ERR_INVALID, "null env handle or pointer");
+    *p = e->stats;
+    return NIG_OK;
+}
+
+int nig_read_stats(nig_env_t* e, int64_t* counters24, double* sums8)
+{
+    NIG_CHECK_ENV(e);
+    unsigned long long h[NIG_STATS_SLOTS];
+    NIG_CUDA(cudaDeviceSynchronize());
+    NIG_CUDA(cudaMemcpy(h, e->stats, sizeof h, cudaMemcpyDeviceToHost));
+    if (counters24) for (int k = 0; k < 24; ++k) counters24[k] = (int64_t)h[k];
+    if (sums8) memcpy(sums8, &h[24], 8 * sizeof(double));
+    return NIG_OK;
+}
+
+int nig_clear_stats(nig_env_t* e, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    NIG_CUDA(cudaMemsetAsync(e->stats, 0, NIG_STATS_SLOTS * sizeof(unsigned long long), (cudaStream_t)stream));
+    return NIG_OK;
+}
+
+int nig_sync(nig_env_t* e)
+{
+    NIG_CHECK_ENV(e);
+    NIG_CUDA(cudaDeviceSynchronize());
+    return NIG_OK;
+}
+
+int nig_host_alloc(size_t bytes, void** out)
+{
+    if (!out) return fail(NIG_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    NIG_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return NIG_OK;
+}
+int nig_host_free(void* p)
+{
+    if (p) NIG_CUDA(cudaFreeHost(p));
+    return NIG_OK;
+}
+
+int nig_fp32_probe(int device, int32_t iters, double* ops, void* stream)
+{
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    static float* sink = nullptr;
+    if (!sink) NIG_CUDA(cudaMalloc((void**)&sink, 256));
+    const int blocks = 148 * 8;
+    fp32_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters);
+    NIG_CUDA(cudaGetLastError());
+    if (ops) *ops = (double)blocks * 256.0 * (double)iters * 16.0;
+    return NIG_OK;
+}
+
+} // extern "C"

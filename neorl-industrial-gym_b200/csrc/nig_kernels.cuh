@@ -1,0 +1,664 @@
+// nig_kernels.cuh -- the sm_100a kernels of the batched IndustrialEnv step path.
+//
+//  step_kernel     one IndustrialEnv.step (environments/base.py:157-213) for every env: clip, constraints on
+//                  the pre-step state, dynamics, reward, penalties, counters, termination, critical
+//                  shutdown, auto-reset. HBM-bound: SoA fp32 state, VEC consecutive envs per thread so
+//                  every state/action/reward access is one 32*VEC*4-byte coalesced request (128-bit
+//                  LDG/STG at VEC = 4). Algorithmic traffic 122 B / env-step (reactor).
+//  rollout_kernel  K fused steps with the state in registers (the reset/step loops of
+//                  performance_benchmark.py:106-133, utils.py:82-125, chemical_reactor.py:355-405):
+//                  actions from a TMA-staged [K][A][pitch] tensor or generated in-kernel, Philox
+//                  process noise, ballot/popc + shuffle reductions for the violation/return statistics.
+//                  FP32-pipe bound.
+//  reset_kernel    IndustrialEnv.reset (base.py:133-155) for masked envs.
+#pragma once
+#include <cuda.h>
+#include "../../include/nig_b200.h"
+#include "nig_envs.cuh"
+
+namespace nig {
+
+constexpr int kThreads = 128;
+
+struct ConsParams {
+    int32_t n;
+    int32_t is_default;
+    nig_constraint_t c[NIG_MAX_CONSTRAINTS];
+};
+
+// ---- vector access helpers -----------------------------------------------------------------------
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int VEC>
+__device__ __forceinline__ void ldvec(const float* p, float (&v)[VEC])
+{
+    using T = typename VecT<VEC>::type;
+    const T t = *reinterpret_cast<const T*>(p);
+    if constexpr (VEC == 1) { v[0] = t; }
+    else if constexpr (VEC == 2) { v[0] = t.x; v[1] = t.y; }
+    else { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+}
+template <int VEC>
+__device__ __forceinline__ void stvec(float* p, const float (&v)[VEC])
+{
+    using T = typename VecT<VEC>::type;
+    T t;
+    if constexpr (VEC == 1) { t = v[0]; }
+    else if constexpr (VEC == 2) { t.x = v[0]; t.y = v[1]; }
+    else { t.x = v[0]; t.y = v[1]; t.z = v[2]; t.w = v[3]; }
+    *reinterpret_cast<T*>(p) = t;
+}
+
+template <int S>
+__device__ __forceinline__ float pick(const float (&s)[S], int i)
+{
+    float v = s[0];
+#pragma unroll
+    for (int k = 1; k < S; ++k) v = (i == k) ? s[k] : v;
+    return v;
+}
+
+// ep_word: bits 0..15 episode step, bits 16..30 episode violation count (saturating), bit 31 done latch
+__device__ __forceinline__ uint32_t epw_step(uint32_t w) { return w & 0xffffu; }
+__device__ __forceinline__ uint32_t epw_viol(uint32_t w) { return (w >> 16) & 0x7fffu; }
+__device__ __forceinline__ uint32_t epw_make(uint32_t step, uint32_t viol, uint32_t done)
+{
+    return (step & 0xffffu) | ((viol > 0x7fffu ? 0x7fffu : viol) << 16) | (done << 31);
+}
+
+// ---- one env step in registers (base.py:157-213) --------------------------------------------------
+template <class Env, bool DEFCONS>
+__device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
+                                          const float (&s)[Env::S], const float (&a_raw)[Env::A],
+                                          const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
+                                          uint32_t& ep_word, float (&ns)[Env::S],
+                                          typename Env::acc_t& reward, uint32_t& flags, uint32_t& vmask)
+{
+    using acc_t = typename Env::acc_t;
+    float a[Env::A];
+#pragma unroll
+    for (int j = 0; j < Env::A; ++j) {               // base.py:167 np.clip(action, -1, 1)
+        float v = a_raw[j];
+        v = v < -1.0f ? -1.0f : v;
+        v = v > 1.0f ? 1.0f : v;
+        a[j] = v;
+    }
+    // base.py:170 -- constraints on the PRE-step state (the reference calls every check_fn twice with
+    // identical arguments, :102 and :180; evaluated once here)
+    uint32_t vm = 0, crit = 0;
+    if constexpr (DEFCONS) {
+#pragma unroll
+        for (int k = 0; k < Env::NB; ++k)
+            if (!Env::builtin(k, s, a)) vm |= 1u << k;
+        crit = vm & Env::CRIT_MASK;
+    } else {
+        for (int k = 0; k < cp.n; ++k) {
+            const nig_constraint_t& c = cp.c[k];
+            bool ok;
+            if (c.kind == NIG_CON_BUILTIN) ok = Env::builtin(c.id, s, a);
+            else if (c.kind == NIG_CON_BOUND) {
+                float v = pick<Env::S>(s, c.si);
+                if (c.ai >= 0) v = add(v, mul(c.coef, pick<Env::A>(a, c.ai)));
+                ok = (c.lo <= v) && (v <= c.hi);
+            } else ok = !((hostmask >> c.id) & 1u);
+            if (!ok) { vm |= 1u << k; if (c.critical) crit |= 1u << k; }
+        }
+    }
+    Env::dynamics(s, a, nz, ns);                      // base.py:173
+    acc_t r = Env::reward(ns, a);                     // base.py:176
+    if constexpr (DEFCONS) {                          // base.py:179-183, in constraint order
+#pragma unroll
+        for (int k = 0; k < Env::NB; ++k)
+            if ((vm >> k) & 1u) r = r + (acc_t)Env::penalty(k);
+    } else {
+        for (int k = 0; k < cp.n; ++k)
+            if ((vm >> k) & 1u) r = r + (acc_t)cp.c[k].penalty;
+    }
+    const uint32_t step = epw_step(ep_word) + 1u;     // base.py:187
+    const uint32_t viol = epw_viol(ep_word) + (uint32_t)__popc(vm);
+    bool terminated = Env::is_done(ns);               // base.py:190
+    const bool truncated = step >= (uint32_t)max_steps;   // base.py:191
+    uint32_t f = 0;
+    if (crit) { terminated = true; r = r - (acc_t)1000.0f; f |= NIG_F_CRITICAL; }   // base.py:195-198
+    if (terminated) f |= NIG_F_TERMINATED;
+    if (truncated) f |= NIG_F_TRUNCATED;
+    ep_word = epw_make(step, viol, 0u);
+    reward = r; flags = f; vmask = vm;
+}
+
+// ---- block-level statistics: per-thread counts -> REDUX -> shared atomics -> one global atomic per slot
+struct BlockStats {
+    unsigned int* sh;   // [NIG_STATS_SLOTS] shared counters
+    __device__ __forceinline__ void init(unsigned int* smem)
+    {
+        sh = smem;
+        if (threadIdx.x < NIG_STATS_SLOTS) sh[threadIdx.x] = 0u;
+        __syncthreads();
+    }
+    __device__ __forceinline__ void warp_add(int slot, unsigned int v)
+    {
+        const unsigned int t = __reduce_add_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0 && t) atomicAdd(&sh[slot], t);
+    }
+    __device__ __forceinline__ void flush(unsigned long long* g)
+    {
+        __syncthreads();
+        if (threadIdx.x < 24 && sh[threadIdx.x]) atomicAdd(&g[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+    }
+};
+
+// ================================================================================================
+// single-step kernel
+// ================================================================================================
+struct StepArgs {
+    float* state;            // [S][pitch]
+    uint32_t* ep_word;       // [pitch]
+    int64_t n, pitch;
+    uint32_t env0, tick, epoch;
+    RngKey key;
+    int32_t max_steps, auto_reset;
+    const float* actions;
+    const float* noise;
+    const float* reset_states;
+    const uint8_t* hostmask;
+    float* obs;
+    float* next_obs;
+    float* reward;
+    uint8_t* flags;
+    uint8_t* viol_mask;
+    int32_t action_aos, aux_aos;
+    unsigned long long* stats;
+    ConsParams cons;
+};
+
+template <int D, int VEC>
+__device__ __forceinline__ void load_rows(const float* base, int64_t pitch, int64_t n, int64_t i0, bool aos, float (&v)[D][VEC])
+{
+    if (!aos) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) ldvec<VEC>(base + k * pitch + i0, v[k]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+#pragma unroll
+            for (int k = 0; k < D; ++k) v[k][e] = (i0 + e < n) ? base[(i0 + e) * D + k] : 0.0f;
+    }
+}
+template <int D, int VEC>
+__device__ __forceinline__ void store_rows(float* base, int64_t pitch, int64_t n, int64_t i0, bool aos, const float (&v)[D][VEC])
+{
+    if (!aos) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) stvec<VEC>(base + k * pitch + i0, v[k]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+            if (i0 + e < n) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) base[(i0 + e) * D + k] = v[k][e];
+            }
+    }
+}
+
+template <class Env, int VEC, bool DEFCONS>
+__global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ StepArgs p)
+{
+    constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
+    using acc_t = typename Env::acc_t;
+    __shared__ unsigned int sstat[NIG_STATS_SLOTS];
+    BlockStats bs;
+    bs.init(sstat);
+
+    const int64_t i0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
+    unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0, c_con = 0;  // c_con: 4 bits/constraint
+    if (i0 < p.pitch) {
+        float sv[S][VEC], av[A][VEC], nzv[NZA][VEC], rs[S][VEC];
+        load_rows<S, VEC>(p.state, p.pitch, p.n, i0, false, sv);
+        load_rows<A, VEC>(p.actions, p.pitch, p.n, i0, p.action_aos != 0, av);
+        float wv[VEC];
+        ldvec<VEC>(reinterpret_cast<const float*>(p.ep_word) + i0, wv);
+        if (NZ > 0 && p.noise) load_rows<NZA, VEC>(p.noise, p.pitch, p.n, i0, p.aux_aos != 0, nzv);
+        if (p.reset_states) load_rows<S, VEC>(p.reset_states, p.pitch, p.n, i0, p.aux_aos != 0, rs);
+
+        float nsv[S][VEC], rw[VEC];
+        uint32_t fl[VEC], vmk[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int64_t i = i0 + e;
+            const uint32_t env = p.env0 + (uint32_t)i;
+            uint32_t w = __float_as_uint(wv[e]);
+            float s[S], a[A], nz[NZA], ns[S];
+#pragma unroll
+            for (int k = 0; k < S; ++k) s[k] = sv[k][e];
+#pragma unroll
+            for (int k = 0; k < A; ++k) a[k] = av[k][e];
+            const bool valid = i < p.n;
+            const bool active = valid && !(w >> 31);
+            if (NZ > 0) {
+                if (p.noise) {
+#pragma unroll
+                    for (int k = 0; k < NZA; ++k) nz[k] = nzv[k][e];
+                } else {
+                    typename Env::NoiseGen g;
+                    g.get(p.key, env, p.tick, nz);
+                }
+            } else nz[0] = 0.0f;
+            acc_t r; uint32_t f, vm;
+            const uint32_t hm = p.hostmask && valid ? p.hostmask[i] : 0u;
+            step_core<Env, DEFCONS>(p.cons, p.max_steps, s, a, nz, hm, w, ns, r, f, vm);
+            if (!active) {            // finished env without auto-reset (or padding lane): nothing happens
+#pragma unroll
+                for (int k = 0; k < S; ++k) ns[k] = s[k];
+                r = (acc_t)0; f = NIG_F_INACTIVE; vm = 0; w = __float_as_uint(wv[e]);
+            }
+            const bool done = active && (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED));
+#pragma unroll
+            for (int k = 0; k < S; ++k) nsv[k][e] = ns[k];     // s' of the transition (pre-reset)
+            if (done) {
+                if (p.auto_reset) {
+                    if (p.reset_states) {
+#pragma unroll
+                        for (int k = 0; k < S; ++k) s[k] = rs[k][e];
+                    } else {
+                        Env::reset(p.key, env, p.tick + 1u, p.epoch, s);
+                    }
+                    w = 0u; f |= NIG_F_RESET;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < S; ++k) s[k] = ns[k];
+                    w |= 0x80000000u;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < S; ++k) s[k] = ns[k];
+            }
+#pragma unroll
+            for (int k = 0; k < S; ++k) sv[k][e] = s[k];
+            wv[e] = __uint_as_float(w);
+            rw[e] = (float)r; fl[e] = f; vmk[e] = vm;
+            if (active) {
+                c_steps += 1; c_viol += __popc(vm);
+                c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
+                if (done) { c_ep += 1; c_term += (f & NIG_F_TERMINATED) ? 1u : 0u; c_trunc += (f & NIG_F_TRUNCATED) ? 1u : 0u; }
+#pragma unroll
+                for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) c_con += ((vm >> k) & 1u) << (4 * k);
+            }
+        }
+        store_rows<S, VEC>(p.state, p.pitch, p.n, i0, false, sv);
+        stvec<VEC>(reinterpret_cast<float*>(p.ep_word) + i0, wv);
+        if (p.obs) store_rows<S, VEC>(p.obs, p.pitch, p.n, i0, p.aux_aos != 0, sv);
+        if (p.next_obs) store_rows<S, VEC>(p.next_obs, p.pitch, p.n, i0, p.aux_aos != 0, nsv);
+        if (p.reward) stvec<VEC>(p.reward + i0, rw);
+        if (p.flags) {
+            if constexpr (VEC == 4) *reinterpret_cast<uchar4*>(p.flags + i0) = make_uchar4(fl[0], fl[1], fl[2], fl[3]);
+            else if constexpr (VEC == 2) *reinterpret_cast<uchar2*>(p.flags + i0) = make_uchar2(fl[0], fl[1]);
+            else p.flags[i0] = (uint8_t)fl[0];
+        }
+        if (p.viol_mask) {
+            if constexpr (VEC == 4) *reinterpret_cast<uchar4*>(p.viol_mask + i0) = make_uchar4(vmk[0], vmk[1], vmk[2], vmk[3]);
+            else if constexpr (VEC == 2) *reinterpret_cast<uchar2*>(p.viol_mask + i0) = make_uchar2(vmk[0], vmk[1]);
+            else p.viol_mask[i0] = (uint8_t)vmk[0];
+        }
+    }
+    bs.warp_add(NIG_ST_STEPS, c_steps);
+    if (__any_sync(0xffffffffu, (c_ep | c_viol | c_crit) != 0u)) {
+        bs.warp_add(NIG_ST_EPISODES, c_ep);
+        bs.warp_add(NIG_ST_TERMINATED, c_term);
+        bs.warp_add(NIG_ST_TRUNCATED, c_trunc);
+        bs.warp_add(NIG_ST_CRITICAL, c_crit);
+        bs.warp_add(NIG_ST_VIOLATIONS, c_viol);
+        for (int k = 0; k < p.cons.n; ++k) bs.warp_add(NIG_ST_CON0 + k, (c_con >> (4 * k)) & 0xfu);
+    }
+    bs.flush(p.stats);
+}
+
+// ================================================================================================
+// reset kernel
+// ================================================================================================
+struct ResetArgs {
+    float* state; uint32_t* ep_word; double* ep_return;
+    int64_t n, pitch;
+    uint32_t env0, tick, epoch;
+    RngKey key;
+    const uint8_t* mask;
+    const float* init_states;
+    int32_t init_aos;
+};
+
+template <class Env>
+__global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__ ResetArgs p)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= p.n) return;
+    if (p.mask && !p.mask[i]) return;
+    float s[Env::S];
+    if (p.init_states) {
+#pragma unroll
+        for (int k = 0; k < Env::S; ++k) s[k] = p.init_aos ? p.init_states[i * Env::S + k] : p.init_states[k * p.pitch + i];
+    } else {
+        Env::reset(p.key, p.env0 + (uint32_t)i, p.tick, p.epoch, s);
+    }
+#pragma unroll
+    for (int k = 0; k < Env::S; ++k) p.state[k * p.pitch + i] = s[k];
+    p.ep_word[i] = 0u;
+    p.ep_return[i] = 0.0;
+}
+
+// SoA <-> AoS / ep_word <-> (step, viol, done) conversion for get/set_state
+struct StateIoArgs {
+    float* state; uint32_t* ep_word;
+    int64_t n, pitch;
+    float* ext_state; int32_t* ext_step; int32_t* ext_viol; uint8_t* ext_done;
+    int32_t S, aos, to_ext;
+};
+__global__ void __launch_bounds__(kThreads) state_io_kernel(const __grid_constant__ StateIoArgs p)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= p.n) return;
+    if (p.ext_state) {
+        for (int k = 0; k < p.S; ++k) {
+            float* ext = p.ext_state + (p.aos ? i * p.S + k : (int64_t)k * p.pitch + i);
+            float* in = p.state + (int64_t)k * p.pitch + i;
+            if (p.to_ext) *ext = *in; else *in = *ext;
+        }
+    }
+    if (p.to_ext) {
+        const uint32_t w = p.ep_word[i];
+        if (p.ext_step) p.ext_step[i] = (int32_t)epw_step(w);
+        if (p.ext_viol) p.ext_viol[i] = (int32_t)epw_viol(w);
+        if (p.ext_done) p.ext_done[i] = (uint8_t)(w >> 31);
+    } else if (p.ext_step || p.ext_viol || p.ext_done) {
+        const uint32_t w = p.ep_word[i];
+        const uint32_t st = p.ext_step ? (uint32_t)p.ext_step[i] : epw_step(w);
+        const uint32_t vi = p.ext_viol ? (uint32_t)p.ext_viol[i] : epw_viol(w);
+        const uint32_t dn = p.ext_done ? (uint32_t)(p.ext_done[i] != 0) : (w >> 31);
+        p.ep_word[i] = epw_make(st, vi, dn);
+    }
+}
+
+// ================================================================================================
+// fused K-step rollout kernel
+// ================================================================================================
+constexpr int kTmaChunk = 16;   // steps of actions staged per TMA box
+
+struct RolloutArgs {
+    float* state; uint32_t* ep_word; double* ep_return;
+    int64_t n, pitch;
+    uint32_t env0, tick, epoch;
+    RngKey key;
+    int32_t max_steps, auto_reset, n_steps;
+    const float* actions;      // [K][A][pitch]
+    const float* noise;        // [K][NZ][pitch] or null
+    nig_policy_params_t pp;
+    float* reward_sum; int32_t* viol_count; int32_t* done_count;
+    unsigned long long* stats;
+    ConsParams cons;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "NIG_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra NIG_DONE_%=;\n\t"
+        "bra NIG_WAIT_%=;\n\t"
+        "NIG_DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// in-kernel policies ---------------------------------------------------------------------------------
+template <class Env>
+__device__ __forceinline__ void policy_uniform(const RngKey& key, uint32_t env, uint32_t tick, float (&a)[Env::A])
+{
+#pragma unroll
+    for (int j = 0; j < (Env::A + 3) / 4; ++j) {
+        const uint4 w = rng_words(key, env, tick, STREAM_POLICY, (uint32_t)j);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (4 * j + q < Env::A) a[4 * j + q] = u_sym(ww[q]);
+    }
+}
+
+// get_dataset mixes (chemical_reactor.py:364-390, power_grid.py:216-232, robot_assembly.py:266-291):
+// block 0 word 0 of the POLICY stream is the np.random.random() coin; the controller branch gets 8
+// normals (blocks 1, 2) and 4 words (block 3); the random branch uses words 1..3 of block 0 and blocks 8..
+template <class Env>
+__device__ __forceinline__ void policy_pctrl(const RngKey& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
+                                             const float (&s)[Env::S], float (&a)[Env::A])
+{
+    const uint4 w0 = rng_words(key, env, tick, STREAM_POLICY, 0u);
+    const float coin = u_open(w0.x);                       // (0, 1]
+    if (coin <= pp.p_ctrl) {
+        Env::policy_ctrl(key, pp, env, tick, s, a);
+    } else {
+        const uint32_t ww[3] = {w0.y, w0.z, w0.w};
+#pragma unroll
+        for (int k = 0; k < Env::A; ++k) {
+            if (k < 3) a[k] = mul(pp.uniform_scale, u_sym(ww[k]));
+        }
+        if constexpr (Env::A > 3) {
+#pragma unroll
+            for (int j = 0; j < (Env::A - 3 + 3) / 4; ++j) {
+                const uint4 w = rng_words(key, env, tick, STREAM_POLICY, (uint32_t)(8 + j));
+                const uint32_t wq[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (3 + 4 * j + q < Env::A) a[3 + 4 * j + q] = mul(pp.uniform_scale, u_sym(wq[q]));
+            }
+        }
+    }
+}
+
+template <class T> __device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <class Env, bool DEFCONS, int POLICY, bool TMA>
+__global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant__ RolloutArgs p, const __grid_constant__ CUtensorMap amap)
+{
+    constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
+    using acc_t = typename Env::acc_t;
+    __shared__ unsigned int sstat[NIG_STATS_SLOTS];
+    __shared__ double sfl[4];
+    __shared__ alignas(8) uint64_t bars[2];
+    extern __shared__ __align__(128) float act_smem[];     // [2][kTmaChunk][A][kThreads] when TMA
+    BlockStats bs;
+    if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
+    bs.init(sstat);
+
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool valid = i < p.n;
+    const int64_t ic = valid ? i : 0;      // padding lanes shadow env 0 without side effects
+    const uint32_t env = p.env0 + (uint32_t)ic;
+
+    constexpr uint32_t kChunkBytes = kTmaChunk * A * kThreads * sizeof(float);
+    int n_chunks = 0;
+    if constexpr (TMA) {
+        n_chunks = (p.n_steps + kTmaChunk - 1) / kTmaChunk;
+        if (threadIdx.x == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int c = 0; c < 2 && c < n_chunks; ++c) {
+                mbar_expect_tx(&bars[c], kChunkBytes);
+                tma_load_3d(act_smem + (size_t)c * kTmaChunk * A * kThreads, &amap, (int)(blockIdx.x * kThreads), 0, c * kTmaChunk, &bars[c]);
+            }
+        }
+    }
+
+    float s[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) s[k] = p.state[k * p.pitch + ic];
+    uint32_t w = p.ep_word[ic];
+    acc_t ep_ret = (acc_t)p.ep_return[ic];
+    typename Env::NoiseGen ng;
+
+    float rsum = 0.0f;
+    unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0, c_succ = 0, c_done = 0;
+    unsigned int c_con[NIG_MAX_CONSTRAINTS];
+#pragma unroll
+    for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] = 0;
+    unsigned long long len_sum = 0, len_sq = 0;
+    double ret_sum = 0.0, ret_sq = 0.0, rew_sum = 0.0;
+
+    for (int t = 0; t < p.n_steps; ++t) {
+        const uint32_t tick = p.tick + (uint32_t)t;
+        float a[A], nz[NZA], ns[S];
+        if constexpr (POLICY == NIG_POLICY_ACTIONS) {
+            if constexpr (TMA) {
+                const int c = t / kTmaChunk, tt = t % kTmaChunk, b = c & 1;
+                if (tt == 0) mbar_wait(&bars[b], (uint32_t)((c >> 1) & 1));
+                const float* src = act_smem + ((size_t)b * kTmaChunk + tt) * A * kThreads;
+#pragma unroll
+                for (int k = 0; k < A; ++k) a[k] = src[k * kThreads + threadIdx.x];
+                if (tt == kTmaChunk - 1 || t == p.n_steps - 1) {
+                    __syncthreads();                       // everyone finished reading buffer b
+                    if (threadIdx.x == 0 && c + 2 < n_chunks) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_expect_tx(&bars[b], kChunkBytes);
+                        tma_load_3d(act_smem + (size_t)b * kTmaChunk * A * kThreads, &amap, (int)(blockIdx.x * kThreads), 0, (c + 2) * kTmaChunk, &bars[b]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < A; ++k) a[k] = __ldcs(p.actions + ((int64_t)t * A + k) * p.pitch + ic);
+            }
+        } else if constexpr (POLICY == NIG_POLICY_UNIFORM) {
+            policy_uniform<Env>(p.key, env, tick, a);
+        } else if constexpr (POLICY == NIG_POLICY_PCTRL) {
+            policy_pctrl<Env>(p.key, p.pp, env, tick, s, a);
+        } else {
+#pragma unroll
+            for (int k = 0; k < A; ++k) a[k] = 0.0f;
+        }
+        if (NZ > 0) {
+            if (p.noise) {
+#pragma unroll
+                for (int k = 0; k < NZA; ++k) nz[k] = p.noise[((int64_t)t * NZA + k) * p.pitch + ic];
+            } else ng.get(p.key, env, tick, nz);
+        } else nz[0] = 0.0f;
+
+        const bool active = valid && !(w >> 31);
+        uint32_t w2 = w, f, vm;
+        acc_t r;
+        step_core<Env, DEFCONS>(p.cons, p.max_steps, s, a, nz, 0u, w2, ns, r, f, vm);
+        if (active) {
+            const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
+            rsum = add(rsum, (float)r);
+            ep_ret = ep_ret + r;
+            rew_sum += (double)r;
+            c_steps += 1; c_viol += __popc(vm);
+            c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
+            if constexpr (DEFCONS) {
+#pragma unroll
+                for (int k = 0; k < Env::NB; ++k) c_con[k] += (vm >> k) & 1u;
+            } else {
+#pragma unroll
+                for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] += (vm >> k) & 1u;
+            }
+            w = w2;
+            if (done) {
+                const unsigned long long len = epw_step(w2);
+                c_ep += 1; c_done += 1;
+                c_term += (f & NIG_F_TERMINATED) ? 1u : 0u;
+                c_trunc += (f & NIG_F_TRUNCATED) ? 1u : 0u;
+                c_succ += (ep_ret > (acc_t)0) ? 1u : 0u;
+                len_sum += len; len_sq += len * len;
+                ret_sum += (double)ep_ret; ret_sq += (double)ep_ret * (double)ep_ret;
+                if (p.auto_reset) {
+                    Env::reset(p.key, env, tick + 1u, p.epoch, s);
+                    w = 0u; ep_ret = (acc_t)0;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < S; ++k) s[k] = ns[k];
+                    w |= 0x80000000u;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < S; ++k) s[k] = ns[k];
+            }
+        }
+    }
+
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < S; ++k) p.state[k * p.pitch + i] = s[k];
+        p.ep_word[i] = w;
+        p.ep_return[i] = (double)ep_ret;
+        if (p.reward_sum) p.reward_sum[i] = rsum;
+        if (p.viol_count) p.viol_count[i] = (int32_t)c_viol;
+        if (p.done_count) p.done_count[i] = (int32_t)c_done;
+    }
+    // violation / episode statistics: warp REDUX + shuffle trees -> one global atomic per slot per block
+    bs.warp_add(NIG_ST_STEPS, c_steps);
+    bs.warp_add(NIG_ST_VIOLATIONS, c_viol);
+    bs.warp_add(NIG_ST_CRITICAL, c_crit);
+#pragma unroll
+    for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k)
+        if (k < p.cons.n) bs.warp_add(NIG_ST_CON0 + k, c_con[k]);
+    if (__any_sync(0xffffffffu, c_ep != 0u)) {
+        bs.warp_add(NIG_ST_EPISODES, c_ep);
+        bs.warp_add(NIG_ST_TERMINATED, c_term);
+        bs.warp_add(NIG_ST_TRUNCATED, c_trunc);
+        bs.warp_add(NIG_ST_SUCCESSES, c_succ);
+        const unsigned long long ls = warp_sum(len_sum), lq = warp_sum(len_sq);
+        const double rs_ = warp_sum(ret_sum), rq = warp_sum(ret_sq);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&p.stats[NIG_ST_EP_LEN_SUM], ls);
+            atomicAdd(&p.stats[NIG_ST_EP_LEN_SQ], lq);
+            atomicAdd(&sfl[0], rs_);
+            atomicAdd(&sfl[1], rq);
+        }
+    }
+    {
+        const double rw_ = warp_sum(rew_sum);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sfl[2], rw_);
+    }
+    bs.flush(p.stats);
+    if (threadIdx.x < 3 && sfl[threadIdx.x] != 0.0)
+        atomicAdd(reinterpret_cast<double*>(p.stats) + NIG_ST_F_RETURN_SUM + threadIdx.x, sfl[threadIdx.x]);
+}
+
+// ---- measured-peak probe: independent unfused FADD/FMUL chains (what the physics is made of) ------
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters)
+{
+    float x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = 1.0f + 1e-3f * (float)(threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x[k] = __fmul_rn(x[k], 1.0000001f); x[k] = __fadd_rn(x[k], 1e-7f); }
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += x[k];
+    if (acc == 123.456f) out[0] = acc;
+}
+
+} // namespace nig

@@ -1,0 +1,54 @@
+"""get_dataset-style generation on the device (reference chemical_reactor.py:324-420, power_grid.py:194-249,
+robot_assembly.py:246-308): every episode is an independent env; a length-probe pass, an exclusive scan
+and a write pass emit episode-contiguous D4RL arrays straight into HBM, exported with pinned async copies."""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+
+from . import _native as N
+
+
+def generate_dataset_device(native, n_episodes: int, n_steps: int, policy: int, params, *, extensions: bool = False,
+                            timeouts: bool = True):
+    """Returns (dict of torch CUDA tensors, n_transitions). Layout: observations [M,S] f32, actions [M,A] f32,
+    rewards [M] f32, terminals [M] u8, timeouts [M] u8 (+ next_observations [M,S], safety [M] u8)."""
+    import torch
+    dev = native.torch_device()
+    m = native.dataset_size(n_episodes, n_steps, policy, params)
+    cap = max(m, 1)
+    out = {
+        "observations": torch.empty((cap, native.S), dtype=torch.float32, device=dev),
+        "actions": torch.empty((cap, native.A), dtype=torch.float32, device=dev),
+        "rewards": torch.empty((cap,), dtype=torch.float32, device=dev),
+        "terminals": torch.empty((cap,), dtype=torch.uint8, device=dev),
+    }
+    if timeouts:
+        out["timeouts"] = torch.empty((cap,), dtype=torch.uint8, device=dev)
+    if extensions:
+        out["next_observations"] = torch.empty((cap, native.S), dtype=torch.float32, device=dev)
+        out["safety"] = torch.empty((cap,), dtype=torch.uint8, device=dev)
+    written = native.dataset_device(n_episodes, n_steps, policy, params, out, cap)
+    assert written == m, (written, m)
+    return {k: v[:m] for k, v in out.items()}, m
+
+
+def generate_dataset(env, n_episodes: int, n_steps: int, policy: int, params, *, terminals_include_truncation: bool,
+                     timeouts_key: bool, extensions: bool = False) -> Dict[str, np.ndarray]:
+    """Host dict with the reference's keys and dtypes (bool terminals / timeouts)."""
+    import torch
+    params.mode = int(params.mode) | (0x100 if terminals_include_truncation else 0)
+    dev_out, m = generate_dataset_device(env.native, n_episodes, n_steps, policy, params, extensions=extensions,
+                                         timeouts=timeouts_key)
+    host = {}
+    for k, v in dev_out.items():
+        pinned = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+        pinned.copy_(v, non_blocking=True)
+        host[k] = pinned
+    torch.cuda.synchronize(env.native.torch_device())
+    res = {k: v.numpy().copy() for k, v in host.items()}
+    for k in ("terminals", "timeouts"):
+        if k in res:
+            res[k] = res[k].astype(bool)
+    return res

@@ -736,6 +736,73 @@ ORC_API void orc_reset_batch(const orc_cfg_t* cfg, int64_t n, int64_t env_id0, u
     }
 }
 
+
+/* ------------------------------------------------------------------------------------------- */
+/* In-kernel policies of the fused rollout / dataset kernels (project spec, DESIGN.md "Policies")  */
+/* ------------------------------------------------------------------------------------------- */
+enum { ORC_POLICY_ACTIONS = 0, ORC_POLICY_UNIFORM = 1, ORC_POLICY_ZERO = 2, ORC_POLICY_PCTRL = 3 };
+typedef struct {
+    float p_ctrl, uniform_scale, store_clip;
+    int32_t mode;
+    float gain[8][2];
+    float sigma[8];
+} orc_pp_t;
+
+static void policy_one(const orc_cfg_t* cfg, int policy, const orc_pp_t* pp, uint32_t env, uint32_t tick, const float* s, float* a)
+{
+    const int A = kA[cfg->kind];
+    uint32_t w[4];
+    if (policy == ORC_POLICY_ZERO) { for (int k = 0; k < A; ++k) a[k] = 0.0f; return; }
+    if (policy == ORC_POLICY_UNIFORM) {
+        for (int j = 0; j < (A + 3) / 4; ++j) {
+            words4(cfg, env, tick, STREAM_POLICY, (uint32_t)j, w);
+            for (int q = 0; q < 4; ++q) if (4 * j + q < A) a[4 * j + q] = u_sym(w[q]);
+        }
+        return;
+    }
+    /* PCTRL: chemical_reactor.py:364-390, power_grid.py:216-232, robot_assembly.py:266-291 */
+    uint32_t w0[4];
+    words4(cfg, env, tick, STREAM_POLICY, 0u, w0);
+    const float coin = u_open(w0[0]);
+    if (coin <= pp->p_ctrl) {
+        if (cfg->kind == ORC_REACTOR) {
+            float z[4];
+            normals4(cfg, env, tick, STREAM_POLICY, 1u, z);
+            const float te = (s[0] - 320.0f) / 50.0f, le = (s[10] - 55.0f) / 50.0f;
+            for (int k = 0; k < 3; ++k) a[k] = (pp->gain[k][0] * te + pp->gain[k][1] * le) + pp->sigma[k] * z[k];
+        } else if (cfg->kind == ORC_GRID) {
+            float z[8];
+            normals4(cfg, env, tick, STREAM_POLICY, 1u, z);
+            normals4(cfg, env, tick, STREAM_POLICY, 2u, z + 4);
+            const float imb8 = (pairwise8(s + 17) - pairwise8(s + 9)) / 8.0f;
+            for (int k = 0; k < 8; ++k) a[k] = (pp->gain[k][0] * s[0] + pp->gain[k][1] * imb8) + pp->sigma[k] * z[k];
+        } else {
+            a[0] = pp->gain[0][0] * (0.3f - s[0]);
+            a[1] = pp->gain[0][0] * (0.0f - s[1]);
+            a[2] = pp->gain[0][0] * (0.4f - s[2]);
+            words4(cfg, env, tick, STREAM_POLICY, 3u, w);
+            for (int k = 0; k < 4; ++k) a[3 + k] = pp->mode == 0 ? pp->gain[3][0] * s[10 + k] : pp->sigma[3] * u_sym(w[k]);
+        }
+    } else {
+        for (int k = 0; k < A && k < 3; ++k) a[k] = pp->uniform_scale * u_sym(w0[1 + k]);
+        for (int j = 0; 3 + 4 * j < A; ++j) {
+            words4(cfg, env, tick, STREAM_POLICY, (uint32_t)(8 + j), w);
+            for (int q = 0; q < 4; ++q) if (3 + 4 * j + q < A) a[3 + 4 * j + q] = pp->uniform_scale * u_sym(w[q]);
+        }
+    }
+}
+
+ORC_API void orc_policy_batch(const orc_cfg_t* cfg, int policy, const orc_pp_t* pp, int64_t n, int64_t env_id0,
+                              uint32_t tick, const float* state, float* actions, int n_threads)
+{
+    const int S = kS[cfg->kind], A = kA[cfg->kind];
+    (void)n_threads;
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static) num_threads(n_threads > 0 ? n_threads : 1)
+#endif
+    for (int64_t i = 0; i < n; ++i) policy_one(cfg, policy, pp, (uint32_t)(env_id0 + i), tick, state + i * S, actions + i * A);
+}
+
 /* component functions exposed for direct pinning against the reference's _dynamics/_compute_reward/_is_done */
 ORC_API void orc_dynamics(int kind, int exp_mode, int64_t n, const float* s, const float* a, const float* nz, float* o)
 {

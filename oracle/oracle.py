@@ -101,6 +101,23 @@ def hostmask_con(bit, penalty, critical=False):
     return Con(CON_HOSTMASK, bit, 0, -1, 0.0, 0.0, 0.0, penalty, int(critical))
 
 
+class PolicyParams(C.Structure):
+    _fields_ = [("p_ctrl", C.c_float), ("uniform_scale", C.c_float), ("store_clip", C.c_float), ("mode", C.c_int32),
+                ("gain", (C.c_float * 2) * 8), ("sigma", C.c_float * 8)]
+
+
+POLICY_ACTIONS, POLICY_UNIFORM, POLICY_ZERO, POLICY_PCTRL = 0, 1, 2, 3
+
+
+def copy_policy_params(src) -> "PolicyParams":
+    """Field-wise copy from any ctypes struct with the same field names (e.g. the product's PolicyParams)."""
+    pp = PolicyParams()
+    pp.p_ctrl, pp.uniform_scale, pp.store_clip, pp.mode = src.p_ctrl, src.uniform_scale, src.store_clip, src.mode
+    for k in range(8):
+        pp.gain[k][0], pp.gain[k][1], pp.sigma[k] = src.gain[k][0], src.gain[k][1], src.sigma[k]
+    return pp
+
+
 class OracleEnv:
     """Batched AoS env state stepped by the C oracle (mirrors IndustrialEnv.step, base.py:157-213)."""
 
@@ -148,6 +165,15 @@ class OracleEnv:
                              C.c_int(self.threads))
         self.tick += 1
         return next_obs, reward, flags, viol
+
+
+def policy_actions(env: "OracleEnv", policy, pp=None):
+    """Actions the in-kernel policy produces for every env at env.tick (before stepping)."""
+    a = np.empty((env.n, env.A), np.float32)
+    pp = pp if pp is not None else PolicyParams()
+    lib().orc_policy_batch(C.byref(env.cfg), C.c_int(policy), C.byref(pp), C.c_int64(env.n), C.c_int64(env.env_id0),
+                           C.c_uint32(env.tick), _p(env.state), _p(a), C.c_int(env.threads))
+    return a
 
 
 def dynamics(kind, s, a, nz=None, exp_mode=0):

@@ -1,0 +1,93 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol include/nig_b200.h declares,
+struct layouts agree, metadata is right, and without a GPU every compute entry point fails LOUDLY
+(no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import neorl_industrial as ni
+from neorl_industrial import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "nig_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"NIG_API\s+[\w\s\*]+?\b(nig_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_symbols()
+    assert len(names) >= 30
+    raw = C.CDLL(N.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/nig_b200.h but not exported by libnig_b200.so"
+    assert set(names) == set(N.SYMBOLS), set(names) ^ set(N.SYMBOLS)
+
+
+def test_abi_version_and_specs():
+    lib = N.lib()
+    assert lib.nig_abi_version() == N.ABI_VERSION
+    expect = {0: (12, 3, 2, 500), 1: (32, 8, 23, 1000), 2: (24, 7, 0, 1000)}
+    pens = {0: [(-100, 1), (-50, 1), (-25, 0)], 1: [(-50, 1), (-30, 1), (-20, 0)], 2: [(-100, 1), (-200, 1), (-50, 0)]}
+    for kind, (s, a, nz, ms) in expect.items():
+        sp = N.env_spec(kind)
+        assert (sp.state_dim, sp.action_dim, sp.noise_dim, sp.max_episode_steps, sp.n_constraints) == (s, a, nz, ms, 3)
+        got = [(sp.constraints[k].penalty, sp.constraints[k].critical) for k in range(3)]
+        assert got == pens[kind]
+    with pytest.raises(ValueError):
+        N.env_spec(7)
+
+
+def test_struct_sizes_match_header():
+    # nig_constraint_t: 9 x 4 bytes; nig_config_t: 4+4+8+8+8+4*4 + 8*36; policy params: 16 + 64 + 32
+    assert C.sizeof(N.Constraint) == 36
+    assert C.sizeof(N.Config) == 48 + 8 * 36
+    assert C.sizeof(N.PolicyParams) == 16 + 64 + 32
+    assert C.sizeof(N.StepIO) == 9 * 8 + 8
+
+
+def test_make_registry_errors():
+    with pytest.raises(ValueError, match="Unknown environment 'Nope-v0'. Available: "):
+        ni.make("Nope-v0")
+    with pytest.raises(NotImplementedError):
+        ni.make("AdvancedPowerGrid-v0")
+
+
+def test_no_gpu_means_loud_failure():
+    if N.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ni.make("ChemicalReactor-v0")
+    with pytest.raises(ValueError):
+        ni.make("ChemicalReactor-v0", device="cpu")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "neorl-industrial-gym_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU fallback and nothing under oracle/ is ever imported", "") \
+                    .replace("The CPU oracle", "").replace("CPU oracle", ""), os.path.join(dirpath, f)
+
+
+def test_types_and_spaces():
+    sm = ni.SafetyMetrics(2, 3, 1, 1, 2 / 3)
+    assert abs(sm.satisfaction_rate - 2 / 3) < 1e-12 and sm.violation_severity == {}
+    c = ni.BoundConstraint("t_band", 0, 280, 320, penalty=-100, action_index=0, action_coef=0.1)
+    assert c.check_fn(np.array([300.0] + [0] * 11, np.float32), np.zeros(3, np.float32))
+    assert not c.check_fn(np.array([320.0] + [0] * 11, np.float32), np.ones(3, np.float32))
+    assert c._native[0] == "bound"
+    from neorl_industrial.spaces import Box
+    b = Box(-1.0, 1.0, (3,), np.float32, seed=0)
+    x = b.sample()
+    assert x.dtype == np.float32 and x.shape == (3,) and b.contains(x)
+    bm = ni.BatchedSafetyMetrics(np.array([0, 1, 3, 7], np.uint8), 3, 0b011)
+    assert bm.violation_count.tolist() == [0, 1, 2, 3] and bm.critical_violations.tolist() == [0, 1, 2, 2]
+    assert bm[2].constraints_satisfied == 1

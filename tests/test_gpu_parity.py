@@ -1,0 +1,488 @@
+"""GPU parity tests (run with -m gpu on a B200). Everything goes through the C ABI (libnig_b200.so):
+CUDA kernels vs (a) the golden vectors produced by the unmodified reference and (b) the CPU oracle.
+
+Contract:
+  * vs the oracle in spec-exp mode: EVERYTHING bit-exact (states, rewards, flags, masks, counters, RNG draws),
+    teacher-forced and free-running, single-step kernel (all vector widths / layouts) and fused rollout.
+  * vs the reference goldens: flags / masks / counters bit-exact; next-state bit-exact except the reactor's
+    concentration (downstream of numpy's non-correctly-rounded SIMD exp): <= 2 ulp; rewards within 1e-5 relative
+    (reactor, scaled by the conc' term) / 1e-6 relative (grid, robot: libm powf in numpy's scalar x**2).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from util import ENV_IDS, KINDS, assert_bits_equal, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    import neorl_industrial as ni
+    from neorl_industrial import _native as N
+    from oracle import oracle as O
+    return ni, N, O, torch
+
+
+def _native_env(ni, kind, n, **kw):
+    return ni.NativeEnv(kind, n, device=0, **kw)
+
+
+def _wide_states(rng, O, kind, n):
+    """Random states that reach every branch (same recipe family as the golden sampler)."""
+    S = O.STATE_DIM[kind]
+    if kind == O.REACTOR:
+        s = np.stack([rng.uniform(300, 360, n), rng.uniform(2e5, 5.3e5, n), rng.uniform(8, 102, n), rng.uniform(4, 52, n),
+                      rng.uniform(0, 2, n) * (rng.random(n) < 0.9), rng.uniform(49.9, 100, n), rng.uniform(285, 300, n),
+                      rng.uniform(0, 100, n) * (rng.random(n) < 0.5), (rng.random(n) < 0.3) * 1.0, (rng.random(n) < 0.4) * 1.0,
+                      rng.uniform(0, 100, n), rng.uniform(0, 51, n)], 1)
+    elif kind == O.GRID:
+        base = np.array([50, 60, 45, 55, 40, 65, 35, 50], np.float64)
+        s = np.concatenate([rng.normal(0, 0.4, (n, 1)), rng.uniform(0.88, 1.12, (n, 8)), base + rng.normal(0, 30, (n, 8)),
+                            np.maximum(base + rng.normal(0, 15, (n, 8)), 0), rng.normal(0, 10, (n, 7))], 1)
+    else:
+        q = rng.uniform(-np.pi, np.pi, (n, 7))
+        s = np.concatenate([rng.uniform(-0.7, 0.7, (n, 3)), np.tile([0, 0, 0, 1.0], (n, 1)), q, rng.normal(0, 0.5, (n, 4)),
+                            rng.choice([0.0, 10.0, 49.9, 50.0, 79.0, 81.0, -60.0], (n, 3)), rng.uniform(0, 1, (n, 3))], 1)
+    assert s.shape == (n, S)
+    return s.astype(np.float32)
+
+
+def _noise(rng, O, kind, n):
+    nz = O.NOISE_DIM[kind]
+    if nz == 0:
+        return None
+    sig = {O.REACTOR: [0.1, 500.0], O.GRID: [0.005] * 8 + [1.0] * 8 + [2.0] * 7}[kind]
+    return (rng.normal(0, 1, (n, nz)) * np.array(sig)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+def test_step_vs_reference_goldens(mods, golden_dir, name):
+    ni, N, O, torch = mods
+    g = np.load(os.path.join(golden_dir, f"{name}_forced.npz"))
+    kind, m = KINDS[name], len(g["reward"])
+    env = _native_env(ni, kind, m, auto_reset=False)
+    env.set_state_host(g["state"], g["ep_step"], np.zeros(m, np.int32), np.zeros(m, np.uint8))
+    obs, next_obs, r, fl, vm = env.step_host(g["action"], noise=g["noise"] if env.NZ else None, want_next_obs=True)
+    assert_bits_equal((fl & 1) > 0, g["terminated"], "terminated")
+    assert_bits_equal((fl & 2) > 0, g["truncated"], "truncated")
+    assert_bits_equal((fl & 4) > 0, g["crit"], "critical_shutdown")
+    assert_bits_equal(vm, g["viol_mask"], "violation mask")
+    if name == "reactor":
+        cols = [c for c in range(12) if c != 4]
+        assert_bits_equal(next_obs[:, cols], g["next_state"][:, cols], "next_state (non-exp columns)")
+        assert ulp_diff(next_obs[:, 4], g["next_state"][:, 4]).max() <= 2
+        tol = 1e-5 * (np.abs(g["reward"]) + 100.0 * np.abs(g["next_state"][:, 4])) + 1e-6
+        assert np.all(np.abs(r.astype(np.float64) - g["reward"]) <= tol)
+    else:
+        if name == "robot":   # fp64 sin/cos of two different libms, rounded to fp32: allow 1 ulp, expect ~none
+            assert ulp_diff(next_obs, g["next_state"]).max() <= 1
+            assert np.mean(ulp_diff(next_obs, g["next_state"]) == 0) > 0.9999
+        else:
+            assert_bits_equal(next_obs, g["next_state"], "next_state")
+        assert np.all(np.abs(r.astype(np.float64) - g["reward"]) <= 1e-6 * np.abs(g["reward"]) + 1e-5)
+    assert_bits_equal(obs, next_obs, "without auto-reset the stored state is s'")
+    _, st, vi, dn = env.get_state_host()
+    assert_bits_equal(st, g["ep_step"] + 1, "episode step counter")
+    assert_bits_equal(vi, g["n_viol"], "episode violation counter")
+    assert_bits_equal(dn, g["terminated"] | g["truncated"], "done latch")
+
+
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+def test_trace_replay_gym_api(mods, golden_dir, name):
+    """BASELINE config #1 through the drop-in gym API: ni.make(id) single env, 1000 steps, reset on done."""
+    ni, N, O, torch = mods
+    g = np.load(os.path.join(golden_dir, f"{name}_trace.npz"))
+    env = ni.make(ENV_IDS[name])
+    obs, info = env.reset(options={"init_states": g["state"][:1]})
+    assert obs.dtype == np.float32 and obs.shape == (env.state_dim,)
+    assert info["step"] == 0 and info["violations"] == 0
+    T = len(g["reward"])
+    for t in range(T):
+        if name != "reactor":
+            assert_bits_equal(env.state, g["state"][t], f"state before step {t}")
+        obs, r, term, trunc, info = env.step(g["action"][t], noise=g["noise"][t] if env.native.NZ else None)
+        assert isinstance(term, bool) and isinstance(trunc, bool) and isinstance(info, dict)
+        assert isinstance(r, np.float32 if name == "reactor" else float)
+        assert term == bool(g["terminated"][t]) and trunc == bool(g["truncated"][t]), t
+        assert info["critical_shutdown"] == bool(g["crit"][t])
+        assert info["safety_metrics"].violation_count == g["n_viol"][t]
+        assert info["violations"] == g["ep_violations"][t] and info["total_violations"] == g["total_violations"][t]
+        assert info["step"] == g["ep_step"][t] + 1
+        if name == "reactor":
+            np.testing.assert_allclose(obs, g["next_state"][t], rtol=1e-4, atol=1e-6)
+            assert abs(float(r) - g["reward"][t]) <= 1e-3 * abs(g["reward"][t]) + 1e-2
+        elif name == "grid":
+            assert_bits_equal(obs, g["next_state"][t], f"obs at step {t}")
+        else:
+            assert ulp_diff(obs, g["next_state"][t]).max() <= 1
+        if term or trunc:
+            with pytest.raises(RuntimeError, match="Environment is done"):
+                env.step(g["action"][t])
+            env.reset(options={"init_states": g["reset_state"][t:t + 1]})
+    env.close()
+
+
+@pytest.mark.parametrize("name,vec", [("reactor", 1), ("reactor", 2), ("reactor", 4), ("grid", 1), ("robot", 1)])
+@pytest.mark.parametrize("layout", ["host_aos", "device_soa"])
+def test_step_bitexact_vs_oracle(mods, name, vec, layout, monkeypatch):
+    """Teacher-forced single step, every vector width and both layouts, N not a multiple of anything."""
+    ni, N, O, torch = mods
+    if layout == "host_aos" and vec != 1:
+        pytest.skip("AoS layouts always use VEC=1")
+    kind = KINDS[name]
+    n = 5003
+    rng = np.random.default_rng(10 + kind)
+    s0 = _wide_states(rng, O, kind, n)
+    steps = rng.integers(0, O.MAX_EPISODE_STEPS[kind], n).astype(np.int32)
+    steps[::7] = O.MAX_EPISODE_STEPS[kind] - 1
+    a = rng.uniform(-1.5, 1.5, (n, O.ACTION_DIM[kind])).astype(np.float32)
+    nz = _noise(rng, O, kind, n)
+    rs = _wide_states(rng, O, kind, n)
+    monkeypatch.setenv("NIG_STEP_VEC", str(vec))
+    for auto_reset in (True, False):
+        orc = O.OracleEnv(kind, n, auto_reset=auto_reset, exp_mode=1)
+        orc.state[:] = s0
+        orc.ep_step[:] = steps
+        o_ns, o_r, o_fl, o_vm = orc.step(a, noise=nz, reset_states=rs)
+        env = _native_env(ni, kind, n, auto_reset=auto_reset)
+        env.set_state_host(s0, steps, np.zeros(n, np.int32), np.zeros(n, np.uint8))
+        if layout == "host_aos":
+            obs, next_obs, r, fl, vm = env.step_host(a, noise=nz, reset_states=rs, want_next_obs=True)
+        else:
+            dev = env.torch_device()
+            P = env.pitch
+
+            def soa(x):
+                t = torch.zeros((x.shape[1], P), dtype=torch.float32, device=dev)
+                t[:, :n] = torch.from_numpy(np.ascontiguousarray(x.T)).to(dev)
+                return t
+            d_obs, d_next = env.empty(env.S), env.empty(env.S)
+            d_r, d_fl, d_vm = env.empty(), env.empty(dtype=torch.uint8), env.empty(dtype=torch.uint8)
+            env.step_device(soa(a), noise=soa(nz) if nz is not None else None, reset_states=soa(rs), obs=d_obs,
+                            next_obs=d_next, reward=d_r, flags=d_fl, viol_mask=d_vm)
+            torch.cuda.synchronize()
+            obs, next_obs = d_obs[:, :n].T.cpu().numpy(), d_next[:, :n].T.cpu().numpy()
+            r, fl, vm = d_r[:n].cpu().numpy(), d_fl[:n].cpu().numpy(), d_vm[:n].cpu().numpy()
+            assert_bits_equal(env.state_tensor()[:, :n].T.cpu().numpy(), orc.state, "zero-copy state view")
+        assert_bits_equal(fl, o_fl, "flags")
+        assert_bits_equal(vm, o_vm, "violation mask")
+        assert_bits_equal(next_obs, o_ns, "next_obs")
+        assert_bits_equal(r, o_r, "reward")
+        assert_bits_equal(obs, orc.state, "state after the call")
+        st, es, ev, dn = env.get_state_host()
+        assert_bits_equal(st, orc.state, "device state")
+        assert_bits_equal(es, orc.ep_step, "ep_step")
+        assert_bits_equal(ev, orc.ep_viol, "ep_viol")
+        assert_bits_equal(dn, orc.done_latch.astype(bool), "done latch")
+        counters, _ = env.read_stats()
+        assert counters[:6].tolist() == orc.stats[:6].tolist()
+        assert counters[8:11].tolist() == orc.stats[8:11].tolist()
+        env.close()
+
+
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+def test_free_running_bitexact_vs_oracle(mods, name):
+    """In-kernel Philox noise + reset draws vs the oracle's independent restatement of the RNG spec, with
+    auto-reset, over many steps; then again without auto-reset (done latch)."""
+    ni, N, O, torch = mods
+    kind, n, T = KINDS[name], 777, 120
+    rng = np.random.default_rng(3)
+    for auto_reset in (True, False):
+        env = _native_env(ni, kind, n, auto_reset=auto_reset, seed=1234, env_id_offset=5000)
+        orc = O.OracleEnv(kind, n, auto_reset=auto_reset, seed=1234, env_id0=5000, exp_mode=1)
+        obs0 = env.reset_host()
+        assert_bits_equal(obs0, orc.reset(), "reset draw")
+        for t in range(T):
+            a = rng.uniform(-1, 1, (n, env.A)).astype(np.float32)
+            obs, next_obs, r, fl, vm = env.step_host(a, want_next_obs=True)
+            o_ns, o_r, o_fl, o_vm = orc.step(a)
+            assert_bits_equal(fl, o_fl, f"flags t={t}")
+            assert_bits_equal(next_obs, o_ns, f"next_obs t={t}")
+            assert_bits_equal(obs, orc.state, f"state t={t}")
+            assert_bits_equal(r, o_r, f"reward t={t}")
+            assert_bits_equal(vm, o_vm, f"viol t={t}")
+        counters, _ = env.read_stats()
+        assert counters[:6].tolist() == orc.stats[:6].tolist()
+        if auto_reset:
+            assert counters[N.ST_EPISODES] > (0 if name == "reactor" else n)
+        # masked explicit reset draws fresh (epoch-keyed) states
+        mask = (np.arange(n) % 3 == 0).astype(np.uint8)
+        assert_bits_equal(env.reset_host(mask=mask), orc.reset(mask=mask), "masked reset")
+        env.close()
+
+
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+@pytest.mark.parametrize("policy", ["actions_tma", "actions_ldg", "uniform", "pctrl"])
+def test_rollout_bitexact_vs_oracle(mods, name, policy):
+    """Fused K-step rollout (state in registers) == K oracle steps: final state, counters, per-env sums, stats."""
+    ni, N, O, torch = mods
+    kind, n, K = KINDS[name], 1000, 70      # K not a multiple of the 16-step TMA chunk
+    env = _native_env(ni, kind, n, auto_reset=True, seed=77, env_id_offset=128)
+    orc = O.OracleEnv(kind, n, auto_reset=True, seed=77, env_id0=128, exp_mode=1)
+    env.reset_host(); orc.reset()
+    dev = env.torch_device()
+    rng = np.random.default_rng(5)
+    pp = None
+    if policy == "pctrl":
+        cls = {"reactor": ni.ChemicalReactorEnv, "grid": ni.PowerGridEnv, "robot": ni.RobotAssemblyEnv}[name]
+        _, _, _, pp = cls.dataset_policy("mixed")
+    rsum, vcnt, dcnt = env.empty(), env.empty(dtype=torch.int32), env.empty(dtype=torch.int32)
+    o_rsum = np.zeros(n, np.float32); o_v = np.zeros(n, np.int64); o_d = np.zeros(n, np.int64)
+    ep_ret = np.zeros(n, np.float32 if name == "reactor" else np.float64)
+    ret_sum = ret_sq = 0.0
+    succ = len_sum = 0
+    for rep in range(2):                      # two consecutive launches: tick / episode accumulators carry over
+        acts = rng.uniform(-1.3, 1.3, (K, n, env.A)).astype(np.float32)
+        if policy.startswith("actions"):
+            d_act = torch.zeros((K, env.A, env.pitch), dtype=torch.float32, device=dev)
+            d_act[:, :, :n] = torch.from_numpy(np.ascontiguousarray(acts.transpose(0, 2, 1))).to(dev)
+            env.rollout_device(K, N.POLICY_ACTIONS, actions=d_act, use_tma=(policy == "actions_tma"),
+                               reward_sum=rsum, viol_count=vcnt, done_count=dcnt)
+        elif policy == "uniform":
+            env.rollout_device(K, N.POLICY_UNIFORM, reward_sum=rsum, viol_count=vcnt, done_count=dcnt)
+        else:
+            env.rollout_device(K, N.POLICY_PCTRL, params=pp, reward_sum=rsum, viol_count=vcnt, done_count=dcnt)
+        o_rsum[:] = 0; o_v[:] = 0; o_d[:] = 0
+        for t in range(K):
+            if policy.startswith("actions"):
+                a = acts[t]
+            elif policy == "uniform":
+                a = O.policy_actions(orc, O.POLICY_UNIFORM)
+            else:
+                a = O.policy_actions(orc, O.POLICY_PCTRL, O.copy_policy_params(pp))
+            steps_before = orc.ep_step.copy()
+            ns, r, fl, vm = orc.step(a)
+            o_rsum = (o_rsum + r).astype(np.float32)
+            ep_ret = (ep_ret + r).astype(ep_ret.dtype) if name == "reactor" else ep_ret + r.astype(np.float64)
+            o_v += np.array([bin(int(x)).count("1") for x in vm])
+            done = (fl & 3) > 0
+            o_d += done
+            if done.any():
+                er = ep_ret[done].astype(np.float64)
+                ret_sum += er.sum(); ret_sq += (er * er).sum(); succ += int((er > 0).sum())
+                len_sum += int((steps_before[done] + 1).sum())
+                ep_ret[done] = 0
+        torch.cuda.synchronize()
+        st, es, ev, dn = env.get_state_host()
+        assert_bits_equal(st, orc.state, f"state after rollout {rep}")
+        assert_bits_equal(es, orc.ep_step, "ep_step")
+        assert_bits_equal(ev, orc.ep_viol, "ep_viol")
+        if name == "reactor":
+            assert_bits_equal(rsum[:n].cpu().numpy(), o_rsum, "per-env reward sum")
+        else:   # oracle rewards are rounded to fp32 per step; the kernel sums the same fp32 values
+            assert_bits_equal(rsum[:n].cpu().numpy(), o_rsum, "per-env reward sum")
+        assert_bits_equal(vcnt[:n].cpu().numpy().astype(np.int64), o_v, "per-env violation count")
+        assert_bits_equal(dcnt[:n].cpu().numpy().astype(np.int64), o_d, "per-env done count")
+    d = env.stats_dict()
+    assert d["steps"] == orc.stats[0] == 2 * K * n
+    assert [d["episodes"], d["terminated"], d["truncated"], d["critical_shutdowns"], d["violations"]] == orc.stats[1:6].tolist()
+    assert d["violations_per_constraint"] == orc.stats[8:11].tolist()
+    assert d["episode_length_sum"] == len_sum and d["successes"] == succ
+    if name == "reactor":
+        np.testing.assert_allclose(d["return_sum"], ret_sum, rtol=1e-9, atol=1e-6)
+        np.testing.assert_allclose(d["return_sq"], ret_sq, rtol=1e-9, atol=1e-6)
+    else:     # grid / robot accumulate episode returns in fp64 from unrounded fp64 rewards: tolerance compare
+        np.testing.assert_allclose(d["return_sum"], ret_sum, rtol=1e-6, atol=1e-3)
+    env.close()
+
+
+def test_rollout_equals_single_steps(mods):
+    """The fused rollout kernel and K single-step launches walk the same trajectory bit-for-bit."""
+    ni, N, O, torch = mods
+    n, K = 3000, 48
+    a = _native_env(ni, 0, n, seed=5)
+    b = _native_env(ni, 0, n, seed=5)
+    a.reset_host(); b.reset_host()
+    dev = a.torch_device()
+    acts = torch.rand((K, 3, a.pitch), device=dev) * 2 - 1
+    a.rollout_device(K, N.POLICY_ACTIONS, actions=acts, use_tma=True)
+    for t in range(K):
+        b.step_device(acts[t])
+    torch.cuda.synchronize()
+    sa, sb = a.get_state_host(), b.get_state_host()
+    for x, y, w in zip(sa, sb, ("state", "ep_step", "ep_viol", "done")):
+        assert_bits_equal(x, y, w)
+    ca, cb = a.read_stats()[0], b.read_stats()[0]
+    assert ca[:6].tolist() == cb[:6].tolist() and ca[8:11].tolist() == cb[8:11].tolist()
+    assert a.tick == b.tick == K
+
+
+def test_sharding_invariance(mods):
+    """Shards keyed by global env id reproduce the unsharded run bit-for-bit."""
+    ni, N, O, torch = mods
+    n, K = 4096, 64
+    whole = _native_env(ni, 1, n, seed=42)
+    whole.reset_host()
+    whole.rollout_device(K, N.POLICY_UNIFORM)
+    torch.cuda.synchronize()
+    ref_state = whole.get_state_host()[0]
+    ref_stats = whole.read_stats()[0]
+    for shards in (2, 4):
+        per = n // shards
+        states, stats = [], np.zeros(24, np.int64)
+        for r in range(shards):
+            e = _native_env(ni, 1, per, seed=42, env_id_offset=r * per)
+            e.reset_host()
+            e.rollout_device(K, N.POLICY_UNIFORM)
+            torch.cuda.synchronize()
+            states.append(e.get_state_host()[0])
+            stats += e.read_stats()[0]
+            e.close()
+        assert_bits_equal(np.concatenate(states), ref_state, f"{shards} shards")
+        assert stats.tolist() == ref_stats.tolist()
+
+
+def test_constraint_descriptors_vs_oracle(mods):
+    """SafetyWrapper-style declarative bounds + host-evaluated masks, evaluated in-kernel == oracle."""
+    ni, N, O, torch = mods
+    from neorl_industrial.vector import make_constraint
+    n = 4099
+    rng = np.random.default_rng(8)
+    s0 = _wide_states(rng, O, O.REACTOR, n)
+    a = rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32)
+    nz = _noise(rng, O, O.REACTOR, n)
+    hm = rng.integers(0, 4, n).astype(np.uint8)
+    f32 = lambda x: float(np.float32(x))
+    native_cons = [
+        make_constraint(N.CON_BUILTIN, cid=2, penalty=-25.0),                       # re-ordered built-ins
+        make_constraint(N.CON_BOUND, si=0, ai=0, coef=f32(0.1), lo=280.0, hi=320.0, penalty=-100.0),   # README band
+        make_constraint(N.CON_BUILTIN, cid=0, penalty=-100.0, critical=True),
+        make_constraint(N.CON_BOUND, si=1, lo=f32(1.5e5), hi=f32(4.5e5), penalty=-70.0, critical=True),
+        make_constraint(N.CON_HOSTMASK, cid=0, penalty=-7.5),
+        make_constraint(N.CON_HOSTMASK, cid=1, penalty=-11.0, critical=True),
+    ]
+    orc_cons = [O.Con(c.kind, c.id, c.si, c.ai, c.coef, c.lo, c.hi, c.penalty, c.critical) for c in native_cons]
+    orc = O.OracleEnv(O.REACTOR, n, auto_reset=False, exp_mode=1, builtin=False, extra_cons=orc_cons)
+    orc.state[:] = s0
+    o_ns, o_r, o_fl, o_vm = orc.step(a, noise=nz, hostmask=hm)
+    env = _native_env(ni, 0, n, auto_reset=False, constraints=native_cons)
+    env.set_state_host(s0, np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8))
+    obs, next_obs, r, fl, vm = env.step_host(a, noise=nz, hostmask=hm, want_next_obs=True)
+    assert_bits_equal(vm, o_vm, "violation mask")
+    assert_bits_equal(fl, o_fl, "flags")
+    assert_bits_equal(r, o_r, "reward with penalties in constraint order")
+    assert len(set(vm.tolist())) > 20
+    counters, _ = env.read_stats()
+    assert counters[8:14].tolist() == orc.stats[8:14].tolist()
+    with pytest.raises(NotImplementedError):
+        env.rollout_device(4, N.POLICY_UNIFORM)      # host-evaluated constraints cannot run in a fused rollout
+    env.close()
+
+
+def test_safety_wrapper_api(mods):
+    """README.md:126-139: SafetyWrapper(env, constraints=[fn], penalty=-100) with a Python callable and with the
+    declarative BoundConstraint give identical results; penalties and violation counts follow base.py:179-183."""
+    ni, N, O, torch = mods
+    from neorl_industrial.safety import SafetyWrapper, BoundConstraint
+
+    def temperature_constraint(state, action):
+        next_temp = state[0] + 0.1 * action[0]
+        return 280 <= next_temp <= 320
+
+    e1 = SafetyWrapper(ni.make("ChemicalReactor-v0", seed=3), constraints=[temperature_constraint], penalty=-100)
+    e2 = SafetyWrapper(ni.make("ChemicalReactor-v0", seed=3),
+                       constraints=[BoundConstraint("temperature_constraint", 0, 280, 320, penalty=-100,
+                                                    action_index=0, action_coef=0.1)])
+    e0 = ni.make("ChemicalReactor-v0", seed=3)
+    o1, _ = e1.reset(); o2, _ = e2.reset(); o0, _ = e0.reset()
+    assert_bits_equal(o1, o2, "same seed -> same initial state")
+    assert len(e1.safety_constraints) == 4
+    rng = np.random.default_rng(0)
+    n_extra = 0
+    for t in range(300):
+        a = rng.uniform(-1, 1, 3).astype(np.float32)
+        r1 = e1.step(a); r2 = e2.step(a); r0 = e0.step(a)
+        assert_bits_equal(r1[0], r2[0], "obs"); assert r1[1] == r2[1] and r1[2:4] == r2[2:4]
+        assert_bits_equal(r1[0], r0[0], "the wrapper does not change the dynamics")
+        v1, v0 = r1[4]["safety_metrics"].violation_count, r0[4]["safety_metrics"].violation_count
+        assert r1[4]["safety_metrics"].total_constraints == 4
+        if v1 > v0:
+            n_extra += 1
+            if not r0[4]["critical_shutdown"]:      # (base + penalties) + (-100); the -1000 of a shutdown comes after
+                assert np.float32(r0[1] + np.float32(-100.0)) == r1[1]
+        if r1[2] or r1[3]:
+            break
+    assert n_extra > 10      # T starts at ~320 K: the README's 280..320 band is violated about half the time
+    assert e1.unwrap() is e1.env and len(e1.env.safety_constraints) == 3
+
+
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+def test_api_contract(mods, name):
+    """Port of the reference's own real-env assertions (tests/test_comprehensive_system.py:24-107, :581-628)."""
+    ni, N, O, torch = mods
+    env = ni.make(ENV_IDS[name])
+    assert env.observation_space.shape == (env.state_dim,) and env.action_space.shape == (env.action_dim,)
+    obs, info = env.reset()
+    assert obs.shape == (env.state_dim,) and isinstance(info, dict)
+    total = 0.0
+    for _ in range(100):
+        a = env.action_space.sample()
+        obs, reward, terminated, truncated, info = env.step(a)
+        assert obs.shape == (env.state_dim,)
+        assert isinstance(reward, (int, float, np.floating)) and isinstance(terminated, bool) and isinstance(truncated, bool)
+        assert hasattr(info["safety_metrics"], "violation_count") and hasattr(info["safety_metrics"], "safety_score")
+        total += float(reward)
+        if terminated or truncated:
+            obs, info = env.reset()
+    assert abs(total) < 1e6
+    for c in env.safety_constraints:
+        assert isinstance(c.check_fn(obs, a), (bool, np.bool_))
+    assert isinstance(env.state, np.ndarray) and isinstance(env.current_step, int)
+    ck = env.get_state()
+    o1 = env.step(np.zeros(env.action_dim, np.float32))
+    env.set_state(ck)
+    o2 = env.step(np.zeros(env.action_dim, np.float32))
+    assert_bits_equal(o1[0], o2[0], "checkpoint/resume reproduces the step (state + RNG position)")
+    env.close()
+
+
+def test_batched_gym_api(mods):
+    ni, N, O, torch = mods
+    n = 1000
+    env = ni.make("PowerGrid-v0", num_envs=n, seed=1)
+    obs, info = env.reset()
+    assert obs.shape == (n, 32) and obs.dtype == np.float32
+    ndone = 0
+    for _ in range(30):
+        a = np.stack([env.action_space.sample() for _ in range(4)]).repeat(n // 4, 0)
+        obs, r, term, trunc, info = env.step(a)
+        assert obs.shape == (n, 32) and r.shape == (n,) and term.dtype == bool and trunc.dtype == bool
+        ndone += int((term | trunc).sum())
+        sm = info["safety_metrics"]
+        assert sm.violation_count.shape == (n,) and np.all(sm.safety_score <= 1.0)
+        assert info["final_observation"].shape == (n, 32)
+    assert ndone > n          # grid episodes last ~5 steps under random actions -> auto-reset is the common case
+    assert env.total_violations > 0 and env.current_step.shape == (n,)
+    assert env.native.stats_dict()["episodes"] == ndone
+    env.close()
+
+
+def test_full_size_rollout_property(mods):
+    """BASELINE config #2 at full size: 65,536 envs x 1,000 steps (15 x K=64 + 40) of the fused kernel against the
+    multi-threaded oracle: a checksum of the final state plus every counter must agree exactly."""
+    ni, N, O, torch = mods
+    n, T, K = 65536, 1000, 64
+    env = _native_env(ni, 0, n, seed=2024)
+    env.reset_host()
+    done = 0
+    while done < T:
+        k = min(K, T - done)
+        env.rollout_device(k, N.POLICY_UNIFORM)
+        done += k
+    torch.cuda.synchronize()
+    st, es, ev, dn = env.get_state_host()
+    d = env.stats_dict()
+    assert d["steps"] == n * T and env.tick == T
+    orc = O.OracleEnv(0, n, seed=2024, exp_mode=1, threads=max(1, O.max_threads()))
+    orc.reset()
+    for t in range(T):
+        orc.step(O.policy_actions(orc, O.POLICY_UNIFORM), want_next_obs=False)
+    assert_bits_equal(st, orc.state, "final state of 65,536 envs after 1,000 free-running steps")
+    assert_bits_equal(es, orc.ep_step, "ep_step")
+    assert [d["steps"], d["episodes"], d["terminated"], d["truncated"], d["critical_shutdowns"], d["violations"]] == orc.stats[:6].tolist()
+    assert d["episodes"] > 100000

@@ -1,0 +1,153 @@
+"""CPU tests: the oracle (oracle/nig_oracle.c) against golden vectors produced by the UNMODIFIED reference
+(tests/golden/make_golden.py). This is what pins the oracle; the GPU tests then compare CUDA vs oracle.
+
+Tolerances (written here because they are the contract):
+  * every flag, mask, counter: bit-exact.
+  * reactor next-state: bit-exact except component 4 (concentration), the only value downstream of exp() within
+    a step -- numpy's float32 exp is a SIMD routine that is not correctly rounded, so <= 2 ulp there.
+  * reactor reward: |diff| <= 1e-5 * (|reward| + 100*conc') (it contains conc' * 100).
+  * grid / robot next-state: bit-exact. Reward: <= 1e-6 relative (numpy's scalar ``x**2`` calls libm powf, which
+    is not correctly rounded; everything else is bit-exact).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from util import KINDS, assert_bits_equal, ulp_diff
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _check_step_outputs(kind_name, g, ns, r, fl, vm):
+    assert_bits_equal((fl & 1) > 0, g["terminated"], "terminated")
+    assert_bits_equal((fl & 2) > 0, g["truncated"], "truncated")
+    assert_bits_equal((fl & 4) > 0, g["crit"], "critical_shutdown")
+    assert_bits_equal(vm, g["viol_mask"], "violation mask")
+    ref_r = g["reward"]
+    if kind_name == "reactor":
+        cols = [c for c in range(12) if c != 4]
+        assert_bits_equal(ns[:, cols], g["next_state"][:, cols], "reactor next_state (non-exp columns)")
+        assert ulp_diff(ns[:, 4], g["next_state"][:, 4]).max() <= 2
+        tol = 1e-5 * (np.abs(ref_r) + 100.0 * np.abs(g["next_state"][:, 4])) + 1e-6
+        assert np.all(np.abs(r.astype(np.float64) - ref_r) <= tol)
+        # where conc' is bit-identical the reward must be too
+        same = ulp_diff(ns[:, 4], g["next_state"][:, 4]) == 0
+        assert_bits_equal(r[same], ref_r.astype(np.float32)[same], "reactor reward where conc' matches")
+    else:
+        assert_bits_equal(ns, g["next_state"], f"{kind_name} next_state")
+        assert np.all(np.abs(r.astype(np.float64) - ref_r) <= 1e-6 * np.abs(ref_r) + 1e-6)
+        assert np.mean(r == ref_r.astype(np.float32)) > 0.995
+
+
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+def test_forced_tuples(golden_dir, name):
+    """M independent (state, step counter, action, noise) -> env.step() tuples covering every branch."""
+    g = _load(golden_dir, f"{name}_forced.npz")
+    kind = KINDS[name]
+    m = len(g["reward"])
+    env = O.OracleEnv(kind, m, auto_reset=False)
+    env.state[:] = g["state"]
+    env.ep_step[:] = g["ep_step"]
+    ns, r, fl, vm = env.step(g["action"], noise=g["noise"] if O.NOISE_DIM[kind] else None)
+    _check_step_outputs(name, g, ns, r, fl, vm)
+    assert_bits_equal(env.ep_viol, g["n_viol"], "episode violation counter")
+    # the golden set must really exercise the logic
+    assert g["terminated"].sum() > 100 and g["truncated"].sum() > 50 and g["crit"].sum() > 100
+
+
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+def test_trace_replay(golden_dir, name):
+    """BASELINE config #1: one env, 1000 random-action steps, reset on done, replayed teacher-forced."""
+    g = _load(golden_dir, f"{name}_trace.npz")
+    kind = KINDS[name]
+    T = len(g["reward"])
+    env = O.OracleEnv(kind, 1, auto_reset=True)
+    env.reset(init_states=g["state"][:1])
+    total_viol = 0
+    for t in range(T):
+        if name != "reactor":
+            assert_bits_equal(env.state[0], g["state"][t], f"state before step {t}")
+        assert env.ep_step[0] == g["ep_step"][t]
+        ns, r, fl, vm = env.step(g["action"][t:t + 1], noise=g["noise"][t:t + 1] if O.NOISE_DIM[kind] else None,
+                                 reset_states=g["reset_state"][t:t + 1])
+        assert bool(fl[0] & 1) == g["terminated"][t] and bool(fl[0] & 2) == g["truncated"][t], t
+        assert vm[0] == g["viol_mask"][t]
+        total_viol += bin(int(vm[0])).count("1")
+        assert total_viol == g["total_violations"][t]
+        if name == "reactor":
+            # free-running inside an episode: exp ulps may accumulate (stated drift tolerance 1e-4 relative)
+            np.testing.assert_allclose(ns[0], g["next_state"][t], rtol=1e-4, atol=1e-6)
+        else:
+            assert_bits_equal(ns[0], g["next_state"][t], f"next_state at step {t}")
+
+
+def test_reactor_freerun_drift(golden_dir):
+    """Free-running 500-step episodes (same actions / noise / initial state as the reference run): flags and
+    episode lengths identical; state drift <= 1e-3 relative (measured 2e-6 .. 7.5e-5)."""
+    g = _load(golden_dir, "reactor_freerun.npz")
+    n_ep, T = g["action"].shape[:2]
+    for exp_mode in (0, 1):
+        env = O.OracleEnv(O.REACTOR, n_ep, auto_reset=False, exp_mode=exp_mode)
+        env.reset(init_states=g["init"])
+        worst = 0.0
+        for t in range(T):
+            live = g["length"] > t
+            ns, r, fl, vm = env.step(g["action"][:, t], noise=g["noise"][:, t])
+            assert_bits_equal((fl & 7)[live], g["flags"][live, t], f"flags at t={t}")
+            ref = g["states"][live, t]
+            rel = np.abs(ns[live] - ref) / np.maximum(np.abs(ref), 1e-3)
+            worst = max(worst, float(rel.max()))
+            rr = g["rewards"][live, t]
+            assert np.all(np.abs(r[live] - rr) <= 1e-3 * np.abs(rr) + 1e-2)
+        assert worst <= 1e-3, worst
+        lengths = np.array([np.argmax(env.done_latch[i] > 0) for i in range(n_ep)])
+        assert env.done_latch.sum() == (g["length"] < T).sum() + np.sum((g["length"] == T))
+
+
+def test_spec_exp_accuracy():
+    """The fmaf-polynomial exp of the math spec is < 1 ulp from the true value and handles the edges."""
+    xs = np.concatenate([np.linspace(-87, 88, 20001), np.linspace(-3, 3, 20001)]).astype(np.float32)
+    got = np.array([O.lib().orc_spec_expf(float(x)) for x in xs], np.float32)
+    ref = np.exp(xs.astype(np.float64))
+    ulp = np.abs(got.astype(np.float64) - ref) / np.spacing(ref.astype(np.float32)).astype(np.float64)
+    assert ulp.max() < 1.0
+    assert O.lib().orc_spec_expf(100.0) == np.inf and O.lib().orc_spec_expf(-200.0) == 0.0
+    assert np.isnan(O.lib().orc_spec_expf(float("nan")))
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    assert [hex(x) for x in O.philox((0, 0, 0, 0), (0, 0))] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
+    assert [hex(x) for x in O.philox((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2)] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
+    assert [hex(x) for x in O.philox((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0))] == \
+        ["0xd16cfe09", "0x94fdcceb", "0x5001e420", "0x24126ea1"]
+
+
+def test_spec_normals_are_gaussian():
+    z = np.array([O.spec_normals4(3, i, 5, 0, 0) for i in range(40000)]).ravel()
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+    kurt = ((z - z.mean()) ** 4).mean() / z.var() ** 2
+    assert abs(kurt - 3) < 0.1
+    assert abs(np.corrcoef(z[0::4], z[1::4])[0, 1]) < 0.03
+
+
+def test_oracle_auto_reset_and_latch():
+    env = O.OracleEnv(O.GRID, 64, auto_reset=True, seed=9)
+    env.reset()
+    rng = np.random.default_rng(0)
+    n_done = 0
+    for _ in range(40):
+        ns, r, fl, vm = env.step(rng.uniform(-1, 1, (64, 8)).astype(np.float32))
+        done = (fl & 3) > 0
+        n_done += int(done.sum())
+        assert np.all(env.ep_step[done] == 0) and np.all((fl[done] & 8) > 0)
+    assert n_done == env.stats[1] and n_done > 64     # grid episodes last ~5 steps under random actions
+    env2 = O.OracleEnv(O.GRID, 64, auto_reset=False, seed=9)
+    env2.reset()
+    for _ in range(40):
+        ns, r, fl, vm = env2.step(rng.uniform(-1, 1, (64, 8)).astype(np.float32))
+    assert env2.done_latch.all() and np.all(fl == 128) and np.all(r == 0)

@@ -1,0 +1,31 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+
+def ulp_diff(a, b):
+    """Distance in units-in-the-last-place between two float32 arrays (0 == bit-identical up to +-0)."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, -(ai & 0x7FFFFFFF), ai)
+    bi = np.where(bi < 0, -(bi & 0x7FFFFFFF), bi)
+    return np.abs(ai - bi)
+
+
+def assert_bits_equal(a, b, what=""):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.dtype == np.float32:
+        same = (a.view(np.uint32) == b.view(np.uint32)) | ((a == 0) & (b == 0))
+    else:
+        same = a == b
+    if not same.all():
+        idx = np.argwhere(~same)[:5]
+        raise AssertionError(f"{what}: {np.count_nonzero(~same)} / {same.size} elements differ, first at {idx.tolist()}: "
+                             f"{a[tuple(idx[0])]!r} vs {b[tuple(idx[0])]!r}")
+
+
+KINDS = {"reactor": 0, "grid": 1, "robot": 2}
+ENV_IDS = {"reactor": "ChemicalReactor-v0", "grid": "PowerGrid-v0", "robot": "RobotAssembly-v0"}
