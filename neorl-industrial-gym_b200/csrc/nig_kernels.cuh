@@ -88,12 +88,18 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
     }
     // base.py:170 -- constraints on the PRE-step state (the reference calls every check_fn twice with
     // identical arguments, :102 and :180; evaluated once here)
-    uint32_t vm = 0, crit = 0;
+    // NOTE: `crit` is carried as a predicate of its own, never derived from the integer mask: ptxas 12.9
+    // (sm_100a) mis-folds `((p ? 0 : 2) | (q ? 1 : 0)) != 0` into a PLOP3 with the polarity of q inverted
+    // (found by the oracle parity tests on RobotAssembly; PTX correct, SASS wrong -- see DESIGN.md).
+    uint32_t vm = 0;
+    bool crit = false;
     if constexpr (DEFCONS) {
 #pragma unroll
-        for (int k = 0; k < Env::NB; ++k)
-            if (!Env::builtin(k, s, a)) vm |= 1u << k;
-        crit = vm & Env::CRIT_MASK;
+        for (int k = 0; k < Env::NB; ++k) {
+            const bool ok = Env::builtin(k, s, a);
+            vm |= ok ? 0u : (1u << k);
+            if ((Env::CRIT_MASK >> k) & 1u) crit = crit || !ok;
+        }
     } else {
         for (int k = 0; k < cp.n; ++k) {
             const nig_constraint_t& c = cp.c[k];
@@ -104,7 +110,8 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
                 if (c.ai >= 0) v = add(v, mul(c.coef, pick<Env::A>(a, c.ai)));
                 ok = (c.lo <= v) && (v <= c.hi);
             } else ok = !((hostmask >> c.id) & 1u);
-            if (!ok) { vm |= 1u << k; if (c.critical) crit |= 1u << k; }
+            vm |= ok ? 0u : (1u << k);
+            crit = crit || (!ok && c.critical != 0);
         }
     }
     Env::dynamics(s, a, nz, ns);                      // base.py:173

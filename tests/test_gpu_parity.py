@@ -79,9 +79,16 @@ def test_step_vs_reference_goldens(mods, golden_dir, name):
         tol = 1e-5 * (np.abs(g["reward"]) + 100.0 * np.abs(g["next_state"][:, 4])) + 1e-6
         assert np.all(np.abs(r.astype(np.float64) - g["reward"]) <= tol)
     else:
-        if name == "robot":   # fp64 sin/cos of two different libms, rounded to fp32: allow 1 ulp, expect ~none
-            assert ulp_diff(next_obs, g["next_state"]).max() <= 1
-            assert np.mean(ulp_diff(next_obs, g["next_state"]) == 0) > 0.9999
+        if name == "robot":
+            # FK runs in fp64 with sin/cos from two different libms (numpy's vs CUDA's, both ~1 ulp fp64): after
+            # rounding to fp32 nearly every value is bit-identical; the end-effector velocity (pos' - pos) / dt is a
+            # cancellation, so there the difference is bounded absolutely (1e-12 of fp64 noise / 0.1) instead.
+            ref = g["next_state"]
+            assert np.mean(ulp_diff(next_obs, ref) == 0) > 0.999
+            vel = [14, 15, 16]
+            rest = [c for c in range(24) if c not in vel]
+            assert ulp_diff(next_obs[:, rest], ref[:, rest]).max() <= 1
+            np.testing.assert_allclose(next_obs[:, vel], ref[:, vel], rtol=1e-5, atol=1e-9)
         else:
             assert_bits_equal(next_obs, g["next_state"], "next_state")
         assert np.all(np.abs(r.astype(np.float64) - g["reward"]) <= 1e-6 * np.abs(g["reward"]) + 1e-5)
@@ -190,7 +197,8 @@ def test_free_running_bitexact_vs_oracle(mods, name):
     """In-kernel Philox noise + reset draws vs the oracle's independent restatement of the RNG spec, with
     auto-reset, over many steps; then again without auto-reset (done latch)."""
     ni, N, O, torch = mods
-    kind, n, T = KINDS[name], 777, 120
+    kind, n = KINDS[name], 777
+    T = 450 if name == "reactor" else 120      # reactor episodes last ~370 steps: run long enough to auto-reset
     rng = np.random.default_rng(3)
     for auto_reset in (True, False):
         env = _native_env(ni, kind, n, auto_reset=auto_reset, seed=1234, env_id_offset=5000)
@@ -391,6 +399,10 @@ def test_safety_wrapper_api(mods):
     e0 = ni.make("ChemicalReactor-v0", seed=3)
     o1, _ = e1.reset(); o2, _ = e2.reset(); o0, _ = e0.reset()
     assert_bits_equal(o1, o2, "same seed -> same initial state")
+    init = o0.copy()[None]
+    init[0, 0] = 320.02        # T + 0.1*a0 straddles the README's 320 K bound -> violated about half the time
+    o1, _ = e1.reset(options={"init_states": init}); o2, _ = e2.reset(options={"init_states": init})
+    o0, _ = e0.reset(options={"init_states": init})
     assert len(e1.safety_constraints) == 4
     rng = np.random.default_rng(0)
     n_extra = 0
@@ -407,7 +419,7 @@ def test_safety_wrapper_api(mods):
                 assert np.float32(r0[1] + np.float32(-100.0)) == r1[1]
         if r1[2] or r1[3]:
             break
-    assert n_extra > 10      # T starts at ~320 K: the README's 280..320 band is violated about half the time
+    assert n_extra > 10
     assert e1.unwrap() is e1.env and len(e1.env.safety_constraints) == 3
 
 
