@@ -803,6 +803,59 @@ ORC_API void orc_policy_batch(const orc_cfg_t* cfg, int policy, const orc_pp_t* 
     for (int64_t i = 0; i < n; ++i) policy_one(cfg, policy, pp, (uint32_t)(env_id0 + i), tick, state + i * S, actions + i * A);
 }
 
+
+/* T free-running steps with an in-kernel policy for every env, each thread owning a contiguous block of envs
+ * for the whole horizon (the CPU analogue of the fused rollout kernel; used as the timed CPU baseline and by the
+ * full-size parity test). Semantics identical to T x (orc_policy_batch + orc_step_batch). */
+ORC_API void orc_rollout_batch(const orc_cfg_t* cfg, int policy, const orc_pp_t* pp, int64_t n, int64_t env_id0,
+                               uint32_t tick0, uint32_t epoch, int32_t n_steps,
+                               float* state, int32_t* ep_step, int32_t* ep_viol, uint8_t* done_latch,
+                               float* reward_sum, int64_t* stats, int n_threads)
+{
+    const int S = kS[cfg->kind], NZ = kNZ[cfg->kind];
+    int64_t st[16]; memset(st, 0, sizeof st);
+#if defined(_OPENMP)
+    if (n_threads <= 0) n_threads = 1;
+#pragma omp parallel num_threads(n_threads)
+#endif
+    {
+        int64_t lst[16]; memset(lst, 0, sizeof lst);
+#if defined(_OPENMP)
+#pragma omp for schedule(static)
+#endif
+        for (int64_t i = 0; i < n; ++i) {
+            float* s = state + i * S;
+            const uint32_t env = (uint32_t)(env_id0 + i);
+            float rsum = 0.0f;
+            for (int32_t t = 0; t < n_steps && !done_latch[i]; ++t) {
+                const uint32_t tick = tick0 + (uint32_t)t;
+                float a[ORC_MAX_A], nz[ORC_MAX_NZ], ns[ORC_MAX_S];
+                policy_one(cfg, policy, pp, env, tick, s, a);
+                if (NZ > 0) noise_one(cfg, env, tick, nz);
+                orc_out_t o;
+                step_one(cfg, s, &ep_step[i], &ep_viol[i], a, nz, 0, ns, &o);
+                rsum = rsum + o.reward;
+                lst[ST_STEPS]++; lst[ST_VIOL] += o.n_viol;
+                for (int k = 0; k < cfg->n_cons; ++k) lst[ST_CON0 + k] += (o.viol_mask >> k) & 1;
+                if (o.flags & ORC_F_CRITICAL) lst[ST_CRITICAL]++;
+                if (o.flags & (ORC_F_TERMINATED | ORC_F_TRUNCATED)) {
+                    lst[ST_EPISODES]++;
+                    if (o.flags & ORC_F_TERMINATED) lst[ST_TERMINATED]++;
+                    if (o.flags & ORC_F_TRUNCATED) lst[ST_TRUNCATED]++;
+                    if (cfg->auto_reset) { reset_one(cfg, env, tick + 1u, epoch, s); ep_step[i] = 0; ep_viol[i] = 0; }
+                    else { memcpy(s, ns, sizeof(float) * S); done_latch[i] = 1; }
+                } else memcpy(s, ns, sizeof(float) * S);
+            }
+            if (reward_sum) reward_sum[i] = rsum;
+        }
+#if defined(_OPENMP)
+#pragma omp critical
+#endif
+        for (int k = 0; k < 16; ++k) st[k] += lst[k];
+    }
+    if (stats) for (int k = 0; k < 16; ++k) stats[k] += st[k];
+}
+
 /* component functions exposed for direct pinning against the reference's _dynamics/_compute_reward/_is_done */
 ORC_API void orc_dynamics(int kind, int exp_mode, int64_t n, const float* s, const float* a, const float* nz, float* o)
 {

@@ -167,6 +167,18 @@ class OracleEnv:
         return next_obs, reward, flags, viol
 
 
+def rollout(env: "OracleEnv", n_steps, policy, pp=None, want_reward_sum=False):
+    """n_steps free-running steps inside one C call (threads own env blocks for the whole horizon)."""
+    pp = pp if pp is not None else PolicyParams()
+    rs = np.zeros(env.n, np.float32) if want_reward_sum else None
+    lib().orc_rollout_batch(C.byref(env.cfg), C.c_int(policy), C.byref(pp), C.c_int64(env.n), C.c_int64(env.env_id0),
+                            C.c_uint32(env.tick), C.c_uint32(env.epoch), C.c_int32(n_steps),
+                            _p(env.state), _p(env.ep_step), _p(env.ep_viol), _p(env.done_latch), _p(rs), _p(env.stats),
+                            C.c_int(env.threads))
+    env.tick += n_steps
+    return rs
+
+
 def policy_actions(env: "OracleEnv", policy, pp=None):
     """Actions the in-kernel policy produces for every env at env.tick (before stepping)."""
     a = np.empty((env.n, env.A), np.float32)

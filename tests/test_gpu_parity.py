@@ -492,8 +492,7 @@ def test_full_size_rollout_property(mods):
     assert d["steps"] == n * T and env.tick == T
     orc = O.OracleEnv(0, n, seed=2024, exp_mode=1, threads=max(1, O.max_threads()))
     orc.reset()
-    for t in range(T):
-        orc.step(O.policy_actions(orc, O.POLICY_UNIFORM), want_next_obs=False)
+    O.rollout(orc, T, O.POLICY_UNIFORM)
     assert_bits_equal(st, orc.state, "final state of 65,536 envs after 1,000 free-running steps")
     assert_bits_equal(es, orc.ep_step, "ep_step")
     assert [d["steps"], d["episodes"], d["terminated"], d["truncated"], d["critical_shutdowns"], d["violations"]] == orc.stats[:6].tolist()
