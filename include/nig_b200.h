@@ -184,6 +184,9 @@ typedef struct nig_dataset_out {
     float* next_observations;   /* [M][S] extension; NULL ok */
     uint8_t* safety;            /* [M]    extension: violation mask of the transition; NULL ok */
     int64_t capacity;
+    int32_t terminals_include_truncation; /* 1: terminals = terminated | truncated (chemical_reactor.py:394-399);
+                                             0: terminals = terminated (power_grid.py:239, robot_assembly.py:298) */
+    int32_t reserved;
 } nig_dataset_out_t;
 
 /* stats block: NIG_STATS_SLOTS x 8 bytes on the device; slots < 24 are int64 counters, slots >= 24 are

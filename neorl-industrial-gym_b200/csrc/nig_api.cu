@@ -84,8 +84,10 @@ struct nig_env {
     int64_t launches;
     int step_vec;              // 0 = auto
     PFN_encodeTiled encode_tiled;
-    int64_t* d_len;            // dataset: per-episode lengths / offsets
+    int64_t *d_len, *d_off, *d_total;   // dataset: per-episode lengths, offsets, total
     int64_t d_len_cap;
+    uint32_t dataset_gen;      // datasets generated so far (each one draws from a fresh derived key)
+    struct { int64_t n_episodes; int32_t n_steps, policy; nig_policy_params_t pp; ConsParams cons; uint32_t gen; int64_t total; bool valid; } probe;
 };
 
 namespace {
@@ -332,7 +334,7 @@ int nig_destroy(nig_env_t* e)
     cudaFree(e->state); cudaFree(e->ep_word); cudaFree(e->ep_return); cudaFree(e->stats);
     cudaFree(e->h_actions); cudaFree(e->h_noise); cudaFree(e->h_reset); cudaFree(e->h_obs); cudaFree(e->h_next_obs);
     cudaFree(e->h_reward); cudaFree(e->h_hostmask); cudaFree(e->h_flags); cudaFree(e->h_viol); cudaFree(e->h_mask);
-    cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->d_len);
+    cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->d_len); cudaFree(e->d_off); cudaFree(e->d_total);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return NIG_OK;
@@ -491,15 +493,117 @@ int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
     return rc;
 }
 
-int nig_dataset(nig_env_t* e, int64_t, int32_t, int32_t, const nig_policy_params_t*, const nig_dataset_out_t*, int64_t*, void*)
+} // extern "C"
+
+namespace {
+
+template <class Env, bool WRITE>
+void launch_dataset_t(nig_env* e, const DatasetArgs& a, cudaStream_t st)
 {
-    (void)e;
-    return fail(NIG_ERR_UNSUPPORTED, "nig_dataset: not built yet");
+    const unsigned g = grid_for(a.n_episodes);
+    if (e->cons.is_default) dataset_kernel<Env, true, WRITE><<<g, kThreads, 0, st>>>(a);
+    else dataset_kernel<Env, false, WRITE><<<g, kThreads, 0, st>>>(a);
+    e->launches++;
 }
-int nig_dataset_size(nig_env_t* e, int64_t, int32_t, int32_t, const nig_policy_params_t*, int64_t*, void*)
+
+template <bool WRITE>
+int launch_dataset(nig_env* e, const DatasetArgs& a, cudaStream_t st)
 {
-    (void)e;
-    return fail(NIG_ERR_UNSUPPORTED, "nig_dataset_size: not built yet");
+    switch (e->kind) {
+    case NIG_ENV_CHEMICAL_REACTOR: launch_dataset_t<Reactor, WRITE>(e, a, st); break;
+    case NIG_ENV_POWER_GRID: launch_dataset_t<Grid, WRITE>(e, a, st); break;
+    default: launch_dataset_t<Robot, WRITE>(e, a, st); break;
+    }
+    NIG_CUDA(cudaGetLastError());
+    return NIG_OK;
+}
+
+int dataset_args(nig_env* e, int64_t n_episodes, int32_t n_steps, int32_t policy, const nig_policy_params_t* pp, DatasetArgs* a)
+{
+    if (n_episodes <= 0 || n_episodes > (1LL << 31)) return fail(NIG_ERR_INVALID, "n_episodes %lld outside [1, 2^31]", (long long)n_episodes);
+    if (n_steps <= 0) return fail(NIG_ERR_INVALID, "n_steps must be positive (got %d)", n_steps);
+    if (policy != NIG_POLICY_UNIFORM && policy != NIG_POLICY_ZERO && policy != NIG_POLICY_PCTRL)
+        return fail(NIG_ERR_INVALID, "dataset policy must be UNIFORM, ZERO or PCTRL (got %d)", policy);
+    if (policy == NIG_POLICY_PCTRL && !pp) return fail(NIG_ERR_INVALID, "NIG_POLICY_PCTRL needs policy parameters");
+    for (int k = 0; k < e->cons.n; ++k)
+        if (e->cons.c[k].kind == NIG_CON_HOSTMASK) return fail(NIG_ERR_UNSUPPORTED, "host-evaluated constraints cannot run inside the dataset kernels");
+    if (n_episodes > e->d_len_cap) {
+        cudaFree(e->d_len); cudaFree(e->d_off); e->d_len = e->d_off = nullptr; e->d_len_cap = 0;
+        int rc;
+        if ((rc = dev_alloc(&e->d_len, (size_t)n_episodes)) != NIG_OK) return rc;
+        if ((rc = dev_alloc(&e->d_off, (size_t)n_episodes)) != NIG_OK) return rc;
+        e->d_len_cap = n_episodes;
+    }
+    int rc;
+    if ((rc = dev_alloc(&e->d_total, 1)) != NIG_OK) return rc;
+    memset(a, 0, sizeof *a);
+    a->n_episodes = n_episodes; a->n_steps = n_steps; a->max_steps = e->max_steps; a->policy = policy;
+    a->env0 = (uint32_t)e->cfg.env_id_offset; a->epoch = 0;
+    // every dataset draws from its own key derived from (seed, number of datasets generated so far)
+    a->key = RngKey{e->key.k0 ^ (0x9E3779B9u * (e->dataset_gen + 1u)), e->key.k1 ^ 0x85EBCA6Bu};
+    if (pp) a->pp = *pp;
+    a->cons = e->cons;
+    a->lengths = e->d_len; a->offsets = e->d_off;
+    return NIG_OK;
+}
+
+// pass 1 + scan; the result is cached so that nig_dataset() right after nig_dataset_size() does not repeat it
+int dataset_probe(nig_env* e, int64_t n_episodes, int32_t n_steps, int32_t policy, const nig_policy_params_t* pp, DatasetArgs* a,
+                  int64_t* total, cudaStream_t st)
+{
+    int rc;
+    if ((rc = dataset_args(e, n_episodes, n_steps, policy, pp, a)) != NIG_OK) return rc;
+    auto& c = e->probe;
+    const bool hit = c.valid && c.n_episodes == n_episodes && c.n_steps == n_steps && c.policy == policy && c.gen == e->dataset_gen &&
+                     memcmp(&c.pp, &a->pp, sizeof c.pp) == 0 && memcmp(&c.cons, &e->cons, sizeof c.cons) == 0;
+    if (!hit) {
+        if ((rc = launch_dataset<false>(e, *a, st)) != NIG_OK) return rc;
+        scan_lengths_kernel<<<1, 1024, 0, st>>>(e->d_len, e->d_off, n_episodes, e->d_total);
+        e->launches++;
+        NIG_CUDA(cudaGetLastError());
+        int64_t t = 0;
+        NIG_CUDA(cudaMemcpyAsync(&t, e->d_total, sizeof t, cudaMemcpyDeviceToHost, st));
+        NIG_CUDA(cudaStreamSynchronize(st));
+        c.n_episodes = n_episodes; c.n_steps = n_steps; c.policy = policy; c.pp = a->pp; c.cons = e->cons; c.gen = e->dataset_gen;
+        c.total = t; c.valid = true;
+    }
+    *total = c.total;
+    return NIG_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int nig_dataset_size(nig_env_t* e, int64_t n_episodes, int32_t n_steps, int32_t policy, const nig_policy_params_t* pp,
+                     int64_t* n_transitions, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    if (!n_transitions) return fail(NIG_ERR_INVALID, "null n_transitions");
+    DatasetArgs a;
+    return dataset_probe(e, n_episodes, n_steps, policy, pp, &a, n_transitions, (cudaStream_t)stream);
+}
+
+int nig_dataset(nig_env_t* e, int64_t n_episodes, int32_t n_steps, int32_t policy, const nig_policy_params_t* pp,
+                const nig_dataset_out_t* out, int64_t* n_written, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    if (!out || !out->observations || !out->actions || !out->rewards || !out->terminals)
+        return fail(NIG_ERR_INVALID, "nig_dataset: observations, actions, rewards and terminals are required");
+    DatasetArgs a;
+    int64_t total = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = dataset_probe(e, n_episodes, n_steps, policy, pp, &a, &total, st);
+    if (rc != NIG_OK) return rc;
+    if (total > out->capacity) return fail(NIG_ERR_INVALID, "nig_dataset: %lld transitions exceed the capacity %lld", (long long)total, (long long)out->capacity);
+    a.terminals_include_truncation = out->terminals_include_truncation;
+    a.observations = out->observations; a.actions = out->actions; a.rewards = out->rewards; a.terminals = out->terminals;
+    a.timeouts = out->timeouts; a.next_observations = out->next_observations; a.safety = out->safety;
+    if ((rc = launch_dataset<true>(e, a, st)) != NIG_OK) return rc;
+    e->dataset_gen += 1;
+    e->probe.valid = false;
+    if (n_written) *n_written = total;
+    return NIG_OK;
 }
 
 int nig_get_state(nig_env_t* e, float* state_dev, int32_t layout, int32_t* st, int32_t* vi, uint8_t* dn, void* stream)

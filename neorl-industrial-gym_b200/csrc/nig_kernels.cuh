@@ -652,6 +652,107 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
         atomicAdd(reinterpret_cast<double*>(p.stats) + NIG_ST_F_RETURN_SUM + threadIdx.x, sfl[threadIdx.x]);
 }
 
+
+// ================================================================================================
+// dataset writer (get_dataset: chemical_reactor.py:324-420, power_grid.py:194-249, robot_assembly.py:246-308)
+// ================================================================================================
+// One thread = one episode (an independent env with global id env0 + e): reset, then up to n_steps
+// policy/step iterations, stopping at done. WRITE=false only records the episode length (pass 1); after an
+// exclusive scan of the lengths WRITE=true replays the identical counter-based random streams and stores every
+// transition at row offsets[e] + t, so the arrays come out episode-contiguous like the reference's lists.
+struct DatasetArgs {
+    int64_t n_episodes;
+    int32_t n_steps, max_steps, policy, terminals_include_truncation;
+    uint32_t env0, epoch;
+    RngKey key;
+    nig_policy_params_t pp;
+    ConsParams cons;
+    int64_t* lengths;          // pass 1 out
+    const int64_t* offsets;    // pass 2 in (exclusive scan of lengths)
+    float* observations; float* actions; float* rewards; uint8_t* terminals; uint8_t* timeouts;
+    float* next_observations; uint8_t* safety;
+};
+
+template <class Env, bool DEFCONS, bool WRITE>
+__global__ void __launch_bounds__(kThreads) dataset_kernel(const __grid_constant__ DatasetArgs p)
+{
+    constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
+    using acc_t = typename Env::acc_t;
+    const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (e >= p.n_episodes) return;
+    const uint32_t env = p.env0 + (uint32_t)e;
+    float s[S];
+    Env::reset(p.key, env, 0u, p.epoch, s);
+    typename Env::NoiseGen ng;
+    uint32_t w = 0u;
+    int64_t row = WRITE ? p.offsets[e] : 0;
+    int32_t len = 0;
+    for (int t = 0; t < p.n_steps; ++t) {
+        float a[A], nz[NZA], ns[S];
+        if (p.policy == NIG_POLICY_UNIFORM) policy_uniform<Env>(p.key, env, (uint32_t)t, a);
+        else if (p.policy == NIG_POLICY_PCTRL) policy_pctrl<Env>(p.key, p.pp, env, (uint32_t)t, s, a);
+        else {
+#pragma unroll
+            for (int k = 0; k < A; ++k) a[k] = 0.0f;
+        }
+        if (p.pp.store_clip > 0.0f) {        // np.clip(action, -c, c) BEFORE env.step and before storing
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                float v = a[k];
+                v = v < -p.pp.store_clip ? -p.pp.store_clip : v;
+                v = v > p.pp.store_clip ? p.pp.store_clip : v;
+                a[k] = v;
+            }
+        }
+        if (NZ > 0) ng.get(p.key, env, (uint32_t)t, nz); else nz[0] = 0.0f;
+        acc_t r; uint32_t f, vm;
+        step_core<Env, DEFCONS>(p.cons, p.max_steps, s, a, nz, 0u, w, ns, r, f, vm);
+        const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
+        if constexpr (WRITE) {
+#pragma unroll
+            for (int k = 0; k < S; ++k) p.observations[row * S + k] = s[k];
+#pragma unroll
+            for (int k = 0; k < A; ++k) p.actions[row * A + k] = a[k];
+            p.rewards[row] = (float)r;
+            p.terminals[row] = (uint8_t)(p.terminals_include_truncation ? done : ((f & NIG_F_TERMINATED) != 0));
+            if (p.timeouts) p.timeouts[row] = 0;      // chemical_reactor.py:419
+            if (p.next_observations) {
+#pragma unroll
+                for (int k = 0; k < S; ++k) p.next_observations[row * S + k] = ns[k];
+            }
+            if (p.safety) p.safety[row] = (uint8_t)vm;
+            row += 1;
+        }
+        len = t + 1;
+        if (done) break;
+#pragma unroll
+        for (int k = 0; k < S; ++k) s[k] = ns[k];
+    }
+    if constexpr (!WRITE) p.lengths[e] = len;
+}
+
+// exclusive scan of n int64 lengths (one 1024-thread block; n is a few thousand .. a few million episodes)
+__global__ void __launch_bounds__(1024) scan_lengths_kernel(const int64_t* __restrict__ len, int64_t* __restrict__ off, int64_t n, int64_t* total)
+{
+    __shared__ long long part[1024];
+    const int t = threadIdx.x;
+    const int64_t chunk = (n + 1023) / 1024;
+    const int64_t lo = (int64_t)t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    long long sum = 0;
+    for (int64_t i = lo; i < hi; ++i) sum += len[i];
+    part[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const long long v = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    long long run = part[t] - sum;      // exclusive prefix of this thread's chunk
+    for (int64_t i = lo; i < hi; ++i) { off[i] = run; run += len[i]; }
+    if (t == 1023) *total = part[1023];
+}
+
 // ---- measured-peak probe: independent unfused FADD/FMUL chains (what the physics is made of) ------
 __global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters)
 {

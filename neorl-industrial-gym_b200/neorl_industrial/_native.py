@@ -73,7 +73,8 @@ class Rollout(C.Structure):
 class DatasetOut(C.Structure):
     _fields_ = [("observations", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p),
                 ("terminals", C.c_void_p), ("timeouts", C.c_void_p), ("next_observations", C.c_void_p),
-                ("safety", C.c_void_p), ("capacity", C.c_int64)]
+                ("safety", C.c_void_p), ("capacity", C.c_int64), ("terminals_include_truncation", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 # every symbol include/nig_b200.h declares: (restype, argtypes)

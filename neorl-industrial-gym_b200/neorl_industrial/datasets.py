@@ -11,7 +11,7 @@ from . import _native as N
 
 
 def generate_dataset_device(native, n_episodes: int, n_steps: int, policy: int, params, *, extensions: bool = False,
-                            timeouts: bool = True):
+                            timeouts: bool = True, terminals_include_truncation: bool = True):
     """Returns (dict of torch CUDA tensors, n_transitions). Layout: observations [M,S] f32, actions [M,A] f32,
     rewards [M] f32, terminals [M] u8, timeouts [M] u8 (+ next_observations [M,S], safety [M] u8)."""
     import torch
@@ -29,7 +29,7 @@ def generate_dataset_device(native, n_episodes: int, n_steps: int, policy: int, 
     if extensions:
         out["next_observations"] = torch.empty((cap, native.S), dtype=torch.float32, device=dev)
         out["safety"] = torch.empty((cap,), dtype=torch.uint8, device=dev)
-    written = native.dataset_device(n_episodes, n_steps, policy, params, out, cap)
+    written = native.dataset_device(n_episodes, n_steps, policy, params, out, cap, terminals_include_truncation)
     assert written == m, (written, m)
     return {k: v[:m] for k, v in out.items()}, m
 
@@ -38,9 +38,8 @@ def generate_dataset(env, n_episodes: int, n_steps: int, policy: int, params, *,
                      timeouts_key: bool, extensions: bool = False) -> Dict[str, np.ndarray]:
     """Host dict with the reference's keys and dtypes (bool terminals / timeouts)."""
     import torch
-    params.mode = int(params.mode) | (0x100 if terminals_include_truncation else 0)
     dev_out, m = generate_dataset_device(env.native, n_episodes, n_steps, policy, params, extensions=extensions,
-                                         timeouts=timeouts_key)
+                                         timeouts=timeouts_key, terminals_include_truncation=terminals_include_truncation)
     host = {}
     for k, v in dev_out.items():
         pinned = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)

@@ -1,0 +1,93 @@
+"""Batched evaluation loops: the ``reset -> while not done: step`` loops of utils.evaluate_with_safety
+(utils.py:82-154) and OfflineAgent.evaluate (agents/base.py:330-393) over N envs at once.
+
+Two flavours:
+  * ``evaluate_policy_device``: the policy runs inside the fused rollout kernel (uniform random, zero, the
+    get_dataset P-controllers) -- no host round trips; aggregates come from the device stats block, which
+    ``distributed.allreduce_stats`` can sum across GPUs.
+  * ``evaluate_agent_batched``: an arbitrary ``agent.predict(obs, deterministic=True)`` callback drives the
+    batched ``env.step`` (host arrays).
+Both return the reference's result keys.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import _native as N
+
+
+def metrics_from_stats(stats: Dict[str, Any], n_constraints: int, critical_flags) -> Dict[str, Any]:
+    """Reference result dict (utils.py:128-152) from summed device counters."""
+    ep = max(int(stats["episodes"]), 1)
+    steps = max(int(stats["steps"]), 1)
+    mean = stats["return_sum"] / ep
+    var = max(stats["return_sq"] / ep - mean * mean, 0.0)
+    lmean = stats["episode_length_sum"] / ep
+    lvar = max(stats["episode_length_sq"] / ep - lmean * lmean, 0.0)
+    per_con = stats["violations_per_constraint"]
+    crit = sum(int(v) for v, c in zip(per_con, critical_flags) if c)
+    return {
+        "return_mean": mean, "return_std": math.sqrt(var), "return_min": None, "return_max": None,
+        "length_mean": lmean, "length_std": math.sqrt(lvar),
+        "safety_violations": int(stats["violations"]), "safety_violations_per_episode": stats["violations"] / ep,
+        "critical_violations": crit, "emergency_shutdowns": int(stats["critical_shutdowns"]),
+        "constraint_satisfaction_rate": 1.0 - stats["violations"] / (steps * max(n_constraints, 1)),
+        "successful_episodes": int(stats["successes"]), "success_rate": stats["successes"] / ep,
+        "episodes": int(stats["episodes"]), "steps": int(stats["steps"]),
+    }
+
+
+def evaluate_policy_device(env, n_steps: int, policy: int = N.POLICY_UNIFORM, params=None, *, chunk: int = 64,
+                           reduce_fn=None) -> Dict[str, Any]:
+    """Run ``n_steps`` env-steps per env with an in-kernel policy (auto-reset on) and return the reference's
+    evaluation keys over every episode that finished. ``reduce_fn(counters, sums) -> (counters, sums)`` hooks in the
+    cross-GPU all-reduce (see distributed.allreduce_stats)."""
+    nat = env.native
+    nat.clear_stats()
+    done = 0
+    while done < n_steps:
+        k = min(chunk, n_steps - done)
+        nat.rollout_device(k, policy, params=params)
+        done += k
+    counters, sums = nat.read_stats()
+    if reduce_fn is not None:
+        counters, sums = reduce_fn(counters, sums)
+    stats = nat.stats_dict(counters, sums)
+    return metrics_from_stats(stats, len(env.safety_constraints), [c.critical for c in env.safety_constraints])
+
+
+def evaluate_agent_batched(agent: Any, env: Any, n_episodes: int = 100) -> Dict[str, Any]:
+    """utils.py:82-154 with a batched env: every env runs episodes until ``n_episodes`` have finished in total."""
+    if not getattr(env, "auto_reset", False):
+        raise ValueError("batched evaluation needs an auto-resetting env (ni.make(..., num_envs=N))")
+    n = env.num_envs
+    obs, _ = env.reset()
+    ep_ret = np.zeros(n, np.float64)
+    ep_len = np.zeros(n, np.int64)
+    returns, lengths, sat = [], [], []
+    viol = crit = shut = 0
+    while len(returns) < n_episodes:
+        action = np.asarray(agent.predict(obs, deterministic=True), np.float32).reshape(n, env.action_dim)
+        obs, reward, terminated, truncated, info = env.step(action)
+        ep_ret += reward
+        ep_len += 1
+        sm = info["safety_metrics"]
+        viol += int(sm.violation_count.sum()); crit += int(sm.critical_violations.sum())
+        sat.append(float(np.mean(sm.satisfaction_rate)))
+        shut += int(np.sum(info["critical_shutdown"]))
+        done = terminated | truncated
+        for i in np.flatnonzero(done):
+            returns.append(float(ep_ret[i])); lengths.append(int(ep_len[i]))
+        ep_ret[done] = 0.0; ep_len[done] = 0
+    returns, lengths = np.array(returns[:n_episodes]), np.array(lengths[:n_episodes])
+    succ = int(np.sum(returns > 0))
+    return {
+        "return_mean": returns.mean(), "return_std": returns.std(), "return_min": returns.min(), "return_max": returns.max(),
+        "length_mean": lengths.mean(), "length_std": lengths.std(),
+        "safety_violations": viol, "safety_violations_per_episode": viol / n_episodes, "critical_violations": crit,
+        "emergency_shutdowns": shut, "constraint_satisfaction_rate": float(np.mean(sat)) if sat else 1.0,
+        "successful_episodes": succ, "success_rate": succ / n_episodes,
+    }

@@ -282,12 +282,14 @@ class NativeEnv:
         N.check(N.lib().nig_set_state(self._h, N.ptr_of(state), layout, N.ptr_of(ep_step), N.ptr_of(ep_viol),
                                       N.ptr_of(done), self._stream(stream)))
 
-    def dataset_device(self, n_episodes: int, n_steps: int, policy: int, params, out: dict, capacity: int, stream=None) -> int:
+    def dataset_device(self, n_episodes: int, n_steps: int, policy: int, params, out: dict, capacity: int,
+                       terminals_include_truncation: bool = True, stream=None) -> int:
         d = N.DatasetOut()
         d.observations, d.actions, d.rewards = N.ptr_of(out["observations"]), N.ptr_of(out["actions"]), N.ptr_of(out["rewards"])
         d.terminals, d.timeouts = N.ptr_of(out["terminals"]), N.ptr_of(out.get("timeouts"))
         d.next_observations, d.safety = N.ptr_of(out.get("next_observations")), N.ptr_of(out.get("safety"))
         d.capacity = int(capacity)
+        d.terminals_include_truncation = int(bool(terminals_include_truncation))
         nw = C.c_int64(0)
         N.check(N.lib().nig_dataset(self._h, int(n_episodes), int(n_steps), int(policy), C.byref(params), C.byref(d),
                                     C.byref(nw), self._stream(stream)))
