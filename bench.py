@@ -16,7 +16,8 @@ Also measured in the same run and reported in the JSON line:
                    non-FMA issue peak measured live with a probe kernel (the path is element-wise ODE integration).
   single_step   -- the single-step kernel: env-steps/s at 65,536 envs (launch-bound) and its HBM roofline at 4M envs
                    (state larger than L2), achieved GB/s vs MEASURED_PEAKS.json.
-  e2e           -- env.step(host actions) -> host obs/reward/flags through the Python drop-in API, copies included.
+  e2e           -- env.rollout(1000, "random", init_states=host) -> host returns / violations / obs: the same workload
+                   through the drop-in API with host buffers (nig_rollout_host); e2e_step_api = one env.step() per call.
   cpu_baseline  -- the CPU oracle port (C, all host threads) on a bounded sample of the same workload.
 """
 from __future__ import annotations
@@ -224,7 +225,12 @@ def run_gpu(args):
     counters, fsum = env.read_stats()
 
     extra = {}
+    e2e = None
+    if "e2e" in args.sections:
+        e2e = e2e_rollout(ni, n, local, rank, world, max(3, min(args.steps, 20)), args.warmup, args.seed, dist, torch)
     if rank == 0:
+        if e2e is not None:
+            extra["e2e"] = e2e
         # ---- roofline of the dominant kernel of the timed region (fused rollout): fp32 pipe
         kernel_ms = total_ms / (args.steps * launches_per_pass())        # average launch (15 x K=64 and one K=40)
         ops_per_launch = ALG_OPS_PER_STEP * n * HORIZON / launches_per_pass()
@@ -253,7 +259,7 @@ def run_gpu(args):
             extra["single_step"] = single_step_section(torch, ni, N, local, dev, flush, hbm_peak, peak_src, args)
         # ---- e2e through the Python drop-in API with host buffers
         if "e2e" in args.sections:
-            extra["e2e"] = e2e_section(torch, ni, n, local, args)
+            extra["e2e_step_api"] = e2e_step_api(ni, n, local, args)
         if "cpu" in args.sections:
             extra["cpu_baseline"] = cpu_baseline()
     if dist is not None:
@@ -300,8 +306,9 @@ def single_step_section(torch, ni, N, local, dev, flush, hbm_peak, peak_src, arg
     out["envs_64k"] = {"value": ENVS_PER_GPU * HORIZON / (ms * 1e-3), "unit": UNIT, "us_per_launch": ms * 1e3 / HORIZON,
                        "note": "1,000 back-to-back launches; 8 MB working set is L2-resident, launch-latency bound"}
     env.close()
-    # (b) HBM roofline: 4,194,304 envs (512 MB of state+io per step, > L2), in-kernel Philox noise, auto-reset
-    n_big = 1 << 22
+    # (b) HBM roofline: 16,777,216 envs (2 GB of state + io per launch, >> L2; the copy that MEASURED_PEAKS.json times
+    # moves 4 GB), in-kernel Philox noise, auto-reset
+    n_big = 1 << 24
     env = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n_big, device=local, seed=args.seed)
     env.reset_device()
     acts = torch.rand((3, env.pitch), device=dev) * 2 - 1
@@ -318,7 +325,7 @@ def single_step_section(torch, ni, N, local, dev, flush, hbm_peak, peak_src, arg
     torch.cuda.synchronize()
     ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     gbs = ALG_BYTES_PER_STEP * n_big / (ms * 1e-3) / 1e9
-    out["roofline"] = {"kernel": "step_kernel<Reactor, VEC=4, default constraints>", "bound": "hbm", "achieved": gbs,
+    out["roofline"] = {"kernel": "step_kernel<Reactor, VEC=2, default constraints>", "bound": "hbm", "achieved": gbs,
                        "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                        "envs": n_big, "ms_per_launch": ms, "value": n_big / (ms * 1e-3),
                        "note": f"{ALG_BYTES_PER_STEP} algorithmic B/env-step x {n_big} envs per launch / mean launch time; inputs larger than L2"}
@@ -326,8 +333,41 @@ def single_step_section(torch, ni, N, local, dev, flush, hbm_peak, peak_src, arg
     return out
 
 
-def e2e_section(torch, ni, n, local, args):
-    """env.step(host actions) -> host obs / reward / terminated / truncated, as a user of the drop-in API calls it."""
+def e2e_rollout(ni, n, local, rank, world, steps, warmup, seed, dist=None, torch=None):
+    """The metric end to end through the drop-in API with HOST buffers: one bench step = one
+    ``env.rollout(1000, "random", steps_per_launch=64, init_states=<pinned host array>)`` call per rank, i.e. H2D of the
+    65,536 x 12 synthetic initial states, 16 fused launches, D2H of per-env returns / violation counts / episode
+    counts / final observations and the stats block. Wall clock around the synchronous calls, max over ranks."""
+    env = ni.make("ChemicalReactor-v0", num_envs=n, device=f"cuda:{local}", seed=seed, copy=False, env_id_offset=rank * n)
+    init = env.native.pinned("init_states", (n, 12), np.float32)
+    rng = np.random.default_rng(1 + rank)
+    init[:] = (np.array([320, 253312.5, 50, 30, 0.5, 95, 295, 0, 0, 0, 60, 0], np.float32) +
+               rng.standard_normal((n, 12)).astype(np.float32) * np.array([2, 1e4, 5, 3, 0.1, 2, 1, 0, 0, 0, 5, 0], np.float32))
+    for _ in range(max(warmup, 3)):
+        res = env.rollout(HORIZON, "random", steps_per_launch=K, init_states=init)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = env.rollout(HORIZON, "random", steps_per_launch=K, init_states=init)
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    h2d = n * 12 * 4
+    d2h = n * (4 + 4 + 4 + 12 * 4) + 32 * 8
+    checksum = float(res["reward_sum"].astype(np.float64).sum())
+    env.close()
+    return {"value": world * n * HORIZON * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": dt / steps * 1e3, "steps": steps,
+            "api": "ni.make('ChemicalReactor-v0', num_envs=65536).rollout(1000, 'random', steps_per_launch=64, init_states=host[65536,12]) "
+                   "-> host reward_sum / violations / episodes / obs / stats (C ABI: nig_rollout_host)",
+            "reward_checksum_rank0": checksum}
+
+
+def e2e_step_api(ni, n, local, args):
+    """Secondary: one env.step(host actions) -> host obs / reward / terminated / truncated per call (PCIe-bound)."""
     env = ni.make("ChemicalReactor-v0", num_envs=n, device=f"cuda:{local}", seed=args.seed, copy=False)
     env.reset()
     rng = np.random.default_rng(0)
@@ -340,11 +380,9 @@ def e2e_section(torch, ni, n, local, args):
     for _ in range(reps):
         obs, r, term, trunc, info = env.step(a_buf)
     dt = time.perf_counter() - t0
-    h2d = n * 3 * 4
-    d2h = n * (12 * 4 * 2 + 4 + 1 + 1)          # obs + final_observation + reward + flags + violation mask
     env.close()
-    return {"value": n * reps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "api": "ni.make('ChemicalReactor-v0', num_envs=65536).step(actions[65536,3] host) -> obs, reward, terminated, truncated, info",
+    return {"value": n * reps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 3 * 4, "d2h_bytes_per_step": n * (12 * 4 * 2 + 4 + 1 + 1),
+            "api": "env.step(actions[65536,3] host) -> obs, reward, terminated, truncated, info (one PCIe round trip per env-step)",
             "ms_per_call": dt / reps * 1e3}
 
 

@@ -157,7 +157,10 @@ typedef struct nig_policy_params {
     float sigma[NIG_MAX_ACTION_DIM];
 } nig_policy_params_t;
 
-enum { NIG_ROLLOUT_USE_TMA = 1 /* stage NIG_POLICY_ACTIONS through cp.async.bulk.tensor */ };
+enum {
+    NIG_ROLLOUT_USE_TMA = 1,     /* stage NIG_POLICY_ACTIONS through cp.async.bulk.tensor */
+    NIG_ROLLOUT_ACCUMULATE = 2   /* reward_sum / viol_count / done_count: add to the arrays instead of overwriting them */
+};
 
 typedef struct nig_rollout {
     int32_t n_steps;            /* K */
@@ -232,6 +235,31 @@ NIG_API int nig_step_host(nig_env_t* env, const nig_step_io_t* io);
  * performance_benchmark.py:106-133, utils.evaluate_with_safety (utils.py:82-125) and get_dataset */
 NIG_API int nig_rollout(nig_env_t* env, const nig_rollout_t* r, void* stream);
 
+/* The same loops with HOST buffers: what performance_benchmark.py:106-133 / utils.evaluate_with_safety do per env in
+ * Python, for every env of the handle in one call. Host arrays are exact-size ([n] or [n][dim]); the call stages
+ * them through device buffers (cudaMemcpyAsync, true DMA when the host arrays are page-locked, see nig_host_alloc),
+ * runs ceil(n_steps / steps_per_launch) fused launches and returns synchronised.
+ * Teacher-forced inputs (optional): init_states [n][S]; actions [T][A][n] with policy == NIG_POLICY_ACTIONS and
+ * noise [T][NZ][n] (time-major, SoA per step -- the layout the kernel consumes; copied chunk by chunk,
+ * double-buffered so the copy of chunk c+1 overlaps the launch of chunk c). */
+typedef struct nig_rollout_host {
+    int32_t n_steps;            /* T: total steps per env */
+    int32_t steps_per_launch;   /* K fused steps per kernel launch; 0 = T */
+    int32_t policy;             /* NIG_POLICY_* */
+    int32_t reset_first;        /* 1: IndustrialEnv.reset() of every env before stepping (drawn, or init_states) */
+    const float* init_states;   /* in  [n][S] AoS or NULL */
+    const float* actions;       /* in  [T][A][n] (NIG_POLICY_ACTIONS) or NULL */
+    const float* noise;         /* in  [T][NZ][n] or NULL (in-kernel Philox) */
+    nig_policy_params_t pp;
+    float* reward_sum;          /* out [n] sum of rewards over the T steps (fp32; per launch in step order, launches added in order) */
+    int32_t* viol_count;        /* out [n] constraint violations over the T steps */
+    int32_t* done_count;        /* out [n] episodes finished over the T steps */
+    float* final_obs;           /* out [n][S] AoS state after the last step (post auto-reset) */
+    int64_t* counters24;        /* out [24] the stats block after the call (NULL ok) */
+    double* sums8;              /* out [8] */
+} nig_rollout_host_t;
+NIG_API int nig_rollout_host(nig_env_t* env, const nig_rollout_host_t* r);
+
 /* get_dataset (chemical_reactor.py:324-420): n_episodes episodes of <= n_steps steps each with the given
  * policy, written episode-contiguously in D4RL layout on the device. Episodes are independent envs with
  * global ids env_id_offset + [0, n_episodes). *n_written receives the transition count. */
@@ -267,6 +295,10 @@ NIG_API int nig_host_free(void* p);
 NIG_API int64_t nig_launch_count(const nig_env_t* env);
 /* measured-peak probe: issues a dependent-free stream of unfused fp32 add/mul and returns ops per launch */
 NIG_API int nig_fp32_probe(int device, int32_t iters, double* ops, void* stream);
+
+/* self-test of the guarded fast divisions of the step kernels against IEEE division, on the device: n Philox-drawn
+ * operand sets (all-exponent pairs, physics-regime pairs, every constant divisor); *mismatches must come back 0 */
+NIG_API int nig_selftest_division(int device, int64_t n, uint64_t seed, int64_t* mismatches, int64_t* accepted);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@
 #include <cstring>
 #include <new>
 
-#include "nig_kernels.cuh"
+#include "nig_launch.h"
 
 using namespace nig;
 
@@ -77,12 +77,19 @@ struct nig_env {
     double* ep_return;
     unsigned long long* stats;
     cudaStream_t stream;       // internal stream of the *_host calls
+    cudaStream_t dev_stream;   // stream of the last device-API call that was not on `stream` ...
+    bool dev_dirty;            // ... and whether a *_host call still has to wait for it
     // device staging of the *_host calls (lazily allocated)
     float *h_actions, *h_noise, *h_reset, *h_obs, *h_next_obs, *h_reward;
     uint8_t *h_hostmask, *h_flags, *h_viol, *h_mask;
     int32_t *h_i32a, *h_i32b;
+    float *r_act[2], *r_nz[2];  // nig_rollout_host: double-buffered action / noise chunks
+    int32_t r_cap;              // steps each chunk buffer holds
+    cudaStream_t copy_stream;
+    cudaEvent_t r_ev_copy[2], r_ev_done[2];
     int64_t launches;
     int step_vec;              // 0 = auto
+    int rollout_block;         // 0 = 128
     PFN_encodeTiled encode_tiled;
     int64_t *d_len, *d_off, *d_total;   // dataset: per-episode lengths, offsets, total
     int64_t d_len_cap;
@@ -112,17 +119,18 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-inline unsigned grid_for(int64_t items) { return (unsigned)((items + kThreads - 1) / kThreads); }
-
-template <class Env, int VEC>
-int launch_step_t(nig_env* e, const StepArgs& a, cudaStream_t st)
+// device-API calls run on the caller's stream, *_host calls on e->stream: a *_host call first waits for the device
+// work submitted since the last one (no cost for loops of device calls; the *_host calls are synchronous anyway)
+inline void note_device_work(nig_env* e, cudaStream_t st)
 {
-    const int64_t threads = (e->pitch + VEC - 1) / VEC;
-    const unsigned g = grid_for(threads);
-    if (e->cons.is_default) step_kernel<Env, VEC, true><<<g, kThreads, 0, st>>>(a);
-    else step_kernel<Env, VEC, false><<<g, kThreads, 0, st>>>(a);
-    e->launches++;
-    NIG_CUDA(cudaGetLastError());
+    if (st != e->stream) { e->dev_stream = st; e->dev_dirty = true; }
+}
+int host_entry(nig_env* e)
+{
+    if (e->dev_dirty) {
+        NIG_CUDA(cudaStreamSynchronize(e->dev_stream));
+        e->dev_dirty = false;
+    }
     return NIG_OK;
 }
 
@@ -130,53 +138,20 @@ int pick_vec(const nig_env* e, bool soa)
 {
     if (e->step_vec) return e->step_vec;
     if (!soa) return 1;
-    // enough threads to fill 148 SMs x 2048 threads twice over before widening the per-thread vector
+    // reactor: two envs per thread (64-bit LDG/STG, 96 registers) once there are enough threads to fill the GPU
+    // twice over; measured on B200 (tools/perf_sweep.py): VEC=2 beats VEC=1 and VEC=4 from 1M envs up.
     const int64_t full = 148LL * 2048;
-    if (e->kind == NIG_ENV_CHEMICAL_REACTOR) return e->pitch >= 8 * full ? 4 : (e->pitch >= 4 * full ? 2 : 1);
-    return 1;   // 32-/24-d states: two envs per thread would need > 250 registers
+    if (e->kind == NIG_ENV_CHEMICAL_REACTOR) return e->pitch >= 2 * full ? 2 : 1;
+    return 1;   // 32-/24-d states: two envs per thread would need > 190 registers
 }
 
 int launch_step(nig_env* e, const StepArgs& a, cudaStream_t st)
 {
     const int vec = pick_vec(e, a.action_aos == 0 && a.aux_aos == 0);
-    switch (e->kind) {
-    case NIG_ENV_CHEMICAL_REACTOR:
-        return vec == 4 ? launch_step_t<Reactor, 4>(e, a, st) : vec == 2 ? launch_step_t<Reactor, 2>(e, a, st) : launch_step_t<Reactor, 1>(e, a, st);
-    case NIG_ENV_POWER_GRID:
-        return vec >= 2 ? launch_step_t<Grid, 2>(e, a, st) : launch_step_t<Grid, 1>(e, a, st);
-    default:
-        return vec >= 2 ? launch_step_t<Robot, 2>(e, a, st) : launch_step_t<Robot, 1>(e, a, st);
-    }
-}
-
-template <class Env, int POLICY, bool TMA>
-int launch_rollout_t(nig_env* e, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
-{
-    const unsigned g = grid_for(e->pitch);
-    const size_t smem = TMA ? (size_t)2 * kTmaChunk * Env::A * kThreads * sizeof(float) : 0;
-    if (e->cons.is_default) {
-        if (TMA) NIG_CUDA(cudaFuncSetAttribute(rollout_kernel<Env, true, POLICY, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rollout_kernel<Env, true, POLICY, TMA><<<g, kThreads, smem, st>>>(a, map);
-    } else {
-        if (TMA) NIG_CUDA(cudaFuncSetAttribute(rollout_kernel<Env, false, POLICY, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rollout_kernel<Env, false, POLICY, TMA><<<g, kThreads, smem, st>>>(a, map);
-    }
     e->launches++;
-    NIG_CUDA(cudaGetLastError());
+    note_device_work(e, st);
+    NIG_CUDA(nig::launch_step(e->kind, vec, e->cons.is_default != 0, e->pitch, a, st));
     return NIG_OK;
-}
-
-template <class Env>
-int launch_rollout_env(nig_env* e, const RolloutArgs& a, int policy, bool tma, const CUtensorMap& map, cudaStream_t st)
-{
-    switch (policy) {
-    case NIG_POLICY_ACTIONS:
-        return tma ? launch_rollout_t<Env, NIG_POLICY_ACTIONS, true>(e, a, map, st) : launch_rollout_t<Env, NIG_POLICY_ACTIONS, false>(e, a, map, st);
-    case NIG_POLICY_UNIFORM: return launch_rollout_t<Env, NIG_POLICY_UNIFORM, false>(e, a, map, st);
-    case NIG_POLICY_ZERO: return launch_rollout_t<Env, NIG_POLICY_ZERO, false>(e, a, map, st);
-    case NIG_POLICY_PCTRL: return launch_rollout_t<Env, NIG_POLICY_PCTRL, false>(e, a, map, st);
-    default: return fail(NIG_ERR_INVALID, "unknown rollout policy %d", policy);
-    }
 }
 
 int make_action_map(nig_env* e, const float* actions, int n_steps, CUtensorMap* map)
@@ -238,9 +213,9 @@ void set_cons(nig_env* e, const nig_constraint_t* c, int n)
 int state_io(nig_env* e, float* ext_state, int layout, int32_t* st, int32_t* vi, uint8_t* dn, bool to_ext, cudaStream_t s)
 {
     StateIoArgs a{e->state, e->ep_word, e->n, e->pitch, ext_state, st, vi, dn, e->S, layout == NIG_LAYOUT_AOS ? 1 : 0, to_ext ? 1 : 0};
-    state_io_kernel<<<grid_for(e->n), kThreads, 0, s>>>(a);
     e->launches++;
-    NIG_CUDA(cudaGetLastError());
+    note_device_work(e, s);
+    NIG_CUDA(nig::launch_state_io(a, s));
     return NIG_OK;
 }
 
@@ -308,6 +283,8 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     e->max_steps = cfg->max_episode_steps ? cfg->max_episode_steps : kMaxSteps[e->kind];
     e->key = RngKey{(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)};
     if (const char* v = getenv("NIG_STEP_VEC")) e->step_vec = atoi(v);
+    if (const char* v = getenv("NIG_ROLLOUT_BLOCK")) e->rollout_block = atoi(v);
+    if (e->rollout_block != 0 && e->rollout_block != 32 && e->rollout_block != 64 && e->rollout_block != 128) e->rollout_block = 0;
     nig_constraint_t def[3];
     const nig_constraint_t* c = cfg->constraints;
     int nc = cfg->n_constraints;
@@ -322,6 +299,7 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     if (rc == NIG_OK) rc = dev_alloc(&e->stats, (size_t)NIG_STATS_SLOTS);
     if (rc == NIG_OK && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(NIG_ERR_CUDA, "cudaStreamCreate failed");
+
     if (rc != NIG_OK) { nig_destroy(e); return rc; }
     *out = e;
     return NIG_OK;
@@ -335,6 +313,12 @@ int nig_destroy(nig_env_t* e)
     cudaFree(e->h_actions); cudaFree(e->h_noise); cudaFree(e->h_reset); cudaFree(e->h_obs); cudaFree(e->h_next_obs);
     cudaFree(e->h_reward); cudaFree(e->h_hostmask); cudaFree(e->h_flags); cudaFree(e->h_viol); cudaFree(e->h_mask);
     cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->d_len); cudaFree(e->d_off); cudaFree(e->d_total);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(e->r_act[b]); cudaFree(e->r_nz[b]);
+        if (e->r_ev_copy[b]) cudaEventDestroy(e->r_ev_copy[b]);
+        if (e->r_ev_done[b]) cudaEventDestroy(e->r_ev_done[b]);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return NIG_OK;
@@ -360,21 +344,16 @@ int nig_reset(nig_env_t* e, const uint8_t* mask, const float* init_states, int32
     e->epoch += 1;     // explicit resets draw with a fresh epoch; auto-resets reuse the current one
     ResetArgs a{e->state, e->ep_word, e->ep_return, e->n, e->pitch, (uint32_t)e->cfg.env_id_offset, e->tick, e->epoch, e->key,
                 mask, init_states, layout == NIG_LAYOUT_AOS ? 1 : 0};
-    cudaStream_t st = (cudaStream_t)stream;
-    const unsigned g = grid_for(e->n);
-    switch (e->kind) {
-    case NIG_ENV_CHEMICAL_REACTOR: reset_kernel<Reactor><<<g, kThreads, 0, st>>>(a); break;
-    case NIG_ENV_POWER_GRID: reset_kernel<Grid><<<g, kThreads, 0, st>>>(a); break;
-    default: reset_kernel<Robot><<<g, kThreads, 0, st>>>(a); break;
-    }
     e->launches++;
-    NIG_CUDA(cudaGetLastError());
+    note_device_work(e, (cudaStream_t)stream);
+    NIG_CUDA(nig::launch_reset(e->kind, a, (cudaStream_t)stream));
     return NIG_OK;
 }
 
 int nig_reset_host(nig_env_t* e, const uint8_t* mask, const float* init_states_aos, float* obs_aos_out)
 {
     NIG_CHECK_ENV(e);
+    if (int hrc = host_entry(e)) return hrc;
     int rc;
     const uint8_t* dmask = nullptr;
     const float* dinit = nullptr;
@@ -420,6 +399,7 @@ int nig_step(nig_env_t* e, const nig_step_io_t* io, void* stream)
 int nig_step_host(nig_env_t* e, const nig_step_io_t* io)
 {
     NIG_CHECK_ENV(e);
+    if (int hrc = host_entry(e)) return hrc;
     if (!io || !io->actions) return fail(NIG_ERR_INVALID, "nig_step_host: null io or actions");
     if (io->noise && e->NZ == 0) return fail(NIG_ERR_INVALID, "nig_step_host: env kind %d has no process noise", e->kind);
     int rc;
@@ -468,6 +448,9 @@ int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
     if (r->n_steps <= 0) return fail(NIG_ERR_INVALID, "nig_rollout: n_steps must be positive (got %d)", r->n_steps);
     if (r->policy == NIG_POLICY_ACTIONS && !r->actions) return fail(NIG_ERR_INVALID, "nig_rollout: NIG_POLICY_ACTIONS needs an actions tensor");
     if (r->noise && e->NZ == 0) return fail(NIG_ERR_INVALID, "nig_rollout: env kind %d has no process noise", e->kind);
+    if (r->noise && r->policy != NIG_POLICY_ACTIONS)
+        return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: teacher-forced noise is only available together with teacher-forced actions (NIG_POLICY_ACTIONS)");
+    if (r->policy < NIG_POLICY_ACTIONS || r->policy > NIG_POLICY_PCTRL) return fail(NIG_ERR_INVALID, "unknown rollout policy %d", r->policy);
     for (int k = 0; k < e->cons.n; ++k)
         if (e->cons.c[k].kind == NIG_CON_HOSTMASK) return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: host-evaluated constraints cannot run inside a fused rollout");
     RolloutArgs a;
@@ -477,44 +460,129 @@ int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
     a.max_steps = e->max_steps; a.auto_reset = e->cfg.auto_reset; a.n_steps = r->n_steps;
     a.actions = r->actions; a.noise = r->noise; a.pp = r->pp;
     a.reward_sum = r->reward_sum; a.viol_count = r->viol_count; a.done_count = r->done_count;
+    a.accumulate = (r->flags & NIG_ROLLOUT_ACCUMULATE) ? 1 : 0;
     a.stats = e->stats; a.cons = e->cons;
     CUtensorMap map;
     memset(&map, 0, sizeof map);
     const bool tma = r->policy == NIG_POLICY_ACTIONS && (r->flags & NIG_ROLLOUT_USE_TMA);
     int rc;
     if (tma && (rc = make_action_map(e, r->actions, r->n_steps, &map)) != NIG_OK) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    switch (e->kind) {
-    case NIG_ENV_CHEMICAL_REACTOR: rc = launch_rollout_env<Reactor>(e, a, r->policy, tma, map, st); break;
-    case NIG_ENV_POWER_GRID: rc = launch_rollout_env<Grid>(e, a, r->policy, tma, map, st); break;
-    default: rc = launch_rollout_env<Robot>(e, a, r->policy, tma, map, st); break;
+    RolloutLaunch cfg;
+    cfg.policy = r->policy; cfg.defcons = e->cons.is_default != 0; cfg.tma = tma; cfg.tf_noise = r->noise != nullptr;
+    cfg.block = e->rollout_block ? e->rollout_block : 128;
+    e->launches++;
+    note_device_work(e, (cudaStream_t)stream);
+    NIG_CUDA(nig::launch_rollout(e->kind, cfg, e->pitch, a, map, (cudaStream_t)stream));
+    e->tick += (uint32_t)r->n_steps;
+    return NIG_OK;
+}
+
+int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
+{
+    NIG_CHECK_ENV(e);
+    if (int hrc = host_entry(e)) return hrc;
+    if (!r) return fail(NIG_ERR_INVALID, "nig_rollout_host: null descriptor");
+    if (r->n_steps <= 0) return fail(NIG_ERR_INVALID, "nig_rollout_host: n_steps must be positive (got %d)", r->n_steps);
+    if (r->steps_per_launch < 0) return fail(NIG_ERR_INVALID, "nig_rollout_host: steps_per_launch must be >= 0");
+    if (r->policy == NIG_POLICY_ACTIONS && !r->actions) return fail(NIG_ERR_INVALID, "nig_rollout_host: NIG_POLICY_ACTIONS needs actions");
+    if (r->noise && r->policy != NIG_POLICY_ACTIONS) return fail(NIG_ERR_UNSUPPORTED, "nig_rollout_host: teacher-forced noise needs NIG_POLICY_ACTIONS");
+    if (r->noise && e->NZ == 0) return fail(NIG_ERR_INVALID, "nig_rollout_host: env kind %d has no process noise", e->kind);
+    int rc;
+    const size_t n = (size_t)e->n, cap = (size_t)e->pitch;
+    const int32_t T = r->n_steps, K = r->steps_per_launch > 0 && r->steps_per_launch < T ? r->steps_per_launch : T;
+    cudaStream_t st = e->stream;
+    const bool forced = r->policy == NIG_POLICY_ACTIONS;
+    if (forced) {
+        if (!e->copy_stream) {
+            NIG_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                NIG_CUDA(cudaEventCreateWithFlags(&e->r_ev_copy[b], cudaEventDisableTiming));
+                NIG_CUDA(cudaEventCreateWithFlags(&e->r_ev_done[b], cudaEventDisableTiming));
+            }
+        }
+        if (K > e->r_cap) {
+            NIG_CUDA(cudaDeviceSynchronize());
+            for (int b = 0; b < 2; ++b) { cudaFree(e->r_act[b]); cudaFree(e->r_nz[b]); e->r_act[b] = e->r_nz[b] = nullptr; }
+            e->r_cap = 0;
+            for (int b = 0; b < 2; ++b) {
+                NIG_CUDA(cudaMalloc((void**)&e->r_act[b], (size_t)K * e->A * cap * sizeof(float)));
+                NIG_CUDA(cudaMemset(e->r_act[b], 0, (size_t)K * e->A * cap * sizeof(float)));
+                if (e->NZ > 0) {
+                    NIG_CUDA(cudaMalloc((void**)&e->r_nz[b], (size_t)K * e->NZ * cap * sizeof(float)));
+                    NIG_CUDA(cudaMemset(e->r_nz[b], 0, (size_t)K * e->NZ * cap * sizeof(float)));
+                }
+            }
+            e->r_cap = K;
+        }
     }
-    if (rc == NIG_OK) e->tick += (uint32_t)r->n_steps;
-    return rc;
+    if (r->reset_first || r->init_states) {
+        const float* dinit = nullptr;
+        if (r->init_states) {
+            if ((rc = dev_alloc(&e->h_reset, cap * e->S)) != NIG_OK) return rc;
+            NIG_CUDA(cudaMemcpyAsync(e->h_reset, r->init_states, n * e->S * sizeof(float), cudaMemcpyHostToDevice, st));
+            dinit = e->h_reset;
+        }
+        if ((rc = nig_reset(e, nullptr, dinit, NIG_LAYOUT_AOS, st)) != NIG_OK) return rc;
+    }
+    if (r->reward_sum && (rc = dev_alloc(&e->h_reward, cap)) != NIG_OK) return rc;
+    if (r->viol_count && (rc = dev_alloc(&e->h_i32a, cap)) != NIG_OK) return rc;
+    if (r->done_count && (rc = dev_alloc(&e->h_i32b, cap)) != NIG_OK) return rc;
+    // rows of a [T][D][n] host tensor -> [K][D][pitch] device chunk
+    auto copy_chunk = [&](float* dst, const float* src, int D, int32_t t0, int32_t k) -> cudaError_t {
+        return cudaMemcpy2DAsync(dst, cap * sizeof(float), src + (size_t)t0 * D * n, n * sizeof(float), n * sizeof(float),
+                                 (size_t)k * D, cudaMemcpyHostToDevice, e->copy_stream);
+    };
+    int32_t done = 0;
+    for (int c = 0; done < T; ++c) {
+        const int32_t k = T - done < K ? T - done : K;
+        const int b = c & 1;
+        nig_rollout_t d;
+        memset(&d, 0, sizeof d);
+        d.n_steps = k; d.policy = r->policy; d.pp = r->pp;
+        d.flags = c > 0 ? NIG_ROLLOUT_ACCUMULATE : 0;
+        if (forced) {
+            NIG_CUDA(cudaStreamWaitEvent(e->copy_stream, e->r_ev_done[b], 0));     // the launch that last read this buffer
+            NIG_CUDA(copy_chunk(e->r_act[b], r->actions, e->A, done, k));
+            if (r->noise) NIG_CUDA(copy_chunk(e->r_nz[b], r->noise, e->NZ, done, k));
+            NIG_CUDA(cudaEventRecord(e->r_ev_copy[b], e->copy_stream));
+            NIG_CUDA(cudaStreamWaitEvent(st, e->r_ev_copy[b], 0));
+            d.actions = e->r_act[b];
+            d.noise = r->noise ? e->r_nz[b] : nullptr;
+            d.flags |= NIG_ROLLOUT_USE_TMA;
+        }
+        d.reward_sum = r->reward_sum ? e->h_reward : nullptr;
+        d.viol_count = r->viol_count ? e->h_i32a : nullptr;
+        d.done_count = r->done_count ? e->h_i32b : nullptr;
+        if ((rc = nig_rollout(e, &d, st)) != NIG_OK) return rc;
+        if (forced) NIG_CUDA(cudaEventRecord(e->r_ev_done[b], st));
+        done += k;
+    }
+    if (r->final_obs) {
+        if ((rc = dev_alloc(&e->h_obs, cap * e->S)) != NIG_OK) return rc;
+        if ((rc = state_io(e, e->h_obs, NIG_LAYOUT_AOS, nullptr, nullptr, nullptr, true, st)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(r->final_obs, e->h_obs, n * e->S * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (r->reward_sum) NIG_CUDA(cudaMemcpyAsync(r->reward_sum, e->h_reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (r->viol_count) NIG_CUDA(cudaMemcpyAsync(r->viol_count, e->h_i32a, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (r->done_count) NIG_CUDA(cudaMemcpyAsync(r->done_count, e->h_i32b, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    unsigned long long hs[NIG_STATS_SLOTS];
+    if (r->counters24 || r->sums8) NIG_CUDA(cudaMemcpyAsync(hs, e->stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+    NIG_CUDA(cudaStreamSynchronize(st));
+    if (r->counters24) for (int k = 0; k < 24; ++k) r->counters24[k] = (int64_t)hs[k];
+    if (r->sums8) memcpy(r->sums8, &hs[24], 8 * sizeof(double));
+    return NIG_OK;
 }
 
 } // extern "C"
 
 namespace {
 
-template <class Env, bool WRITE>
-void launch_dataset_t(nig_env* e, const DatasetArgs& a, cudaStream_t st)
-{
-    const unsigned g = grid_for(a.n_episodes);
-    if (e->cons.is_default) dataset_kernel<Env, true, WRITE><<<g, kThreads, 0, st>>>(a);
-    else dataset_kernel<Env, false, WRITE><<<g, kThreads, 0, st>>>(a);
-    e->launches++;
-}
-
 template <bool WRITE>
 int launch_dataset(nig_env* e, const DatasetArgs& a, cudaStream_t st)
 {
-    switch (e->kind) {
-    case NIG_ENV_CHEMICAL_REACTOR: launch_dataset_t<Reactor, WRITE>(e, a, st); break;
-    case NIG_ENV_POWER_GRID: launch_dataset_t<Grid, WRITE>(e, a, st); break;
-    default: launch_dataset_t<Robot, WRITE>(e, a, st); break;
-    }
-    NIG_CUDA(cudaGetLastError());
+    e->launches++;
+    note_device_work(e, st);
+    NIG_CUDA(nig::launch_dataset(e->kind, e->cons.is_default != 0, WRITE, a, st));
     return NIG_OK;
 }
 
@@ -558,9 +626,8 @@ int dataset_probe(nig_env* e, int64_t n_episodes, int32_t n_steps, int32_t polic
                      memcmp(&c.pp, &a->pp, sizeof c.pp) == 0 && memcmp(&c.cons, &e->cons, sizeof c.cons) == 0;
     if (!hit) {
         if ((rc = launch_dataset<false>(e, *a, st)) != NIG_OK) return rc;
-        scan_lengths_kernel<<<1, 1024, 0, st>>>(e->d_len, e->d_off, n_episodes, e->d_total);
         e->launches++;
-        NIG_CUDA(cudaGetLastError());
+        NIG_CUDA(nig::launch_scan_lengths(e->d_len, e->d_off, n_episodes, e->d_total, st));
         int64_t t = 0;
         NIG_CUDA(cudaMemcpyAsync(&t, e->d_total, sizeof t, cudaMemcpyDeviceToHost, st));
         NIG_CUDA(cudaStreamSynchronize(st));
@@ -620,6 +687,7 @@ int nig_set_state(nig_env_t* e, const float* state_dev, int32_t layout, const in
 int nig_get_state_host(nig_env_t* e, float* state_aos, int32_t* st, int32_t* vi, uint8_t* dn)
 {
     NIG_CHECK_ENV(e);
+    if (int hrc = host_entry(e)) return hrc;
     int rc;
     const size_t n = (size_t)e->n, cap = (size_t)e->pitch;
     if ((rc = dev_alloc(&e->h_obs, cap * e->S)) != NIG_OK) return rc;
@@ -638,6 +706,7 @@ int nig_get_state_host(nig_env_t* e, float* state_aos, int32_t* st, int32_t* vi,
 int nig_set_state_host(nig_env_t* e, const float* state_aos, const int32_t* st, const int32_t* vi, const uint8_t* dn)
 {
     NIG_CHECK_ENV(e);
+    if (int hrc = host_entry(e)) return hrc;
     int rc;
     const size_t n = (size_t)e->n, cap = (size_t)e->pitch;
     float* ds = nullptr; int32_t *dst = nullptr, *dvi = nullptr; uint8_t* ddn = nullptr;
@@ -741,6 +810,26 @@ int nig_host_free(void* p)
     return NIG_OK;
 }
 
+int nig_selftest_division(int device, int64_t n, uint64_t seed, int64_t* mismatches, int64_t* accepted)
+{
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    if (n <= 0 || !mismatches) return fail(NIG_ERR_INVALID, "nig_selftest_division: n must be positive and mismatches non-null");
+    unsigned long long* d = nullptr;
+    NIG_CUDA(cudaMalloc((void**)&d, 2 * sizeof(unsigned long long)));
+    NIG_CUDA(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+    const int blocks = 148 * 8, threads = blocks * 256;
+    const int iters = (int)((n + threads - 1) / threads);
+    cudaError_t ce = nig::launch_selftest_division(RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)}, iters, blocks, d, nullptr);
+    unsigned long long h[2] = {0, 0};
+    if (ce == cudaSuccess) ce = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    NIG_CUDA(ce);
+    *mismatches = (int64_t)h[0];
+    if (accepted) *accepted = (int64_t)h[1];
+    return NIG_OK;
+}
+
 int nig_fp32_probe(int device, int32_t iters, double* ops, void* stream)
 {
     DeviceGuard guard(device);
@@ -748,8 +837,7 @@ int nig_fp32_probe(int device, int32_t iters, double* ops, void* stream)
     static float* sink = nullptr;
     if (!sink) NIG_CUDA(cudaMalloc((void**)&sink, 256));
     const int blocks = 148 * 8;
-    fp32_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(sink, iters);
-    NIG_CUDA(cudaGetLastError());
+    NIG_CUDA(nig::launch_fp32_probe(sink, iters, blocks, (cudaStream_t)stream));
     if (ops) *ops = (double)blocks * 256.0 * (double)iters * 16.0;
     return NIG_OK;
 }

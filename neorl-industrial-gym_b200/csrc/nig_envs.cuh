@@ -36,6 +36,7 @@ __device__ __forceinline__ double pairwise8d(const double (&x)[8])
 // ================================================================================================
 struct Reactor {
     static constexpr int KIND = 0, S = 12, A = 3, NZ = 2, NB = 3, MAX_STEPS = 500;
+    static constexpr bool FAST_DIV = true;           // 5 divisions by constants per step (dynamics 3, reward 2)
     static constexpr uint32_t CRIT_MASK = 0x3;       // temperature_limit, pressure_limit (:38-52)
     using acc_t = float;                              // reward stays np.float32 upstream
     __device__ static constexpr float penalty(int k) { return k == 0 ? -100.0f : (k == 1 ? -50.0f : -25.0f); }
@@ -80,8 +81,9 @@ struct Reactor {
         return id == 0 ? (s[0] <= 350.0f) : id == 1 ? (s[1] <= 506625.0f) : (20.0f <= s[10] && s[10] <= 90.0f);
     }
 
-    // _dynamics (:109-226)
-    __device__ static __forceinline__ void dynamics(const float (&s)[S], const float (&a)[A], const float (&nz)[NZ], float (&o)[S])
+    // _dynamics (:109-226). `div` performs the divisions by constants (DivExact / DivFast, nig_math.cuh)
+    template <class Div>
+    __device__ static __forceinline__ void dynamics(const float (&s)[S], const float (&a)[A], const float (&nz)[NZ], float (&o)[S], Div& div)
     {
         const float temp = s[0], pressure = s[1], cool = s[2], feed = s[3], conc = s[4], cat = s[5];
         const float hx = s[6], relief = s[7], estop = s[8], alarm = s[9], level = s[10], bt = s[11];
@@ -89,14 +91,14 @@ struct Reactor {
         const float hp = manual ? mul(a[0], 50000.0f) : -10000.0f;            // :127 / :132
         const float cadj = manual ? mul(a[1], 0.1f) : 0.1f;                   // :128 / :133
         const float fadj = manual ? mul(a[2], 0.1f) : -0.1f;                  // :129 / :134
-        const float kca = mul(mul(0.1f, conc), fdiv(cat, 100.0f));            // k * conc * (cat / 100)
+        const float kca = mul(mul(0.1f, conc), NIG_CDIV(div, cat, 100.0f));            // k * conc * (cat / 100)
         const float rh = mul(kca, 10000.0f);                                  // :137-140
         const float ch = mul(mul(mul(cool, 100.0f), sub(temp, hx)), 0.1f);    // :141
-        float dT = fdiv(sub(add(hp, rh), ch), 418000.0f);                     // :143-146 (4.18e3*1000*0.1)
+        float dT = NIG_CDIV(div, sub(add(hp, rh), ch), 418000.0f);                     // :143-146 (4.18e3*1000*0.1)
         dT = add(dT, nz[0]);                                                  // :149
         const float nT = add(temp, mul(dT, 0.1f));                            // :151
         const float pfr = mul(mul(conc, 0.1f), 1000.0f);                      // :156
-        float nP = add(mul(pressure, fdiv(nT, temp)), mul(pfr, 0.1f));        // :155, :158
+        float nP = add(mul(pressure, div.vdiv(nT, temp)), mul(pfr, 0.1f));        // :155, :158
         nP = add(nP, nz[1]);                                                  // :159
         const float nrv = py_clamp(add(relief, mul(sub(nP, 506625.0f), 0.001f)), 0.0f, 100.0f);  // :162-163
         if (nrv > 0.0f) {                                                     // :166-168
@@ -106,7 +108,7 @@ struct Reactor {
         const float ncool = py_clamp(add(cool, cadj), 10.0f, 100.0f);         // :171
         const float feed_v = add(feed, fadj);                                 // :172
         const float nfeed = py_clamp(feed_v, 5.0f, 50.0f);
-        const float ex = spec_expf(fdiv(-sub(nT, 320.0f), 20.0f));            // :177
+        const float ex = spec_expf(NIG_CDIV(div, -sub(nT, 320.0f), 20.0f));            // :177
         const float rr = mul(kca, ex);                                        // :175-178
         // :180 -- a clamped feed is the Python int 5 / 50 upstream, so 5*0.001 is a Python float (0.005)
         // rounded to binary32, which differs from float32(5)*float32(0.001) in the last bit.
@@ -128,12 +130,13 @@ struct Reactor {
     }
 
     // _compute_reward (:228-270)
-    __device__ static __forceinline__ acc_t reward(const float (&ns)[S], const float (&a)[A])
+    template <class Div>
+    __device__ static __forceinline__ acc_t reward(const float (&ns)[S], const float (&a)[A], Div& div)
     {
         float r = add(0.0f, mul(ns[4], 100.0f));                                   // :238-241
         r = sub(r, mul(fabsf(sub(ns[0], 320.0f)), 0.5f));                          // :244-245
-        r = sub(r, mul(fdiv(fabsf(sub(ns[1], 253312.5f)), 1000.0f), 0.1f));        // :248-249
-        r = add(r, mul(fdiv(ns[5], 100.0f), 10.0f));                               // :252
+        r = sub(r, mul(NIG_CDIV(div, fabsf(sub(ns[1], 253312.5f)), 1000.0f), 0.1f));        // :248-249
+        r = add(r, mul(NIG_CDIV(div, ns[5], 100.0f), 10.0f));                               // :252
         const bool band = (30.0f <= ns[10]) && (ns[10] <= 80.0f);                  // :255-258
         r = band ? add(r, 5.0f) : sub(r, mul(fabsf(sub(ns[10], 55.0f)), 0.2f));
         if (ns[9] > 0.5f) r = sub(r, 50.0f);                                       // :261-262
@@ -154,8 +157,9 @@ struct Reactor {
     {
         float z[4];
         rng_normals4(key, env, tick, STREAM_POLICY, 1u, z);
-        const float te = fdiv(sub(s[0], 320.0f), 50.0f);
-        const float le = fdiv(sub(s[10], 55.0f), 50.0f);
+        DivExact div;    // the controller branch is taken by a subset of the lanes: keep the IEEE division here
+        const float te = NIG_CDIV(div, sub(s[0], 320.0f), 50.0f);
+        const float le = NIG_CDIV(div, sub(s[10], 55.0f), 50.0f);
 #pragma unroll
         for (int k = 0; k < A; ++k)
             a[k] = add(add(mul(pp.gain[k][0], te), mul(pp.gain[k][1], le)), mul(pp.sigma[k], z[k]));
@@ -167,6 +171,7 @@ struct Reactor {
 // ================================================================================================
 struct Grid {
     static constexpr int KIND = 1, S = 32, A = 8, NZ = 23, NB = 3, MAX_STEPS = 1000;
+    static constexpr bool FAST_DIV = true;           // one fp32 division by 5 per step
     static constexpr uint32_t CRIT_MASK = 0x3;       // frequency_stability, voltage_limits (:53-65)
     using acc_t = double;                             // _compute_reward returns a Python float (:177)
     __device__ static constexpr float penalty(int k) { return k == 0 ? -50.0f : (k == 1 ? -30.0f : -20.0f); }
@@ -244,7 +249,8 @@ struct Grid {
         return ok;
     }
 
-    __device__ static __forceinline__ void dynamics(const float (&s)[S], const float (&a)[A], const float (&nz)[NZ], float (&o)[S])
+    template <class Div>
+    __device__ static __forceinline__ void dynamics(const float (&s)[S], const float (&a)[A], const float (&nz)[NZ], float (&o)[S], Div& div)
     {   // _dynamics (:112-153)
         float gen[8], load[8];
 #pragma unroll
@@ -255,7 +261,7 @@ struct Grid {
             gen[i] = g; load[i] = s[17 + i];
         }
         const float imb = sub(pairwise8(gen), pairwise8(load));                  // :127-129
-        const float fd = fdiv(add(mul(-1.0f, s[0]), imb), 5.0f);                 // :132
+        const float fd = NIG_CDIV(div, add(mul(-1.0f, s[0]), imb), 5.0f);                 // :132
         o[0] = add(s[0], mul(fd, 0.1f));                                         // :133
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -268,7 +274,8 @@ struct Grid {
         for (int i = 0; i < 7; ++i) o[25 + i] = add(s[25 + i], nz[16 + i]);      // :144
     }
 
-    __device__ static __forceinline__ acc_t reward(const float (&ns)[S], const float (&a)[A])
+    template <class Div>
+    __device__ static __forceinline__ acc_t reward(const float (&ns)[S], const float (&a)[A], Div&)
     {   // _compute_reward (:155-177): fp32 terms, fp64 cost term, summed left to right
         const float fr = mul(-100.0f, mul(ns[0], ns[0]));                        // :162
         float d2[8], a2[8]; double cg[8];
@@ -319,6 +326,7 @@ struct Grid {
 // ================================================================================================
 struct Robot {
     static constexpr int KIND = 2, S = 24, A = 7, NZ = 0, NB = 3, MAX_STEPS = 1000;
+    static constexpr bool FAST_DIV = false;          // fp64 divisions only
     static constexpr uint32_t CRIT_MASK = 0x3;       // force_limits, collision_avoidance (:56-68)
     using acc_t = double;
     __device__ static constexpr float penalty(int k) { return k == 0 ? -100.0f : (k == 1 ? -200.0f : -50.0f); }
@@ -381,7 +389,8 @@ struct Robot {
         return ok;
     }
 
-    __device__ static __forceinline__ void dynamics(const float (&s)[S], const float (&a)[A], const float (&)[1], float (&o)[S])
+    template <class Div>
+    __device__ static __forceinline__ void dynamics(const float (&s)[S], const float (&a)[A], const float (&)[1], float (&o)[S], Div&)
     {   // _dynamics (:139-188)
         double q[7], pos[3];
 #pragma unroll
@@ -419,7 +428,8 @@ struct Robot {
         o[21] = (float)align; o[22] = (float)depth; o[23] = (float)dmul(align, depth);               // :178
     }
 
-    __device__ static __forceinline__ acc_t reward(const float (&ns)[S], const float (&a)[A])
+    template <class Div>
+    __device__ static __forceinline__ acc_t reward(const float (&ns)[S], const float (&a)[A], Div&)
     {   // _compute_reward (:190-222)
         const double completion = (double)mul(100.0f, ns[23]);                   // :197 (fp32)
         const double dx = dsub((double)ns[0], 0.3), dy = dsub((double)ns[1], 0.0), dz = dsub((double)ns[2], 0.4);

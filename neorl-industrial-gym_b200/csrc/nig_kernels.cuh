@@ -70,12 +70,14 @@ __device__ __forceinline__ uint32_t epw_make(uint32_t step, uint32_t viol, uint3
 }
 
 // ---- one env step in registers (base.py:157-213) --------------------------------------------------
-template <class Env, bool DEFCONS>
-__device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
-                                          const float (&s)[Env::S], const float (&a_raw)[Env::A],
-                                          const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
-                                          uint32_t& ep_word, float (&ns)[Env::S],
-                                          typename Env::acc_t& reward, uint32_t& flags, uint32_t& vmask)
+// `div` carries out the divisions (DivExact = IEEE; DivFast = guarded fast path, see nig_math.cuh). With DivFast
+// the outputs are only valid if div.ok() afterwards -- the callers redo the step with DivExact otherwise.
+template <class Env, bool DEFCONS, class Div>
+__device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_steps,
+                                               const float (&s)[Env::S], const float (&a_raw)[Env::A],
+                                               const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
+                                               uint32_t ep_word_in, uint32_t& ep_word, float (&ns)[Env::S],
+                                               typename Env::acc_t& reward, uint32_t& flags, uint32_t& vmask, Div& div)
 {
     using acc_t = typename Env::acc_t;
     float a[Env::A];
@@ -114,8 +116,8 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
             crit = crit || (!ok && c.critical != 0);
         }
     }
-    Env::dynamics(s, a, nz, ns);                      // base.py:173
-    acc_t r = Env::reward(ns, a);                     // base.py:176
+    Env::dynamics(s, a, nz, ns, div);                 // base.py:173
+    acc_t r = Env::reward(ns, a, div);                // base.py:176
     if constexpr (DEFCONS) {                          // base.py:179-183, in constraint order
 #pragma unroll
         for (int k = 0; k < Env::NB; ++k)
@@ -124,8 +126,8 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
         for (int k = 0; k < cp.n; ++k)
             if ((vm >> k) & 1u) r = r + (acc_t)cp.c[k].penalty;
     }
-    const uint32_t step = epw_step(ep_word) + 1u;     // base.py:187
-    const uint32_t viol = epw_viol(ep_word) + (uint32_t)__popc(vm);
+    const uint32_t step = epw_step(ep_word_in) + 1u;  // base.py:187
+    const uint32_t viol = epw_viol(ep_word_in) + (uint32_t)__popc(vm);
     bool terminated = Env::is_done(ns);               // base.py:190
     const bool truncated = step >= (uint32_t)max_steps;   // base.py:191
     uint32_t f = 0;
@@ -134,6 +136,24 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
     if (truncated) f |= NIG_F_TRUNCATED;
     ep_word = epw_make(step, viol, 0u);
     reward = r; flags = f; vmask = vm;
+}
+
+// one step with the fast divisions and the deferred guard: the common path is a single basic block
+template <class Env, bool DEFCONS>
+__device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
+                                          const float (&s)[Env::S], const float (&a_raw)[Env::A],
+                                          const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
+                                          uint32_t& ep_word, float (&ns)[Env::S],
+                                          typename Env::acc_t& reward, uint32_t& flags, uint32_t& vmask)
+{
+    const uint32_t w_in = ep_word;
+    if constexpr (Env::FAST_DIV) {
+        DivFast df;
+        step_core_impl<Env, DEFCONS>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, df);
+        if (__builtin_expect(df.ok(), 1)) return;
+    }
+    DivExact de;
+    step_core_impl<Env, DEFCONS>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, de);
 }
 
 // ---- block-level statistics: per-thread counts -> REDUX -> shared atomics -> one global atomic per slot
@@ -361,7 +381,7 @@ struct StateIoArgs {
     float* ext_state; int32_t* ext_step; int32_t* ext_viol; uint8_t* ext_done;
     int32_t S, aos, to_ext;
 };
-__global__ void __launch_bounds__(kThreads) state_io_kernel(const __grid_constant__ StateIoArgs p)
+static __global__ void __launch_bounds__(kThreads) state_io_kernel(const __grid_constant__ StateIoArgs p)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= p.n) return;
@@ -401,6 +421,7 @@ struct RolloutArgs {
     const float* noise;        // [K][NZ][pitch] or null
     nig_policy_params_t pp;
     float* reward_sum; int32_t* viol_count; int32_t* done_count;
+    int32_t accumulate;        // per-env outputs: out[i] += this launch's value instead of out[i] = ...
     unsigned long long* stats;
     ConsParams cons;
 };
@@ -483,10 +504,16 @@ template <class T> __device__ __forceinline__ T warp_sum(T v)
     return v;
 }
 
-template <class Env, bool DEFCONS, int POLICY, bool TMA>
+// TFNOISE: process noise teacher-forced from p.noise (POLICY_ACTIONS only). The LDG flavour of POLICY_ACTIONS
+// prefetches the next step's actions / noise into registers one step ahead, so the L2 latency of the loads is
+// hidden behind a whole step of arithmetic. Block size is a launch parameter (blockDim.x <= kThreads; TMA launches
+// use kThreads).
+template <class Env, bool DEFCONS, int POLICY, bool TMA, bool TFNOISE>
 __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant__ RolloutArgs p, const __grid_constant__ CUtensorMap amap)
 {
+    static_assert(!TFNOISE || POLICY == NIG_POLICY_ACTIONS, "teacher-forced noise comes with teacher-forced actions");
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
+    constexpr bool PREFETCH = (POLICY == NIG_POLICY_ACTIONS) && !TMA;
     using acc_t = typename Env::acc_t;
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
     __shared__ double sfl[4];
@@ -496,7 +523,7 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
     if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
     bs.init(sstat);
 
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < p.n;
     const int64_t ic = valid ? i : 0;      // padding lanes shadow env 0 without side effects
     const uint32_t env = p.env0 + (uint32_t)ic;
@@ -534,6 +561,16 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
     unsigned long long len_sum = 0, len_sq = 0;
     double ret_sum = 0.0, ret_sq = 0.0, rew_sum = 0.0;
 
+    float a_pf[A], nz_pf[NZA];             // PREFETCH: the values of step t, loaded during step t - 1
+    if constexpr (PREFETCH) {
+#pragma unroll
+        for (int k = 0; k < A; ++k) a_pf[k] = __ldcs(p.actions + (int64_t)k * p.pitch + ic);
+        if constexpr (TFNOISE) {
+#pragma unroll
+            for (int k = 0; k < NZA; ++k) nz_pf[k] = __ldcs(p.noise + (int64_t)k * p.pitch + ic);
+        }
+    }
+
     for (int t = 0; t < p.n_steps; ++t) {
         const uint32_t tick = p.tick + (uint32_t)t;
         float a[A], nz[NZA], ns[S];
@@ -554,7 +591,10 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < A; ++k) a[k] = __ldcs(p.actions + ((int64_t)t * A + k) * p.pitch + ic);
+                for (int k = 0; k < A; ++k) a[k] = a_pf[k];
+                const int tn = t + 1 < p.n_steps ? t + 1 : t;     // last step re-reads its own row (in bounds, unused)
+#pragma unroll
+                for (int k = 0; k < A; ++k) a_pf[k] = __ldcs(p.actions + ((int64_t)tn * A + k) * p.pitch + ic);
             }
         } else if constexpr (POLICY == NIG_POLICY_UNIFORM) {
             policy_uniform<Env>(p.key, env, tick, a);
@@ -564,10 +604,18 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
 #pragma unroll
             for (int k = 0; k < A; ++k) a[k] = 0.0f;
         }
-        if (NZ > 0) {
-            if (p.noise) {
+        if constexpr (NZ > 0) {
+            if constexpr (TFNOISE) {
+                if constexpr (PREFETCH) {
 #pragma unroll
-                for (int k = 0; k < NZA; ++k) nz[k] = p.noise[((int64_t)t * NZA + k) * p.pitch + ic];
+                    for (int k = 0; k < NZA; ++k) nz[k] = nz_pf[k];
+                    const int tn = t + 1 < p.n_steps ? t + 1 : t;
+#pragma unroll
+                    for (int k = 0; k < NZA; ++k) nz_pf[k] = __ldcs(p.noise + ((int64_t)tn * NZA + k) * p.pitch + ic);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NZA; ++k) nz[k] = __ldcs(p.noise + ((int64_t)t * NZA + k) * p.pitch + ic);
+                }
             } else ng.get(p.key, env, tick, nz);
         } else nz[0] = 0.0f;
 
@@ -618,9 +666,15 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
         for (int k = 0; k < S; ++k) p.state[k * p.pitch + i] = s[k];
         p.ep_word[i] = w;
         p.ep_return[i] = (double)ep_ret;
-        if (p.reward_sum) p.reward_sum[i] = rsum;
-        if (p.viol_count) p.viol_count[i] = (int32_t)c_viol;
-        if (p.done_count) p.done_count[i] = (int32_t)c_done;
+        if (p.accumulate) {
+            if (p.reward_sum) p.reward_sum[i] = add(p.reward_sum[i], rsum);
+            if (p.viol_count) p.viol_count[i] += (int32_t)c_viol;
+            if (p.done_count) p.done_count[i] += (int32_t)c_done;
+        } else {
+            if (p.reward_sum) p.reward_sum[i] = rsum;
+            if (p.viol_count) p.viol_count[i] = (int32_t)c_viol;
+            if (p.done_count) p.done_count[i] = (int32_t)c_done;
+        }
     }
     // violation / episode statistics: warp REDUX + shuffle trees -> one global atomic per slot per block
     bs.warp_add(NIG_ST_STEPS, c_steps);
@@ -651,7 +705,6 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
     if (threadIdx.x < 3 && sfl[threadIdx.x] != 0.0)
         atomicAdd(reinterpret_cast<double*>(p.stats) + NIG_ST_F_RETURN_SUM + threadIdx.x, sfl[threadIdx.x]);
 }
-
 
 // ================================================================================================
 // dataset writer (get_dataset: chemical_reactor.py:324-420, power_grid.py:194-249, robot_assembly.py:246-308)
@@ -732,7 +785,7 @@ __global__ void __launch_bounds__(kThreads) dataset_kernel(const __grid_constant
 }
 
 // exclusive scan of n int64 lengths (one 1024-thread block; n is a few thousand .. a few million episodes)
-__global__ void __launch_bounds__(1024) scan_lengths_kernel(const int64_t* __restrict__ len, int64_t* __restrict__ off, int64_t n, int64_t* total)
+static __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int64_t* __restrict__ len, int64_t* __restrict__ off, int64_t n, int64_t* total)
 {
     __shared__ long long part[1024];
     const int t = threadIdx.x;
@@ -753,8 +806,45 @@ __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int64_t* __res
     if (t == 1023) *total = part[1023];
 }
 
+// ---- self-test of the guarded fast divisions (nig_math.cuh) against the IEEE division -------------------------
+// mode 0: x, y = raw Philox words (all exponents, ~22 % inside the vdiv guard); mode 1: the physics regime
+// (y ~ 300, x = y * (1 + small)); mode 2: x = raw word divided by each constant the kernels use.
+static __global__ void __launch_bounds__(256) selftest_division_kernel(RngKey key, int iters, unsigned long long* out)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bad = 0, acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        const uint4 w = philox4x32_10(tid, (uint32_t)it, 7u, 0u, key.k0, key.k1);
+        {   // mode 0
+            DivFast d;
+            const float x = __uint_as_float(w.x), y = __uint_as_float(w.y);
+            const float q = d.vdiv(x, y);
+            if (d.ok()) { acc++; bad += __float_as_uint(q) != __float_as_uint(__fdiv_rn(x, y)); }
+        }
+        {   // mode 1
+            DivFast d;
+            const float y = __fadd_rn(250.0f, __fmul_rn(150.0f, u_open(w.z)));
+            const float x = __fmul_rn(y, __fadd_rn(1.0f, __fmul_rn(0.01f, u_sym(w.w))));
+            const float q = d.vdiv(x, y);
+            if (d.ok()) { acc++; bad += __float_as_uint(q) != __float_as_uint(__fdiv_rn(x, y)); }
+        }
+        {   // mode 2
+            const float x = __uint_as_float(w.x ^ w.z);
+            const float cs[6] = {5.0f, 20.0f, 50.0f, 100.0f, 1000.0f, 418000.0f};
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                DivFast d;
+                const float q = d(x, cs[k], 1.0f / cs[k]);
+                if (d.ok()) { acc++; bad += __float_as_uint(q) != __float_as_uint(__fdiv_rn(x, cs[k])); }
+            }
+        }
+    }
+    atomicAdd(&out[0], bad);
+    atomicAdd(&out[1], acc);
+}
+
 // ---- measured-peak probe: independent unfused FADD/FMUL chains (what the physics is made of) ------
-__global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters)
+static __global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters)
 {
     float x[8];
 #pragma unroll

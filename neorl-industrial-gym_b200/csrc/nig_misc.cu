@@ -1,0 +1,37 @@
+// reset, state import/export and the fp32 issue-rate probe (see nig_kernels.cuh)
+#include "nig_launch.h"
+namespace nig {
+cudaError_t launch_reset(int kind, const ResetArgs& a, cudaStream_t st)
+{
+    const unsigned g = grid_for(a.n);
+    switch (kind) {
+    case NIG_ENV_CHEMICAL_REACTOR: reset_kernel<Reactor><<<g, kThreads, 0, st>>>(a); break;
+    case NIG_ENV_POWER_GRID: reset_kernel<Grid><<<g, kThreads, 0, st>>>(a); break;
+    default: reset_kernel<Robot><<<g, kThreads, 0, st>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+cudaError_t launch_state_io(const StateIoArgs& a, cudaStream_t st)
+{
+    state_io_kernel<<<grid_for(a.n), kThreads, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_fp32_probe(float* sink, int iters, int blocks, cudaStream_t st)
+{
+    fp32_probe_kernel<<<blocks, 256, 0, st>>>(sink, iters);
+    return cudaGetLastError();
+}
+cudaError_t launch_selftest_division(RngKey key, int iters, int blocks, unsigned long long* out, cudaStream_t st)
+{
+    selftest_division_kernel<<<blocks, 256, 0, st>>>(key, iters, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_rollout(int kind, const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
+{
+    switch (kind) {
+    case NIG_ENV_CHEMICAL_REACTOR: return launch_rollout_reactor(cfg, pitch, a, map, st);
+    case NIG_ENV_POWER_GRID: return launch_rollout_grid(cfg, pitch, a, map, st);
+    default: return launch_rollout_robot(cfg, pitch, a, map, st);
+    }
+}
+} // namespace nig

@@ -1,0 +1,45 @@
+// nig_rollout_launch.cuh -- instantiates the fused rollout kernel for one env kind (included by one .cu per env).
+#pragma once
+#include "nig_launch.h"
+
+namespace nig {
+
+template <class Env, bool DEFCONS, int POLICY, bool TMA, bool TFNOISE>
+cudaError_t rollout_go(const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
+{
+    auto kern = rollout_kernel<Env, DEFCONS, POLICY, TMA, TFNOISE>;
+    const int block = TMA ? kThreads : cfg.block;
+    const size_t smem = TMA ? (size_t)2 * kTmaChunk * Env::A * kThreads * sizeof(float) : 0;
+    if (TMA) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<grid_for(pitch, block), block, smem, st>>>(a, map);
+    return cudaGetLastError();
+}
+
+template <class Env, bool DEFCONS>
+cudaError_t rollout_policy(const RolloutLaunch& c, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
+{
+    switch (c.policy) {
+    case NIG_POLICY_ACTIONS:
+        if (c.tma) {
+            if constexpr (Env::NZ > 0) { if (c.tf_noise) return rollout_go<Env, DEFCONS, NIG_POLICY_ACTIONS, true, true>(c, pitch, a, map, st); }
+            return rollout_go<Env, DEFCONS, NIG_POLICY_ACTIONS, true, false>(c, pitch, a, map, st);
+        }
+        if constexpr (Env::NZ > 0) { if (c.tf_noise) return rollout_go<Env, DEFCONS, NIG_POLICY_ACTIONS, false, true>(c, pitch, a, map, st); }
+        return rollout_go<Env, DEFCONS, NIG_POLICY_ACTIONS, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_UNIFORM: return rollout_go<Env, DEFCONS, NIG_POLICY_UNIFORM, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_ZERO: return rollout_go<Env, DEFCONS, NIG_POLICY_ZERO, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_PCTRL: return rollout_go<Env, DEFCONS, NIG_POLICY_PCTRL, false, false>(c, pitch, a, map, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <class Env>
+cudaError_t rollout_env(const RolloutLaunch& c, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
+{
+    return c.defcons ? rollout_policy<Env, true>(c, pitch, a, map, st) : rollout_policy<Env, false>(c, pitch, a, map, st);
+}
+
+} // namespace nig

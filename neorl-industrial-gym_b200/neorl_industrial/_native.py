@@ -27,6 +27,7 @@ F_TERMINATED, F_TRUNCATED, F_CRITICAL, F_RESET, F_INACTIVE = 1, 2, 4, 8, 128
 LAYOUT_SOA, LAYOUT_AOS = 0, 1
 POLICY_ACTIONS, POLICY_UNIFORM, POLICY_ZERO, POLICY_PCTRL = 0, 1, 2, 3
 ROLLOUT_USE_TMA = 1
+ROLLOUT_ACCUMULATE = 2
 ST_STEPS, ST_EPISODES, ST_TERMINATED, ST_TRUNCATED, ST_CRITICAL, ST_VIOLATIONS, ST_SUCCESSES, ST_EP_LEN_SUM = range(8)
 ST_CON0 = 8
 ST_EP_LEN_SQ = 16
@@ -70,6 +71,13 @@ class Rollout(C.Structure):
                 ("reward_sum", C.c_void_p), ("viol_count", C.c_void_p), ("done_count", C.c_void_p)]
 
 
+class RolloutHost(C.Structure):
+    _fields_ = [("n_steps", C.c_int32), ("steps_per_launch", C.c_int32), ("policy", C.c_int32), ("reset_first", C.c_int32),
+                ("init_states", C.c_void_p), ("actions", C.c_void_p), ("noise", C.c_void_p), ("pp", PolicyParams),
+                ("reward_sum", C.c_void_p), ("viol_count", C.c_void_p), ("done_count", C.c_void_p),
+                ("final_obs", C.c_void_p), ("counters24", C.c_void_p), ("sums8", C.c_void_p)]
+
+
 class DatasetOut(C.Structure):
     _fields_ = [("observations", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p),
                 ("terminals", C.c_void_p), ("timeouts", C.c_void_p), ("next_observations", C.c_void_p),
@@ -94,6 +102,7 @@ SYMBOLS = {
     "nig_step": (C.c_int, [_VP, C.POINTER(StepIO), _VP]),
     "nig_step_host": (C.c_int, [_VP, C.POINTER(StepIO)]),
     "nig_rollout": (C.c_int, [_VP, C.POINTER(Rollout), _VP]),
+    "nig_rollout_host": (C.c_int, [_VP, C.POINTER(RolloutHost)]),
     "nig_dataset": (C.c_int, [_VP, _I64, _I32, _I32, C.POINTER(PolicyParams), C.POINTER(DatasetOut), C.POINTER(_I64), _VP]),
     "nig_dataset_size": (C.c_int, [_VP, _I64, _I32, _I32, C.POINTER(PolicyParams), C.POINTER(_I64), _VP]),
     "nig_get_state": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
@@ -112,6 +121,7 @@ SYMBOLS = {
     "nig_host_free": (C.c_int, [_VP]),
     "nig_launch_count": (_I64, [_VP]),
     "nig_fp32_probe": (C.c_int, [C.c_int, _I32, C.POINTER(C.c_double), _VP]),
+    "nig_selftest_division": (C.c_int, [C.c_int, _I64, _U64, C.POINTER(_I64), C.POINTER(_I64)]),
 }
 
 

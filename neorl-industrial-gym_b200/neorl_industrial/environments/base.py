@@ -304,6 +304,52 @@ class IndustrialEnv:
             return obs.copy(), reward.copy(), terminated, truncated, info
         return obs, reward, terminated, truncated, info
 
+    _POLICY_IDS = {"random": N.POLICY_UNIFORM, "uniform": N.POLICY_UNIFORM, "zero": N.POLICY_ZERO}
+
+    def rollout(self, n_steps: int, policy="random", *, steps_per_launch: int = 64, reset: bool = False, init_states=None,
+                actions=None, noise=None, params=None) -> Dict[str, Any]:
+        """The reference's timing / evaluation loop -- ``for _ in range(n_steps): env.step(policy(obs))`` with reset on done
+        (performance_benchmark.py:106-133, utils.py:82-125) -- for every env of this object in one call: ``n_steps``
+        fused in ``steps_per_launch``-step kernel launches, host arrays in and out.
+
+        ``policy``: "random" (= ``action_space.sample()`` per step, drawn in-kernel), "zero", "dataset" with ``params``
+        (the get_dataset controllers), or "actions" with ``actions`` [T, num_envs, A] (and optionally ``noise``
+        [T, num_envs, NZ]) teacher-forcing every step. Returns per-env ``reward_sum`` / ``violations`` / ``episodes``,
+        the final ``obs`` and the lifetime ``stats`` (the evaluate_with_safety aggregates)."""
+        nat = self.native
+        if self._host_constraints():
+            raise NotImplementedError("callable safety constraints cannot run inside the fused rollout kernel; "
+                                      "use BoundConstraint / built-in constraints, or step()")
+        if actions is not None or policy == "actions":
+            if actions is None:
+                raise ValueError("policy='actions' needs an actions array [T, num_envs, A]")
+            pid = N.POLICY_ACTIONS
+            a = np.asarray(actions, np.float32).reshape(int(n_steps), self.num_envs, self.action_dim)
+            actions = np.ascontiguousarray(a.transpose(0, 2, 1))            # [T, A, n]: what the kernel streams
+            if noise is not None:
+                z = np.asarray(noise, np.float32).reshape(int(n_steps), self.num_envs, nat.NZ)
+                noise = np.ascontiguousarray(z.transpose(0, 2, 1))
+        elif policy == "dataset":
+            if params is None:
+                raise ValueError("policy='dataset' needs PolicyParams (see datasets.policy_params)")
+            pid = N.POLICY_PCTRL
+        else:
+            try:
+                pid = self._POLICY_IDS[policy]
+            except KeyError:
+                raise ValueError(f"unknown rollout policy {policy!r}; expected one of "
+                                 f"{sorted(self._POLICY_IDS) + ['dataset', 'actions']}") from None
+        out = nat.rollout_host(n_steps, pid, steps_per_launch=steps_per_launch, params=params, init_states=init_states,
+                               reset_first=reset or self._state is None, actions=actions, noise=noise)
+        self._state = out["obs"]
+        if not self.batched:
+            self._pull()
+        res = {"reward_sum": out["reward_sum"], "violations": out["violations"], "episodes": out["episodes"],
+               "obs": out["obs"], "stats": nat.stats_dict(out["counters"], out["sums"])}
+        if self.copy:
+            res = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in res.items()}
+        return res
+
     def get_dataset(self, quality: str = "mixed") -> Dict[str, np.ndarray]:
         raise NotImplementedError
 

@@ -176,6 +176,43 @@ class NativeEnv:
         N.check(N.lib().nig_step_host(self._h, C.byref(io)))
         return obs, next_obs, reward, flags, viol
 
+    def rollout_host(self, n_steps: int, policy: int = N.POLICY_UNIFORM, *, steps_per_launch: int = 64, params=None,
+                     init_states=None, reset_first: bool = False, actions=None, noise=None, want_obs: bool = True):
+        """``n_steps`` env-steps per env in ceil(n_steps / steps_per_launch) fused launches with HOST buffers in and out
+        (nig_rollout_host). ``actions`` [T, A, n] / ``noise`` [T, NZ, n] teacher-force the run (policy ACTIONS).
+        Returns a dict of page-locked arrays (overwritten by the next call): reward_sum [n], violations [n],
+        episodes [n], obs [n, S], counters [24], sums [8]."""
+        r = N.RolloutHost()
+        r.n_steps, r.steps_per_launch, r.policy, r.reset_first = int(n_steps), int(steps_per_launch), int(policy), int(bool(reset_first))
+        keep = []
+        if init_states is not None:
+            buf = self.pinned("init_states", (self.n, self.S), np.float32)
+            if init_states is not buf:
+                np.copyto(buf, np.asarray(init_states, np.float32).reshape(self.n, self.S))
+            r.init_states = N.ptr_of(buf)
+        if actions is not None:
+            a = np.ascontiguousarray(actions, np.float32).reshape(int(n_steps), self.A, self.n)
+            keep.append(a)
+            r.actions = N.ptr_of(a)
+        if noise is not None:
+            z = np.ascontiguousarray(noise, np.float32).reshape(int(n_steps), self.NZ, self.n)
+            keep.append(z)
+            r.noise = N.ptr_of(z)
+        if params is not None:
+            r.pp = params
+        out = {"reward_sum": self.pinned("ro_reward", (self.n,), np.float32),
+               "violations": self.pinned("ro_viol", (self.n,), np.int32),
+               "episodes": self.pinned("ro_done", (self.n,), np.int32),
+               "counters": self.pinned("ro_counters", (24,), np.int64),
+               "sums": self.pinned("ro_sums", (8,), np.float64)}
+        r.reward_sum, r.viol_count, r.done_count = N.ptr_of(out["reward_sum"]), N.ptr_of(out["violations"]), N.ptr_of(out["episodes"])
+        r.counters24, r.sums8 = N.ptr_of(out["counters"]), N.ptr_of(out["sums"])
+        if want_obs:
+            out["obs"] = self.pinned("obs", (self.n, self.S), np.float32)
+            r.final_obs = N.ptr_of(out["obs"])
+        N.check(N.lib().nig_rollout_host(self._h, C.byref(r)))
+        return out
+
     def get_state_host(self):
         state = np.empty((self.n, self.S), np.float32)
         step = np.empty(self.n, np.int32)
