@@ -55,6 +55,15 @@ struct Reactor {
             nz[0] = mul(0.1f, za);      // np.random.normal(0, temp_noise_std / 10)      (:149)
             nz[1] = mul(500.0f, zb);    // np.random.normal(0, pressure_noise_std / 10)  (:159)
         }
+        // the same two values for ONE tick (single-step kernel): only the Box-Muller pair of this tick's parity
+        __device__ static __forceinline__ void get_single(const RngKey& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
+        {
+            const uint4 w = rng_words(key, env, tick >> 1, STREAM_NOISE, 0u);
+            float za, zb;
+            box_muller((tick & 1u) ? w.z : w.x, (tick & 1u) ? w.w : w.y, za, zb);
+            nz[0] = mul(0.1f, za);
+            nz[1] = mul(500.0f, zb);
+        }
     };
 
     // _get_initial_state (:89-107) drawn from the RESET stream
@@ -198,6 +207,11 @@ struct Grid {
                     if (4 * j + q < NZ) nz[4 * j + q] = mul(sg, z[q]);
             }
         }
+        __device__ static __forceinline__ void get_single(const RngKey& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
+        {
+            NoiseGen g;
+            g.get(key, env, tick, nz);
+        }
     };
 
     __device__ static __forceinline__ void reset(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, float (&s)[S])
@@ -338,6 +352,7 @@ struct Robot {
 
     struct NoiseGen {
         __device__ __forceinline__ void get(const RngKey&, uint32_t, uint32_t, float (&)[1]) {}
+        __device__ static __forceinline__ void get_single(const RngKey&, uint32_t, uint32_t, float (&)[1]) {}
     };
 
     __device__ static __forceinline__ void fk(const double (&q)[7], double (&pos)[3])

@@ -269,8 +269,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < NZA; ++k) nz[k] = nzv[k][e];
                 } else {
-                    typename Env::NoiseGen g;
-                    g.get(p.key, env, p.tick, nz);
+                    Env::NoiseGen::get_single(p.key, env, p.tick, nz);
                 }
             } else nz[0] = 0.0f;
             acc_t r; uint32_t f, vm;

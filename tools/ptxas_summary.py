@@ -1,9 +1,9 @@
-"""Summarise `nvcc -Xptxas -v` output of the CUDA library: registers / spills / smem per kernel instantiation."""
+"""Summarise `nvcc -Xptxas -v` for one TU of the CUDA library: python tools/ptxas_summary.py [name-filter] [file.cu]"""
 import re, subprocess, sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 csrc = os.path.join(ROOT, "neorl-industrial-gym_b200", "csrc")
 cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xptxas", "-v",
-       "-c", os.path.join(csrc, "nig_api.cu"), "-o", "/tmp/nig_ptxas.o"]
+       "-c", os.path.join(csrc, sys.argv[2] if len(sys.argv) > 2 else "nig_step.cu"), "-o", "/tmp/nig_ptxas.o"]
 out = subprocess.run(cmd, capture_output=True, text=True).stderr
 out = subprocess.run(["c++filt"], input=out, capture_output=True, text=True).stdout
 pat = sys.argv[1] if len(sys.argv) > 1 else ""
