@@ -34,6 +34,21 @@ def generate_dataset_device(native, n_episodes: int, n_steps: int, policy: int, 
     return {k: v[:m] for k, v in out.items()}, m
 
 
+def episodes_for_transitions(native, n_transitions: int, n_steps: int, policy: int, params) -> int:
+    """Smallest episode count found whose dataset holds >= n_transitions rows. Episodes are independent envs keyed by
+    their index, so the row count is monotone in the episode count; the length-probe pass (nig_dataset_size) of the
+    final count is cached by the library and not repeated by the write pass."""
+    if n_transitions <= 0:
+        raise ValueError("n_transitions must be positive")
+    n_ep = max(1, -(-n_transitions // n_steps))
+    for _ in range(32):
+        m = native.dataset_size(n_ep, n_steps, policy, params)
+        if m >= n_transitions:
+            return n_ep
+        n_ep = max(n_ep + 1, int(n_ep * (n_transitions / max(m, 1)) * 1.02) + 1)
+    raise RuntimeError("could not reach the requested number of transitions (episodes end immediately?)")
+
+
 def generate_dataset(env, n_episodes: int, n_steps: int, policy: int, params, *, terminals_include_truncation: bool,
                      timeouts_key: bool, extensions: bool = False) -> Dict[str, np.ndarray]:
     """Host dict with the reference's keys and dtypes (bool terminals / timeouts)."""

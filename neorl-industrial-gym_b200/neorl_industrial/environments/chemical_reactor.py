@@ -11,7 +11,7 @@ import numpy as np
 
 from .. import _native as N
 from ..core.types import SafetyConstraint
-from ..datasets import generate_dataset
+from ..datasets import episodes_for_transitions, generate_dataset
 from .base import IndustrialEnv
 
 
@@ -81,8 +81,10 @@ class ChemicalReactorEnv(IndustrialEnv):
             pp.sigma[0], pp.sigma[1], pp.sigma[2] = noise * 0.3, noise * 0.5, noise * 0.3
         return n_ep, n_steps, N.POLICY_PCTRL, pp
 
-    def get_dataset(self, quality: str = "mixed", *, n_episodes=None, extensions: bool = False) -> Dict[str, np.ndarray]:
+    def get_dataset(self, quality: str = "mixed", *, n_episodes=None, n_transitions=None, extensions: bool = False) -> Dict[str, np.ndarray]:
         """chemical_reactor.py:324-420, generated on the device in D4RL layout."""
         n_ep, n_steps, policy, pp = self.dataset_policy(quality)
+        if n_transitions is not None:      # as many whole episodes as it takes to reach n_transitions (SURVEY 8d.5)
+            n_episodes = episodes_for_transitions(self.native, int(n_transitions), n_steps, policy, pp)
         return generate_dataset(self, n_episodes or n_ep, n_steps, policy, pp, terminals_include_truncation=True,
                                 timeouts_key=True, extensions=extensions)

@@ -190,3 +190,16 @@ def test_evaluate_with_safety_single_and_batched(mods):
     assert set(batched) == keys and batched["length_mean"] > 10 and batched["return_max"] >= batched["return_min"]
     with pytest.raises(RuntimeError, match="must be trained"):
         ni.evaluate_with_safety(object(), ni.make("ChemicalReactor-v0"), n_episodes=1)
+
+
+def test_dataset_n_transitions_target():
+    """get_dataset(..., n_transitions=M): whole episodes until at least M rows (BASELINE config 5 asks for 1M rows)."""
+    import neorl_industrial as ni
+    env = ni.make("ChemicalReactor-v0")
+    ds = env.get_dataset("mixed", n_transitions=20_000)
+    m = ds["rewards"].shape[0]
+    assert 20_000 <= m < 20_000 + 2 * 300, m               # overshoot bounded by a couple of 300-step episodes
+    assert ds["observations"].shape == (m, 12) and ds["actions"].shape == (m, 3)
+    assert ds["terminals"].dtype == bool and ds["timeouts"].dtype == bool and not ds["timeouts"].any()
+    assert np.abs(ds["actions"]).max() <= 1.0
+    env.close()
