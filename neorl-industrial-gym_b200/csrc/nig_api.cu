@@ -3,6 +3,7 @@
 // There is no CPU implementation of the step path in this library: without an sm_100 device
 // nig_create() fails with NIG_ERR_NO_DEVICE.
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -90,6 +91,7 @@ struct nig_env {
     int64_t launches;
     int step_vec;              // 0 = auto
     int rollout_block;         // 0 = 128
+    int step_pipe;             // 1 (default): large plain SoA steps take the persistent TMA-pipelined kernel
     PFN_encodeTiled encode_tiled;
     int64_t *d_len, *d_off, *d_total;   // dataset: per-episode lengths, offsets, total
     int64_t d_len_cap;
@@ -150,6 +152,14 @@ int launch_step(nig_env* e, const StepArgs& a, cudaStream_t st)
     const int vec = pick_vec(e, a.action_aos == 0 && a.aux_aos == 0);
     e->launches++;
     note_device_work(e, st);
+    // plain SoA step (no teacher forcing, no observation copies, no host-evaluated constraints): persistent TMA pipeline
+    const bool plain = !a.action_aos && !a.noise && !a.reset_states && !a.hostmask && !a.obs && !a.next_obs &&
+                       ((uintptr_t)a.actions & 15u) == 0 && e->step_pipe != 0 && e->step_vec == 0;
+    if (plain) {
+        bool used = false;
+        NIG_CUDA(nig::launch_step_pipelined(e->kind, e->cons.is_default != 0, e->pitch, a, st, &used));
+        if (used) return NIG_OK;
+    }
     NIG_CUDA(nig::launch_step(e->kind, vec, e->cons.is_default != 0, e->pitch, a, st));
     return NIG_OK;
 }
@@ -284,6 +294,8 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     e->key = RngKey{(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)};
     if (const char* v = getenv("NIG_STEP_VEC")) e->step_vec = atoi(v);
     if (const char* v = getenv("NIG_ROLLOUT_BLOCK")) e->rollout_block = atoi(v);
+    e->step_pipe = 1;
+    if (const char* v = getenv("NIG_STEP_PIPE")) e->step_pipe = atoi(v);
     if (e->rollout_block != 0 && e->rollout_block != 32 && e->rollout_block != 64 && e->rollout_block != 128) e->rollout_block = 0;
     nig_constraint_t def[3];
     const nig_constraint_t* c = cfg->constraints;

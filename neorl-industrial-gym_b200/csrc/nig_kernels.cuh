@@ -177,6 +177,40 @@ struct BlockStats {
     }
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "NIG_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra NIG_DONE_%=;\n\t"
+        "bra NIG_WAIT_%=;\n\t"
+        "NIG_DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// 1-D bulk copy global -> shared through the TMA unit (UBLKCP), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // ================================================================================================
 // single-step kernel
 // ================================================================================================
@@ -342,6 +376,157 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 }
 
 // ================================================================================================
+// single-step kernel, persistent + TMA-pipelined (the production fast path: SoA actions, in-kernel noise and reset draws)
+// ================================================================================================
+// step_kernel above keeps one tile per CTA in registers, so the bytes in flight per SM are bounded by the
+// register-limited occupancy (4 CTAs x 15 KB at 100 registers) -- short of the ~52 KB/SM that 6.4 TB/s x ~1.2 us
+// of loaded latency needs. Here each CTA is persistent (grid = SMs x resident CTAs), walks tiles of kThreads x VEC
+// envs with stride gridDim.x, and stages every input row of a tile (S state rows, A action rows, the episode word)
+// in shared memory with 1-D bulk copies (cp.async.bulk -> UBLKCP) on a kStepStages-deep mbarrier ring, issued by
+// one thread two tiles ahead: loads in flight no longer depend on occupancy. Arithmetic and stores are those of
+// step_kernel (same step_core, bit-identical results).
+constexpr int kStepStages = 3;
+
+template <class Env, int VEC>
+constexpr size_t step_pipe_smem() { return (size_t)kStepStages * (Env::S + Env::A + 1) * kThreads * VEC * sizeof(float); }
+
+template <class Env, int VEC, bool DEFCONS>
+__global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_constant__ StepArgs p)
+{
+    constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
+    constexpr int TILE = kThreads * VEC, ROWS = S + A + 1;
+    using acc_t = typename Env::acc_t;
+    extern __shared__ __align__(128) float stage_smem[];     // [kStepStages][ROWS][TILE]
+    __shared__ unsigned int sstat[NIG_STATS_SLOTS];
+    __shared__ alignas(8) uint64_t full[kStepStages];
+    BlockStats bs;
+    bs.init(sstat);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < kStepStages; ++k) mbar_init(&full[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t n_tiles = (p.pitch + TILE - 1) / TILE;
+    auto issue = [&](int64_t tile, int stage) {            // thread 0 only
+        const int64_t i0 = tile * TILE;
+        const int64_t left = p.pitch - i0;
+        const uint32_t bytes = (uint32_t)(left < TILE ? left : TILE) * (uint32_t)sizeof(float);
+        float* dst = stage_smem + (size_t)stage * ROWS * TILE;
+        mbar_expect_tx(&full[stage], bytes * ROWS);
+#pragma unroll
+        for (int r = 0; r < S; ++r) bulk_load(dst + r * TILE, p.state + r * p.pitch + i0, bytes, &full[stage]);
+#pragma unroll
+        for (int r = 0; r < A; ++r) bulk_load(dst + (S + r) * TILE, p.actions + r * p.pitch + i0, bytes, &full[stage]);
+        bulk_load(dst + (S + A) * TILE, p.ep_word + i0, bytes, &full[stage]);
+    };
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < kStepStages; ++k) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+            if (tile < n_tiles) issue(tile, k);
+        }
+    }
+
+    unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0;
+    unsigned int c_con[NIG_MAX_CONSTRAINTS];
+#pragma unroll
+    for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] = 0;
+
+    for (int it = 0;; ++it) {
+        const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+        if (tile >= n_tiles) break;
+        const int stage = it % kStepStages;
+        mbar_wait(&full[stage], (uint32_t)((it / kStepStages) & 1));
+        const float* src = stage_smem + (size_t)stage * ROWS * TILE + threadIdx.x * VEC;
+        float sv[S][VEC], av[A][VEC], wv[VEC];
+#pragma unroll
+        for (int k = 0; k < S; ++k) ldvec<VEC>(src + k * TILE, sv[k]);
+#pragma unroll
+        for (int k = 0; k < A; ++k) ldvec<VEC>(src + (S + k) * TILE, av[k]);
+        ldvec<VEC>(src + (S + A) * TILE, wv);
+        __syncthreads();                                    // every thread has its tile in registers: the stage is free
+        if (threadIdx.x == 0) {
+            const int64_t next = tile + (int64_t)kStepStages * gridDim.x;
+            if (next < n_tiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(next, stage);
+            }
+        }
+        const int64_t i0 = tile * TILE + (int64_t)threadIdx.x * VEC;
+        if (i0 >= p.pitch) continue;
+        float rw[VEC];
+        uint32_t fl[VEC], vmk[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int64_t i = i0 + e;
+            const uint32_t env = p.env0 + (uint32_t)i;
+            uint32_t w = __float_as_uint(wv[e]);
+            float s[S], a[A], nz[NZA], ns[S];
+#pragma unroll
+            for (int k = 0; k < S; ++k) s[k] = sv[k][e];
+#pragma unroll
+            for (int k = 0; k < A; ++k) a[k] = av[k][e];
+            const bool valid = i < p.n;
+            const bool active = valid && !(w >> 31);
+            if constexpr (NZ > 0) Env::NoiseGen::get_single(p.key, env, p.tick, nz);
+            else nz[0] = 0.0f;
+            acc_t r; uint32_t f, vm;
+            step_core<Env, DEFCONS>(p.cons, p.max_steps, s, a, nz, 0u, w, ns, r, f, vm);
+            if (!active) {            // finished env without auto-reset (or padding lane): nothing happens
+#pragma unroll
+                for (int k = 0; k < S; ++k) ns[k] = s[k];
+                r = (acc_t)0; f = NIG_F_INACTIVE; vm = 0; w = __float_as_uint(wv[e]);
+            }
+            const bool done = active && (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED));
+            if (done) {
+                if (p.auto_reset) {
+                    Env::reset(p.key, env, p.tick + 1u, p.epoch, ns);
+                    w = 0u; f |= NIG_F_RESET;
+                } else w |= 0x80000000u;
+            }
+#pragma unroll
+            for (int k = 0; k < S; ++k) sv[k][e] = ns[k];
+            wv[e] = __uint_as_float(w);
+            rw[e] = (float)r; fl[e] = f; vmk[e] = vm;
+            if (active) {
+                c_steps += 1; c_viol += __popc(vm);
+                c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
+                if (done) { c_ep += 1; c_term += (f & NIG_F_TERMINATED) ? 1u : 0u; c_trunc += (f & NIG_F_TRUNCATED) ? 1u : 0u; }
+#pragma unroll
+                for (int k = 0; k < (DEFCONS ? Env::NB : NIG_MAX_CONSTRAINTS); ++k) c_con[k] += (vm >> k) & 1u;
+            }
+        }
+        store_rows<S, VEC>(p.state, p.pitch, p.n, i0, false, sv);
+        stvec<VEC>(reinterpret_cast<float*>(p.ep_word) + i0, wv);
+        if (p.reward) stvec<VEC>(p.reward + i0, rw);
+        if (p.flags) {
+            if constexpr (VEC == 4) *reinterpret_cast<uchar4*>(p.flags + i0) = make_uchar4(fl[0], fl[1], fl[2], fl[3]);
+            else if constexpr (VEC == 2) *reinterpret_cast<uchar2*>(p.flags + i0) = make_uchar2(fl[0], fl[1]);
+            else p.flags[i0] = (uint8_t)fl[0];
+        }
+        if (p.viol_mask) {
+            if constexpr (VEC == 4) *reinterpret_cast<uchar4*>(p.viol_mask + i0) = make_uchar4(vmk[0], vmk[1], vmk[2], vmk[3]);
+            else if constexpr (VEC == 2) *reinterpret_cast<uchar2*>(p.viol_mask + i0) = make_uchar2(vmk[0], vmk[1]);
+            else p.viol_mask[i0] = (uint8_t)vmk[0];
+        }
+    }
+    bs.warp_add(NIG_ST_STEPS, c_steps);
+    if (__any_sync(0xffffffffu, (c_ep | c_viol | c_crit) != 0u)) {
+        bs.warp_add(NIG_ST_EPISODES, c_ep);
+        bs.warp_add(NIG_ST_TERMINATED, c_term);
+        bs.warp_add(NIG_ST_TRUNCATED, c_trunc);
+        bs.warp_add(NIG_ST_CRITICAL, c_crit);
+        bs.warp_add(NIG_ST_VIOLATIONS, c_viol);
+#pragma unroll
+        for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k)
+            if (k < p.cons.n) bs.warp_add(NIG_ST_CON0 + k, c_con[k]);
+    }
+    bs.flush(p.stats);
+}
+
+// ================================================================================================
 // reset kernel
 // ================================================================================================
 struct ResetArgs {
@@ -424,33 +609,6 @@ struct RolloutArgs {
     unsigned long long* stats;
     ConsParams cons;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "NIG_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra NIG_DONE_%=;\n\t"
-        "bra NIG_WAIT_%=;\n\t"
-        "NIG_DONE_%=:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
-}
 
 // in-kernel policies ---------------------------------------------------------------------------------
 template <class Env>

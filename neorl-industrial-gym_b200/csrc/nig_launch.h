@@ -14,6 +14,7 @@ struct RolloutLaunch {
 };
 
 cudaError_t launch_step(int kind, int vec, bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st);
+cudaError_t launch_step_pipelined(int kind, bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used);
 cudaError_t launch_rollout(int kind, const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st);
 cudaError_t launch_rollout_reactor(const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st);
 cudaError_t launch_rollout_grid(const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st);

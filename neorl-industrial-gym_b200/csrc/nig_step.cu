@@ -10,7 +10,49 @@ cudaError_t go(bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st)
     else step_kernel<Env, VEC, false><<<g, kThreads, 0, st>>>(a);
     return cudaGetLastError();
 }
+
+// persistent launch geometry of one step_pipe_kernel instantiation: SMs x resident CTAs, cached per device
+template <class Env, int VEC, bool DEFCONS>
+cudaError_t pipe_capacity(int* ctas)
+{
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!cache[dev]) {
+        auto kern = step_pipe_kernel<Env, VEC, DEFCONS>;
+        const size_t smem = step_pipe_smem<Env, VEC>();
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        int per_sm = 0, sms = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        cache[dev] = per_sm > 0 ? per_sm * sms : sms;
+    }
+    *ctas = cache[dev];
+    return cudaSuccess;
+}
+
+template <class Env, int VEC, bool DEFCONS>
+cudaError_t go_pipe_t(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
+{
+    int cap = 0;
+    const cudaError_t e = pipe_capacity<Env, VEC, DEFCONS>(&cap);
+    if (e != cudaSuccess) return e;
+    const int64_t tiles = (pitch + kThreads * VEC - 1) / (kThreads * VEC);
+    if (tiles <= cap) { *used = false; return cudaSuccess; }      // one tile per CTA: nothing to pipeline
+    step_pipe_kernel<Env, VEC, DEFCONS><<<(unsigned)cap, kThreads, step_pipe_smem<Env, VEC>(), st>>>(a);
+    *used = true;
+    return cudaGetLastError();
+}
+
+template <class Env, int VEC>
+cudaError_t go_pipe(bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
+{
+    return defcons ? go_pipe_t<Env, VEC, true>(pitch, a, st, used) : go_pipe_t<Env, VEC, false>(pitch, a, st, used);
+}
 } // namespace
+
 cudaError_t launch_step(int kind, int vec, bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st)
 {
     switch (kind) {
@@ -18,6 +60,20 @@ cudaError_t launch_step(int kind, int vec, bool defcons, int64_t pitch, const St
         return vec == 4 ? go<Reactor, 4>(defcons, pitch, a, st) : vec == 2 ? go<Reactor, 2>(defcons, pitch, a, st) : go<Reactor, 1>(defcons, pitch, a, st);
     case NIG_ENV_POWER_GRID: return vec >= 2 ? go<Grid, 2>(defcons, pitch, a, st) : go<Grid, 1>(defcons, pitch, a, st);
     default: return vec >= 2 ? go<Robot, 2>(defcons, pitch, a, st) : go<Robot, 1>(defcons, pitch, a, st);
+    }
+}
+
+// the persistent TMA-pipelined flavour (plain SoA step: no teacher forcing, no obs copies); *used = false when the
+// population is too small to give every resident CTA more than one tile (the caller then takes launch_step)
+cudaError_t launch_step_pipelined(int kind, bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
+{
+    switch (kind) {
+    case NIG_ENV_CHEMICAL_REACTOR: return go_pipe<Reactor, 2>(defcons, pitch, a, st, used);
+    default:
+        // PowerGrid (23 Gaussian draws per step) and RobotAssembly (fp64 kinematics) are issue-bound, not HBM-bound:
+        // measured on B200 the pipeline gains nothing there (tools/step_sweep_all.py), so they keep step_kernel.
+        *used = false;
+        return cudaSuccess;
     }
 }
 } // namespace nig
