@@ -66,22 +66,38 @@ struct Reactor {
         }
     };
 
-    // _get_initial_state (:89-107) drawn from the RESET stream
+    // _get_initial_state (:89-107) drawn from the RESET stream: 8 standard normals = Box-Muller pairs 0..3 of
+    // Philox blocks (epoch << 8) | {0, 1}
+    // measured on B200 (tools/steady_step.py, tools/rollout_sweep.py): the single-step kernels gain 6 % at 16M envs
+    // (0.86 -> 0.92 of the HBM peak), the fused rollout loses 2 % (one extra ballot per step) and keeps Env::reset()
+    static constexpr bool COOP_RESET = true;
+    static constexpr int RESET_NORMALS = 8;
+    __device__ static __forceinline__ void reset_from_normals(const float (&z)[8], float (&s)[S])
+    {
+        s[0] = add(320.0f, mul(2.0f, z[0]));
+        s[1] = add(253312.5f, mul(10000.0f, z[1]));
+        s[2] = add(50.0f, mul(5.0f, z[2]));
+        s[3] = add(30.0f, mul(3.0f, z[3]));
+        s[4] = add(0.5f, mul(0.1f, z[4]));
+        s[5] = add(95.0f, mul(2.0f, z[5]));
+        s[6] = add(295.0f, mul(1.0f, z[6]));
+        s[7] = 0.0f; s[8] = 0.0f; s[9] = 0.0f;
+        s[10] = add(60.0f, mul(5.0f, z[7]));
+        s[11] = 0.0f;
+    }
+    // Box-Muller pair `pair` (0..3) of the 8: the unit of work of the warp-cooperative reset (one pair per lane)
+    __device__ static __forceinline__ void reset_pair(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t pair,
+                                                      float& z0, float& z1)
+    {
+        const uint4 w = rng_words(key, env, tick, STREAM_RESET, (epoch << 8) | (pair >> 1));
+        box_muller((pair & 1u) ? w.z : w.x, (pair & 1u) ? w.w : w.y, z0, z1);
+    }
     __device__ static __forceinline__ void reset(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, float (&s)[S])
     {
-        float za[4], zb[4];
-        rng_normals4(key, env, tick, STREAM_RESET, (epoch << 8) | 0u, za);
-        rng_normals4(key, env, tick, STREAM_RESET, (epoch << 8) | 1u, zb);
-        s[0] = add(320.0f, mul(2.0f, za[0]));
-        s[1] = add(253312.5f, mul(10000.0f, za[1]));
-        s[2] = add(50.0f, mul(5.0f, za[2]));
-        s[3] = add(30.0f, mul(3.0f, za[3]));
-        s[4] = add(0.5f, mul(0.1f, zb[0]));
-        s[5] = add(95.0f, mul(2.0f, zb[1]));
-        s[6] = add(295.0f, mul(1.0f, zb[2]));
-        s[7] = 0.0f; s[8] = 0.0f; s[9] = 0.0f;
-        s[10] = add(60.0f, mul(5.0f, zb[3]));
-        s[11] = 0.0f;
+        float z[8];
+        rng_normals4(key, env, tick, STREAM_RESET, (epoch << 8) | 0u, reinterpret_cast<float (&)[4]>(z[0]));
+        rng_normals4(key, env, tick, STREAM_RESET, (epoch << 8) | 1u, reinterpret_cast<float (&)[4]>(z[4]));
+        reset_from_normals(z, s);
     }
 
     // constraint check_fns (:292-305): true = satisfied
@@ -181,6 +197,7 @@ struct Reactor {
 struct Grid {
     static constexpr int KIND = 1, S = 32, A = 8, NZ = 23, NB = 3, MAX_STEPS = 1000;
     static constexpr bool FAST_DIV = true;           // one fp32 division by 5 per step
+    static constexpr bool COOP_RESET = false;
     static constexpr uint32_t CRIT_MASK = 0x3;       // frequency_stability, voltage_limits (:53-65)
     using acc_t = double;                             // _compute_reward returns a Python float (:177)
     __device__ static constexpr float penalty(int k) { return k == 0 ? -50.0f : (k == 1 ? -30.0f : -20.0f); }
@@ -341,6 +358,7 @@ struct Grid {
 struct Robot {
     static constexpr int KIND = 2, S = 24, A = 7, NZ = 0, NB = 3, MAX_STEPS = 1000;
     static constexpr bool FAST_DIV = false;          // fp64 divisions only
+    static constexpr bool COOP_RESET = false;
     static constexpr uint32_t CRIT_MASK = 0x3;       // force_limits, collision_avoidance (:56-68)
     using acc_t = double;
     __device__ static constexpr float penalty(int k) { return k == 0 ? -100.0f : (k == 1 ? -200.0f : -50.0f); }

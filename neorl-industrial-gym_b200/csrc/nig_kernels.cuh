@@ -156,6 +156,32 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
     step_core_impl<Env, DEFCONS>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, de);
 }
 
+// ---- warp-cooperative auto-reset ---------------------------------------------------------------------------------
+// A finished env needs Env::RESET_NORMALS fresh Gaussians (reactor: 2 Philox blocks + 4 Box-Muller pairs, ~370
+// instructions) and on average only 1 lane in 12 warp-steps finishes: instead of the whole warp walking the full draw
+// for one lane, every resetting lane in turn broadcasts its env id, lanes 0..3 each produce ONE Box-Muller pair of its
+// draw, and the 8 normals are shuffled back. Same counters, same values as Env::reset(). Must be called convergently.
+template <class Env>
+__device__ __forceinline__ void coop_reset(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, bool need, float (&s)[Env::S])
+{
+    unsigned m = __ballot_sync(0xffffffffu, need);
+    const uint32_t lane = threadIdx.x & 31u;
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t e_src = __shfl_sync(0xffffffffu, env, src);
+        float z0, z1;
+        Env::reset_pair(key, e_src, tick, epoch, lane & 3u, z0, z1);
+        float z[Env::RESET_NORMALS];
+#pragma unroll
+        for (int q = 0; q < Env::RESET_NORMALS / 2; ++q) {
+            z[2 * q] = __shfl_sync(0xffffffffu, z0, q);
+            z[2 * q + 1] = __shfl_sync(0xffffffffu, z1, q);
+        }
+        if ((int)lane == src) Env::reset_from_normals(z, s);
+    }
+}
+
 // ---- block-level statistics: per-thread counts -> REDUX -> shared atomics -> one global atomic per slot
 struct BlockStats {
     unsigned int* sh;   // [NIG_STATS_SLOTS] shared counters
@@ -315,6 +341,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                 r = (acc_t)0; f = NIG_F_INACTIVE; vm = 0; w = __float_as_uint(wv[e]);
             }
             const bool done = active && (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED));
+            bool need_reset = false;
 #pragma unroll
             for (int k = 0; k < S; ++k) nsv[k][e] = ns[k];     // s' of the transition (pre-reset)
             if (done) {
@@ -323,7 +350,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < S; ++k) s[k] = rs[k][e];
                     } else {
-                        Env::reset(p.key, env, p.tick + 1u, p.epoch, s);
+                        if constexpr (Env::COOP_RESET) need_reset = true;
+                        else Env::reset(p.key, env, p.tick + 1u, p.epoch, s);
                     }
                     w = 0u; f |= NIG_F_RESET;
                 } else {
@@ -335,6 +363,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 #pragma unroll
                 for (int k = 0; k < S; ++k) s[k] = ns[k];
             }
+            if constexpr (Env::COOP_RESET) coop_reset<Env>(p.key, env, p.tick + 1u, p.epoch, need_reset, s);
 #pragma unroll
             for (int k = 0; k < S; ++k) sv[k][e] = s[k];
             wv[e] = __uint_as_float(w);
@@ -480,12 +509,15 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
                 r = (acc_t)0; f = NIG_F_INACTIVE; vm = 0; w = __float_as_uint(wv[e]);
             }
             const bool done = active && (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED));
+            bool need_reset = false;
             if (done) {
                 if (p.auto_reset) {
-                    Env::reset(p.key, env, p.tick + 1u, p.epoch, ns);
+                    if constexpr (Env::COOP_RESET) need_reset = true;
+                    else Env::reset(p.key, env, p.tick + 1u, p.epoch, ns);
                     w = 0u; f |= NIG_F_RESET;
                 } else w |= 0x80000000u;
             }
+            if constexpr (Env::COOP_RESET) coop_reset<Env>(p.key, env, p.tick + 1u, p.epoch, need_reset, ns);
 #pragma unroll
             for (int k = 0; k < S; ++k) sv[k][e] = ns[k];
             wv[e] = __uint_as_float(w);
