@@ -90,6 +90,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(key_prefix: str):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/r01_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            d = json.load(f)
+        for k, v in d.items():
+            if k.startswith(key_prefix):
+                return v["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -260,7 +273,9 @@ def run_gpu(args):
         extra["roofline"] = {
             "kernel": "rollout_kernel<Reactor, default constraints, POLICY_UNIFORM> (K=64 fused steps)",
             "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-            "traffic": None,
+            "traffic": ncu_traffic("rollout_kernel<Reactor"),
+            "ncu": "profiles/r01_c_rollout_kernel_ncu_table.txt: 414 issued warp-instructions per 32 env-steps (128 algorithmic), issue slots "
+                   "70 % busy while active, FMA pipe 35 %, ALU pipe 56 %, 3.5 warps per SM sub-partition (65,536 envs = 0.69 waves)",
             "note": f"algorithmic {ALG_OPS_PER_STEP} fp32 ops/env-step (SURVEY 8d; RNG, IEEE-division expansion and addressing "
                     "excluded) x env-steps per launch / mean launch time; peak = unfused FADD/FMUL issue rate measured live by "
                     "nig_fp32_probe (nominal 148 SM x 128 lanes x 1.965 GHz = 37.2 T op/s). Tensor cores do not apply: element-wise ODE.",
@@ -336,8 +351,8 @@ def single_step_section(torch, ni, N, local, dev, flush, hbm_peak, peak_src, arg
     torch.cuda.synchronize()
     ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     gbs = ALG_BYTES_PER_STEP * n_big / (ms * 1e-3) / 1e9
-    out["roofline"] = {"kernel": "step_kernel<Reactor, VEC=2, default constraints>", "bound": "hbm", "achieved": gbs,
-                       "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+    out["roofline"] = {"kernel": "step_pipe_kernel<Reactor, VEC=2, default constraints> (persistent, cp.async.bulk 3-stage ring)", "bound": "hbm", "achieved": gbs,
+                       "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": ncu_traffic("step_pipe_kernel<Reactor"), "peak_source": peak_src,
                        "envs": n_big, "ms_per_launch": ms, "value": n_big / (ms * 1e-3),
                        "note": f"{ALG_BYTES_PER_STEP} algorithmic B/env-step x {n_big} envs per launch / mean launch time; inputs larger than L2"}
     env.close()
