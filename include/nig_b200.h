@@ -36,7 +36,7 @@ extern "C" {
 #define NIG_API
 #endif
 
-#define NIG_ABI_VERSION 1
+#define NIG_ABI_VERSION 2
 #define NIG_MAX_CONSTRAINTS 8
 #define NIG_MAX_STATE_DIM 32
 #define NIG_MAX_ACTION_DIM 8
@@ -136,8 +136,26 @@ enum {
     NIG_POLICY_UNIFORM = 1,  /* a ~ U(-1,1)^A from the in-kernel Philox policy stream (= action_space.sample(),
                                 the reference's timing harness performance_benchmark.py:106-133) */
     NIG_POLICY_ZERO = 2,
-    NIG_POLICY_PCTRL = 3     /* get_dataset's "PID-like" P-controller mixes (chemical_reactor.py:364-390) */
+    NIG_POLICY_PCTRL = 3,    /* get_dataset's "PID-like" P-controller mixes (chemical_reactor.py:364-390) */
+    NIG_POLICY_BASELINE = 4  /* the benchmark baseline controllers (benchmarks/baseline_agents.py:28-114), nig_baseline_t */
 };
+
+/* Baseline controllers evaluated inside the fused rollout kernel (benchmarks/baseline_agents.py). The reference
+ * computes them in numpy float64 from the float32 observation; so does the kernel (fp64 registers), then the action
+ * is rounded to fp32 and clipped by the env like any other action.
+ *  RANDOM   : a ~ U(setpoint[0], setpoint[1])^A (RandomAgent :28-43; drawn from the Philox policy stream)
+ *  PID      : e = setpoint - s[:A]; I += e; a = clip(kp*e + ki*I + kd*(e - e_prev), -1, 1) (PIDControllerAgent :46-81).
+ *             I and e_prev persist across episodes like the agent object does; nig_reset_policy_state() zeroes them
+ *             (= constructing a new agent).
+ *  MPC      : a = clip(0.5 * (0 - s[:A]), -1, 1) (MPC_Agent :84-100, the "simplified MPC" heuristic)
+ *  CONSTANT : a = setpoint (ConstantAgent :103-114) */
+enum { NIG_BASELINE_RANDOM = 0, NIG_BASELINE_PID = 1, NIG_BASELINE_MPC = 2, NIG_BASELINE_CONSTANT = 3 };
+typedef struct nig_baseline {
+    int32_t kind;
+    int32_t reserved;
+    double kp, ki, kd;
+    double setpoint[NIG_MAX_ACTION_DIM];
+} nig_baseline_t;
 
 /* get_dataset policy parameters (chemical_reactor.py:333-390, power_grid.py:216-232,
  * robot_assembly.py:266-291). Per step, with probability p_ctrl the env's controller
@@ -155,6 +173,7 @@ typedef struct nig_policy_params {
     int32_t mode;
     float gain[NIG_MAX_ACTION_DIM][2];
     float sigma[NIG_MAX_ACTION_DIM];
+    nig_baseline_t baseline;    /* NIG_POLICY_BASELINE only */
 } nig_policy_params_t;
 
 enum {
@@ -259,6 +278,9 @@ typedef struct nig_rollout_host {
     double* sums8;              /* out [8] */
 } nig_rollout_host_t;
 NIG_API int nig_rollout_host(nig_env_t* env, const nig_rollout_host_t* r);
+
+/* zero the persistent controller state of NIG_POLICY_BASELINE / NIG_BASELINE_PID (integral, previous error) */
+NIG_API int nig_reset_policy_state(nig_env_t* env, void* stream);
 
 /* get_dataset (chemical_reactor.py:324-420): n_episodes episodes of <= n_steps steps each with the given
  * policy, written episode-contiguously in D4RL layout on the device. Episodes are independent envs with

@@ -48,15 +48,18 @@ void builtin_constraints(int kind, nig_constraint_t* c)
     }
 }
 
-bool cons_is_default(int kind, const nig_constraint_t* c, int n)
+// how the kernels evaluate a constraint set: CONS_DEFAULT = exactly the env's three built-ins in registration order with
+// their default penalties (compile-time code); CONS_PREFIX = those three first, then extra descriptors (a SafetyWrapper
+// that appends constraints: built-ins stay compile-time code, a loop walks descriptors 3..n-1); CONS_GENERIC otherwise.
+int cons_mode(int kind, const nig_constraint_t* c, int n)
 {
-    if (n != 3) return false;
+    if (n < 3) return CONS_GENERIC;
     nig_constraint_t d[3];
     builtin_constraints(kind, d);
     for (int k = 0; k < 3; ++k)
         if (c[k].kind != NIG_CON_BUILTIN || c[k].id != k || c[k].penalty != d[k].penalty || (c[k].critical != 0) != (d[k].critical != 0))
-            return false;
-    return true;
+            return CONS_GENERIC;
+    return n == 3 ? CONS_DEFAULT : CONS_PREFIX;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -84,6 +87,7 @@ struct nig_env {
     float *h_actions, *h_noise, *h_reset, *h_obs, *h_next_obs, *h_reward;
     uint8_t *h_hostmask, *h_flags, *h_viol, *h_mask;
     int32_t *h_i32a, *h_i32b;
+    double* pid_state;          // [2][A][pitch] PID integral / previous error of NIG_POLICY_BASELINE (lazily allocated, zeroed)
     float *r_act[2], *r_nz[2];  // nig_rollout_host: double-buffered action / noise chunks
     int32_t r_cap;              // steps each chunk buffer holds
     cudaStream_t copy_stream;
@@ -157,10 +161,10 @@ int launch_step(nig_env* e, const StepArgs& a, cudaStream_t st)
                        ((uintptr_t)a.actions & 15u) == 0 && e->step_pipe != 0 && e->step_vec == 0;
     if (plain) {
         bool used = false;
-        NIG_CUDA(nig::launch_step_pipelined(e->kind, e->cons.is_default != 0, e->pitch, a, st, &used));
+        NIG_CUDA(nig::launch_step_pipelined(e->kind, e->cons.is_default, e->pitch, a, st, &used));
         if (used) return NIG_OK;
     }
-    NIG_CUDA(nig::launch_step(e->kind, vec, e->cons.is_default != 0, e->pitch, a, st));
+    NIG_CUDA(nig::launch_step(e->kind, vec, e->cons.is_default, e->pitch, a, st));
     return NIG_OK;
 }
 
@@ -212,7 +216,7 @@ void set_cons(nig_env* e, const nig_constraint_t* c, int n)
     memset(&e->cons, 0, sizeof e->cons);
     e->cons.n = n;
     for (int k = 0; k < n; ++k) e->cons.c[k] = c[k];
-    e->cons.is_default = cons_is_default(e->kind, c, n) ? 1 : 0;
+    e->cons.is_default = cons_mode(e->kind, c, n);
 }
 
 #define NIG_CHECK_ENV(e)                                                        \
@@ -324,7 +328,7 @@ int nig_destroy(nig_env_t* e)
     cudaFree(e->state); cudaFree(e->ep_word); cudaFree(e->ep_return); cudaFree(e->stats);
     cudaFree(e->h_actions); cudaFree(e->h_noise); cudaFree(e->h_reset); cudaFree(e->h_obs); cudaFree(e->h_next_obs);
     cudaFree(e->h_reward); cudaFree(e->h_hostmask); cudaFree(e->h_flags); cudaFree(e->h_viol); cudaFree(e->h_mask);
-    cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->d_len); cudaFree(e->d_off); cudaFree(e->d_total);
+    cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->pid_state); cudaFree(e->d_len); cudaFree(e->d_off); cudaFree(e->d_total);
     for (int b = 0; b < 2; ++b) {
         cudaFree(e->r_act[b]); cudaFree(e->r_nz[b]);
         if (e->r_ev_copy[b]) cudaEventDestroy(e->r_ev_copy[b]);
@@ -462,7 +466,15 @@ int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
     if (r->noise && e->NZ == 0) return fail(NIG_ERR_INVALID, "nig_rollout: env kind %d has no process noise", e->kind);
     if (r->noise && r->policy != NIG_POLICY_ACTIONS)
         return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: teacher-forced noise is only available together with teacher-forced actions (NIG_POLICY_ACTIONS)");
-    if (r->policy < NIG_POLICY_ACTIONS || r->policy > NIG_POLICY_PCTRL) return fail(NIG_ERR_INVALID, "unknown rollout policy %d", r->policy);
+    if (r->policy < NIG_POLICY_ACTIONS || r->policy > NIG_POLICY_BASELINE) return fail(NIG_ERR_INVALID, "unknown rollout policy %d", r->policy);
+    if (r->policy == NIG_POLICY_BASELINE) {
+        const nig_baseline_t& b = r->pp.baseline;
+        if (b.kind < NIG_BASELINE_RANDOM || b.kind > NIG_BASELINE_CONSTANT) return fail(NIG_ERR_INVALID, "unknown baseline controller %d", b.kind);
+        if (b.kind == NIG_BASELINE_PID) {
+            const int prc = dev_alloc(&e->pid_state, (size_t)2 * e->A * e->pitch);      // zero-initialised = a fresh agent
+            if (prc != NIG_OK) return prc;
+        }
+    }
     for (int k = 0; k < e->cons.n; ++k)
         if (e->cons.c[k].kind == NIG_CON_HOSTMASK) return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: host-evaluated constraints cannot run inside a fused rollout");
     RolloutArgs a;
@@ -473,6 +485,7 @@ int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
     a.actions = r->actions; a.noise = r->noise; a.pp = r->pp;
     a.reward_sum = r->reward_sum; a.viol_count = r->viol_count; a.done_count = r->done_count;
     a.accumulate = (r->flags & NIG_ROLLOUT_ACCUMULATE) ? 1 : 0;
+    a.pid_state = e->pid_state;
     a.stats = e->stats; a.cons = e->cons;
     CUtensorMap map;
     memset(&map, 0, sizeof map);
@@ -480,12 +493,19 @@ int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
     int rc;
     if (tma && (rc = make_action_map(e, r->actions, r->n_steps, &map)) != NIG_OK) return rc;
     RolloutLaunch cfg;
-    cfg.policy = r->policy; cfg.defcons = e->cons.is_default != 0; cfg.tma = tma; cfg.tf_noise = r->noise != nullptr;
+    cfg.policy = r->policy; cfg.cons = e->cons.is_default; cfg.tma = tma; cfg.tf_noise = r->noise != nullptr;
     cfg.block = e->rollout_block ? e->rollout_block : 128;
     e->launches++;
     note_device_work(e, (cudaStream_t)stream);
     NIG_CUDA(nig::launch_rollout(e->kind, cfg, e->pitch, a, map, (cudaStream_t)stream));
     e->tick += (uint32_t)r->n_steps;
+    return NIG_OK;
+}
+
+int nig_reset_policy_state(nig_env_t* e, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    if (e->pid_state) NIG_CUDA(cudaMemsetAsync(e->pid_state, 0, (size_t)2 * e->A * e->pitch * sizeof(double), (cudaStream_t)stream));
     return NIG_OK;
 }
 
@@ -594,7 +614,7 @@ int launch_dataset(nig_env* e, const DatasetArgs& a, cudaStream_t st)
 {
     e->launches++;
     note_device_work(e, st);
-    NIG_CUDA(nig::launch_dataset(e->kind, e->cons.is_default != 0, WRITE, a, st));
+    NIG_CUDA(nig::launch_dataset(e->kind, e->cons.is_default, WRITE, a, st));
     return NIG_OK;
 }
 

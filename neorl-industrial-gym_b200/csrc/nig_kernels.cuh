@@ -19,10 +19,12 @@
 namespace nig {
 
 constexpr int kThreads = 128;
+// how a kernel instantiation evaluates the safety constraints (see step_core_impl)
+enum : int { CONS_GENERIC = 0, CONS_DEFAULT = 1, CONS_PREFIX = 2 };
 
 struct ConsParams {
     int32_t n;
-    int32_t is_default;
+    int32_t is_default;        // CONS_GENERIC / CONS_DEFAULT / CONS_PREFIX (host-side dispatch only)
     nig_constraint_t c[NIG_MAX_CONSTRAINTS];
 };
 
@@ -52,13 +54,30 @@ __device__ __forceinline__ void stvec(float* p, const float (&v)[VEC])
     *reinterpret_cast<T*>(p) = t;
 }
 
-template <int S>
+// s[i] for a runtime i: the index comes from a constraint descriptor in the kernel parameters, i.e. it is
+// warp-uniform -- a select chain over all S registers
+template <int S, int LO = 0, int N = S>
 __device__ __forceinline__ float pick(const float (&s)[S], int i)
 {
-    float v = s[0];
-#pragma unroll
-    for (int k = 1; k < S; ++k) v = (i == k) ? s[k] : v;
-    return v;
+    // binary branch tree on the (uniform) index: log2(S) uniform branches instead of S - 1 selects
+    if constexpr (N == 1) return s[LO];
+    else {
+        constexpr int H = N / 2;
+        return i < LO + H ? pick<S, LO, H>(s, i) : pick<S, LO + H, N - H>(s, i);
+    }
+}
+
+// one runtime constraint descriptor (SafetyConstraint, core/types.py:56-64) on the pre-step state / clipped action
+template <class Env>
+__device__ __forceinline__ bool eval_constraint(const nig_constraint_t& c, const float (&s)[Env::S], const float (&a)[Env::A], uint32_t hostmask)
+{
+    if (c.kind == NIG_CON_BUILTIN) return Env::builtin(c.id, s, a);
+    if (c.kind == NIG_CON_BOUND) {
+        float v = pick<Env::S>(s, c.si);
+        if (c.ai >= 0) v = add(v, mul(c.coef, pick<Env::A>(a, c.ai)));
+        return (c.lo <= v) && (v <= c.hi);
+    }
+    return !((hostmask >> c.id) & 1u);
 }
 
 // ep_word: bits 0..15 episode step, bits 16..30 episode violation count (saturating), bit 31 done latch
@@ -72,7 +91,7 @@ __device__ __forceinline__ uint32_t epw_make(uint32_t step, uint32_t viol, uint3
 // ---- one env step in registers (base.py:157-213) --------------------------------------------------
 // `div` carries out the divisions (DivExact = IEEE; DivFast = guarded fast path, see nig_math.cuh). With DivFast
 // the outputs are only valid if div.ok() afterwards -- the callers redo the step with DivExact otherwise.
-template <class Env, bool DEFCONS, class Div>
+template <class Env, int CONS, class Div>
 __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_steps,
                                                const float (&s)[Env::S], const float (&a_raw)[Env::A],
                                                const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
@@ -95,6 +114,11 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
     // (found by the oracle parity tests on RobotAssembly; PTX correct, SASS wrong -- see DESIGN.md).
     uint32_t vm = 0;
     bool crit = false;
+    // CONS_DEFAULT: exactly the env's built-ins with their default penalties (the env as registered upstream): compile-time
+    // code, no loop. CONS_PREFIX: the built-ins first, then extra descriptors (a SafetyWrapper that ADDS constraints): the
+    // built-ins stay compile-time code, the loop walks only the extras. CONS_GENERIC: every descriptor at run time.
+    constexpr bool DEFCONS = CONS != CONS_GENERIC, EXTRAS = CONS != CONS_DEFAULT;
+    constexpr int K0 = DEFCONS ? Env::NB : 0;
     if constexpr (DEFCONS) {
 #pragma unroll
         for (int k = 0; k < Env::NB; ++k) {
@@ -102,18 +126,15 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
             vm |= ok ? 0u : (1u << k);
             if ((Env::CRIT_MASK >> k) & 1u) crit = crit || !ok;
         }
-    } else {
-        for (int k = 0; k < cp.n; ++k) {
-            const nig_constraint_t& c = cp.c[k];
-            bool ok;
-            if (c.kind == NIG_CON_BUILTIN) ok = Env::builtin(c.id, s, a);
-            else if (c.kind == NIG_CON_BOUND) {
-                float v = pick<Env::S>(s, c.si);
-                if (c.ai >= 0) v = add(v, mul(c.coef, pick<Env::A>(a, c.ai)));
-                ok = (c.lo <= v) && (v <= c.hi);
-            } else ok = !((hostmask >> c.id) & 1u);
-            vm |= ok ? 0u : (1u << k);
-            crit = crit || (!ok && c.critical != 0);
+    }
+    if constexpr (EXTRAS) {
+#pragma unroll
+        for (int k = K0; k < NIG_MAX_CONSTRAINTS; ++k) {
+            if (k < cp.n) {                 // uniform: the descriptor count is a kernel parameter
+                const bool ok = eval_constraint<Env>(cp.c[k], s, a, hostmask);
+                vm |= ok ? 0u : (1u << k);
+                crit = crit || (!ok && cp.c[k].critical != 0);
+            }
         }
     }
     Env::dynamics(s, a, nz, ns, div);                 // base.py:173
@@ -122,9 +143,11 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
 #pragma unroll
         for (int k = 0; k < Env::NB; ++k)
             if ((vm >> k) & 1u) r = r + (acc_t)Env::penalty(k);
-    } else {
-        for (int k = 0; k < cp.n; ++k)
-            if ((vm >> k) & 1u) r = r + (acc_t)cp.c[k].penalty;
+    }
+    if constexpr (EXTRAS) {
+#pragma unroll
+        for (int k = K0; k < NIG_MAX_CONSTRAINTS; ++k)
+            if (k < cp.n && ((vm >> k) & 1u)) r = r + (acc_t)cp.c[k].penalty;
     }
     const uint32_t step = epw_step(ep_word_in) + 1u;  // base.py:187
     const uint32_t viol = epw_viol(ep_word_in) + (uint32_t)__popc(vm);
@@ -139,7 +162,7 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
 }
 
 // one step with the fast divisions and the deferred guard: the common path is a single basic block
-template <class Env, bool DEFCONS>
+template <class Env, int CONS>
 __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
                                           const float (&s)[Env::S], const float (&a_raw)[Env::A],
                                           const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
@@ -149,11 +172,11 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
     const uint32_t w_in = ep_word;
     if constexpr (Env::FAST_DIV) {
         DivFast df;
-        step_core_impl<Env, DEFCONS>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, df);
+        step_core_impl<Env, CONS>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, df);
         if (__builtin_expect(df.ok(), 1)) return;
     }
     DivExact de;
-    step_core_impl<Env, DEFCONS>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, de);
+    step_core_impl<Env, CONS>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, de);
 }
 
 // ---- warp-cooperative auto-reset ---------------------------------------------------------------------------------
@@ -290,7 +313,7 @@ __device__ __forceinline__ void store_rows(float* base, int64_t pitch, int64_t n
     }
 }
 
-template <class Env, int VEC, bool DEFCONS>
+template <class Env, int VEC, int CONS>
 __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ StepArgs p)
 {
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
@@ -334,7 +357,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
             } else nz[0] = 0.0f;
             acc_t r; uint32_t f, vm;
             const uint32_t hm = p.hostmask && valid ? p.hostmask[i] : 0u;
-            step_core<Env, DEFCONS>(p.cons, p.max_steps, s, a, nz, hm, w, ns, r, f, vm);
+            step_core<Env, CONS>(p.cons, p.max_steps, s, a, nz, hm, w, ns, r, f, vm);
             if (!active) {            // finished env without auto-reset (or padding lane): nothing happens
 #pragma unroll
                 for (int k = 0; k < S; ++k) ns[k] = s[k];
@@ -419,7 +442,7 @@ constexpr int kStepStages = 3;
 template <class Env, int VEC>
 constexpr size_t step_pipe_smem() { return (size_t)kStepStages * (Env::S + Env::A + 1) * kThreads * VEC * sizeof(float); }
 
-template <class Env, int VEC, bool DEFCONS>
+template <class Env, int VEC, int CONS>
 __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_constant__ StepArgs p)
 {
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
@@ -502,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             if constexpr (NZ > 0) Env::NoiseGen::get_single(p.key, env, p.tick, nz);
             else nz[0] = 0.0f;
             acc_t r; uint32_t f, vm;
-            step_core<Env, DEFCONS>(p.cons, p.max_steps, s, a, nz, 0u, w, ns, r, f, vm);
+            step_core<Env, CONS>(p.cons, p.max_steps, s, a, nz, 0u, w, ns, r, f, vm);
             if (!active) {            // finished env without auto-reset (or padding lane): nothing happens
 #pragma unroll
                 for (int k = 0; k < S; ++k) ns[k] = s[k];
@@ -527,7 +550,11 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
                 c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
                 if (done) { c_ep += 1; c_term += (f & NIG_F_TERMINATED) ? 1u : 0u; c_trunc += (f & NIG_F_TRUNCATED) ? 1u : 0u; }
 #pragma unroll
-                for (int k = 0; k < (DEFCONS ? Env::NB : NIG_MAX_CONSTRAINTS); ++k) c_con[k] += (vm >> k) & 1u;
+                for (int k = 0; k < Env::NB; ++k) c_con[k] += (vm >> k) & 1u;
+                if constexpr (CONS != CONS_DEFAULT) {
+#pragma unroll
+                    for (int k = Env::NB; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] += (vm >> k) & 1u;
+                }
             }
         }
         store_rows<S, VEC>(p.state, p.pitch, p.n, i0, false, sv);
@@ -638,6 +665,7 @@ struct RolloutArgs {
     nig_policy_params_t pp;
     float* reward_sum; int32_t* viol_count; int32_t* done_count;
     int32_t accumulate;        // per-env outputs: out[i] += this launch's value instead of out[i] = ...
+    double* pid_state;         // [2][A][pitch] fp64: PID integral rows, then previous-error rows (POLICY_BASELINE / PID)
     unsigned long long* stats;
     ConsParams cons;
 };
@@ -686,6 +714,47 @@ __device__ __forceinline__ void policy_pctrl(const RngKey& key, const nig_policy
     }
 }
 
+// benchmarks/baseline_agents.py controllers in fp64 like numpy computes them; integ / prev are the PID agent's state
+template <class Env>
+__device__ __forceinline__ void policy_baseline(const RngKey& key, const nig_baseline_t& b, uint32_t env, uint32_t tick,
+                                                const float (&s)[Env::S], float (&a)[Env::A],
+                                                double (&integ)[Env::A], double (&prev)[Env::A])
+{
+    constexpr int A = Env::A;
+    if (b.kind == NIG_BASELINE_PID) {
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+            const double e = dsub(b.setpoint[k], (double)s[k]);                    // :67 (first action_dim states)
+            const double prop = dmul(b.kp, e);                                     // :70
+            integ[k] = dadd(integ[k], e);                                          // :71
+            const double it = dmul(b.ki, integ[k]);                                // :72
+            const double der = dmul(b.kd, dsub(e, prev[k]));                       // :73
+            double u = dadd(dadd(prop, it), der);                                  // :76
+            u = u < -1.0 ? -1.0 : u;                                               // :77 np.clip
+            u = u > 1.0 ? 1.0 : u;
+            prev[k] = e;                                                           // :79
+            a[k] = (float)u;
+        }
+    } else if (b.kind == NIG_BASELINE_MPC) {
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+            double u = dmul(0.5, dsub(0.0, (double)s[k]));                         // :93-97
+            u = u < -1.0 ? -1.0 : u;
+            u = u > 1.0 ? 1.0 : u;
+            a[k] = (float)u;
+        }
+    } else if (b.kind == NIG_BASELINE_CONSTANT) {
+#pragma unroll
+        for (int k = 0; k < A; ++k) a[k] = (float)b.setpoint[k];                   // :112
+    } else {
+        float u[A];
+        policy_uniform<Env>(key, env, tick, u);                                    // :38-42
+        const float mid = (float)(0.5 * (b.setpoint[0] + b.setpoint[1])), half = (float)(0.5 * (b.setpoint[1] - b.setpoint[0]));
+#pragma unroll
+        for (int k = 0; k < A; ++k) a[k] = add(mid, mul(half, u[k]));
+    }
+}
+
 template <class T> __device__ __forceinline__ T warp_sum(T v)
 {
 #pragma unroll
@@ -697,7 +766,7 @@ template <class T> __device__ __forceinline__ T warp_sum(T v)
 // prefetches the next step's actions / noise into registers one step ahead, so the L2 latency of the loads is
 // hidden behind a whole step of arithmetic. Block size is a launch parameter (blockDim.x <= kThreads; TMA launches
 // use kThreads).
-template <class Env, bool DEFCONS, int POLICY, bool TMA, bool TFNOISE>
+template <class Env, int CONS, int POLICY, bool TMA, bool TFNOISE>
 __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant__ RolloutArgs p, const __grid_constant__ CUtensorMap amap)
 {
     static_assert(!TFNOISE || POLICY == NIG_POLICY_ACTIONS, "teacher-forced noise comes with teacher-forced actions");
@@ -750,6 +819,15 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
     unsigned long long len_sum = 0, len_sq = 0;
     double ret_sum = 0.0, ret_sq = 0.0, rew_sum = 0.0;
 
+    double pid_i[A], pid_e[A];             // POLICY_BASELINE: the PID agent's integral and previous error
+    if constexpr (POLICY == NIG_POLICY_BASELINE) {
+        const bool pid = p.pp.baseline.kind == NIG_BASELINE_PID && p.pid_state != nullptr;
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+            pid_i[k] = pid ? p.pid_state[(int64_t)k * p.pitch + ic] : 0.0;
+            pid_e[k] = pid ? p.pid_state[(int64_t)(A + k) * p.pitch + ic] : 0.0;
+        }
+    }
     float a_pf[A], nz_pf[NZA];             // PREFETCH: the values of step t, loaded during step t - 1
     if constexpr (PREFETCH) {
 #pragma unroll
@@ -789,6 +867,8 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
             policy_uniform<Env>(p.key, env, tick, a);
         } else if constexpr (POLICY == NIG_POLICY_PCTRL) {
             policy_pctrl<Env>(p.key, p.pp, env, tick, s, a);
+        } else if constexpr (POLICY == NIG_POLICY_BASELINE) {
+            policy_baseline<Env>(p.key, p.pp.baseline, env, tick, s, a, pid_i, pid_e);
         } else {
 #pragma unroll
             for (int k = 0; k < A; ++k) a[k] = 0.0f;
@@ -811,7 +891,7 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
         const bool active = valid && !(w >> 31);
         uint32_t w2 = w, f, vm;
         acc_t r;
-        step_core<Env, DEFCONS>(p.cons, p.max_steps, s, a, nz, 0u, w2, ns, r, f, vm);
+        step_core<Env, CONS>(p.cons, p.max_steps, s, a, nz, 0u, w2, ns, r, f, vm);
         if (active) {
             const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
             rsum = add(rsum, (float)r);
@@ -819,12 +899,11 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
             rew_sum += (double)r;
             c_steps += 1; c_viol += __popc(vm);
             c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
-            if constexpr (DEFCONS) {
 #pragma unroll
-                for (int k = 0; k < Env::NB; ++k) c_con[k] += (vm >> k) & 1u;
-            } else {
+            for (int k = 0; k < Env::NB; ++k) c_con[k] += (vm >> k) & 1u;
+            if constexpr (CONS != CONS_DEFAULT) {
 #pragma unroll
-                for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] += (vm >> k) & 1u;
+                for (int k = Env::NB; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] += (vm >> k) & 1u;
             }
             w = w2;
             if (done) {
@@ -855,6 +934,15 @@ __global__ void __launch_bounds__(kThreads) rollout_kernel(const __grid_constant
         for (int k = 0; k < S; ++k) p.state[k * p.pitch + i] = s[k];
         p.ep_word[i] = w;
         p.ep_return[i] = (double)ep_ret;
+        if constexpr (POLICY == NIG_POLICY_BASELINE) {
+            if (p.pp.baseline.kind == NIG_BASELINE_PID && p.pid_state != nullptr) {
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    p.pid_state[(int64_t)k * p.pitch + i] = pid_i[k];
+                    p.pid_state[(int64_t)(A + k) * p.pitch + i] = pid_e[k];
+                }
+            }
+        }
         if (p.accumulate) {
             if (p.reward_sum) p.reward_sum[i] = add(p.reward_sum[i], rsum);
             if (p.viol_count) p.viol_count[i] += (int32_t)c_viol;
@@ -915,7 +1003,7 @@ struct DatasetArgs {
     float* next_observations; uint8_t* safety;
 };
 
-template <class Env, bool DEFCONS, bool WRITE>
+template <class Env, int CONS, bool WRITE>
 __global__ void __launch_bounds__(kThreads) dataset_kernel(const __grid_constant__ DatasetArgs p)
 {
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
@@ -948,7 +1036,7 @@ __global__ void __launch_bounds__(kThreads) dataset_kernel(const __grid_constant
         }
         if (NZ > 0) ng.get(p.key, env, (uint32_t)t, nz); else nz[0] = 0.0f;
         acc_t r; uint32_t f, vm;
-        step_core<Env, DEFCONS>(p.cons, p.max_steps, s, a, nz, 0u, w, ns, r, f, vm);
+        step_core<Env, CONS>(p.cons, p.max_steps, s, a, nz, 0u, w, ns, r, f, vm);
         const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
         if constexpr (WRITE) {
 #pragma unroll

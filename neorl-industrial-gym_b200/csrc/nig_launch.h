@@ -7,19 +7,19 @@ namespace nig {
 
 struct RolloutLaunch {
     int policy;        // NIG_POLICY_*
-    bool defcons;      // built-in constraints with their default penalties (compile-time path)
+    int cons;          // CONS_GENERIC / CONS_DEFAULT / CONS_PREFIX
     bool tma;          // stage POLICY_ACTIONS through cp.async.bulk.tensor
     bool tf_noise;     // teacher-forced process noise (POLICY_ACTIONS only)
     int block;         // threads per CTA: 32, 64 or 128
 };
 
-cudaError_t launch_step(int kind, int vec, bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st);
-cudaError_t launch_step_pipelined(int kind, bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used);
+cudaError_t launch_step(int kind, int vec, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st);
+cudaError_t launch_step_pipelined(int kind, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used);
 cudaError_t launch_rollout(int kind, const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st);
 cudaError_t launch_rollout_reactor(const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st);
 cudaError_t launch_rollout_grid(const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st);
 cudaError_t launch_rollout_robot(const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st);
-cudaError_t launch_dataset(int kind, bool defcons, bool write, const DatasetArgs& a, cudaStream_t st);
+cudaError_t launch_dataset(int kind, int cons, bool write, const DatasetArgs& a, cudaStream_t st);
 cudaError_t launch_reset(int kind, const ResetArgs& a, cudaStream_t st);
 cudaError_t launch_state_io(const StateIoArgs& a, cudaStream_t st);
 cudaError_t launch_scan_lengths(const int64_t* len, int64_t* off, int64_t n, int64_t* total, cudaStream_t st);

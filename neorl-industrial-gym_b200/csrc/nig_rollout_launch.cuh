@@ -4,10 +4,10 @@
 
 namespace nig {
 
-template <class Env, bool DEFCONS, int POLICY, bool TMA, bool TFNOISE>
+template <class Env, int CONS, int POLICY, bool TMA, bool TFNOISE>
 cudaError_t rollout_go(const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
 {
-    auto kern = rollout_kernel<Env, DEFCONS, POLICY, TMA, TFNOISE>;
+    auto kern = rollout_kernel<Env, CONS, POLICY, TMA, TFNOISE>;
     const int block = TMA ? kThreads : cfg.block;
     const size_t smem = TMA ? (size_t)2 * kTmaChunk * Env::A * kThreads * sizeof(float) : 0;
     if (TMA) {
@@ -18,20 +18,21 @@ cudaError_t rollout_go(const RolloutLaunch& cfg, int64_t pitch, const RolloutArg
     return cudaGetLastError();
 }
 
-template <class Env, bool DEFCONS>
+template <class Env, int CONS>
 cudaError_t rollout_policy(const RolloutLaunch& c, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
 {
     switch (c.policy) {
     case NIG_POLICY_ACTIONS:
         if (c.tma) {
-            if constexpr (Env::NZ > 0) { if (c.tf_noise) return rollout_go<Env, DEFCONS, NIG_POLICY_ACTIONS, true, true>(c, pitch, a, map, st); }
-            return rollout_go<Env, DEFCONS, NIG_POLICY_ACTIONS, true, false>(c, pitch, a, map, st);
+            if constexpr (Env::NZ > 0) { if (c.tf_noise) return rollout_go<Env, CONS, NIG_POLICY_ACTIONS, true, true>(c, pitch, a, map, st); }
+            return rollout_go<Env, CONS, NIG_POLICY_ACTIONS, true, false>(c, pitch, a, map, st);
         }
-        if constexpr (Env::NZ > 0) { if (c.tf_noise) return rollout_go<Env, DEFCONS, NIG_POLICY_ACTIONS, false, true>(c, pitch, a, map, st); }
-        return rollout_go<Env, DEFCONS, NIG_POLICY_ACTIONS, false, false>(c, pitch, a, map, st);
-    case NIG_POLICY_UNIFORM: return rollout_go<Env, DEFCONS, NIG_POLICY_UNIFORM, false, false>(c, pitch, a, map, st);
-    case NIG_POLICY_ZERO: return rollout_go<Env, DEFCONS, NIG_POLICY_ZERO, false, false>(c, pitch, a, map, st);
-    case NIG_POLICY_PCTRL: return rollout_go<Env, DEFCONS, NIG_POLICY_PCTRL, false, false>(c, pitch, a, map, st);
+        if constexpr (Env::NZ > 0) { if (c.tf_noise) return rollout_go<Env, CONS, NIG_POLICY_ACTIONS, false, true>(c, pitch, a, map, st); }
+        return rollout_go<Env, CONS, NIG_POLICY_ACTIONS, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_UNIFORM: return rollout_go<Env, CONS, NIG_POLICY_UNIFORM, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_ZERO: return rollout_go<Env, CONS, NIG_POLICY_ZERO, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_PCTRL: return rollout_go<Env, CONS, NIG_POLICY_PCTRL, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_BASELINE: return rollout_go<Env, CONS, NIG_POLICY_BASELINE, false, false>(c, pitch, a, map, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -39,7 +40,9 @@ cudaError_t rollout_policy(const RolloutLaunch& c, int64_t pitch, const RolloutA
 template <class Env>
 cudaError_t rollout_env(const RolloutLaunch& c, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
 {
-    return c.defcons ? rollout_policy<Env, true>(c, pitch, a, map, st) : rollout_policy<Env, false>(c, pitch, a, map, st);
+    return c.cons == CONS_DEFAULT ? rollout_policy<Env, CONS_DEFAULT>(c, pitch, a, map, st)
+         : c.cons == CONS_PREFIX  ? rollout_policy<Env, CONS_PREFIX>(c, pitch, a, map, st)
+                                  : rollout_policy<Env, CONS_GENERIC>(c, pitch, a, map, st);
 }
 
 } // namespace nig

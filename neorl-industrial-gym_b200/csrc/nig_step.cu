@@ -3,16 +3,17 @@
 namespace nig {
 namespace {
 template <class Env, int VEC>
-cudaError_t go(bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st)
+cudaError_t go(int cons, int64_t pitch, const StepArgs& a, cudaStream_t st)
 {
     const unsigned g = grid_for((pitch + VEC - 1) / VEC);
-    if (defcons) step_kernel<Env, VEC, true><<<g, kThreads, 0, st>>>(a);
-    else step_kernel<Env, VEC, false><<<g, kThreads, 0, st>>>(a);
+    if (cons == CONS_DEFAULT) step_kernel<Env, VEC, CONS_DEFAULT><<<g, kThreads, 0, st>>>(a);
+    else if (cons == CONS_PREFIX) step_kernel<Env, VEC, CONS_PREFIX><<<g, kThreads, 0, st>>>(a);
+    else step_kernel<Env, VEC, CONS_GENERIC><<<g, kThreads, 0, st>>>(a);
     return cudaGetLastError();
 }
 
 // persistent launch geometry of one step_pipe_kernel instantiation: SMs x resident CTAs, cached per device
-template <class Env, int VEC, bool DEFCONS>
+template <class Env, int VEC, int CONS>
 cudaError_t pipe_capacity(int* ctas)
 {
     static int cache[64] = {0};
@@ -21,7 +22,7 @@ cudaError_t pipe_capacity(int* ctas)
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     if (!cache[dev]) {
-        auto kern = step_pipe_kernel<Env, VEC, DEFCONS>;
+        auto kern = step_pipe_kernel<Env, VEC, CONS>;
         const size_t smem = step_pipe_smem<Env, VEC>();
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         int per_sm = 0, sms = 0;
@@ -33,42 +34,44 @@ cudaError_t pipe_capacity(int* ctas)
     return cudaSuccess;
 }
 
-template <class Env, int VEC, bool DEFCONS>
+template <class Env, int VEC, int CONS>
 cudaError_t go_pipe_t(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
 {
     int cap = 0;
-    const cudaError_t e = pipe_capacity<Env, VEC, DEFCONS>(&cap);
+    const cudaError_t e = pipe_capacity<Env, VEC, CONS>(&cap);
     if (e != cudaSuccess) return e;
     const int64_t tiles = (pitch + kThreads * VEC - 1) / (kThreads * VEC);
     if (tiles <= cap) { *used = false; return cudaSuccess; }      // one tile per CTA: nothing to pipeline
-    step_pipe_kernel<Env, VEC, DEFCONS><<<(unsigned)cap, kThreads, step_pipe_smem<Env, VEC>(), st>>>(a);
+    step_pipe_kernel<Env, VEC, CONS><<<(unsigned)cap, kThreads, step_pipe_smem<Env, VEC>(), st>>>(a);
     *used = true;
     return cudaGetLastError();
 }
 
 template <class Env, int VEC>
-cudaError_t go_pipe(bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
+cudaError_t go_pipe(int cons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
 {
-    return defcons ? go_pipe_t<Env, VEC, true>(pitch, a, st, used) : go_pipe_t<Env, VEC, false>(pitch, a, st, used);
+    return cons == CONS_DEFAULT ? go_pipe_t<Env, VEC, CONS_DEFAULT>(pitch, a, st, used)
+         : cons == CONS_PREFIX  ? go_pipe_t<Env, VEC, CONS_PREFIX>(pitch, a, st, used)
+                                : go_pipe_t<Env, VEC, CONS_GENERIC>(pitch, a, st, used);
 }
 } // namespace
 
-cudaError_t launch_step(int kind, int vec, bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st)
+cudaError_t launch_step(int kind, int vec, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st)
 {
     switch (kind) {
     case NIG_ENV_CHEMICAL_REACTOR:
-        return vec == 4 ? go<Reactor, 4>(defcons, pitch, a, st) : vec == 2 ? go<Reactor, 2>(defcons, pitch, a, st) : go<Reactor, 1>(defcons, pitch, a, st);
-    case NIG_ENV_POWER_GRID: return vec >= 2 ? go<Grid, 2>(defcons, pitch, a, st) : go<Grid, 1>(defcons, pitch, a, st);
-    default: return vec >= 2 ? go<Robot, 2>(defcons, pitch, a, st) : go<Robot, 1>(defcons, pitch, a, st);
+        return vec == 4 ? go<Reactor, 4>(cons, pitch, a, st) : vec == 2 ? go<Reactor, 2>(cons, pitch, a, st) : go<Reactor, 1>(cons, pitch, a, st);
+    case NIG_ENV_POWER_GRID: return vec >= 2 ? go<Grid, 2>(cons, pitch, a, st) : go<Grid, 1>(cons, pitch, a, st);
+    default: return vec >= 2 ? go<Robot, 2>(cons, pitch, a, st) : go<Robot, 1>(cons, pitch, a, st);
     }
 }
 
 // the persistent TMA-pipelined flavour (plain SoA step: no teacher forcing, no obs copies); *used = false when the
 // population is too small to give every resident CTA more than one tile (the caller then takes launch_step)
-cudaError_t launch_step_pipelined(int kind, bool defcons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
+cudaError_t launch_step_pipelined(int kind, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
 {
     switch (kind) {
-    case NIG_ENV_CHEMICAL_REACTOR: return go_pipe<Reactor, 2>(defcons, pitch, a, st, used);
+    case NIG_ENV_CHEMICAL_REACTOR: return go_pipe<Reactor, 2>(cons, pitch, a, st, used);
     default:
         // PowerGrid (23 Gaussian draws per step) and RobotAssembly (fp64 kinematics) are issue-bound, not HBM-bound:
         // measured on B200 the pipeline gains nothing there (tools/step_sweep_all.py), so they keep step_kernel.

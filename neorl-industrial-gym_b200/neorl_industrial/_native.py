@@ -16,7 +16,7 @@ _ROOT = os.path.dirname(_PKG_DIR)                       # neorl-industrial-gym_b
 LIB_PATH = os.path.join(_ROOT, "libnig_b200.so")
 CSRC_DIR = os.path.join(_ROOT, "csrc")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_CONSTRAINTS = 8
 STATS_SLOTS = 32
 
@@ -25,7 +25,8 @@ ENV_CHEMICAL_REACTOR, ENV_POWER_GRID, ENV_ROBOT_ASSEMBLY = 0, 1, 2
 CON_BUILTIN, CON_BOUND, CON_HOSTMASK = 0, 1, 2
 F_TERMINATED, F_TRUNCATED, F_CRITICAL, F_RESET, F_INACTIVE = 1, 2, 4, 8, 128
 LAYOUT_SOA, LAYOUT_AOS = 0, 1
-POLICY_ACTIONS, POLICY_UNIFORM, POLICY_ZERO, POLICY_PCTRL = 0, 1, 2, 3
+POLICY_ACTIONS, POLICY_UNIFORM, POLICY_ZERO, POLICY_PCTRL, POLICY_BASELINE = 0, 1, 2, 3, 4
+BASELINE_RANDOM, BASELINE_PID, BASELINE_MPC, BASELINE_CONSTANT = 0, 1, 2, 3
 ROLLOUT_USE_TMA = 1
 ROLLOUT_ACCUMULATE = 2
 ST_STEPS, ST_EPISODES, ST_TERMINATED, ST_TRUNCATED, ST_CRITICAL, ST_VIOLATIONS, ST_SUCCESSES, ST_EP_LEN_SUM = range(8)
@@ -60,9 +61,14 @@ class StepIO(C.Structure):
                 ("action_layout", C.c_int32), ("aux_layout", C.c_int32)]
 
 
+class Baseline(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("kp", C.c_double), ("ki", C.c_double), ("kd", C.c_double),
+                ("setpoint", C.c_double * 8)]
+
+
 class PolicyParams(C.Structure):
     _fields_ = [("p_ctrl", C.c_float), ("uniform_scale", C.c_float), ("store_clip", C.c_float), ("mode", C.c_int32),
-                ("gain", (C.c_float * 2) * 8), ("sigma", C.c_float * 8)]
+                ("gain", (C.c_float * 2) * 8), ("sigma", C.c_float * 8), ("baseline", Baseline)]
 
 
 class Rollout(C.Structure):
@@ -103,6 +109,7 @@ SYMBOLS = {
     "nig_step_host": (C.c_int, [_VP, C.POINTER(StepIO)]),
     "nig_rollout": (C.c_int, [_VP, C.POINTER(Rollout), _VP]),
     "nig_rollout_host": (C.c_int, [_VP, C.POINTER(RolloutHost)]),
+    "nig_reset_policy_state": (C.c_int, [_VP, _VP]),
     "nig_dataset": (C.c_int, [_VP, _I64, _I32, _I32, C.POINTER(PolicyParams), C.POINTER(DatasetOut), C.POINTER(_I64), _VP]),
     "nig_dataset_size": (C.c_int, [_VP, _I64, _I32, _I32, C.POINTER(PolicyParams), C.POINTER(_I64), _VP]),
     "nig_get_state": (C.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),

@@ -313,7 +313,8 @@ class IndustrialEnv:
         fused in ``steps_per_launch``-step kernel launches, host arrays in and out.
 
         ``policy``: "random" (= ``action_space.sample()`` per step, drawn in-kernel), "zero", "dataset" with ``params``
-        (the get_dataset controllers), or "actions" with ``actions`` [T, num_envs, A] (and optionally ``noise``
+        (the get_dataset controllers), a ``benchmarks.baseline_agents`` controller object (PID / MPC / constant / random,
+        evaluated in-kernel), or "actions" with ``actions`` [T, num_envs, A] (and optionally ``noise``
         [T, num_envs, NZ]) teacher-forcing every step. Returns per-env ``reward_sum`` / ``violations`` / ``episodes``,
         the final ``obs`` and the lifetime ``stats`` (the evaluate_with_safety aggregates)."""
         nat = self.native
@@ -329,6 +330,8 @@ class IndustrialEnv:
             if noise is not None:
                 z = np.asarray(noise, np.float32).reshape(int(n_steps), self.num_envs, nat.NZ)
                 noise = np.ascontiguousarray(z.transpose(0, 2, 1))
+        elif hasattr(policy, "device_policy"):                 # benchmarks.baseline_agents controllers, in-kernel
+            pid, params = policy.device_policy()
         elif policy == "dataset":
             if params is None:
                 raise ValueError("policy='dataset' needs PolicyParams (see datasets.policy_params)")

@@ -128,6 +128,10 @@ class NativeEnv:
     def set_tick(self, tick: int, epoch: Optional[int] = None):
         N.check(N.lib().nig_set_tick(self._h, int(tick), self.epoch if epoch is None else int(epoch)))
 
+    def reset_policy_state(self, stream=None):
+        """Zero the device-resident PID controller state (= constructing a new PIDControllerAgent)."""
+        N.check(N.lib().nig_reset_policy_state(self._h, self._stream(stream)))
+
     def sync(self):
         N.check(N.lib().nig_sync(self._h))
 
