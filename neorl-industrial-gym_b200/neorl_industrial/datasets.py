@@ -3,7 +3,8 @@ robot_assembly.py:246-308): every episode is an independent env; a length-probe 
 and a write pass emit episode-contiguous D4RL arrays straight into HBM, exported with pinned async copies."""
 from __future__ import annotations
 
-from typing import Dict
+import os
+from typing import Dict, Optional
 
 import numpy as np
 
@@ -66,3 +67,93 @@ def generate_dataset(env, n_episodes: int, n_steps: int, policy: int, params, *,
         if k in res:
             res[k] = res[k].astype(bool)
     return res
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Dataset containers and file formats. The reference keeps datasets in memory only; its docs promise HDF5 export
+# (docs/ARCHITECTURE.md:65,77; h5py in pyproject.toml:36) and its test fixture (tests/fixtures/industrial_data.py:11-21)
+# uses the 8-field layout below. Host-side plumbing: nothing here touches the step path.
+FIXTURE_FIELDS = ("observations", "actions", "rewards", "next_observations", "terminals", "timeouts", "safety_violations")
+
+
+def to_fixture_layout(ds: Dict[str, np.ndarray], metadata: Optional[dict] = None) -> Dict[str, object]:
+    """A get_dataset(..., extensions=True) dict in the IndustrialDataset layout of tests/fixtures/industrial_data.py:
+    observations, actions, rewards, next_observations, terminals, timeouts, safety_violations (bool), metadata."""
+    if "next_observations" not in ds or "safety" not in ds:
+        raise KeyError("the fixture layout needs next_observations and safety: call get_dataset(..., extensions=True)")
+    m = int(ds["rewards"].shape[0])
+    out = {k: ds[k] for k in ("observations", "actions", "rewards", "next_observations", "terminals")}
+    out["timeouts"] = ds["timeouts"] if "timeouts" in ds else np.zeros(m, bool)
+    out["safety_violations"] = np.asarray(ds["safety"]) != 0
+    out["metadata"] = dict(metadata or {})
+    out["metadata"].setdefault("n_transitions", m)
+    return out
+
+
+def save_dataset(path: str, ds: Dict[str, object], metadata: Optional[dict] = None) -> str:
+    """Write a dataset dict to ``.npz`` (numpy, compressed), ``.h5`` / ``.hdf5`` (needs h5py) or ``.pt`` (torch.save).
+    ``metadata`` (or ds['metadata']) is stored as a JSON string / HDF5 attributes."""
+    import json
+    meta = dict(ds.get("metadata", {}) or {})
+    meta.update(metadata or {})
+    arrays = {k: np.asarray(v) for k, v in ds.items() if k != "metadata"}
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".npz":
+        np.savez_compressed(path, __metadata__=np.array(json.dumps(meta)), **arrays)
+    elif ext in (".h5", ".hdf5"):
+        try:
+            import h5py
+        except ImportError as e:
+            raise ImportError("HDF5 export needs h5py, which is not installed; use .npz or .pt") from e
+        with h5py.File(path, "w") as f:
+            for k, v in arrays.items():
+                f.create_dataset(k, data=v, compression="gzip")
+            for k, v in meta.items():
+                f.attrs[k] = json.dumps(v)
+    elif ext == ".pt":
+        import torch
+        torch.save({"metadata": meta, **{k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in arrays.items()}}, path)
+    else:
+        raise ValueError(f"unknown dataset file extension {ext!r}; expected .npz, .h5/.hdf5 or .pt")
+    return path
+
+
+def load_dataset(path: str) -> Dict[str, object]:
+    """Inverse of save_dataset: dict of numpy arrays + 'metadata'."""
+    import json
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".npz":
+        with np.load(path, allow_pickle=False) as z:
+            out = {k: z[k] for k in z.files if k != "__metadata__"}
+            out["metadata"] = json.loads(str(z["__metadata__"])) if "__metadata__" in z.files else {}
+        return out
+    if ext in (".h5", ".hdf5"):
+        try:
+            import h5py
+        except ImportError as e:
+            raise ImportError("reading HDF5 needs h5py, which is not installed") from e
+        with h5py.File(path, "r") as f:
+            out = {k: f[k][()] for k in f.keys()}
+            out["metadata"] = {k: json.loads(v) for k, v in f.attrs.items()}
+        return out
+    if ext == ".pt":
+        import torch
+        d = torch.load(path, weights_only=False)
+        return {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in d.items()}
+    raise ValueError(f"unknown dataset file extension {ext!r}")
+
+
+def as_torch(ds: Dict[str, object], device=None, pin_memory: bool = False):
+    """Torch-tensor view of a dataset dict for offline-RL data loaders (zero-copy from numpy on the host; ``device``
+    moves it). bool arrays stay bool."""
+    import torch
+    out = {}
+    for k, v in ds.items():
+        if k == "metadata":
+            out[k] = v
+            continue
+        t = torch.from_numpy(np.ascontiguousarray(v))
+        if pin_memory:
+            t = t.pin_memory()
+        out[k] = t.to(device, non_blocking=pin_memory) if device is not None else t
+    return out
