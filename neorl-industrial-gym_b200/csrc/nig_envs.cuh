@@ -71,6 +71,7 @@ struct Reactor {
     // measured on B200 (tools/steady_step.py, tools/rollout_sweep.py): the single-step kernels gain 6 % at 16M envs
     // (0.86 -> 0.92 of the HBM peak), the fused rollout loses 2 % (one extra ballot per step) and keeps Env::reset()
     static constexpr bool COOP_RESET = true;
+    static constexpr int COOP_BLOCKS = 0;
     static constexpr int RESET_NORMALS = 8;
     __device__ static __forceinline__ void reset_from_normals(const float (&z)[8], float (&s)[S])
     {
@@ -231,39 +232,34 @@ struct Grid {
         }
     };
 
-    __device__ static __forceinline__ void reset(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, float (&s)[S])
-    {   // _get_initial_state (:90-110)
+    // _get_initial_state (:90-110): 8 Philox blocks of the RESET stream -- blocks 0,1 voltages ~ N(1, .01), 2,3
+    // generation ~ N(base_load, 2), 4,5 loads = base_load * U(.8, 1.2), 6,7 line flows ~ N(0, 10). One block (4 raw
+    // values) is the unit of work of the warp-cooperative reset.
+    static constexpr int COOP_BLOCKS = 8;
+    __device__ static __forceinline__ void reset_block(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t j, float (&v)[4])
+    {
+        if (j == 4u || j == 5u) {
+            const uint4 w = rng_words(key, env, tick, STREAM_RESET, (epoch << 8) | j);
+            v[0] = u_sym(w.x); v[1] = u_sym(w.y); v[2] = u_sym(w.z); v[3] = u_sym(w.w);
+        } else rng_normals4(key, env, tick, STREAM_RESET, (epoch << 8) | j, v);
+    }
+    __device__ static __forceinline__ void reset_from_values(const float (&v)[32], float (&s)[S])
+    {
         s[0] = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            float z[4];
-            rng_normals4(key, env, tick, STREAM_RESET, (epoch << 8) | (uint32_t)j, z);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s[1 + 4 * j + q] = add(1.0f, mul(0.01f, z[q]));
+        for (int i = 0; i < 8; ++i) {
+            s[1 + i] = add(1.0f, mul(0.01f, v[i]));
+            s[9 + i] = add(base_load(i), mul(2.0f, v[8 + i]));
+            s[17 + i] = mul(base_load(i), add(1.0f, mul(0.2f, v[16 + i])));
+            if (i < 7) s[25 + i] = mul(10.0f, v[24 + i]);
         }
+    }
+    __device__ static __forceinline__ void reset(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, float (&s)[S])
+    {
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            float z[4];
-            rng_normals4(key, env, tick, STREAM_RESET, (epoch << 8) | (uint32_t)(2 + j), z);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) s[9 + 4 * j + q] = add(base_load(4 * j + q), mul(2.0f, z[q]));
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const uint4 w = rng_words(key, env, tick, STREAM_RESET, (epoch << 8) | (uint32_t)(4 + j));
-            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                s[17 + 4 * j + q] = mul(base_load(4 * j + q), add(1.0f, mul(0.2f, u_sym(ww[q]))));
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            float z[4];
-            rng_normals4(key, env, tick, STREAM_RESET, (epoch << 8) | (uint32_t)(6 + j), z);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (4 * j + q < 7) s[25 + 4 * j + q] = mul(10.0f, z[q]);
-        }
+        for (int j = 0; j < 8; ++j) reset_block(key, env, tick, epoch, (uint32_t)j, reinterpret_cast<float (&)[4]>(v[4 * j]));
+        reset_from_values(v, s);
     }
 
     __device__ static __forceinline__ bool builtin(int id, const float (&s)[S], const float (&a)[A])
@@ -359,6 +355,7 @@ struct Robot {
     static constexpr int KIND = 2, S = 24, A = 7, NZ = 0, NB = 3, MAX_STEPS = 1000;
     static constexpr bool FAST_DIV = false;          // fp64 divisions only
     static constexpr bool COOP_RESET = false;
+    static constexpr int COOP_BLOCKS = 0;
     static constexpr uint32_t CRIT_MASK = 0x3;       // force_limits, collision_avoidance (:56-68)
     using acc_t = double;
     __device__ static constexpr float penalty(int k) { return k == 0 ? -100.0f : (k == 1 ? -200.0f : -50.0f); }

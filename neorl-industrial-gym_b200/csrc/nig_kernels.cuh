@@ -205,6 +205,48 @@ __device__ __forceinline__ void coop_reset(const RngKey& key, uint32_t env, uint
     }
 }
 
+// Block-granular flavour for envs whose draw is long AND whose episodes are short (PowerGrid: 8 Philox blocks, 26
+// Gaussians + 8 uniforms per reset, ~18 % of the envs reset every step under random actions, i.e. ~6 lanes of every
+// warp): the work items (resetting lane, block) of the whole warp are dealt round-robin to the 32 lanes, the raw values
+// go through a per-warp shared-memory buffer [32 resetting lanes][COOP_BLOCKS * 4], the owners rebuild their state.
+template <class Env>
+struct CoopSmem { static constexpr int floats = Env::COOP_BLOCKS > 0 ? (kThreads / 32) * 32 * Env::COOP_BLOCKS * 4 : 1; };
+
+template <class Env>
+__device__ __forceinline__ void coop_reset_blocks(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, bool need,
+                                                  float (&s)[Env::S], float* cta_buf)
+{
+    constexpr int RB = Env::COOP_BLOCKS, NV = RB * 4;
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m == 0u) return;                                        // warp-uniform
+    const uint32_t lane = threadIdx.x & 31u;
+    float* buf = cta_buf + (threadIdx.x >> 5) * 32 * NV;
+    const int items = __popc(m) * RB;
+    for (int base = 0; base < items; base += 32) {
+        const int it = base + (int)lane;
+        const bool live = it < items;
+        const int r = live ? it / RB : 0;                       // rank of the resetting lane this item belongs to
+        const uint32_t j = (uint32_t)(it % RB);
+        const int src = (int)__fns(m, 0u, r + 1);               // lane index of the r-th set bit
+        const uint32_t e_src = __shfl_sync(0xffffffffu, env, src);
+        float v[4];
+        Env::reset_block(key, e_src, tick, epoch, j, v);
+        if (live) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) buf[r * NV + (int)j * 4 + q] = v[q];
+        }
+    }
+    __syncwarp();
+    if (need) {
+        const int r = __popc(m & ((1u << lane) - 1u));
+        float v[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) v[q] = buf[r * NV + q];
+        Env::reset_from_values(v, s);
+    }
+    __syncwarp();
+}
+
 // ---- block-level statistics: per-thread counts -> REDUX -> shared atomics -> one global atomic per slot
 struct BlockStats {
     unsigned int* sh;   // [NIG_STATS_SLOTS] shared counters
@@ -319,6 +361,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
     using acc_t = typename Env::acc_t;
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
+    __shared__ float coop_buf[CoopSmem<Env>::floats];
     BlockStats bs;
     bs.init(sstat);
 
@@ -373,7 +416,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < S; ++k) s[k] = rs[k][e];
                     } else {
-                        if constexpr (Env::COOP_RESET) need_reset = true;
+                        if constexpr (Env::COOP_RESET || Env::COOP_BLOCKS > 0) need_reset = true;
                         else Env::reset(p.key, env, p.tick + 1u, p.epoch, s);
                     }
                     w = 0u; f |= NIG_F_RESET;
@@ -387,6 +430,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                 for (int k = 0; k < S; ++k) s[k] = ns[k];
             }
             if constexpr (Env::COOP_RESET) coop_reset<Env>(p.key, env, p.tick + 1u, p.epoch, need_reset, s);
+            else if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(p.key, env, p.tick + 1u, p.epoch, need_reset, s, coop_buf);
 #pragma unroll
             for (int k = 0; k < S; ++k) sv[k][e] = s[k];
             wv[e] = __uint_as_float(w);
@@ -779,6 +823,7 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
     __shared__ double sfl[4];
     __shared__ alignas(8) uint64_t bars[2];
+    __shared__ float coop_buf[CoopSmem<Env>::floats];
     extern __shared__ __align__(128) float act_smem[];     // [2][kTmaChunk][A][kThreads] when TMA
     BlockStats bs;
     if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
@@ -894,6 +939,7 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
         const bool active = valid && !(w >> 31);
         uint32_t w2 = w, f, vm;
         acc_t r;
+        bool need_reset = false;
         step_core<Env, CONS>(p.cons, p.max_steps, s, a, nz, 0u, w2, ns, r, f, vm);
         if (active) {
             const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
@@ -918,7 +964,8 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
                 len_sum += len; len_sq += len * len;
                 ret_sum += (double)ep_ret; ret_sq += (double)ep_ret * (double)ep_ret;
                 if (p.auto_reset) {
-                    Env::reset(p.key, env, tick + 1u, p.epoch, s);
+                    if constexpr (Env::COOP_BLOCKS > 0) need_reset = true;
+                    else Env::reset(p.key, env, tick + 1u, p.epoch, s);
                     w = 0u; ep_ret = (acc_t)0;
                 } else {
 #pragma unroll
@@ -930,6 +977,7 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
                 for (int k = 0; k < S; ++k) s[k] = ns[k];
             }
         }
+        if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(p.key, env, tick + 1u, p.epoch, need_reset, s, coop_buf);
     }
 
     if (valid) {
