@@ -43,12 +43,24 @@ def test_abi_version_and_specs():
         N.env_spec(7)
 
 
-def test_struct_sizes_match_header():
-    # nig_constraint_t: 9 x 4 bytes; nig_config_t: 4+4+8+8+8+4*4 + 8*36; policy params: 16 + 64 + 32
-    assert C.sizeof(N.Constraint) == 36
-    assert C.sizeof(N.Config) == 48 + 8 * 36
-    assert C.sizeof(N.PolicyParams) == 16 + 64 + 32
-    assert C.sizeof(N.StepIO) == 9 * 8 + 8
+def test_struct_sizes_match_header(tmp_path):
+    """ctypes mirrors == what a C compiler makes of include/nig_b200.h (sizes and a few telling offsets)."""
+    import subprocess
+    src = tmp_path / "sizes.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "nig_b200.h"\n'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(nig_constraint_t), sizeof(nig_config_t),'
+        ' sizeof(nig_policy_params_t), sizeof(nig_step_io_t), sizeof(nig_rollout_t), sizeof(nig_rollout_host_t),'
+        ' sizeof(nig_dataset_out_t), sizeof(nig_env_spec_t), sizeof(nig_baseline_t), offsetof(nig_policy_params_t, baseline),'
+        ' offsetof(nig_rollout_host_t, reward_sum)); return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    want = [C.sizeof(N.Constraint), C.sizeof(N.Config), C.sizeof(N.PolicyParams), C.sizeof(N.StepIO), C.sizeof(N.Rollout),
+            C.sizeof(N.RolloutHost), C.sizeof(N.DatasetOut), C.sizeof(N.EnvSpec), C.sizeof(N.Baseline),
+            N.PolicyParams.baseline.offset, N.RolloutHost.reward_sum.offset]
+    assert got == want, (got, want)
+    assert C.sizeof(N.Constraint) == 36 and C.sizeof(N.Config) == 48 + 8 * 36
 
 
 def test_make_registry_errors():
