@@ -139,6 +139,9 @@ def cpu_baseline(budget_s: float = 12.0):
     n = int(min(ENVS_PER_GPU, max(1024, r1 * threads * 0.5 * budget_s / HORIZON))) // 256 * 256 or 256
     rate, dt = cpu_rollout_rate(n, HORIZON, threads)
     return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "reference_python_loop": {"value": 12177.0, "unit": UNIT, "cores": 1, "note": "the UNMODIFIED reference's own loop "
+                                      "(performance_benchmark.py:106-133) timed at survey time in the build container (BASELINE.md section 2); "
+                                      "the reference publishes 9,378 steps/s (hardware unstated). Not re-measured here: the tree is absent on the GPU box"},
             "sample": f"C oracle port (oracle/nig_oracle.c, scalar per env, same policy/noise/auto-reset), {n} envs x {HORIZON} "
                       f"steps in {dt:.2f} s on {threads} threads; single-thread rate {r1:.3g} env-steps/s. The reference itself is a "
                       "pure-Python per-env loop with no jit/vmap batch path (published 9,378 steps/s, hardware unstated); "
@@ -276,8 +279,9 @@ def run_gpu(args):
             "traffic": ncu_traffic("rollout_kernel<Reactor"),
             "ncu": "profiles/r01_c_rollout_kernel_ncu_table.txt: 414 issued warp-instructions per 32 env-steps (128 algorithmic), issue slots "
                    "70 % busy while active, FMA pipe 35 %, ALU pipe 56 %, 3.5 warps per SM sub-partition (65,536 envs = 0.69 waves)",
+            "frac_with_rng_ops": (ALG_OPS_PER_STEP + 2 * 52) / ALG_OPS_PER_STEP * achieved / fp32_peak,
             "note": f"algorithmic {ALG_OPS_PER_STEP} fp32 ops/env-step (SURVEY 8d; RNG, IEEE-division expansion and addressing "
-                    "excluded) x env-steps per launch / mean launch time; peak = unfused FADD/FMUL issue rate measured live by "
+                    "excluded) x env-steps per launch / mean launch time (frac_with_rng_ops adds the survey's 2 Gaussians x ~52 ops per step); peak = unfused FADD/FMUL issue rate measured live by "
                     "nig_fp32_probe (nominal 148 SM x 128 lanes x 1.965 GHz = 37.2 T op/s). Tensor cores do not apply: element-wise ODE.",
         }
         # ---- single-step kernel at 65,536 envs (launch-bound) and its HBM roofline at 4M envs (> L2)
@@ -405,6 +409,19 @@ def other_configs(torch, ni, N, local, rank, world, dist, seed):
                         "hbm_frac_per_gpu": 302 * cnt / (ms1 * 1e-3) / 1e9 / hbm_peak,
                         "note": "302 algorithmic B/env-step; the 23 in-kernel Gaussian draws per step make this kernel issue-bound, not HBM-bound"},
         "allreduced": {"steps": st["steps"], "episodes": st["episodes"], "violations": st["violations"]}}
+    env.close()
+    # ---- RobotAssembly-v0 (the third env implemented upstream), same sharding
+    env = ni.NativeEnv(N.ENV_ROBOT_ASSEMBLY, cnt, device=local, seed=seed, env_id_offset=off)
+    env.reset_device()
+    ms = timed(lambda: [env.rollout_device(64, N.POLICY_UNIFORM) for _ in range(4)], 3)
+    acts = torch.rand((7, env.pitch), device=dev) * 2 - 1
+    ms1 = timed(lambda: env.step_device(acts, reward=rew, flags=fl, viol_mask=vm), 20)
+    out["robot_assembly_1m"] = {
+        "workload": f"RobotAssembly-v0 (24-d state, 7-d action, fp64 kinematics), {n_total} envs over {world} rank(s), auto-reset",
+        "rollout_k64": {"value": n_total * 256 / (ms * 1e-3), "unit": UNIT, "ms_per_256_steps": ms},
+        "single_step": {"value": n_total / (ms1 * 1e-3), "unit": UNIT, "ms_per_launch": ms1,
+                        "hbm_frac_per_gpu": 234 * cnt / (ms1 * 1e-3) / 1e9 / hbm_peak,
+                        "note": "234 algorithmic B/env-step; 7 fp64 sin/cos pairs per step make this kernel issue-bound"}}
     env.close()
     # ---- configs[3]: reactor + SafetyWrapper bands (declarative bounds evaluated in-kernel), all-reduced counters
     n = ENVS_PER_GPU
