@@ -215,7 +215,13 @@ void set_cons(nig_env* e, const nig_constraint_t* c, int n)
 {
     memset(&e->cons, 0, sizeof e->cons);
     e->cons.n = n;
-    for (int k = 0; k < n; ++k) e->cons.c[k] = c[k];
+    for (int k = 0; k < n; ++k) {
+        e->cons.c[k] = c[k];
+        if (c[k].kind == NIG_CON_BOUND) {
+            e->cons.smask[k][c[k].si] = 0xffffffffu;
+            if (c[k].ai >= 0) e->cons.amask[k][c[k].ai] = 0xffffffffu;
+        }
+    }
     e->cons.is_default = cons_mode(e->kind, c, n);
 }
 

@@ -26,6 +26,8 @@ struct ConsParams {
     int32_t n;
     int32_t is_default;        // CONS_GENERIC / CONS_DEFAULT / CONS_PREFIX (host-side dispatch only)
     nig_constraint_t c[NIG_MAX_CONSTRAINTS];
+    uint32_t smask[NIG_MAX_CONSTRAINTS][NIG_MAX_STATE_DIM];    // NIG_CON_BOUND: all-ones at [k][si], zero elsewhere
+    uint32_t amask[NIG_MAX_CONSTRAINTS][NIG_MAX_ACTION_DIM];   //                all-ones at [k][ai] when ai >= 0
 };
 
 // ---- vector access helpers -----------------------------------------------------------------------
@@ -54,27 +56,26 @@ __device__ __forceinline__ void stvec(float* p, const float (&v)[VEC])
     *reinterpret_cast<T*>(p) = t;
 }
 
-// s[i] for a runtime i: the index comes from a constraint descriptor in the kernel parameters, i.e. it is
-// warp-uniform -- a select chain over all S registers
-template <int S, int LO = 0, int N = S>
-__device__ __forceinline__ float pick(const float (&s)[S], int i)
+// s[i] for a runtime (warp-uniform) index i out of a register array, exact and branch-free: OR of the bit patterns
+// under host-built one-hot masks that live in the kernel parameters (constant bank operands of the LOP3s)
+template <int S>
+__device__ __forceinline__ float pick(const float (&s)[S], const uint32_t* __restrict__ onehot)
 {
-    // binary branch tree on the (uniform) index: log2(S) uniform branches instead of S - 1 selects
-    if constexpr (N == 1) return s[LO];
-    else {
-        constexpr int H = N / 2;
-        return i < LO + H ? pick<S, LO, H>(s, i) : pick<S, LO + H, N - H>(s, i);
-    }
+    uint32_t b = 0u;
+#pragma unroll
+    for (int k = 0; k < S; ++k) b |= __float_as_uint(s[k]) & onehot[k];
+    return __uint_as_float(b);
 }
 
 // one runtime constraint descriptor (SafetyConstraint, core/types.py:56-64) on the pre-step state / clipped action
 template <class Env>
-__device__ __forceinline__ bool eval_constraint(const nig_constraint_t& c, const float (&s)[Env::S], const float (&a)[Env::A], uint32_t hostmask)
+__device__ __forceinline__ bool eval_constraint(const ConsParams& cp, int k, const float (&s)[Env::S], const float (&a)[Env::A], uint32_t hostmask)
 {
+    const nig_constraint_t& c = cp.c[k];
     if (c.kind == NIG_CON_BUILTIN) return Env::builtin(c.id, s, a);
     if (c.kind == NIG_CON_BOUND) {
-        float v = pick<Env::S>(s, c.si);
-        if (c.ai >= 0) v = add(v, mul(c.coef, pick<Env::A>(a, c.ai)));
+        float v = pick<Env::S>(s, cp.smask[k]);
+        if (c.ai >= 0) v = add(v, mul(c.coef, pick<Env::A>(a, cp.amask[k])));
         return (c.lo <= v) && (v <= c.hi);
     }
     return !((hostmask >> c.id) & 1u);
@@ -131,7 +132,7 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
 #pragma unroll
         for (int k = K0; k < NIG_MAX_CONSTRAINTS; ++k) {
             if (k < cp.n) {                 // uniform: the descriptor count is a kernel parameter
-                const bool ok = eval_constraint<Env>(cp.c[k], s, a, hostmask);
+                const bool ok = eval_constraint<Env>(cp, k, s, a, hostmask);
                 vm |= ok ? 0u : (1u << k);
                 crit = crit || (!ok && cp.c[k].critical != 0);
             }
