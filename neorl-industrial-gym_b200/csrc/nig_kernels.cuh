@@ -92,7 +92,7 @@ __device__ __forceinline__ uint32_t epw_make(uint32_t step, uint32_t viol, uint3
 // ---- one env step in registers (base.py:157-213) --------------------------------------------------
 // `div` carries out the divisions (DivExact = IEEE; DivFast = guarded fast path, see nig_math.cuh). With DivFast
 // the outputs are only valid if div.ok() afterwards -- the callers redo the step with DivExact otherwise.
-template <class Env, int CONS, class Div>
+template <class Env, int CONS, class Div, bool CLIP = true>
 __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_steps,
                                                const float (&s)[Env::S], const float (&a_raw)[Env::A],
                                                const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
@@ -104,8 +104,10 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
 #pragma unroll
     for (int j = 0; j < Env::A; ++j) {               // base.py:167 np.clip(action, -1, 1)
         float v = a_raw[j];
-        v = v < -1.0f ? -1.0f : v;
-        v = v > 1.0f ? 1.0f : v;
+        if constexpr (CLIP) {                        // CLIP = false: the caller generated a in [-1, 1] itself (policy_uniform)
+            v = v < -1.0f ? -1.0f : v;
+            v = v > 1.0f ? 1.0f : v;
+        }
         a[j] = v;
     }
     // base.py:170 -- constraints on the PRE-step state (the reference calls every check_fn twice with
@@ -163,7 +165,7 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
 }
 
 // one step with the fast divisions and the deferred guard: the common path is a single basic block
-template <class Env, int CONS>
+template <class Env, int CONS, bool CLIP = true>
 __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
                                           const float (&s)[Env::S], const float (&a_raw)[Env::A],
                                           const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
@@ -173,11 +175,11 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
     const uint32_t w_in = ep_word;
     if constexpr (Env::FAST_DIV) {
         DivFast df;
-        step_core_impl<Env, CONS>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, df);
+        step_core_impl<Env, CONS, DivFast, CLIP>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, df);
         if (__builtin_expect(df.ok(), 1)) return;
     }
     DivExact de;
-    step_core_impl<Env, CONS>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, de);
+    step_core_impl<Env, CONS, DivExact, CLIP>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, de);
 }
 
 // ---- warp-cooperative auto-reset ---------------------------------------------------------------------------------
@@ -941,7 +943,7 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
         uint32_t w2 = w, f, vm;
         acc_t r;
         bool need_reset = false;
-        step_core<Env, CONS>(p.cons, p.max_steps, s, a, nz, 0u, w2, ns, r, f, vm);
+        step_core<Env, CONS, POLICY != NIG_POLICY_UNIFORM>(p.cons, p.max_steps, s, a, nz, 0u, w2, ns, r, f, vm);
         if (active) {
             const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
             rsum = add(rsum, (float)r);
