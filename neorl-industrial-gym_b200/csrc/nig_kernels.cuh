@@ -96,7 +96,8 @@ template <class Env, int CONS, class Div, bool CLIP = true>
 __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_steps,
                                                const float (&s)[Env::S], const float (&a_raw)[Env::A],
                                                const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
-                                               uint32_t ep_word_in, uint32_t& ep_word, float (&ns)[Env::S],
+                                               uint32_t ep_step_in, uint32_t ep_viol_in, uint32_t& ep_step, uint32_t& ep_viol,
+                                               float (&ns)[Env::S],
                                                typename Env::acc_t& reward, uint32_t& flags, uint32_t& vmask, Div& div)
 {
     using acc_t = typename Env::acc_t;
@@ -152,19 +153,39 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
         for (int k = K0; k < NIG_MAX_CONSTRAINTS; ++k)
             if (k < cp.n && ((vm >> k) & 1u)) r = r + (acc_t)cp.c[k].penalty;
     }
-    const uint32_t step = epw_step(ep_word_in) + 1u;  // base.py:187
-    const uint32_t viol = epw_viol(ep_word_in) + (uint32_t)__popc(vm);
+    const uint32_t step = ep_step_in + 1u;            // base.py:187
+    const uint32_t viol = ep_viol_in + (uint32_t)__popc(vm);
     bool terminated = Env::is_done(ns);               // base.py:190
     const bool truncated = step >= (uint32_t)max_steps;   // base.py:191
     uint32_t f = 0;
     if (crit) { terminated = true; r = r - (acc_t)1000.0f; f |= NIG_F_CRITICAL; }   // base.py:195-198
     if (terminated) f |= NIG_F_TERMINATED;
     if (truncated) f |= NIG_F_TRUNCATED;
-    ep_word = epw_make(step, viol, 0u);
+    ep_step = step; ep_viol = viol;
     reward = r; flags = f; vmask = vm;
 }
 
-// one step with the fast divisions and the deferred guard: the common path is a single basic block
+// one step with the fast divisions and the deferred guard: the common path is a single basic block.
+// Episode step / violation counters unpacked (the fused rollout keeps them in separate registers across K steps).
+template <class Env, int CONS, bool CLIP = true>
+__device__ __forceinline__ void step_core_unpacked(const ConsParams& cp, int max_steps,
+                                                   const float (&s)[Env::S], const float (&a_raw)[Env::A],
+                                                   const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
+                                                   uint32_t ep_step_in, uint32_t ep_viol_in, uint32_t& ep_step, uint32_t& ep_viol,
+                                                   float (&ns)[Env::S], typename Env::acc_t& reward, uint32_t& flags, uint32_t& vmask)
+{
+    if constexpr (Env::FAST_DIV) {
+        DivFast df;
+        step_core_impl<Env, CONS, DivFast, CLIP>(cp, max_steps, s, a_raw, nz, hostmask, ep_step_in, ep_viol_in, ep_step, ep_viol,
+                                                 ns, reward, flags, vmask, df);
+        if (__builtin_expect(df.ok(), 1)) return;
+    }
+    DivExact de;
+    step_core_impl<Env, CONS, DivExact, CLIP>(cp, max_steps, s, a_raw, nz, hostmask, ep_step_in, ep_viol_in, ep_step, ep_viol,
+                                              ns, reward, flags, vmask, de);
+}
+
+// the same with the packed episode word of the HBM layout (single-step and dataset kernels)
 template <class Env, int CONS, bool CLIP = true>
 __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
                                           const float (&s)[Env::S], const float (&a_raw)[Env::A],
@@ -172,14 +193,10 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
                                           uint32_t& ep_word, float (&ns)[Env::S],
                                           typename Env::acc_t& reward, uint32_t& flags, uint32_t& vmask)
 {
-    const uint32_t w_in = ep_word;
-    if constexpr (Env::FAST_DIV) {
-        DivFast df;
-        step_core_impl<Env, CONS, DivFast, CLIP>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, df);
-        if (__builtin_expect(df.ok(), 1)) return;
-    }
-    DivExact de;
-    step_core_impl<Env, CONS, DivExact, CLIP>(cp, max_steps, s, a_raw, nz, hostmask, w_in, ep_word, ns, reward, flags, vmask, de);
+    uint32_t st, vi;
+    step_core_unpacked<Env, CONS, CLIP>(cp, max_steps, s, a_raw, nz, hostmask, epw_step(ep_word), epw_viol(ep_word), st, vi,
+                                        ns, reward, flags, vmask);
+    ep_word = epw_make(st, vi, 0u);
 }
 
 // ---- warp-cooperative auto-reset ---------------------------------------------------------------------------------
@@ -858,7 +875,9 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
     float s[S];
 #pragma unroll
     for (int k = 0; k < S; ++k) s[k] = p.state[k * p.pitch + ic];
-    uint32_t w = p.ep_word[ic];
+    const uint32_t w0 = p.ep_word[ic];
+    uint32_t ep_st = epw_step(w0), ep_vi = epw_viol(w0);      // unpacked across the K steps
+    bool latched = (w0 >> 31) != 0u;
     acc_t ep_ret = (acc_t)p.ep_return[ic];
     typename Env::NoiseGen ng;
 
@@ -939,16 +958,16 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
             } else ng.get(p.key, env, tick, nz);
         } else nz[0] = 0.0f;
 
-        const bool active = valid && !(w >> 31);
-        uint32_t w2 = w, f, vm;
+        const bool active = valid && !latched;
+        uint32_t st2, vi2, f, vm;
         acc_t r;
         bool need_reset = false;
-        step_core<Env, CONS, POLICY != NIG_POLICY_UNIFORM>(p.cons, p.max_steps, s, a, nz, 0u, w2, ns, r, f, vm);
+        step_core_unpacked<Env, CONS, POLICY != NIG_POLICY_UNIFORM>(p.cons, p.max_steps, s, a, nz, 0u, ep_st, ep_vi, st2, vi2, ns, r, f, vm);
         if (active) {
             const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
             rsum = add(rsum, (float)r);
             ep_ret = ep_ret + r;
-            rew_sum += (double)r;
+            if constexpr (sizeof(acc_t) == 8) rew_sum += r;      // fp32-reward envs: derived from rsum after the loop
             c_steps += 1; c_viol += __popc(vm);
             c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
 #pragma unroll
@@ -957,9 +976,9 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
 #pragma unroll
                 for (int k = Env::NB; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] += (vm >> k) & 1u;
             }
-            w = w2;
+            ep_st = st2; ep_vi = vi2;
             if (done) {
-                const unsigned long long len = epw_step(w2);
+                const unsigned long long len = st2;
                 c_ep += 1; c_done += 1;
                 c_term += (f & NIG_F_TERMINATED) ? 1u : 0u;
                 c_trunc += (f & NIG_F_TRUNCATED) ? 1u : 0u;
@@ -969,11 +988,11 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
                 if (p.auto_reset) {
                     if constexpr (Env::COOP_BLOCKS > 0) need_reset = true;
                     else Env::reset(p.key, env, tick + 1u, p.epoch, s);
-                    w = 0u; ep_ret = (acc_t)0;
+                    ep_st = 0u; ep_vi = 0u; ep_ret = (acc_t)0;
                 } else {
 #pragma unroll
                     for (int k = 0; k < S; ++k) s[k] = ns[k];
-                    w |= 0x80000000u;
+                    latched = true;
                 }
             } else {
 #pragma unroll
@@ -983,10 +1002,13 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
         if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(p.key, env, tick + 1u, p.epoch, need_reset, s, coop_buf);
     }
 
+    // fp32-reward envs (reactor): the reward statistic of this launch is the fp32 per-env sum (K <= a few hundred
+    // terms) widened once, instead of an F2F + DADD per step on the XU / FP64 pipes
+    if constexpr (sizeof(acc_t) == 4) rew_sum = (double)rsum;
     if (valid) {
 #pragma unroll
         for (int k = 0; k < S; ++k) p.state[k * p.pitch + i] = s[k];
-        p.ep_word[i] = w;
+        p.ep_word[i] = epw_make(ep_st, ep_vi, latched ? 1u : 0u);
         p.ep_return[i] = (double)ep_ret;
         if constexpr (POLICY == NIG_POLICY_BASELINE) {
             if (p.pp.baseline.kind == NIG_BASELINE_PID && p.pid_state != nullptr) {

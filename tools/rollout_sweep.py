@@ -1,4 +1,4 @@
-"""Fused rollout kernel sweep: envs-per-thread x block size x K -> env-steps/s (reactor, uniform policy, 65,536 envs)."""
+"""Fused rollout kernel sweep: population x K x CTA size -> env-steps/s (uniform in-kernel policy)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "neorl-industrial-gym_b200")]
@@ -6,8 +6,7 @@ import numpy as np, torch
 import neorl_industrial as ni
 from neorl_industrial import _native as N
 
-def run(kind, n, ept, block, K, horizon=1024, reps=5, policy=N.POLICY_UNIFORM):
-    pass
+def run(kind, n, block, K, horizon=1024, reps=5, policy=N.POLICY_UNIFORM):
     os.environ["NIG_ROLLOUT_BLOCK"] = str(block)
     env = ni.NativeEnv(kind, n, device=0, seed=0)
     env.reset_device()
@@ -36,8 +35,7 @@ if __name__ == "__main__":
         kind = kinds[name]
         for n in (65536, 1 << 18, 1 << 20):
             for K in (64, 256):
-                for ept in (0,):
-                    for block in (128,):
-                        rate, ms, steps, ret = run(kind, n, ept, block, K)
-                        print(f"{name:8s} n={n:8d} K={K:4d} pipeline={ept} block={block:3d}: {rate:.4g} env-steps/s ({ms:.3f} ms / 1024 steps) "
-                              f"steps={steps} return_sum={ret:.9e}", flush=True)
+                for block in (128,):
+                    rate, ms, steps, ret = run(kind, n, block, K)
+                    print(f"{name:8s} n={n:8d} K={K:4d} block={block:3d}: {rate:.4g} env-steps/s ({ms:.3f} ms / 1024 steps) "
+                          f"steps={steps} return_sum={ret:.9e}", flush=True)
