@@ -335,6 +335,25 @@ def single_step_section(torch, ni, N, local, dev, flush, hbm_peak, peak_src, arg
     ms = e0.elapsed_time(e1)
     out["envs_64k"] = {"value": ENVS_PER_GPU * HORIZON / (ms * 1e-3), "unit": UNIT, "us_per_launch": ms * 1e3 / HORIZON,
                        "note": "1,000 back-to-back launches; 8 MB working set is L2-resident, launch-latency bound"}
+    # the same 1,000 launches as 10 replays of a captured 100-launch CUDA graph (device-resident tick: fresh noise each step)
+    try:
+        env.use_device_tick(True)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(100):
+                env.step_device(acts, reward=rew, flags=fl, viol_mask=vm)
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(HORIZON // 100):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        msg = e0.elapsed_time(e1)
+        out["envs_64k_cuda_graph"] = {"value": ENVS_PER_GPU * HORIZON / (msg * 1e-3), "unit": UNIT, "us_per_launch": msg * 1e3 / HORIZON,
+                                      "note": "10 replays of a 100-launch CUDA graph (nig_use_device_tick)"}
+    except Exception as ex:                                   # graph capture is an optimisation, never a requirement
+        out["envs_64k_cuda_graph"] = {"error": repr(ex)}
     env.close()
     # (b) HBM roofline: 16,777,216 envs (2 GB of state + io per launch, >> L2; the copy that MEASURED_PEAKS.json times
     # moves 4 GB), in-kernel Philox noise, auto-reset

@@ -300,6 +300,11 @@ NIG_API int nig_set_state_host(nig_env_t* env, const float* state_aos, const int
 NIG_API int nig_state_ptr(nig_env_t* env, float** state_dev_soa, uint32_t** ep_word_dev);
 NIG_API int nig_get_tick(const nig_env_t* env, uint32_t* tick, uint32_t* epoch);
 NIG_API int nig_set_tick(nig_env_t* env, uint32_t tick, uint32_t epoch);
+/* CUDA-graph capture: with the device tick enabled the batched-step counter that keys the random streams lives in
+ * device memory and the kernels advance it themselves, so a captured sequence of nig_step / nig_rollout launches can
+ * be replayed any number of times and keeps drawing fresh noise (a host-side counter would be frozen into the graph).
+ * Enable BEFORE capturing; nig_get_tick / nig_set_tick keep working (they synchronise). */
+NIG_API int nig_use_device_tick(nig_env_t* env, int32_t enable);
 /* reset(seed=...) made effective (the reference ignores it, base.py:135) */
 NIG_API int nig_set_seed(nig_env_t* env, uint64_t seed);
 

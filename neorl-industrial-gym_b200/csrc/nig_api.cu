@@ -87,6 +87,8 @@ struct nig_env {
     float *h_actions, *h_noise, *h_reset, *h_obs, *h_next_obs, *h_reward;
     uint8_t *h_hostmask, *h_flags, *h_viol, *h_mask;
     int32_t *h_i32a, *h_i32b;
+    uint32_t* cons_masks;       // device copy of the NIG_CON_BOUND one-hot masks (ConsParams::masks)
+    uint32_t* tick_dev;         // device-tick mode (CUDA-graph capture): [0] tick, [1] finished-CTA counter; null = host tick
     double* pid_state;          // [2][A][pitch] PID integral / previous error of NIG_POLICY_BASELINE (lazily allocated, zeroed)
     float *r_act[2], *r_nz[2];  // nig_rollout_host: double-buffered action / noise chunks
     int32_t r_cap;              // steps each chunk buffer holds
@@ -215,12 +217,19 @@ void set_cons(nig_env* e, const nig_constraint_t* c, int n)
 {
     memset(&e->cons, 0, sizeof e->cons);
     e->cons.n = n;
+    uint32_t host_masks[NIG_MAX_CONSTRAINTS * kConsMaskRow];
+    memset(host_masks, 0, sizeof host_masks);
     for (int k = 0; k < n; ++k) {
         e->cons.c[k] = c[k];
         if (c[k].kind == NIG_CON_BOUND) {
-            e->cons.smask[k][c[k].si] = 0xffffffffu;
-            if (c[k].ai >= 0) e->cons.amask[k][c[k].ai] = 0xffffffffu;
+            host_masks[k * kConsMaskRow + c[k].si] = 0xffffffffu;
+            if (c[k].ai >= 0) host_masks[k * kConsMaskRow + NIG_MAX_STATE_DIM + c[k].ai] = 0xffffffffu;
         }
+    }
+    e->cons.masks = e->cons_masks;
+    if (e->cons_masks) {       // allocated in nig_create before the first set_cons
+        cudaDeviceSynchronize();
+        cudaMemcpy(e->cons_masks, host_masks, sizeof host_masks, cudaMemcpyHostToDevice);
     }
     e->cons.is_default = cons_mode(e->kind, c, n);
 }
@@ -312,6 +321,7 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     int nc = cfg->n_constraints;
     if (nc < 0) { builtin_constraints(e->kind, def); c = def; nc = 3; }
     int rc = validate_constraints(e->kind, c, nc);
+    if (rc == NIG_OK) rc = dev_alloc(&e->cons_masks, (size_t)NIG_MAX_CONSTRAINTS * kConsMaskRow);
     if (rc == NIG_OK) {
         set_cons(e, c, nc);
         rc = dev_alloc(&e->state, (size_t)e->S * e->pitch);
@@ -334,7 +344,7 @@ int nig_destroy(nig_env_t* e)
     cudaFree(e->state); cudaFree(e->ep_word); cudaFree(e->ep_return); cudaFree(e->stats);
     cudaFree(e->h_actions); cudaFree(e->h_noise); cudaFree(e->h_reset); cudaFree(e->h_obs); cudaFree(e->h_next_obs);
     cudaFree(e->h_reward); cudaFree(e->h_hostmask); cudaFree(e->h_flags); cudaFree(e->h_viol); cudaFree(e->h_mask);
-    cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->pid_state); cudaFree(e->d_len); cudaFree(e->d_off); cudaFree(e->d_total);
+    cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->pid_state); cudaFree(e->tick_dev); cudaFree(e->cons_masks); cudaFree(e->d_len); cudaFree(e->d_off); cudaFree(e->d_total);
     for (int b = 0; b < 2; ++b) {
         cudaFree(e->r_act[b]); cudaFree(e->r_nz[b]);
         if (e->r_ev_copy[b]) cudaEventDestroy(e->r_ev_copy[b]);
@@ -356,6 +366,8 @@ int nig_set_constraints(nig_env_t* e, const nig_constraint_t* cons, int32_t n)
     if (n > 0 && !cons) return fail(NIG_ERR_INVALID, "null constraint array");
     const int rc = validate_constraints(e->kind, cons, n);
     if (rc != NIG_OK) return rc;
+    DeviceGuard guard(e->cfg.device);
+    if (!guard.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", e->cfg.device);
     set_cons(e, cons, n);
     return NIG_OK;
 }
@@ -364,8 +376,8 @@ int nig_reset(nig_env_t* e, const uint8_t* mask, const float* init_states, int32
 {
     NIG_CHECK_ENV(e);
     e->epoch += 1;     // explicit resets draw with a fresh epoch; auto-resets reuse the current one
-    ResetArgs a{e->state, e->ep_word, e->ep_return, e->n, e->pitch, (uint32_t)e->cfg.env_id_offset, e->tick, e->epoch, e->key,
-                mask, init_states, layout == NIG_LAYOUT_AOS ? 1 : 0};
+    ResetArgs a{e->state, e->ep_word, e->ep_return, e->n, e->pitch, (uint32_t)e->cfg.env_id_offset, e->tick, e->epoch, e->tick_dev,
+                e->key, mask, init_states, layout == NIG_LAYOUT_AOS ? 1 : 0};
     e->launches++;
     note_device_work(e, (cudaStream_t)stream);
     NIG_CUDA(nig::launch_reset(e->kind, a, (cudaStream_t)stream));
@@ -407,7 +419,7 @@ int nig_step(nig_env_t* e, const nig_step_io_t* io, void* stream)
     StepArgs a;
     memset(&a, 0, sizeof a);
     a.state = e->state; a.ep_word = e->ep_word; a.n = e->n; a.pitch = e->pitch;
-    a.env0 = (uint32_t)e->cfg.env_id_offset; a.tick = e->tick; a.epoch = e->epoch; a.key = e->key;
+    a.env0 = (uint32_t)e->cfg.env_id_offset; a.tick = e->tick; a.epoch = e->epoch; a.key = e->key; a.tick_dev = e->tick_dev;
     a.max_steps = e->max_steps; a.auto_reset = e->cfg.auto_reset;
     a.actions = io->actions; a.noise = io->noise; a.reset_states = io->reset_states; a.hostmask = io->hostmask;
     a.obs = io->obs; a.next_obs = io->next_obs; a.reward = io->reward; a.flags = io->flags; a.viol_mask = io->viol_mask;
@@ -486,7 +498,7 @@ int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
     RolloutArgs a;
     memset(&a, 0, sizeof a);
     a.state = e->state; a.ep_word = e->ep_word; a.ep_return = e->ep_return; a.n = e->n; a.pitch = e->pitch;
-    a.env0 = (uint32_t)e->cfg.env_id_offset; a.tick = e->tick; a.epoch = e->epoch; a.key = e->key;
+    a.env0 = (uint32_t)e->cfg.env_id_offset; a.tick = e->tick; a.epoch = e->epoch; a.key = e->key; a.tick_dev = e->tick_dev;
     a.max_steps = e->max_steps; a.auto_reset = e->cfg.auto_reset; a.n_steps = r->n_steps;
     a.actions = r->actions; a.noise = r->noise; a.pp = r->pp;
     a.reward_sum = r->reward_sum; a.viol_count = r->viol_count; a.done_count = r->done_count;
@@ -784,7 +796,14 @@ int nig_state_ptr(nig_env_t* e, float** state, uint32_t** ep_word)
 int nig_get_tick(const nig_env_t* e, uint32_t* tick, uint32_t* epoch)
 {
     if (!e) return fail(NIG_ERR_INVALID, "null env handle");
-    if (tick) *tick = e->tick;
+    if (tick) {
+        *tick = e->tick;
+        if (e->tick_dev) {          // device-tick mode: the counter lives on the device (graph replays advance it)
+            DeviceGuard guard(e->cfg.device);
+            NIG_CUDA(cudaDeviceSynchronize());
+            NIG_CUDA(cudaMemcpy(tick, e->tick_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        }
+    }
     if (epoch) *epoch = e->epoch;
     return NIG_OK;
 }
@@ -792,6 +811,27 @@ int nig_set_tick(nig_env_t* e, uint32_t tick, uint32_t epoch)
 {
     if (!e) return fail(NIG_ERR_INVALID, "null env handle");
     e->tick = tick; e->epoch = epoch;
+    if (e->tick_dev) {
+        DeviceGuard guard(e->cfg.device);
+        NIG_CUDA(cudaDeviceSynchronize());
+        NIG_CUDA(cudaMemcpy(e->tick_dev, &tick, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    return NIG_OK;
+}
+
+int nig_use_device_tick(nig_env_t* e, int32_t enable)
+{
+    NIG_CHECK_ENV(e);
+    NIG_CUDA(cudaDeviceSynchronize());
+    if (enable && !e->tick_dev) {
+        NIG_CUDA(cudaMalloc((void**)&e->tick_dev, 2 * sizeof(uint32_t)));
+        const uint32_t init[2] = {e->tick, 0u};
+        NIG_CUDA(cudaMemcpy(e->tick_dev, init, sizeof init, cudaMemcpyHostToDevice));
+    } else if (!enable && e->tick_dev) {
+        NIG_CUDA(cudaMemcpy(&e->tick, e->tick_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        cudaFree(e->tick_dev);
+        e->tick_dev = nullptr;
+    }
     return NIG_OK;
 }
 

@@ -26,9 +26,11 @@ struct ConsParams {
     int32_t n;
     int32_t is_default;        // CONS_GENERIC / CONS_DEFAULT / CONS_PREFIX (host-side dispatch only)
     nig_constraint_t c[NIG_MAX_CONSTRAINTS];
-    uint32_t smask[NIG_MAX_CONSTRAINTS][NIG_MAX_STATE_DIM];    // NIG_CON_BOUND: all-ones at [k][si], zero elsewhere
-    uint32_t amask[NIG_MAX_CONSTRAINTS][NIG_MAX_ACTION_DIM];   //                all-ones at [k][ai] when ai >= 0
+    // NIG_CON_BOUND one-hot masks in DEVICE memory (kept out of the kernel parameters: 1.3 KB of them made every launch
+    // measurably slower): row k = [NIG_MAX_STATE_DIM words: all-ones at si][NIG_MAX_ACTION_DIM words: all-ones at ai >= 0]
+    const uint32_t* masks;
 };
+constexpr int kConsMaskRow = NIG_MAX_STATE_DIM + NIG_MAX_ACTION_DIM;
 
 // ---- vector access helpers -----------------------------------------------------------------------
 template <int VEC> struct VecT;
@@ -57,7 +59,7 @@ __device__ __forceinline__ void stvec(float* p, const float (&v)[VEC])
 }
 
 // s[i] for a runtime (warp-uniform) index i out of a register array, exact and branch-free: OR of the bit patterns
-// under host-built one-hot masks that live in the kernel parameters (constant bank operands of the LOP3s)
+// under host-built one-hot masks (device memory, warp-uniform loads)
 template <int S>
 __device__ __forceinline__ float pick(const float (&s)[S], const uint32_t* __restrict__ onehot)
 {
@@ -74,8 +76,8 @@ __device__ __forceinline__ bool eval_constraint(const ConsParams& cp, int k, con
     const nig_constraint_t& c = cp.c[k];
     if (c.kind == NIG_CON_BUILTIN) return Env::builtin(c.id, s, a);
     if (c.kind == NIG_CON_BOUND) {
-        float v = pick<Env::S>(s, cp.smask[k]);
-        if (c.ai >= 0) v = add(v, mul(c.coef, pick<Env::A>(a, cp.amask[k])));
+        float v = pick<Env::S>(s, cp.masks + k * kConsMaskRow);
+        if (c.ai >= 0) v = add(v, mul(c.coef, pick<Env::A>(a, cp.masks + k * kConsMaskRow + NIG_MAX_STATE_DIM)));
         return (c.lo <= v) && (v <= c.hi);
     }
     return !((hostmask >> c.id) & 1u);
@@ -267,6 +269,28 @@ __device__ __forceinline__ void coop_reset_blocks(const RngKey& key, uint32_t en
     __syncwarp();
 }
 
+// ---- device-resident tick (CUDA-graph capture) --------------------------------------------------------------------
+// The batched-step counter that keys the random streams is normally a kernel argument (host-side state of the handle).
+// A captured graph replays the SAME arguments, so in device-tick mode the kernels read the counter from tick_dev[0]
+// instead, and the last CTA of a launch to finish (tick_dev[1] counts finished CTAs) advances it for the next launch.
+__device__ __forceinline__ uint32_t load_tick(const uint32_t* tick_dev, uint32_t host_tick)
+{
+    return tick_dev ? *reinterpret_cast<const volatile uint32_t*>(tick_dev) : host_tick;
+}
+__device__ __forceinline__ void advance_device_tick(uint32_t* tick_dev, uint32_t by)
+{
+    if (tick_dev == nullptr) return;                // uniform
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(tick_dev + 1, 1u) == gridDim.x * gridDim.y - 1u) {
+            tick_dev[1] = 0u;
+            tick_dev[0] += by;
+            __threadfence();
+        }
+    }
+}
+
 // ---- block-level statistics: per-thread counts -> REDUX -> shared atomics -> one global atomic per slot
 struct BlockStats {
     unsigned int* sh;   // [NIG_STATS_SLOTS] shared counters
@@ -330,6 +354,7 @@ struct StepArgs {
     uint32_t* ep_word;       // [pitch]
     int64_t n, pitch;
     uint32_t env0, tick, epoch;
+    uint32_t* tick_dev;      // non-null: device-resident tick (graph capture), see load_tick()
     RngKey key;
     int32_t max_steps, auto_reset;
     const float* actions;
@@ -384,6 +409,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     __shared__ float coop_buf[CoopSmem<Env>::floats];
     BlockStats bs;
     bs.init(sstat);
+    const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
 
     const int64_t i0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
     unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0, c_con = 0;  // c_con: 4 bits/constraint
@@ -415,7 +441,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < NZA; ++k) nz[k] = nzv[k][e];
                 } else {
-                    Env::NoiseGen::get_single(p.key, env, p.tick, nz);
+                    Env::NoiseGen::get_single(p.key, env, tick0, nz);
                 }
             } else nz[0] = 0.0f;
             acc_t r; uint32_t f, vm;
@@ -437,7 +463,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                         for (int k = 0; k < S; ++k) s[k] = rs[k][e];
                     } else {
                         if constexpr (Env::COOP_RESET || Env::COOP_BLOCKS > 0) need_reset = true;
-                        else Env::reset(p.key, env, p.tick + 1u, p.epoch, s);
+                        else Env::reset(p.key, env, tick0 + 1u, p.epoch, s);
                     }
                     w = 0u; f |= NIG_F_RESET;
                 } else {
@@ -449,8 +475,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 #pragma unroll
                 for (int k = 0; k < S; ++k) s[k] = ns[k];
             }
-            if constexpr (Env::COOP_RESET) coop_reset<Env>(p.key, env, p.tick + 1u, p.epoch, need_reset, s);
-            else if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(p.key, env, p.tick + 1u, p.epoch, need_reset, s, coop_buf);
+            if constexpr (Env::COOP_RESET) coop_reset<Env>(p.key, env, tick0 + 1u, p.epoch, need_reset, s);
+            else if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(p.key, env, tick0 + 1u, p.epoch, need_reset, s, coop_buf);
 #pragma unroll
             for (int k = 0; k < S; ++k) sv[k][e] = s[k];
             wv[e] = __uint_as_float(w);
@@ -489,6 +515,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
         for (int k = 0; k < p.cons.n; ++k) bs.warp_add(NIG_ST_CON0 + k, (c_con >> (4 * k)) & 0xfu);
     }
     bs.flush(p.stats);
+    advance_device_tick(p.tick_dev, 1u);
 }
 
 // ================================================================================================
@@ -517,6 +544,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
     __shared__ alignas(8) uint64_t full[kStepStages];
     BlockStats bs;
     bs.init(sstat);
+    const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < kStepStages; ++k) mbar_init(&full[k], 1);
@@ -586,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             for (int k = 0; k < A; ++k) a[k] = av[k][e];
             const bool valid = i < p.n;
             const bool active = valid && !(w >> 31);
-            if constexpr (NZ > 0) Env::NoiseGen::get_single(p.key, env, p.tick, nz);
+            if constexpr (NZ > 0) Env::NoiseGen::get_single(p.key, env, tick0, nz);
             else nz[0] = 0.0f;
             acc_t r; uint32_t f, vm;
             step_core<Env, CONS>(p.cons, p.max_steps, s, a, nz, 0u, w, ns, r, f, vm);
@@ -600,11 +628,11 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             if (done) {
                 if (p.auto_reset) {
                     if constexpr (Env::COOP_RESET) need_reset = true;
-                    else Env::reset(p.key, env, p.tick + 1u, p.epoch, ns);
+                    else Env::reset(p.key, env, tick0 + 1u, p.epoch, ns);
                     w = 0u; f |= NIG_F_RESET;
                 } else w |= 0x80000000u;
             }
-            if constexpr (Env::COOP_RESET) coop_reset<Env>(p.key, env, p.tick + 1u, p.epoch, need_reset, ns);
+            if constexpr (Env::COOP_RESET) coop_reset<Env>(p.key, env, tick0 + 1u, p.epoch, need_reset, ns);
 #pragma unroll
             for (int k = 0; k < S; ++k) sv[k][e] = ns[k];
             wv[e] = __uint_as_float(w);
@@ -647,6 +675,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             if (k < p.cons.n) bs.warp_add(NIG_ST_CON0 + k, c_con[k]);
     }
     bs.flush(p.stats);
+    advance_device_tick(p.tick_dev, 1u);
 }
 
 // ================================================================================================
@@ -656,6 +685,7 @@ struct ResetArgs {
     float* state; uint32_t* ep_word; double* ep_return;
     int64_t n, pitch;
     uint32_t env0, tick, epoch;
+    uint32_t* tick_dev;
     RngKey key;
     const uint8_t* mask;
     const float* init_states;
@@ -673,7 +703,7 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < Env::S; ++k) s[k] = p.init_aos ? p.init_states[i * Env::S + k] : p.init_states[k * p.pitch + i];
     } else {
-        Env::reset(p.key, p.env0 + (uint32_t)i, p.tick, p.epoch, s);
+        Env::reset(p.key, p.env0 + (uint32_t)i, load_tick(p.tick_dev, p.tick), p.epoch, s);
     }
 #pragma unroll
     for (int k = 0; k < Env::S; ++k) p.state[k * p.pitch + i] = s[k];
@@ -722,6 +752,7 @@ struct RolloutArgs {
     float* state; uint32_t* ep_word; double* ep_return;
     int64_t n, pitch;
     uint32_t env0, tick, epoch;
+    uint32_t* tick_dev;
     RngKey key;
     int32_t max_steps, auto_reset, n_steps;
     const float* actions;      // [K][A][pitch]
@@ -853,6 +884,7 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
     const bool valid = i < p.n;
     const int64_t ic = valid ? i : 0;      // padding lanes shadow env 0 without side effects
     const uint32_t env = p.env0 + (uint32_t)ic;
+    const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
 
     constexpr uint32_t kChunkBytes = kTmaChunk * A * kThreads * sizeof(float);
     int n_chunks = 0;
@@ -909,7 +941,7 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
     }
 
     for (int t = 0; t < p.n_steps; ++t) {
-        const uint32_t tick = p.tick + (uint32_t)t;
+        const uint32_t tick = tick0 + (uint32_t)t;
         float a[A], nz[NZA], ns[S];
         if constexpr (POLICY == NIG_POLICY_ACTIONS) {
             if constexpr (TMA) {
@@ -1057,6 +1089,7 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
     bs.flush(p.stats);
     if (threadIdx.x < 3 && sfl[threadIdx.x] != 0.0)
         atomicAdd(reinterpret_cast<double*>(p.stats) + NIG_ST_F_RETURN_SUM + threadIdx.x, sfl[threadIdx.x]);
+    advance_device_tick(p.tick_dev, (uint32_t)p.n_steps);
 }
 
 // ================================================================================================

@@ -128,6 +128,11 @@ class NativeEnv:
     def set_tick(self, tick: int, epoch: Optional[int] = None):
         N.check(N.lib().nig_set_tick(self._h, int(tick), self.epoch if epoch is None else int(epoch)))
 
+    def use_device_tick(self, enable: bool = True):
+        """Keep the step counter that keys the random streams on the device so that step / rollout launches can be
+        captured in a CUDA graph (torch.cuda.graph) and replayed: every replay advances the counter in-kernel."""
+        N.check(N.lib().nig_use_device_tick(self._h, int(bool(enable))))
+
     def reset_policy_state(self, stream=None):
         """Zero the device-resident PID controller state (= constructing a new PIDControllerAgent)."""
         N.check(N.lib().nig_reset_policy_state(self._h, self._stream(stream)))
