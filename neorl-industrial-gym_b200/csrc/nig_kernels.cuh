@@ -1,16 +1,24 @@
 // nig_kernels.cuh -- the sm_100a kernels of the batched IndustrialEnv step path.
 //
-//  step_kernel     one IndustrialEnv.step (environments/base.py:157-213) for every env: clip, constraints on
-//                  the pre-step state, dynamics, reward, penalties, counters, termination, critical
-//                  shutdown, auto-reset. HBM-bound: SoA fp32 state, VEC consecutive envs per thread so
-//                  every state/action/reward access is one 32*VEC*4-byte coalesced request (128-bit
-//                  LDG/STG at VEC = 4). Algorithmic traffic 122 B / env-step (reactor).
-//  rollout_kernel  K fused steps with the state in registers (the reset/step loops of
-//                  performance_benchmark.py:106-133, utils.py:82-125, chemical_reactor.py:355-405):
-//                  actions from a TMA-staged [K][A][pitch] tensor or generated in-kernel, Philox
-//                  process noise, ballot/popc + shuffle reductions for the violation/return statistics.
-//                  FP32-pipe bound.
-//  reset_kernel    IndustrialEnv.reset (base.py:133-155) for masked envs.
+//  step_core_impl    one env step in registers (environments/base.py:157-213): clip, constraints on the pre-step
+//                    state, dynamics, reward, penalties, counters, termination, critical shutdown. One basic
+//                    block: the divisions are guarded fast paths with ONE deferred guard per step (nig_math.cuh).
+//  step_kernel       one IndustrialEnv.step for every env (+ auto-reset). HBM-bound: SoA fp32 state, VEC consecutive
+//                    envs per thread (64-/128-bit LDG/STG); teacher-forced noise / reset states, AoS layouts,
+//                    observation copies and host-evaluated constraint masks as runtime-uniform branches.
+//                    Algorithmic traffic 122 B / env-step (reactor).
+//  step_pipe_kernel  the plain SoA step of large populations: persistent CTAs, every input row of a 256-env tile
+//                    staged in shared memory by 1-D bulk copies (cp.async.bulk -> UBLKCP) on a 3-stage mbarrier
+//                    ring. 0.93 of the measured HBM copy bandwidth at 16.7M reactor envs.
+//  rollout_kernel    K fused steps with the state in registers (the reset/step loops of
+//                    performance_benchmark.py:106-133, utils.py:82-125, chemical_reactor.py:355-405): actions from a
+//                    TMA-staged [K][A][pitch] tensor (cp.async.bulk.tensor.3d) or from register-prefetched LDGs, or
+//                    generated in-kernel (uniform, get_dataset P-controllers, the benchmark baseline controllers),
+//                    Philox process noise, REDUX / shuffle reductions for the violation / return statistics.
+//                    FP32-issue bound.
+//  dataset_kernel    get_dataset on the device: length-probe pass, scan, write pass (D4RL layout).
+//  reset_kernel      IndustrialEnv.reset (base.py:133-155) for masked envs; coop_reset / coop_reset_blocks are the
+//                    warp-cooperative in-kernel auto-resets.
 #pragma once
 #include <cuda.h>
 #include "../../include/nig_b200.h"
