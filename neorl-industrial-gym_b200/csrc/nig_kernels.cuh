@@ -948,6 +948,7 @@ __global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(con
         }
     }
 
+#pragma unroll 1      // measured: unrolling by 2 (to drop the 12 state moves per step) is 4 % slower
     for (int t = 0; t < p.n_steps; ++t) {
         const uint32_t tick = tick0 + (uint32_t)t;
         float a[A], nz[NZA], ns[S];
