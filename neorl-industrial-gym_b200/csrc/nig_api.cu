@@ -113,6 +113,10 @@ int dev_alloc(T** p, size_t count)
     if (*p) return NIG_OK;
     NIG_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
     NIG_CUDA(cudaMemset(*p, 0, count * sizeof(T)));
+    // cudaMemset runs on the legacy default stream and may return before it has executed; the buffers are used on
+    // non-blocking streams (e->stream, the caller's) that do not synchronise with it -- without this barrier the zero
+    // fill can land AFTER the first cudaMemcpyAsync into a freshly allocated staging buffer (found by tools/soak_parity.py)
+    NIG_CUDA(cudaDeviceSynchronize());
     return NIG_OK;
 }
 
@@ -562,6 +566,7 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
                     NIG_CUDA(cudaMemset(e->r_nz[b], 0, (size_t)K * e->NZ * cap * sizeof(float)));
                 }
             }
+            NIG_CUDA(cudaDeviceSynchronize());      // the zero fills must land before the copies on copy_stream
             e->r_cap = K;
         }
     }

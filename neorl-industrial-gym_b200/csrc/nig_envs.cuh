@@ -376,7 +376,7 @@ struct Robot {
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
             double sn, cs;
-            sincos(q[i], &sn, &cs);
+            spec_sincos_f64(q[i], sn, cs);
             if ((i & 1) == 0) { x = dadd(x, dmul(link(i), cs)); z = dadd(z, dmul(link(i), sn)); }
             else y = dadd(y, dmul(link(i), sn));
         }

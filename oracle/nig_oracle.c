@@ -52,7 +52,7 @@ typedef struct {
     int32_t kind;
     int32_t max_episode_steps;
     int32_t n_cons;
-    int32_t exp_mode;   /* 0 libm expf, 1 spec_expf */
+    int32_t exp_mode;   /* 0 libm expf / sin / cos (what the reference calls), 1 the project's math spec (spec_expf, spec_sincos_f64) */
     int32_t auto_reset;
     int32_t pad;
     uint64_t seed;
@@ -458,17 +458,49 @@ static const double kLink[7] = {0.3, 0.3, 0.25, 0.25, 0.15, 0.1, 0.05};  /* :85 
 static const double kTarget[3] = {0.3, 0.0, 0.4};                        /* :90 */
 #define ORC_PI 3.141592653589793
 
-static void robot_fk(const double* q, double* pos)
+/* sin / cos of a joint angle |x| <= pi in binary64, math spec of this project (exp_mode 1; the CUDA kernels implement the
+ * same operation sequence): k = rint(x * 2/pi), r = x - k * pi/2 in two fma steps, the classic degree-13 / degree-14
+ * minimax kernels on |r| <= pi/4 evaluated with fma in Horner order, quadrant fix-up. < 1 ulp; libm's sin / cos (what numpy
+ * calls upstream, exp_mode 0) are not identical across libm versions, so they cannot be a CPU == GPU contract. */
+static void spec_sincos_f64(double x, double* sn, double* cs)
+{
+    const double kf = rint(x * 0x1.45f306dc9c883p-1);             /* 2/pi */
+    double r = fma(-kf, 0x1.921fb54442d18p+0, x);                /* pi/2 hi */
+    r = fma(-kf, 0x1.1a62633145c07p-54, r);                       /* pi/2 lo */
+    const double z = r * r;
+    double ps = 0x1.5d93a5acfd57cp-33;                            /* S6 */
+    ps = fma(ps, z, -0x1.ae5e68a2b9cebp-26);                      /* S5 */
+    ps = fma(ps, z, 0x1.71de357b1fe7dp-19);                       /* S4 */
+    ps = fma(ps, z, -0x1.a01a019c161d5p-13);                      /* S3 */
+    ps = fma(ps, z, 0x1.111111110f8a6p-7);                        /* S2 */
+    ps = fma(ps, z, -0x1.5555555555549p-3);                       /* S1 */
+    const double s0 = fma(r * z, ps, r);
+    double pc = -0x1.8fae9be8838d4p-37;                           /* C6 */
+    pc = fma(pc, z, 0x1.1ee9ebdb4b1c4p-29);                       /* C5 */
+    pc = fma(pc, z, -0x1.27e4f809c52adp-22);                      /* C4 */
+    pc = fma(pc, z, 0x1.a01a019cb1590p-16);                       /* C3 */
+    pc = fma(pc, z, -0x1.6c16c16c15177p-10);                      /* C2 */
+    pc = fma(pc, z, 0x1.555555555554cp-5);                        /* C1 */
+    const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int k = (int)kf & 3;                                    /* two's complement: -1 -> 3, -2 -> 2 */
+    const double ss = (k & 1) ? c0 : s0, cc = (k & 1) ? s0 : c0;
+    *sn = (k & 2) ? -ss : ss;
+    *cs = ((k + 1) & 2) ? -cc : cc;
+}
+
+static void robot_fk(const double* q, double* pos, int spec)
 {   /* :94-111 */
     double x = 0.0, y = 0.0, z = 0.0;
     for (int i = 0; i < 7; ++i) {
-        if ((i & 1) == 0) { x += kLink[i] * cos(q[i]); z += kLink[i] * sin(q[i]); }
-        else y += kLink[i] * sin(q[i]);
+        double sn, cs;
+        if (spec) spec_sincos_f64(q[i], &sn, &cs); else { sn = sin(q[i]); cs = cos(q[i]); }
+        if ((i & 1) == 0) { x += kLink[i] * cs; z += kLink[i] * sn; }
+        else y += kLink[i] * sn;
     }
     pos[0] = x; pos[1] = y; pos[2] = z;
 }
 
-static void robot_dynamics(const float* s, const float* a, float* o)
+static void robot_dynamics(const float* s, const float* a, float* o, int spec)
 {   /* :139-188 */
     double q[7], pos[3];
     for (int i = 0; i < 7; ++i) {
@@ -478,7 +510,7 @@ static void robot_dynamics(const float* s, const float* a, float* o)
         qd = qd > ORC_PI ? ORC_PI : qd;
         q[i] = qd;
     }
-    robot_fk(q, pos);
+    robot_fk(q, pos, spec);
     double vel[3];
     for (int i = 0; i < 3; ++i) vel[i] = (pos[i] - (double)s[i]) / 0.1;   /* :160 */
     const double dx = pos[0] - kTarget[0], dy = pos[1] - kTarget[1], dz = pos[2] - kTarget[2];
@@ -550,7 +582,7 @@ static void robot_reset(const orc_cfg_t* cfg, uint32_t env, uint32_t tick, uint3
     double q[7], pos[3];
     for (uint32_t j = 0; j < 2; ++j) words4(cfg, env, tick, STREAM_RESET, (epoch << 8) | j, w[j]);
     for (int i = 0; i < 7; ++i) q[i] = (double)(0x1.921fb6p+0f * u_sym(w[i >> 2][i & 3]));
-    robot_fk(q, pos);
+    robot_fk(q, pos, cfg->exp_mode);
     for (int i = 0; i < 24; ++i) s[i] = 0.0f;
     s[0] = (float)pos[0]; s[1] = (float)pos[1]; s[2] = (float)pos[2];
     s[6] = 1.0f;
@@ -612,7 +644,7 @@ static void step_one(const orc_cfg_t* cfg, float* state, int32_t* ep_step, int32
             if ((vm >> k) & 1u) reward32 = reward32 + cfg->cons[k].penalty;
     } else {
         if (cfg->kind == ORC_GRID) { grid_dynamics(state, a, noise, next_state); reward64 = grid_reward(next_state, a); }
-        else { robot_dynamics(state, a, next_state); reward64 = robot_reward(next_state, a); }
+        else { robot_dynamics(state, a, next_state, cfg->exp_mode); reward64 = robot_reward(next_state, a); }
         for (int k = 0; k < cfg->n_cons; ++k)
             if ((vm >> k) & 1u) reward64 = reward64 + (double)cfg->cons[k].penalty;
     }
@@ -863,7 +895,7 @@ ORC_API void orc_dynamics(int kind, int exp_mode, int64_t n, const float* s, con
     for (int64_t i = 0; i < n; ++i) {
         if (kind == ORC_REACTOR) reactor_dynamics(s + i * S, a + i * A, nz + i * NZ, o + i * S, exp_mode);
         else if (kind == ORC_GRID) grid_dynamics(s + i * S, a + i * A, nz + i * NZ, o + i * S);
-        else robot_dynamics(s + i * S, a + i * A, o + i * S);
+        else robot_dynamics(s + i * S, a + i * A, o + i * S, exp_mode);
     }
 }
 ORC_API void orc_reward(int kind, int64_t n, const float* ns, const float* a, double* r)
@@ -889,3 +921,6 @@ ORC_API int orc_max_threads(void)
     return 1;
 #endif
 }
+
+/* test hook: the binary64 sin / cos of the math spec */
+ORC_API void orc_spec_sincos_f64(double x, double* sn, double* cs) { spec_sincos_f64(x, sn, cs); }

@@ -85,6 +85,28 @@ def test_trace_replay(golden_dir, name):
             assert_bits_equal(ns[0], g["next_state"][t], f"next_state at step {t}")
 
 
+def test_robot_spec_trig_vs_reference(golden_dir):
+    """RobotAssembly with the project's specified binary64 sin / cos (exp_mode 1 = what the CUDA kernels compute) against
+    the reference's outputs (numpy -> libm): flags / masks identical; positions, joints, forces and scores bit-identical
+    (the two sin / cos differ by <= 2 ulp of fp64, which does not survive the rounding to fp32); end-effector
+    velocities within 1e-12 absolute (a cancelling difference of positions); reward <= 1e-6 relative."""
+    g = _load(golden_dir, "robot_forced.npz")
+    m = len(g["reward"])
+    env = O.OracleEnv(O.ROBOT, m, auto_reset=False, exp_mode=1)
+    env.state[:] = g["state"]
+    env.ep_step[:] = g["ep_step"]
+    ns, r, fl, vm = env.step(g["action"])
+    assert np.array_equal((fl & 1) != 0, g["terminated"]) and np.array_equal((fl & 2) != 0, g["truncated"])
+    assert_bits_equal(vm, g["viol_mask"], "violation mask")
+    vel = [14, 15, 16]                       # (pos' - pos) / dt: a cancelling difference, tiny magnitudes amplify fp64 ulps
+    rest = [k for k in range(24) if k not in vel]
+    assert_bits_equal(ns[:, rest], g["next_state"][:, rest], "positions / joints / forces / scores")
+    dv = np.abs(ns[:, vel].astype(np.float64) - g["next_state"][:, vel].astype(np.float64))
+    assert np.all(dv <= 1e-12 + 1e-6 * np.abs(g["next_state"][:, vel])), dv.max()
+    ref_r = g["reward"].astype(np.float64)
+    assert np.all(np.abs(r.astype(np.float64) - ref_r) <= 1e-6 * np.abs(ref_r) + 1e-6)
+
+
 def test_reactor_freerun_drift(golden_dir):
     """Free-running 500-step episodes (same actions / noise / initial state as the reference run): flags and
     episode lengths identical; state drift <= 1e-3 relative (measured 2e-6 .. 7.5e-5)."""
