@@ -234,6 +234,7 @@ void set_cons(nig_env* e, const nig_constraint_t* c, int n)
     if (e->cons_masks) {       // allocated in nig_create before the first set_cons
         cudaDeviceSynchronize();
         cudaMemcpy(e->cons_masks, host_masks, sizeof host_masks, cudaMemcpyHostToDevice);
+        cudaDeviceSynchronize();   // a pageable H2D cudaMemcpy may return before the DMA lands; kernels run on non-blocking streams
     }
     e->cons.is_default = cons_mode(e->kind, c, n);
 }
@@ -820,6 +821,7 @@ int nig_set_tick(nig_env_t* e, uint32_t tick, uint32_t epoch)
         DeviceGuard guard(e->cfg.device);
         NIG_CUDA(cudaDeviceSynchronize());
         NIG_CUDA(cudaMemcpy(e->tick_dev, &tick, sizeof(uint32_t), cudaMemcpyHostToDevice));
+        NIG_CUDA(cudaDeviceSynchronize());
     }
     return NIG_OK;
 }
@@ -832,6 +834,7 @@ int nig_use_device_tick(nig_env_t* e, int32_t enable)
         NIG_CUDA(cudaMalloc((void**)&e->tick_dev, 2 * sizeof(uint32_t)));
         const uint32_t init[2] = {e->tick, 0u};
         NIG_CUDA(cudaMemcpy(e->tick_dev, init, sizeof init, cudaMemcpyHostToDevice));
+        NIG_CUDA(cudaDeviceSynchronize());
     } else if (!enable && e->tick_dev) {
         NIG_CUDA(cudaMemcpy(&e->tick, e->tick_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         cudaFree(e->tick_dev);
