@@ -541,3 +541,40 @@ def test_step_pipelined_kernel_bitexact_vs_oracle(mods, name, monkeypatch):
         finals.append(state.copy())
         env.close()
     assert_bits_equal(finals[0], finals[1], "pipelined vs one-tile-per-CTA kernel")
+
+
+def test_powergrid_full_size_sharded_property(mods):
+    """BASELINE config #3 at full size: PowerGrid-v0, 1,048,576 envs with auto-reset, as one shard and as 8 shards
+    keyed by global env id: identical states and counter sums; and two 4,096-env windows of the big run (the first and
+    one in the middle of shard 5) equal to the oracle simulating exactly those global ids."""
+    ni, N, O, torch = mods
+    n, K, shards = 1 << 20, 64, 8
+    whole = _native_env(ni, 1, n, seed=314)
+    whole.reset_host(want_obs=False)
+    whole.rollout_device(K, N.POLICY_UNIFORM)
+    whole.rollout_device(K // 2, N.POLICY_UNIFORM)
+    torch.cuda.synchronize()
+    ref_state, ref_step, ref_viol, _ = whole.get_state_host()
+    ref_stats = whole.read_stats()[0].copy()
+    whole.close()
+    assert ref_stats[N.ST_STEPS] == n * (K + K // 2) and ref_stats[N.ST_EPISODES] > n      # short episodes: everyone reset
+    per = n // shards
+    stats = np.zeros(24, np.int64)
+    for r in range(shards):
+        e = _native_env(ni, 1, per, seed=314, env_id_offset=r * per)
+        e.reset_host(want_obs=False)
+        e.rollout_device(K, N.POLICY_UNIFORM)
+        e.rollout_device(K // 2, N.POLICY_UNIFORM)
+        torch.cuda.synchronize()
+        st, es, ev, _ = e.get_state_host()
+        assert_bits_equal(st, ref_state[r * per:(r + 1) * per], f"shard {r} state")
+        assert np.array_equal(es, ref_step[r * per:(r + 1) * per]) and np.array_equal(ev, ref_viol[r * per:(r + 1) * per])
+        stats += e.read_stats()[0]
+        e.close()
+    assert stats.tolist() == ref_stats.tolist()          # integer counters: what the NCCL sum all-reduce returns
+    for off in (0, 5 * per + 77_777):
+        orc = O.OracleEnv(1, 4096, seed=314, env_id0=off, exp_mode=1, threads=8)
+        orc.reset()
+        O.rollout(orc, K + K // 2, O.POLICY_UNIFORM)
+        assert_bits_equal(ref_state[off:off + 4096], orc.state, f"window at global id {off}")
+        assert np.array_equal(ref_step[off:off + 4096], orc.ep_step)
