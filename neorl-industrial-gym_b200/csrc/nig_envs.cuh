@@ -73,6 +73,10 @@ struct Reactor {
     static constexpr bool COOP_RESET = true;
     static constexpr int COOP_BLOCKS = 0;
     static constexpr int RESET_NORMALS = 8;
+    // resident CTAs per SM the fused rollout is compiled for (register cap): measured, more resident warps LOSE for
+    // the reactor (7.0 -> 6.8 -> 6.3e10 env-steps/s at 1M envs for 4 / 6 / 8 CTAs)
+    static constexpr int ROLLOUT_MIN_CTAS = 1;
+    static constexpr int STEP_MIN_CTAS = 1;
     __device__ static __forceinline__ void reset_from_normals(const float (&z)[8], float (&s)[S])
     {
         s[0] = add(320.0f, mul(2.0f, z[0]));
@@ -235,6 +239,10 @@ struct Grid {
     // _get_initial_state (:90-110): 8 Philox blocks of the RESET stream -- blocks 0,1 voltages ~ N(1, .01), 2,3
     // generation ~ N(base_load, 2), 4,5 loads = base_load * U(.8, 1.2), 6,7 line flows ~ N(0, 10). One block (4 raw
     // values) is the unit of work of the warp-cooperative reset.
+    // 206 registers uncapped = 2 resident CTAs per SM; capped at 168 (3 CTAs, 24 B of spills): +15 % at 1M envs, 4 CTAs (128
+    // registers) no better
+    static constexpr int ROLLOUT_MIN_CTAS = 3;
+    static constexpr int STEP_MIN_CTAS = 4;          // single step: 146 -> 128 registers, 3 -> 4 CTAs per SM, +11 % (5, 6: worse)
     static constexpr int COOP_BLOCKS = 8;
     __device__ static __forceinline__ void reset_block(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t j, float (&v)[4])
     {
@@ -356,6 +364,8 @@ struct Robot {
     static constexpr bool FAST_DIV = false;          // fp64 divisions only
     static constexpr bool COOP_RESET = false;
     static constexpr int COOP_BLOCKS = 0;
+    static constexpr int ROLLOUT_MIN_CTAS = 4;       // 177 -> 128 registers: 1.76 -> 2.05e10 env-steps/s at 1M envs
+    static constexpr int STEP_MIN_CTAS = 6;          // 104 -> 80 registers: 0.39 -> 0.47 of the HBM peak at 4M envs
     static constexpr uint32_t CRIT_MASK = 0x3;       // force_limits, collision_avoidance (:56-68)
     using acc_t = double;
     __device__ static constexpr float penalty(int k) { return k == 0 ? -100.0f : (k == 1 ? -200.0f : -50.0f); }

@@ -409,7 +409,7 @@ __device__ __forceinline__ void store_rows(float* base, int64_t pitch, int64_t n
 }
 
 template <class Env, int VEC, int CONS>
-__global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ StepArgs p)
+__global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) step_kernel(const __grid_constant__ StepArgs p)
 {
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
     using acc_t = typename Env::acc_t;
@@ -869,11 +869,8 @@ template <class T> __device__ __forceinline__ T warp_sum(T v)
 // prefetches the next step's actions / noise into registers one step ahead, so the L2 latency of the loads is
 // hidden behind a whole step of arithmetic. Block size is a launch parameter (blockDim.x <= kThreads; TMA launches
 // use kThreads).
-#ifndef NIG_ROLLOUT_MINB
-#define NIG_ROLLOUT_MINB 1
-#endif
 template <class Env, int CONS, int POLICY, bool TMA, bool TFNOISE>
-__global__ void __launch_bounds__(kThreads, NIG_ROLLOUT_MINB) rollout_kernel(const __grid_constant__ RolloutArgs p, const __grid_constant__ CUtensorMap amap)
+__global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kernel(const __grid_constant__ RolloutArgs p, const __grid_constant__ CUtensorMap amap)
 {
     static_assert(!TFNOISE || POLICY == NIG_POLICY_ACTIONS, "teacher-forced noise comes with teacher-forced actions");
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
