@@ -290,6 +290,7 @@ def run_gpu(args):
         # ---- e2e through the Python drop-in API with host buffers
         if "e2e" in args.sections:
             extra["e2e_step_api"] = e2e_step_api(ni, n, local, args)
+            extra["torch_step_api"] = torch_api(torch, ni, n, local, args)
         if "cpu" in args.sections:
             extra["cpu_baseline"] = cpu_baseline()
     if dist is not None:
@@ -509,6 +510,46 @@ def e2e_rollout(ni, n, local, rank, world, steps, warmup, seed, dist=None, torch
             "api": "ni.make('ChemicalReactor-v0', num_envs=65536).rollout(1000, 'random', steps_per_launch=64, init_states=host[65536,12]) "
                    "-> host reward_sum / violations / episodes / obs / stats (C ABI: nig_rollout_host)",
             "reward_checksum_rank0": checksum}
+
+
+def torch_api(torch, ni, n, local, args):
+    """Secondary: the device-tensor gym API (TorchIndustrialEnv.step, zero host copies), eager and as a replayed CUDA
+    graph of 50 x (torch policy -> step)."""
+    env = ni.TorchIndustrialEnv("ChemicalReactor-v0", n, device=f"cuda:{local}", seed=args.seed)
+    obs, _ = env.reset()
+    w = torch.zeros((12, 3), device=env.device)
+    w[0, 0] = -0.004
+
+    def policy(o):
+        return torch.clamp((o - 320.0) @ w, -1.0, 1.0)
+
+    for _ in range(20):
+        env.step(policy(obs))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 500
+    e0.record()
+    for _ in range(reps):
+        obs, r, term, trunc, info = env.step(policy(obs))
+    e1.record()
+    torch.cuda.synchronize()
+    eager = n * reps / (e0.elapsed_time(e1) * 1e-3)
+    out = {"eager": {"value": eager, "unit": UNIT, "us_per_step": e0.elapsed_time(e1) * 1e3 / reps}}
+    try:
+        replay = env.capture_graph(policy, 50)
+        replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            replay()
+        e1.record()
+        torch.cuda.synchronize()
+        out["cuda_graph"] = {"value": n * 500 / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT, "us_per_step": e0.elapsed_time(e1) * 1e3 / 500}
+    except Exception as ex:
+        out["cuda_graph"] = {"error": repr(ex)}
+    out["api"] = "ni.TorchIndustrialEnv('ChemicalReactor-v0', 65536).step(policy(obs)) with a linear torch policy; device tensors in and out"
+    env.close()
+    return out
 
 
 def e2e_step_api(ni, n, local, args):

@@ -36,7 +36,7 @@ extern "C" {
 #define NIG_API
 #endif
 
-#define NIG_ABI_VERSION 2
+#define NIG_ABI_VERSION 3
 #define NIG_MAX_CONSTRAINTS 8
 #define NIG_MAX_STATE_DIM 32
 #define NIG_MAX_ACTION_DIM 8
@@ -128,6 +128,8 @@ typedef struct nig_step_io {
     uint8_t* viol_mask;         /* out: [n] bit k = constraint k violated on the pre-step state */
     int32_t action_layout;      /* NIG_LAYOUT_* of actions */
     int32_t aux_layout;         /* NIG_LAYOUT_* of noise / reset_states / obs / next_obs */
+    uint8_t* terminated;        /* out: [n] 0/1, the gym `terminated` of base.py:190/196 unpacked from flags; NULL ok */
+    uint8_t* truncated;         /* out: [n] 0/1, the gym `truncated` of base.py:191; NULL ok */
 } nig_step_io_t;
 
 /* fused K-step rollout policies */

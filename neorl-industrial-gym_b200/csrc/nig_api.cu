@@ -163,7 +163,7 @@ int launch_step(nig_env* e, const StepArgs& a, cudaStream_t st)
     e->launches++;
     note_device_work(e, st);
     // plain SoA step (no teacher forcing, no observation copies, no host-evaluated constraints): persistent TMA pipeline
-    const bool plain = !a.action_aos && !a.noise && !a.reset_states && !a.hostmask && !a.obs && !a.next_obs &&
+    const bool plain = !a.action_aos && !a.noise && !a.reset_states && !a.hostmask && !a.obs && !a.next_obs && !a.terminated && !a.truncated &&
                        ((uintptr_t)a.actions & 15u) == 0 && e->step_pipe != 0 && e->step_vec == 0;
     if (plain) {
         bool used = false;
@@ -428,6 +428,7 @@ int nig_step(nig_env_t* e, const nig_step_io_t* io, void* stream)
     a.max_steps = e->max_steps; a.auto_reset = e->cfg.auto_reset;
     a.actions = io->actions; a.noise = io->noise; a.reset_states = io->reset_states; a.hostmask = io->hostmask;
     a.obs = io->obs; a.next_obs = io->next_obs; a.reward = io->reward; a.flags = io->flags; a.viol_mask = io->viol_mask;
+    a.terminated = io->terminated; a.truncated = io->truncated;
     a.action_aos = io->action_layout == NIG_LAYOUT_AOS; a.aux_aos = io->aux_layout == NIG_LAYOUT_AOS;
     a.stats = e->stats; a.cons = e->cons;
     const int rc = launch_step(e, a, (cudaStream_t)stream);

@@ -374,6 +374,8 @@ struct StepArgs {
     float* reward;
     uint8_t* flags;
     uint8_t* viol_mask;
+    uint8_t* terminated;     // optional 0/1 arrays (torch bool views): unpacked flags
+    uint8_t* truncated;
     int32_t action_aos, aux_aos;
     unsigned long long* stats;
     ConsParams cons;
@@ -511,6 +513,15 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             if constexpr (VEC == 4) *reinterpret_cast<uchar4*>(p.viol_mask + i0) = make_uchar4(vmk[0], vmk[1], vmk[2], vmk[3]);
             else if constexpr (VEC == 2) *reinterpret_cast<uchar2*>(p.viol_mask + i0) = make_uchar2(vmk[0], vmk[1]);
             else p.viol_mask[i0] = (uint8_t)vmk[0];
+        }
+        if (p.terminated || p.truncated) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                if (i0 + e < p.pitch) {
+                    if (p.terminated) p.terminated[i0 + e] = (uint8_t)((fl[e] & NIG_F_TERMINATED) ? 1 : 0);
+                    if (p.truncated) p.truncated[i0 + e] = (uint8_t)((fl[e] & NIG_F_TRUNCATED) ? 1 : 0);
+                }
+            }
         }
     }
     bs.warp_add(NIG_ST_STEPS, c_steps);

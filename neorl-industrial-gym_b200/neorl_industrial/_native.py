@@ -16,7 +16,7 @@ _ROOT = os.path.dirname(_PKG_DIR)                       # neorl-industrial-gym_b
 LIB_PATH = os.path.join(_ROOT, "libnig_b200.so")
 CSRC_DIR = os.path.join(_ROOT, "csrc")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_CONSTRAINTS = 8
 STATS_SLOTS = 32
 
@@ -58,7 +58,8 @@ class StepIO(C.Structure):
     _fields_ = [("actions", C.c_void_p), ("noise", C.c_void_p), ("reset_states", C.c_void_p),
                 ("hostmask", C.c_void_p), ("obs", C.c_void_p), ("next_obs", C.c_void_p),
                 ("reward", C.c_void_p), ("flags", C.c_void_p), ("viol_mask", C.c_void_p),
-                ("action_layout", C.c_int32), ("aux_layout", C.c_int32)]
+                ("action_layout", C.c_int32), ("aux_layout", C.c_int32),
+                ("terminated", C.c_void_p), ("truncated", C.c_void_p)]
 
 
 class Baseline(C.Structure):

@@ -300,13 +300,14 @@ class NativeEnv:
 
     def step_device(self, actions, *, noise=None, reset_states=None, hostmask=None, obs=None, next_obs=None,
                     reward=None, flags=None, viol_mask=None, action_layout=N.LAYOUT_SOA, aux_layout=N.LAYOUT_SOA,
-                    stream=None):
+                    terminated=None, truncated=None, stream=None):
         io = N.StepIO()
         io.actions, io.noise, io.reset_states = N.ptr_of(actions), N.ptr_of(noise), N.ptr_of(reset_states)
         io.hostmask = N.ptr_of(hostmask)
         io.obs, io.next_obs, io.reward = N.ptr_of(obs), N.ptr_of(next_obs), N.ptr_of(reward)
         io.flags, io.viol_mask = N.ptr_of(flags), N.ptr_of(viol_mask)
         io.action_layout, io.aux_layout = action_layout, aux_layout
+        io.terminated, io.truncated = N.ptr_of(terminated), N.ptr_of(truncated)
         N.check(N.lib().nig_step(self._h, C.byref(io), self._stream(stream)))
 
     def rollout_device(self, n_steps: int, policy: int = N.POLICY_UNIFORM, *, actions=None, noise=None, params=None,
