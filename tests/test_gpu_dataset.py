@@ -203,3 +203,16 @@ def test_dataset_n_transitions_target():
     assert ds["terminals"].dtype == bool and ds["timeouts"].dtype == bool and not ds["timeouts"].any()
     assert np.abs(ds["actions"]).max() <= 1.0
     env.close()
+
+
+def test_reference_timing_harness_keys():
+    """neorl_industrial.benchmarks.performance reproduces the env-path sections of performance_benchmark.py."""
+    from neorl_industrial.benchmarks import performance as P
+    c = P.benchmark_environment_creation(3)
+    assert set(c) == {"avg_creation_time", "memory_per_env", "total_time"} and c["avg_creation_time"] > 0
+    d = P.benchmark_dataset_loading("medium")
+    assert set(d) == {"dataset_size", "load_time", "samples_per_sec"} and d["dataset_size"] > 10_000
+    s1 = P.benchmark_environment_steps(200)
+    assert set(s1) == {"total_time", "steps_per_sec"} and s1["steps_per_sec"] > 0
+    sb = P.benchmark_environment_steps(128, num_envs=4096)
+    assert sb["steps_per_sec"] > s1["steps_per_sec"] and sb["num_envs"] == 4096
