@@ -84,6 +84,7 @@ class NativeEnv:
         self.env_id_offset = int(env_id_offset)
         self.n_constraints = 3 if constraints is None else len(constraints)
         self._pinned = {}
+        self._pinned_by_name = {}
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -99,10 +100,17 @@ class NativeEnv:
 
     # ------------------------------------------------------------------ helpers
     def pinned(self, name: str, shape, dtype) -> np.ndarray:
-        key = (name, tuple(np.atleast_1d(shape)), np.dtype(dtype).str)
+        """Page-locked host array owned by this env, one per (name, shape, dtype); the lookup by name alone is the fast
+        path of the single-env gym API (a few microseconds matter there)."""
+        hit = self._pinned_by_name.get(name)
+        if hit is not None and hit[1] == shape and hit[2] is dtype:
+            return hit[0]
+        key = (name, tuple(int(x) for x in np.atleast_1d(shape)), np.dtype(dtype).str)
         if key not in self._pinned:
             self._pinned[key] = N.PinnedArray(shape, dtype)
-        return self._pinned[key].array
+        arr = self._pinned[key].array
+        self._pinned_by_name[name] = (arr, shape, dtype)
+        return arr
 
     def set_constraints(self, constraints):
         arr = (N.Constraint * max(len(constraints), 1))(*constraints)
