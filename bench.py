@@ -251,7 +251,7 @@ def run_gpu(args):
     extra = {}
     e2e = None
     if "e2e" in args.sections:
-        e2e = e2e_rollout(ni, n, local, rank, world, max(3, min(args.steps, 20)), args.warmup, args.seed, dist, torch)
+        e2e = e2e_rollout(ni, n, local, rank, world, max(3, min(args.steps, 100)), args.warmup, args.seed, dist, torch)
     others = other_configs(torch, ni, N, local, rank, world, dist, args.seed) if "configs" in args.sections else None
     if rank == 0:
         if e2e is not None:
@@ -578,7 +578,7 @@ def e2e_step_api(ni, n, local, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seed", type=int, default=0)
