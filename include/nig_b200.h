@@ -329,6 +329,9 @@ NIG_API int nig_fp32_probe(int device, int32_t iters, double* ops, void* stream)
  * operand sets (all-exponent pairs, physics-regime pairs, every constant divisor); *mismatches must come back 0 */
 NIG_API int nig_selftest_division(int device, int64_t n, uint64_t seed, int64_t* mismatches, int64_t* accepted);
 
+/* self-test of the branch-free Box-Muller square root: every float of [2^-24, 2^6] and -0 against IEEE sqrt */
+NIG_API int nig_selftest_sqrt(int device, int64_t* mismatches, int64_t* checked);
+
 #ifdef __cplusplus
 }
 #endif

@@ -957,6 +957,24 @@ int nig_selftest_division(int device, int64_t n, uint64_t seed, int64_t* mismatc
     return NIG_OK;
 }
 
+int nig_selftest_sqrt(int device, int64_t* mismatches, int64_t* checked)
+{
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    if (!mismatches) return fail(NIG_ERR_INVALID, "nig_selftest_sqrt: null mismatches");
+    unsigned long long* d = nullptr;
+    NIG_CUDA(cudaMalloc((void**)&d, 2 * sizeof(unsigned long long)));
+    NIG_CUDA(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+    cudaError_t ce = nig::launch_selftest_sqrt(d, nullptr);
+    unsigned long long h[2] = {0, 0};
+    if (ce == cudaSuccess) ce = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    NIG_CUDA(ce);
+    *mismatches = (int64_t)h[0];
+    if (checked) *checked = (int64_t)h[1];
+    return NIG_OK;
+}
+
 int nig_fp32_probe(int device, int32_t iters, double* ops, void* stream)
 {
     DeviceGuard guard(device);

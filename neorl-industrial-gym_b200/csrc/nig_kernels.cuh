@@ -1287,6 +1287,25 @@ static __global__ void __launch_bounds__(256) selftest_division_kernel(RngKey ke
     atomicAdd(&out[1], acc);
 }
 
+// every float of [2^-24, 2^6] (and -0): bm_sqrt == __fsqrt_rn
+static __global__ void __launch_bounds__(256) selftest_sqrt_kernel(unsigned long long* out)
+{
+    const uint32_t lo = 0x33800000u, hi = 0x42800000u;       // 2^-24 .. 2^6 inclusive
+    unsigned long long bad = 0, cnt = 0;
+    for (uint64_t b = (uint64_t)lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= hi; b += (uint64_t)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((uint32_t)b);
+        bad += __float_as_uint(bm_sqrt(x)) != __float_as_uint(__fsqrt_rn(x));
+        cnt++;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const float z = __uint_as_float(0x80000000u);
+        bad += __float_as_uint(bm_sqrt(z)) != __float_as_uint(__fsqrt_rn(z));
+        cnt++;
+    }
+    atomicAdd(&out[0], bad);
+    atomicAdd(&out[1], cnt);
+}
+
 // ---- measured-peak probe: independent unfused FADD/FMUL chains (what the physics is made of) ------
 static __global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters)
 {

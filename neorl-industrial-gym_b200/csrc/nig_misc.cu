@@ -21,6 +21,11 @@ cudaError_t launch_fp32_probe(float* sink, int iters, int blocks, cudaStream_t s
     fp32_probe_kernel<<<blocks, 256, 0, st>>>(sink, iters);
     return cudaGetLastError();
 }
+cudaError_t launch_selftest_sqrt(unsigned long long* out, cudaStream_t st)
+{
+    selftest_sqrt_kernel<<<148 * 8, 256, 0, st>>>(out);
+    return cudaGetLastError();
+}
 cudaError_t launch_selftest_division(RngKey key, int iters, int blocks, unsigned long long* out, cudaStream_t st)
 {
     selftest_division_kernel<<<blocks, 256, 0, st>>>(key, iters, out);
