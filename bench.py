@@ -277,8 +277,8 @@ def run_gpu(args):
             "kernel": "rollout_kernel<Reactor, default constraints, POLICY_UNIFORM> (K=64 fused steps)",
             "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
             "traffic": ncu_traffic("rollout_kernel<Reactor"),
-            "ncu": "profiles/r01_d_rollout_kernel_ncu_table.txt: 392 issued warp-instructions per 32 env-steps (128 algorithmic), issue slots "
-                   "70 % busy while active, FMA pipe 38 %, ALU pipe 55 %, 3.5 warps per SM sub-partition (65,536 envs = 0.69 waves)",
+            "ncu": "profiles/r01_e_rollout_kernel_ncu_table.txt: 383 issued warp-instructions per 32 env-steps (128 algorithmic), issue slots "
+                   "71 % busy while active, FMA pipe 38 %, ALU pipe 57 %, 3.5 warps per SM sub-partition (65,536 envs = 0.69 waves)",
             "frac_with_rng_ops": (ALG_OPS_PER_STEP + 2 * 52) / ALG_OPS_PER_STEP * achieved / fp32_peak,
             "note": f"algorithmic {ALG_OPS_PER_STEP} fp32 ops/env-step (SURVEY 8d; RNG, IEEE-division expansion and addressing "
                     "excluded) x env-steps per launch / mean launch time (frac_with_rng_ops adds the survey's 2 Gaussians x ~52 ops per step); peak = unfused FADD/FMUL issue rate measured live by "
