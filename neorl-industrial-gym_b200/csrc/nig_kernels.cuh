@@ -177,7 +177,7 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
 
 // one step with the fast divisions and the deferred guard: the common path is a single basic block.
 // Episode step / violation counters unpacked (the fused rollout keeps them in separate registers across K steps).
-template <class Env, int CONS, bool CLIP = true>
+template <class Env, int CONS, bool CLIP = true, bool WARP_REDO = false>
 __device__ __forceinline__ void step_core_unpacked(const ConsParams& cp, int max_steps,
                                                    const float (&s)[Env::S], const float (&a_raw)[Env::A],
                                                    const float (&nz)[Env::NZ > 0 ? Env::NZ : 1], uint32_t hostmask,
@@ -188,7 +188,10 @@ __device__ __forceinline__ void step_core_unpacked(const ConsParams& cp, int max
         DivFast df;
         step_core_impl<Env, CONS, DivFast, CLIP>(cp, max_steps, s, a_raw, nz, hostmask, ep_step_in, ep_viol_in, ep_step, ep_viol,
                                                  ns, reward, flags, vmask, df);
-        if (__builtin_expect(df.ok(), 1)) return;
+        // WARP_REDO (convergent call sites only): the redo decision is a warp vote, i.e. a uniform branch without a
+        // divergence barrier; lanes whose guard held recompute the same IEEE-exact values
+        if constexpr (WARP_REDO) { if (__builtin_expect(!__any_sync(0xffffffffu, !df.ok()), 1)) return; }
+        else { if (__builtin_expect(df.ok(), 1)) return; }
     }
     DivExact de;
     step_core_impl<Env, CONS, DivExact, CLIP>(cp, max_steps, s, a_raw, nz, hostmask, ep_step_in, ep_viol_in, ep_step, ep_viol,
@@ -1052,7 +1055,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
         uint32_t st2, vi2, f, vm;
         acc_t r;
         bool need_reset = false;
-        step_core_unpacked<Env, CONS, POLICY != NIG_POLICY_UNIFORM>(p.cons, p.max_steps, s, a, nz, 0u, ep_st, ep_vi, st2, vi2, ns, r, f, vm);
+        step_core_unpacked<Env, CONS, POLICY != NIG_POLICY_UNIFORM, true>(p.cons, p.max_steps, s, a, nz, 0u, ep_st, ep_vi, st2, vi2, ns, r, f, vm);
         if (active) {
             const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
             rsum = add(rsum, (float)r);
