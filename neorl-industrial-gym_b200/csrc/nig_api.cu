@@ -218,7 +218,7 @@ int validate_constraints(int kind, const nig_constraint_t* c, int n)
     return NIG_OK;
 }
 
-void set_cons(nig_env* e, const nig_constraint_t* c, int n)
+int set_cons(nig_env* e, const nig_constraint_t* c, int n)
 {
     memset(&e->cons, 0, sizeof e->cons);
     e->cons.n = n;
@@ -233,11 +233,12 @@ void set_cons(nig_env* e, const nig_constraint_t* c, int n)
     }
     e->cons.masks = e->cons_masks;
     if (e->cons_masks) {       // allocated in nig_create before the first set_cons
-        cudaDeviceSynchronize();
-        cudaMemcpy(e->cons_masks, host_masks, sizeof host_masks, cudaMemcpyHostToDevice);
-        cudaDeviceSynchronize();   // a pageable H2D cudaMemcpy may return before the DMA lands; kernels run on non-blocking streams
+        NIG_CUDA(cudaDeviceSynchronize());
+        NIG_CUDA(cudaMemcpy(e->cons_masks, host_masks, sizeof host_masks, cudaMemcpyHostToDevice));
+        NIG_CUDA(cudaDeviceSynchronize());   // a pageable H2D cudaMemcpy may return before the DMA lands; kernels run on non-blocking streams
     }
     e->cons.is_default = cons_mode(e->kind, c, n);
+    return NIG_OK;
 }
 
 #define NIG_CHECK_ENV(e)                                                        \
@@ -331,7 +332,9 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     int rc = validate_constraints(e->kind, c, nc);
     if (rc == NIG_OK) rc = dev_alloc(&e->cons_masks, (size_t)NIG_MAX_CONSTRAINTS * kConsMaskRow);
     if (rc == NIG_OK) {
-        set_cons(e, c, nc);
+        rc = set_cons(e, c, nc);
+    }
+    if (rc == NIG_OK) {
         rc = dev_alloc(&e->state, (size_t)e->S * e->pitch);
     }
     if (rc == NIG_OK) rc = dev_alloc(&e->ep_word, (size_t)e->pitch);
@@ -376,8 +379,7 @@ int nig_set_constraints(nig_env_t* e, const nig_constraint_t* cons, int32_t n)
     if (rc != NIG_OK) return rc;
     DeviceGuard guard(e->cfg.device);
     if (!guard.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", e->cfg.device);
-    set_cons(e, cons, n);
-    return NIG_OK;
+    return set_cons(e, cons, n);
 }
 
 int nig_reset(nig_env_t* e, const uint8_t* mask, const float* init_states, int32_t layout, void* stream)
