@@ -316,6 +316,17 @@ NIG_API int nig_stats_ptr(nig_env_t* env, void** stats_dev);
 NIG_API int nig_read_stats(nig_env_t* env, int64_t* counters24, double* sums8);
 NIG_API int nig_clear_stats(nig_env_t* env, void* stream);
 
+/* smallest / largest return among the episodes finished inside nig_rollout / nig_rollout_host since the last
+ * nig_clear_stats (return_min / return_max of evaluate_with_safety, utils.py:131-132). Opt-in per handle with
+ * nig_track_extrema(env, 1): the rollout then runs the kernel flavour that carries the two running extrema (measured
+ * 2 % slower than the plain one, which is why it is not always on; teacher-forced noise has no such flavour ->
+ * NIG_ERR_UNSUPPORTED). Two order-preserving int64 keys on the device (0 = none yet), kept outside the summable stats
+ * block: ranks combine them with one MAX all-reduce, then decode. Accurate to the last mantissa bit of the fp64 return. */
+NIG_API int nig_track_extrema(nig_env_t* env, int32_t on);
+NIG_API int nig_extrema_ptr(nig_env_t* env, void** keys2_dev);
+NIG_API int nig_read_extrema(nig_env_t* env, double* ret_min, double* ret_max, int32_t* have);
+NIG_API int nig_decode_extrema(const int64_t* keys2, double* ret_min, double* ret_max, int32_t* have);
+
 NIG_API int nig_sync(nig_env_t* env);
 /* page-locked host buffers for the *_host calls (the copies are then true async DMA) */
 NIG_API int nig_host_alloc(size_t bytes, void** out);

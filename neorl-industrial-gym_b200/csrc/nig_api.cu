@@ -87,6 +87,8 @@ struct nig_env {
     float *h_actions, *h_noise, *h_reset, *h_obs, *h_next_obs, *h_reward;
     uint8_t *h_hostmask, *h_flags, *h_viol, *h_mask;
     int32_t *h_i32a, *h_i32b;
+    unsigned long long* extrema; // [2] min / max finished-episode return keys (outside the summable stats block)
+    bool track_extrema;          // nig_track_extrema: rollouts run the EXTREMA kernel flavour
     uint32_t* cons_masks;       // device copy of the NIG_CON_BOUND one-hot masks (ConsParams::masks)
     uint32_t* tick_dev;         // device-tick mode (CUDA-graph capture): [0] tick, [1] finished-CTA counter; null = host tick
     double* pid_state;          // [2][A][pitch] PID integral / previous error of NIG_POLICY_BASELINE (lazily allocated, zeroed)
@@ -298,7 +300,7 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     int ndev = 0;
     if (nig_device_count(&ndev) != NIG_OK || ndev == 0) {
         char why[256];
-        snprintf(why, sizeof why, "%s", ndev == 0 && g_err[0] ? g_err : "device count is 0");
+        snprintf(why, sizeof why, "%.255s", ndev == 0 && g_err[0] ? g_err : "device count is 0");
         return fail(NIG_ERR_NO_DEVICE, "no CUDA device visible (%s): libnig_b200 has no CPU fallback", why);
     }
     if (cfg->device < 0 || cfg->device >= ndev) return fail(NIG_ERR_INVALID, "device %d outside [0, %d)", cfg->device, ndev);
@@ -340,6 +342,7 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     if (rc == NIG_OK) rc = dev_alloc(&e->ep_word, (size_t)e->pitch);
     if (rc == NIG_OK) rc = dev_alloc(&e->ep_return, (size_t)e->pitch);
     if (rc == NIG_OK) rc = dev_alloc(&e->stats, (size_t)NIG_STATS_SLOTS);
+    if (rc == NIG_OK) rc = dev_alloc(&e->extrema, (size_t)2);
     if (rc == NIG_OK && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(NIG_ERR_CUDA, "cudaStreamCreate failed");
 
@@ -355,7 +358,7 @@ int nig_destroy(nig_env_t* e)
     cudaFree(e->state); cudaFree(e->ep_word); cudaFree(e->ep_return); cudaFree(e->stats);
     cudaFree(e->h_actions); cudaFree(e->h_noise); cudaFree(e->h_reset); cudaFree(e->h_obs); cudaFree(e->h_next_obs);
     cudaFree(e->h_reward); cudaFree(e->h_hostmask); cudaFree(e->h_flags); cudaFree(e->h_viol); cudaFree(e->h_mask);
-    cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->pid_state); cudaFree(e->tick_dev); cudaFree(e->cons_masks); cudaFree(e->d_len); cudaFree(e->d_off); cudaFree(e->d_total);
+    cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->pid_state); cudaFree(e->tick_dev); cudaFree(e->cons_masks); cudaFree(e->extrema); cudaFree(e->d_len); cudaFree(e->d_off); cudaFree(e->d_total);
     for (int b = 0; b < 2; ++b) {
         cudaFree(e->r_act[b]); cudaFree(e->r_nz[b]);
         if (e->r_ev_copy[b]) cudaEventDestroy(e->r_ev_copy[b]);
@@ -533,6 +536,8 @@ int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
     if (r->noise && r->policy != NIG_POLICY_ACTIONS)
         return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: teacher-forced noise is only available together with teacher-forced actions (NIG_POLICY_ACTIONS)");
     if (r->policy < NIG_POLICY_ACTIONS || r->policy > NIG_POLICY_BASELINE) return fail(NIG_ERR_INVALID, "unknown rollout policy %d", r->policy);
+    if (r->noise && e->track_extrema)
+        return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: teacher-forced noise has no return-extrema kernel flavour (nig_track_extrema(env, 0) first)");
     if (r->policy == NIG_POLICY_BASELINE) {
         const nig_baseline_t& b = r->pp.baseline;
         if (b.kind < NIG_BASELINE_RANDOM || b.kind > NIG_BASELINE_CONSTANT) return fail(NIG_ERR_INVALID, "unknown baseline controller %d", b.kind);
@@ -552,15 +557,17 @@ int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
     a.reward_sum = r->reward_sum; a.viol_count = r->viol_count; a.done_count = r->done_count;
     a.accumulate = (r->flags & NIG_ROLLOUT_ACCUMULATE) ? 1 : 0;
     a.pid_state = e->pid_state;
+    a.extrema = e->extrema;
     a.stats = e->stats; a.cons = e->cons;
     CUtensorMap map;
     memset(&map, 0, sizeof map);
-    const bool tma = r->policy == NIG_POLICY_ACTIONS && (r->flags & NIG_ROLLOUT_USE_TMA);
+    const bool tma = r->policy == NIG_POLICY_ACTIONS && (r->flags & NIG_ROLLOUT_USE_TMA) && !e->track_extrema;
     int rc;
     if (tma && (rc = make_action_map(e, r->actions, r->n_steps, &map)) != NIG_OK) return rc;
     RolloutLaunch cfg;
     cfg.policy = r->policy; cfg.cons = e->cons.is_default; cfg.tma = tma; cfg.tf_noise = r->noise != nullptr;
     cfg.block = e->rollout_block ? e->rollout_block : 128;
+    cfg.extrema = e->track_extrema;
     e->launches++;
     note_device_work(e, (cudaStream_t)stream);
     NIG_CUDA(nig::launch_rollout(e->kind, cfg, e->pitch, a, map, (cudaStream_t)stream));
@@ -916,7 +923,48 @@ int nig_clear_stats(nig_env_t* e, void* stream)
 {
     NIG_CHECK_ENV(e);
     NIG_CUDA(cudaMemsetAsync(e->stats, 0, NIG_STATS_SLOTS * sizeof(unsigned long long), (cudaStream_t)stream));
+    NIG_CUDA(cudaMemsetAsync(e->extrema, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
     return NIG_OK;
+}
+
+int nig_track_extrema(nig_env_t* e, int32_t on)
+{
+    NIG_CHECK_ENV(e);
+    e->track_extrema = on != 0;
+    return NIG_OK;
+}
+
+int nig_extrema_ptr(nig_env_t* e, void** p)
+{
+    if (!e || !p) return fail(NIG_ERR_INVALID, "null env handle or pointer");
+    *p = e->extrema;
+    return NIG_OK;
+}
+
+int nig_decode_extrema(const int64_t* keys2, double* ret_min, double* ret_max, int32_t* have)
+{
+    if (!keys2) return fail(NIG_ERR_INVALID, "null keys");
+    auto decode = [](unsigned long long k) {
+        const unsigned long long key = k << 1;                    // the dropped mantissa bit comes back as 0
+        const unsigned long long b = (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+        double x;
+        memcpy(&x, &b, sizeof x);
+        return x;
+    };
+    const bool any = keys2[0] != 0 && keys2[1] != 0;
+    if (have) *have = any ? 1 : 0;
+    if (ret_min) *ret_min = any ? -decode((unsigned long long)keys2[0]) : 0.0;
+    if (ret_max) *ret_max = any ? decode((unsigned long long)keys2[1]) : 0.0;
+    return NIG_OK;
+}
+
+int nig_read_extrema(nig_env_t* e, double* ret_min, double* ret_max, int32_t* have)
+{
+    NIG_CHECK_ENV(e);
+    int64_t h[2];
+    NIG_CUDA(cudaDeviceSynchronize());
+    NIG_CUDA(cudaMemcpy(h, e->extrema, sizeof h, cudaMemcpyDeviceToHost));
+    return nig_decode_extrema(h, ret_min, ret_max, have);
 }
 
 int nig_sync(nig_env_t* e)

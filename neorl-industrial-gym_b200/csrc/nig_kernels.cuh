@@ -302,6 +302,17 @@ __device__ __forceinline__ void advance_device_tick(uint32_t* tick_dev, uint32_t
     }
 }
 
+// ---- extrema of finished-episode returns (evaluate_with_safety's return_min / return_max, utils.py:131-132) -------------
+// Kept outside the summable stats block: two order-preserving integer keys combined with atomicMax (0 = no episode
+// yet), so that ranks combine them with ONE max all-reduce. key(x) is monotone in x; slot 0 holds key(-x) (the minimum),
+// slot 1 key(x). The last mantissa bit is dropped to keep the keys non-negative as int64 (NCCL max on int64).
+__device__ __forceinline__ unsigned long long extremum_key(double x)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    const unsigned long long k = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    return k >> 1;                   // 0 only for a NaN bit pattern
+}
+
 // ---- block-level statistics: per-thread counts -> REDUX -> shared atomics -> one global atomic per slot
 struct BlockStats {
     unsigned int* sh;   // [NIG_STATS_SLOTS] shared counters
@@ -823,6 +834,7 @@ struct RolloutArgs {
     nig_policy_params_t pp;
     float* reward_sum; int32_t* viol_count; int32_t* done_count;
     int32_t accumulate;        // per-env outputs: out[i] += this launch's value instead of out[i] = ...
+    unsigned long long* extrema;   // [2] keys of the min / max finished-episode return (see extremum_key); EXTREMA kernels
     double* pid_state;         // [2][A][pitch] fp64: PID integral rows, then previous-error rows (POLICY_BASELINE / PID)
     unsigned long long* stats;
     ConsParams cons;
@@ -924,7 +936,9 @@ template <class T> __device__ __forceinline__ T warp_sum(T v)
 // prefetches the next step's actions / noise into registers one step ahead, so the L2 latency of the loads is
 // hidden behind a whole step of arithmetic. Block size is a launch parameter (blockDim.x <= kThreads; TMA launches
 // use kThreads).
-template <class Env, int CONS, int POLICY, bool TMA, bool TFNOISE>
+// EXTREMA (NIG_ROLLOUT_EXTREMA): also track the smallest / largest finished-episode return. A template flag rather
+// than a run-time one: two more live registers in the step loop moved ptxas' schedule of the throughput kernel by 2 %.
+template <class Env, int CONS, int POLICY, bool TMA, bool TFNOISE, bool EXTREMA = false>
 __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kernel(const __grid_constant__ RolloutArgs p, const __grid_constant__ CUtensorMap amap)
 {
     static_assert(!TFNOISE || POLICY == NIG_POLICY_ACTIONS, "teacher-forced noise comes with teacher-forced actions");
@@ -933,11 +947,13 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     using acc_t = typename Env::acc_t;
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
     __shared__ double sfl[4];
+    __shared__ unsigned long long sext[2];       // extremum keys of the episodes this CTA finished
     __shared__ alignas(8) uint64_t bars[2];
     __shared__ float coop_buf[CoopSmem<Env>::floats];
     extern __shared__ __align__(128) float act_smem[];     // [2][kTmaChunk][A][kThreads] when TMA
     BlockStats bs;
     if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
+    if constexpr (EXTREMA) { if (threadIdx.x < 2) sext[threadIdx.x] = 0ull; }
     bs.init(sstat);
 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -980,6 +996,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] = 0;
     unsigned long long len_sum = 0, len_sq = 0;
     double ret_sum = 0.0, ret_sq = 0.0, rew_sum = 0.0;
+    acc_t r_lo = (acc_t)INFINITY, r_hi = -(acc_t)INFINITY;     // extrema of this thread's finished-episode returns
 
     double pid_i[A], pid_e[A];             // POLICY_BASELINE: the PID agent's integral and previous error
     if constexpr (POLICY == NIG_POLICY_BASELINE) {
@@ -1078,6 +1095,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
                 c_succ += (ep_ret > (acc_t)0) ? 1u : 0u;
                 len_sum += len; len_sq += len * len;
                 ret_sum += (double)ep_ret; ret_sq += (double)ep_ret * (double)ep_ret;
+                if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
                 if (p.auto_reset) {
                     if constexpr (Env::COOP_BLOCKS > 0) need_reset = true;
                     else Env::reset(p.key, env, tick + 1u, p.epoch, s);
@@ -1136,11 +1154,22 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
         bs.warp_add(NIG_ST_SUCCESSES, c_succ);
         const unsigned long long ls = warp_sum(len_sum), lq = warp_sum(len_sq);
         const double rs_ = warp_sum(ret_sum), rq = warp_sum(ret_sq);
+        if constexpr (EXTREMA) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const acc_t a_ = __shfl_xor_sync(0xffffffffu, r_lo, o), b_ = __shfl_xor_sync(0xffffffffu, r_hi, o);
+                r_lo = a_ < r_lo ? a_ : r_lo; r_hi = b_ > r_hi ? b_ : r_hi;
+            }
+        }
         if ((threadIdx.x & 31) == 0) {
             atomicAdd(&p.stats[NIG_ST_EP_LEN_SUM], ls);
             atomicAdd(&p.stats[NIG_ST_EP_LEN_SQ], lq);
             atomicAdd(&sfl[0], rs_);
             atomicAdd(&sfl[1], rq);
+            if constexpr (EXTREMA) {
+                atomicMax(&sext[0], extremum_key(-(double)r_lo));
+                atomicMax(&sext[1], extremum_key((double)r_hi));
+            }
         }
     }
     {
@@ -1150,6 +1179,9 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     bs.flush(p.stats);
     if (threadIdx.x < 3 && sfl[threadIdx.x] != 0.0)
         atomicAdd(reinterpret_cast<double*>(p.stats) + NIG_ST_F_RETURN_SUM + threadIdx.x, sfl[threadIdx.x]);
+    if constexpr (EXTREMA) {
+        if (threadIdx.x < 2 && sext[threadIdx.x] != 0ull) atomicMax(&p.extrema[threadIdx.x], sext[threadIdx.x]);
+    }
     advance_device_tick(p.tick_dev, (uint32_t)p.n_steps);
 }
 

@@ -4,10 +4,10 @@
 
 namespace nig {
 
-template <class Env, int CONS, int POLICY, bool TMA, bool TFNOISE>
+template <class Env, int CONS, int POLICY, bool TMA, bool TFNOISE, bool EXTREMA = false>
 cudaError_t rollout_go(const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
 {
-    auto kern = rollout_kernel<Env, CONS, POLICY, TMA, TFNOISE>;
+    auto kern = rollout_kernel<Env, CONS, POLICY, TMA, TFNOISE, EXTREMA>;
     const int block = TMA ? kThreads : cfg.block;
     const size_t smem = TMA ? (size_t)2 * kTmaChunk * Env::A * kThreads * sizeof(float) : 0;
     if (TMA) {
@@ -37,9 +37,28 @@ cudaError_t rollout_policy(const RolloutLaunch& c, int64_t pitch, const RolloutA
     }
 }
 
+// NIG_ROLLOUT_EXTREMA: the evaluation flavour (return_min / return_max). Action tensors go through the register-prefetch
+// path; teacher-forced noise is a parity-test mode and has no extrema flavour.
+template <class Env, int CONS>
+cudaError_t rollout_policy_extrema(const RolloutLaunch& c, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
+{
+    switch (c.policy) {
+    case NIG_POLICY_ACTIONS: return rollout_go<Env, CONS, NIG_POLICY_ACTIONS, false, false, true>(c, pitch, a, map, st);
+    case NIG_POLICY_UNIFORM: return rollout_go<Env, CONS, NIG_POLICY_UNIFORM, false, false, true>(c, pitch, a, map, st);
+    case NIG_POLICY_ZERO: return rollout_go<Env, CONS, NIG_POLICY_ZERO, false, false, true>(c, pitch, a, map, st);
+    case NIG_POLICY_PCTRL: return rollout_go<Env, CONS, NIG_POLICY_PCTRL, false, false, true>(c, pitch, a, map, st);
+    case NIG_POLICY_BASELINE: return rollout_go<Env, CONS, NIG_POLICY_BASELINE, false, false, true>(c, pitch, a, map, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 template <class Env>
 cudaError_t rollout_env(const RolloutLaunch& c, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
 {
+    if (c.extrema)
+        return c.cons == CONS_DEFAULT ? rollout_policy_extrema<Env, CONS_DEFAULT>(c, pitch, a, map, st)
+             : c.cons == CONS_PREFIX  ? rollout_policy_extrema<Env, CONS_PREFIX>(c, pitch, a, map, st)
+                                      : rollout_policy_extrema<Env, CONS_GENERIC>(c, pitch, a, map, st);
     return c.cons == CONS_DEFAULT ? rollout_policy<Env, CONS_DEFAULT>(c, pitch, a, map, st)
          : c.cons == CONS_PREFIX  ? rollout_policy<Env, CONS_PREFIX>(c, pitch, a, map, st)
                                   : rollout_policy<Env, CONS_GENERIC>(c, pitch, a, map, st);

@@ -125,6 +125,10 @@ SYMBOLS = {
     "nig_stats_ptr": (C.c_int, [_VP, C.POINTER(_VP)]),
     "nig_read_stats": (C.c_int, [_VP, _VP, _VP]),
     "nig_clear_stats": (C.c_int, [_VP, _VP]),
+    "nig_track_extrema": (C.c_int, [_VP, C.c_int32]),
+    "nig_extrema_ptr": (C.c_int, [_VP, C.POINTER(_VP)]),
+    "nig_read_extrema": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I32)]),
+    "nig_decode_extrema": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I32)]),
     "nig_sync": (C.c_int, [_VP]),
     "nig_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_VP)]),
     "nig_host_free": (C.c_int, [_VP]),

@@ -72,3 +72,15 @@ def allreduce_device_stats(native, group=None):
         dist.all_reduce(view[:24], group=group)
         dist.all_reduce(view[24:].view(torch.float64), group=group)
     return view
+
+
+def allreduce_extrema(native, group=None):
+    """(return_min, return_max) over the finished episodes of EVERY rank: one MAX all-reduce of the two order-preserving
+    int64 keys on the device (NCCL), then decode. (None, None) if no rank finished an episode."""
+    import torch.distributed as dist
+    keys = native.extrema_tensor()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)
+    import torch
+    torch.cuda.synchronize(native.torch_device())
+    return native.decode_extrema(keys.cpu().numpy())

@@ -47,16 +47,23 @@ def evaluate_policy_device(env, n_steps: int, policy: int = N.POLICY_UNIFORM, pa
     cross-GPU all-reduce (see distributed.allreduce_stats)."""
     nat = env.native
     nat.clear_stats()
-    done = 0
-    while done < n_steps:
-        k = min(chunk, n_steps - done)
-        nat.rollout_device(k, policy, params=params)
-        done += k
+    nat.track_extrema(True)            # the kernel flavour that also keeps return_min / return_max
+    try:
+        done = 0
+        while done < n_steps:
+            k = min(chunk, n_steps - done)
+            nat.rollout_device(k, policy, params=params)
+            done += k
+    finally:
+        nat.track_extrema(False)
     counters, sums = nat.read_stats()
     if reduce_fn is not None:
         counters, sums = reduce_fn(counters, sums)
     stats = nat.stats_dict(counters, sums)
-    return metrics_from_stats(stats, len(env.safety_constraints), [c.critical for c in env.safety_constraints])
+    out = metrics_from_stats(stats, len(env.safety_constraints), [c.critical for c in env.safety_constraints])
+    # return_min / return_max of this rank's episodes; across ranks: distributed.allreduce_extrema(nat)
+    out["return_min"], out["return_max"] = nat.read_extrema()
+    return out
 
 
 def evaluate_agent_batched(agent: Any, env: Any, n_episodes: int = 100) -> Dict[str, Any]:

@@ -255,6 +255,30 @@ class NativeEnv:
         N.check(N.lib().nig_read_stats(self._h, N.ptr_of(counters), N.ptr_of(sums)))
         return counters, sums
 
+    def track_extrema(self, on: bool = True):
+        """Rollouts of this handle also keep the smallest / largest finished-episode return (a 2 % slower kernel flavour)."""
+        N.check(N.lib().nig_track_extrema(self._h, int(bool(on))))
+
+    def read_extrema(self):
+        """(return_min, return_max) over the episodes finished inside rollouts since the last clear_stats, or (None, None)."""
+        lo, hi, have = C.c_double(), C.c_double(), C.c_int32()
+        N.check(N.lib().nig_read_extrema(self._h, C.byref(lo), C.byref(hi), C.byref(have)))
+        return (lo.value, hi.value) if have.value else (None, None)
+
+    def extrema_tensor(self):
+        """Zero-copy torch view int64[2] of the extremum keys (combine across ranks with all_reduce(MAX), then decode_extrema)."""
+        import torch
+        p = C.c_void_p()
+        N.check(N.lib().nig_extrema_ptr(self._h, C.byref(p)))
+        return torch.as_tensor(_CudaView(p.value, (2,), "<i8", self), device=self.torch_device())
+
+    @staticmethod
+    def decode_extrema(keys):
+        k = np.ascontiguousarray(keys, np.int64)
+        lo, hi, have = C.c_double(), C.c_double(), C.c_int32()
+        N.check(N.lib().nig_decode_extrema(N.ptr_of(k), C.byref(lo), C.byref(hi), C.byref(have)))
+        return (lo.value, hi.value) if have.value else (None, None)
+
     def stats_dict(self, counters=None, sums=None):
         if counters is None:
             counters, sums = self.read_stats()

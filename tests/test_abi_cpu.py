@@ -108,3 +108,23 @@ def test_types_and_spaces():
     bm = ni.BatchedSafetyMetrics(np.array([0, 1, 3, 7], np.uint8), 3, 0b011)
     assert bm.violation_count.tolist() == [0, 1, 2, 3] and bm.critical_violations.tolist() == [0, 1, 2, 2]
     assert bm[2].constraints_satisfied == 1
+
+
+def test_extrema_keys_decode_in_order():
+    """nig_decode_extrema inverts the order-preserving int64 keys the rollout kernel keeps for return_min / return_max
+    (utils.py:131-132): key(x) restated in numpy here, monotone in x, the maximum of the keys decodes to the extremum."""
+    def key(x):
+        b = np.array(x, np.float64).view(np.uint64)
+        k = np.where(b >> np.uint64(63), ~b, b | np.uint64(1 << 63))
+        return (k >> np.uint64(1)).astype(np.int64)
+
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.normal(0, 1e4, 4000), rng.normal(0, 1e-3, 100), [0.0, 1e300, -1e300]])
+    order = np.argsort(xs, kind="stable")
+    ks = key(xs)
+    assert (np.diff(ks[order]) >= 0).all() and (ks > 0).all()
+    assert key(-0.0) < key(0.0) < key(5e-324 * 4)
+    keys = np.array([key(-xs).max(), ks.max()], np.int64)
+    lo, hi = ni.NativeEnv.decode_extrema(keys)
+    assert np.isclose(lo, xs.min(), rtol=3e-16, atol=0) and np.isclose(hi, xs.max(), rtol=3e-16, atol=0)
+    assert ni.NativeEnv.decode_extrema(np.zeros(2, np.int64)) == (None, None)

@@ -226,13 +226,16 @@ def test_free_running_bitexact_vs_oracle(mods, name):
 
 @pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
 @pytest.mark.parametrize("policy", ["actions_tma", "actions_ldg", "uniform", "pctrl"])
-def test_rollout_bitexact_vs_oracle(mods, name, policy):
-    """Fused K-step rollout (state in registers) == K oracle steps: final state, counters, per-env sums, stats."""
+@pytest.mark.parametrize("extrema", [False, True])
+def test_rollout_bitexact_vs_oracle(mods, name, policy, extrema):
+    """Fused K-step rollout (state in registers) == K oracle steps: final state, counters, per-env sums, stats;
+    with nig_track_extrema also the smallest / largest finished-episode return."""
     ni, N, O, torch = mods
     kind, n, K = KINDS[name], 1000, 70      # K not a multiple of the 16-step TMA chunk
     env = _native_env(ni, kind, n, auto_reset=True, seed=77, env_id_offset=128)
     orc = O.OracleEnv(kind, n, auto_reset=True, seed=77, env_id0=128, exp_mode=1)
     env.reset_host(); orc.reset()
+    env.track_extrema(extrema)
     dev = env.torch_device()
     rng = np.random.default_rng(5)
     pp = None
@@ -243,6 +246,7 @@ def test_rollout_bitexact_vs_oracle(mods, name, policy):
     o_rsum = np.zeros(n, np.float32); o_v = np.zeros(n, np.int64); o_d = np.zeros(n, np.int64)
     ep_ret = np.zeros(n, np.float32 if name == "reactor" else np.float64)
     ret_sum = ret_sq = 0.0
+    ret_lo, ret_hi = np.inf, -np.inf
     succ = len_sum = 0
     for rep in range(2):                      # two consecutive launches: tick / episode accumulators carry over
         acts = rng.uniform(-1.3, 1.3, (K, n, env.A)).astype(np.float32)
@@ -273,6 +277,7 @@ def test_rollout_bitexact_vs_oracle(mods, name, policy):
             if done.any():
                 er = ep_ret[done].astype(np.float64)
                 ret_sum += er.sum(); ret_sq += (er * er).sum(); succ += int((er > 0).sum())
+                ret_lo, ret_hi = min(ret_lo, er.min()), max(ret_hi, er.max())
                 len_sum += int((steps_before[done] + 1).sum())
                 ep_ret[done] = 0
         torch.cuda.synchronize()
@@ -296,6 +301,15 @@ def test_rollout_bitexact_vs_oracle(mods, name, policy):
         np.testing.assert_allclose(d["return_sq"], ret_sq, rtol=1e-9, atol=1e-6)
     else:     # grid / robot accumulate episode returns in fp64 from unrounded fp64 rewards: tolerance compare
         np.testing.assert_allclose(d["return_sum"], ret_sum, rtol=1e-6, atol=1e-3)
+    # return_min / return_max of the finished episodes (utils.py:131-132): order-preserving keys, last fp64 mantissa bit dropped
+    lo, hi = env.read_extrema()
+    if d["episodes"] == 0 or not extrema:
+        assert lo is None and hi is None
+    else:
+        tol = 1e-15 if name == "reactor" else 1e-6
+        np.testing.assert_allclose([lo, hi], [ret_lo, ret_hi], rtol=tol, atol=0 if name == "reactor" else 1e-3)
+    env.clear_stats(); torch.cuda.synchronize()
+    assert env.read_extrema() == (None, None)
     env.close()
 
 
