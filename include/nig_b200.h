@@ -340,8 +340,10 @@ NIG_API int nig_fp32_probe(int device, int32_t iters, double* ops, void* stream)
  * operand sets (all-exponent pairs, physics-regime pairs, every constant divisor); *mismatches must come back 0 */
 NIG_API int nig_selftest_division(int device, int64_t n, uint64_t seed, int64_t* mismatches, int64_t* accepted);
 
-/* self-test of the branch-free Box-Muller square root: every float of [2^-24, 2^6] and -0 against IEEE sqrt */
-NIG_API int nig_selftest_sqrt(int device, int64_t* mismatches, int64_t* checked);
+/* self-test of the inverse-CDF Gaussian of the math spec (csrc/nig_math.cuh spec_normal): two wrapping checksums over the
+ * bit patterns of normal(first + k * stride), k < count -- sums2[0] = sum bits, sums2[1] = sum bits * (k + 1). The CPU
+ * oracle computes the same sums; the whole 2^32-word domain is (first 0, stride 1, count 2^32). */
+NIG_API int nig_selftest_normal(int device, uint32_t first, uint32_t stride, int64_t count, uint64_t* sums2);
 
 #ifdef __cplusplus
 }

@@ -1007,21 +1007,20 @@ int nig_selftest_division(int device, int64_t n, uint64_t seed, int64_t* mismatc
     return NIG_OK;
 }
 
-int nig_selftest_sqrt(int device, int64_t* mismatches, int64_t* checked)
+int nig_selftest_normal(int device, uint32_t first, uint32_t stride, int64_t count, uint64_t* sums2)
 {
     DeviceGuard guard(device);
     if (!guard.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    if (!mismatches) return fail(NIG_ERR_INVALID, "nig_selftest_sqrt: null mismatches");
+    if (!sums2 || count < 0) return fail(NIG_ERR_INVALID, "nig_selftest_normal: null sums or negative count");
     unsigned long long* d = nullptr;
     NIG_CUDA(cudaMalloc((void**)&d, 2 * sizeof(unsigned long long)));
     NIG_CUDA(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
-    cudaError_t ce = nig::launch_selftest_sqrt(d, nullptr);
+    cudaError_t ce = nig::launch_selftest_normal(first, stride, (unsigned long long)count, d, nullptr);
     unsigned long long h[2] = {0, 0};
     if (ce == cudaSuccess) ce = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
     cudaFree(d);
     NIG_CUDA(ce);
-    *mismatches = (int64_t)h[0];
-    if (checked) *checked = (int64_t)h[1];
+    sums2[0] = h[0]; sums2[1] = h[1];
     return NIG_OK;
 }
 

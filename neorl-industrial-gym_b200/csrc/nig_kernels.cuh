@@ -1322,23 +1322,18 @@ static __global__ void __launch_bounds__(256) selftest_division_kernel(RngKey ke
     atomicAdd(&out[1], acc);
 }
 
-// every float of [2^-24, 2^6] (and -0): bm_sqrt == __fsqrt_rn
-static __global__ void __launch_bounds__(256) selftest_sqrt_kernel(unsigned long long* out)
+// checksums of spec_normal over the words first + k * stride, k < count (the oracle computes the same two sums on the CPU)
+static __global__ void __launch_bounds__(256) selftest_normal_kernel(uint32_t first, uint32_t stride, unsigned long long count, unsigned long long* out)
 {
-    const uint32_t lo = 0x33800000u, hi = 0x42800000u;       // 2^-24 .. 2^6 inclusive
-    unsigned long long bad = 0, cnt = 0;
-    for (uint64_t b = (uint64_t)lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= hi; b += (uint64_t)gridDim.x * blockDim.x) {
-        const float x = __uint_as_float((uint32_t)b);
-        bad += __float_as_uint(bm_sqrt(x)) != __float_as_uint(__fsqrt_rn(x));
-        cnt++;
+    unsigned long long s0 = 0, s1 = 0;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t w = first + (uint32_t)k * stride;
+        const unsigned long long bits = __float_as_uint(spec_normal(w));
+        s0 += bits;
+        s1 += bits * (k + 1ull);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const float z = __uint_as_float(0x80000000u);
-        bad += __float_as_uint(bm_sqrt(z)) != __float_as_uint(__fsqrt_rn(z));
-        cnt++;
-    }
-    atomicAdd(&out[0], bad);
-    atomicAdd(&out[1], cnt);
+    atomicAdd(&out[0], s0);
+    atomicAdd(&out[1], s1);
 }
 
 // ---- measured-peak probe: independent unfused FADD/FMUL chains (what the physics is made of) ------

@@ -21,9 +21,9 @@ cudaError_t launch_fp32_probe(float* sink, int iters, int blocks, cudaStream_t s
     fp32_probe_kernel<<<blocks, 256, 0, st>>>(sink, iters);
     return cudaGetLastError();
 }
-cudaError_t launch_selftest_sqrt(unsigned long long* out, cudaStream_t st)
+cudaError_t launch_selftest_normal(uint32_t first, uint32_t stride, unsigned long long count, unsigned long long* out, cudaStream_t st)
 {
-    selftest_sqrt_kernel<<<148 * 8, 256, 0, st>>>(out);
+    selftest_normal_kernel<<<148 * 8, 256, 0, st>>>(first, stride, count, out);
     return cudaGetLastError();
 }
 cudaError_t launch_selftest_division(RngKey key, int iters, int blocks, unsigned long long* out, cudaStream_t st)

@@ -135,7 +135,7 @@ SYMBOLS = {
     "nig_launch_count": (_I64, [_VP]),
     "nig_fp32_probe": (C.c_int, [C.c_int, _I32, C.POINTER(C.c_double), _VP]),
     "nig_selftest_division": (C.c_int, [C.c_int, _I64, _U64, C.POINTER(_I64), C.POINTER(_I64)]),
-    "nig_selftest_sqrt": (C.c_int, [C.c_int, C.POINTER(_I64), C.POINTER(_I64)]),
+    "nig_selftest_normal": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_int64, C.POINTER(C.c_uint64)]),
 }
 
 

@@ -97,57 +97,6 @@ static float spec_expf(float x)
     return (p * s1) * s2;
 }
 
-/* log(u) for u in (0, 1] */
-static float spec_logf_unit(float u)
-{
-    uint32_t b = f_bits(u);
-    int e = (int)(b >> 23) - 127;
-    uint32_t mb = (b & 0x007fffffu) | 0x3f800000u;
-    float m = bits_f(mb);
-    if (m > 0x1.6a09e6p+0f) { m = m * 0.5f; e += 1; }
-    float f = m - 1.0f;
-    float q = 0x1.6626eap-4f;
-    q = fmaf(q, f, -0x1.26729ep-3f);
-    q = fmaf(q, f, 0x1.322850p-3f);
-    q = fmaf(q, f, -0x1.5329bep-3f);
-    q = fmaf(q, f, 0x1.98b80ap-3f);
-    q = fmaf(q, f, -0x1.0005a6p-2f);
-    q = fmaf(q, f, 0x1.555790p-2f);
-    q = fmaf(q, f, -0x1.fffff8p-2f);
-    q = fmaf(q, f, 1.0f);
-    float lm = f * q;
-    return fmaf((float)e, 0x1.62e430p-1f, lm);
-}
-
-/* sin and cos of 2*pi*(x / 2^32) by octant reduction */
-static void spec_sincos_turn(uint32_t x, float* s, float* c)
-{
-    uint32_t k = x >> 29;
-    uint32_t rem = x & 0x1fffffffu;
-    float f = fmaf((float)rem, 0x1.0p-29f, 0x1.0p-30f); /* (0,1] */
-    float y = (k & 1u) ? (f - 1.0f) : f;
-    float phi = y * 0x1.921fb6p-1f;
-    float z = phi * phi;
-    float ps = 0x1.6cb76ap-19f;
-    ps = fmaf(ps, z, -0x1.a00ee8p-13f);
-    ps = fmaf(ps, z, 0x1.111108p-7f);
-    ps = fmaf(ps, z, -0x1.555556p-3f);
-    ps = fmaf(ps, z, 1.0f);
-    float sn = phi * ps;
-    float pc = 0x1.9906cap-16f;
-    pc = fmaf(pc, z, -0x1.6c0786p-10f);
-    pc = fmaf(pc, z, 0x1.55553ap-5f);
-    pc = fmaf(pc, z, -0x1.0p-1f);
-    pc = fmaf(pc, z, 1.0f);
-    float cs = pc;
-    uint32_t m = (k + 1u) >> 1; /* multiple of pi/2 */
-    float ss = (m & 1u) ? cs : sn;
-    float cc = (m & 1u) ? sn : cs;
-    if (((m + 0u) & 2u)) ss = -ss;        /* m = 2,3 : sin negated */
-    if (((m + 1u) & 2u)) cc = -cc;        /* m = 1,2 : cos negated */
-    *s = ss; *c = cc;
-}
-
 static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
 {
     for (int r = 0; r < 10; ++r) {
@@ -166,14 +115,27 @@ static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 static inline float u_open(uint32_t x) { return fmaf((float)x, 0x1.0p-32f, 0x1.0p-33f); }  /* (0,1] */
 static inline float u_sym(uint32_t x) { return fmaf((float)x, 0x1.0p-31f, -1.0f); }          /* [-1,1] */
 
-static void box_muller(uint32_t xa, uint32_t xb, float* z0, float* z1)
+/* One standard normal from one 32-bit word (math spec): inverse CDF by a dyadic-segment table.
+ * v = 2 (w mod 2^31) + 1 counts the tail (p = v / 2^33); the binary32 exponent of RN(v) and its top four mantissa
+ * bits select the segment, a cubic in the mantissa t in [1,2) (explicit fmaf, Horner) gives |z|, bit 31 of w the sign.
+ * The table is data of the spec (tools/fit_normal_table.py writes the same numbers for the library and for this file). */
+#include "nig_normal_table.h"
+static const float normal_tab[NIG_NORMAL_TAB_N][4] = { NIG_NORMAL_TAB_VALUES };
+
+static float spec_normal(uint32_t w)
 {
-    float u = u_open(xa);
-    float r = sqrtf(-2.0f * spec_logf_unit(u));
-    float s, c;
-    spec_sincos_turn(xb, &s, &c);
-    *z0 = r * c;
-    *z1 = r * s;
+    const uint32_t v = (w << 1) | 1u;
+    const uint32_t b = f_bits((float)v);                       /* round-to-nearest conversion */
+    const float* c = normal_tab[(b >> 19) - 127u * 16u];
+    const float t = bits_f((b & 0x007fffffu) | 0x3f800000u);
+    const float z = fmaf(fmaf(fmaf(c[3], t, c[2]), t, c[1]), t, c[0]);
+    return bits_f(f_bits(z) ^ (w & 0x80000000u));
+}
+
+static void box_muller(uint32_t xa, uint32_t xb, float* z0, float* z1)   /* historical name: a pair of normals */
+{
+    *z0 = spec_normal(xa);
+    *z1 = spec_normal(xb);
 }
 
 enum { STREAM_NOISE = 0, STREAM_RESET = 1, STREAM_POLICY = 2 };
@@ -196,7 +158,19 @@ ORC_API void orc_spec_normals4(uint64_t seed, uint32_t env, uint32_t tick, uint3
     orc_cfg_t c; memset(&c, 0, sizeof c); c.seed = seed; normals4(&c, env, tick, stream, j, z);
 }
 ORC_API float orc_spec_expf(float x) { return spec_expf(x); }
-ORC_API float orc_spec_logf_unit(float x) { return spec_logf_unit(x); }
+ORC_API float orc_spec_normal(uint32_t w) { return spec_normal(w); }
+/* the two checksums of nig_selftest_normal (include/nig_b200.h), computed on the CPU */
+ORC_API void orc_selftest_normal(uint32_t first, uint32_t stride, int64_t count, uint64_t* sums2)
+{
+    uint64_t s0 = 0, s1 = 0;
+#pragma omp parallel for reduction(+ : s0, s1) schedule(static)
+    for (int64_t k = 0; k < count; ++k) {
+        const uint64_t bits = f_bits(spec_normal(first + (uint32_t)k * stride));
+        s0 += bits;
+        s1 += bits * ((uint64_t)k + 1u);
+    }
+    sums2[0] = s0; sums2[1] = s1;
+}
 ORC_API void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out)
 { philox4x32_10(c0, c1, c2, c3, k0, k1, out); }
 

@@ -62,8 +62,8 @@ def lib():
         assert _lib.orc_cfg_size() == C.sizeof(Cfg)
         _lib.orc_spec_expf.restype = C.c_float
         _lib.orc_spec_expf.argtypes = [C.c_float]
-        _lib.orc_spec_logf_unit.restype = C.c_float
-        _lib.orc_spec_logf_unit.argtypes = [C.c_float]
+        _lib.orc_spec_normal.restype = C.c_float
+        _lib.orc_spec_normal.argtypes = [C.c_uint32]
     return _lib
 
 
@@ -219,6 +219,18 @@ def spec_normals4(seed, env, tick, stream, j):
     z = np.empty(4, np.float32)
     lib().orc_spec_normals4(C.c_uint64(seed), C.c_uint32(env), C.c_uint32(tick), C.c_uint32(stream), C.c_uint32(j), _p(z))
     return z
+
+
+def spec_normal(w) -> float:
+    """The spec's standard normal of one 32-bit word (inverse CDF, dyadic-segment table)."""
+    return float(lib().orc_spec_normal(C.c_uint32(int(w) & 0xFFFFFFFF)))
+
+
+def selftest_normal(first, stride, count):
+    """The two wrapping checksums nig_selftest_normal computes on the device (include/nig_b200.h)."""
+    out = np.zeros(2, np.uint64)
+    lib().orc_selftest_normal(C.c_uint32(first), C.c_uint32(stride), C.c_int64(count), _p(out))
+    return int(out[0]), int(out[1])
 
 
 def philox(c, k):

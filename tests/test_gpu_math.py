@@ -16,10 +16,14 @@ def test_fast_division_matches_ieee_on_guarded_domain():
     assert bad.value == 0, f"{bad.value} of {acc.value} guarded divisions differ from IEEE division"
 
 
-def test_box_muller_sqrt_matches_ieee_on_its_whole_domain():
-    """bm_sqrt (csrc/nig_math.cuh) == __fsqrt_rn for EVERY float of [2^-24, 2^6] and for -0: the radicand -2 log(u) of the
-    Box-Muller transform cannot leave that set."""
-    bad, cnt = C.c_int64(-1), C.c_int64(0)
-    N.check(N.lib().nig_selftest_sqrt(0, C.byref(bad), C.byref(cnt)))
-    assert cnt.value == (0x42800000 - 0x33800000 + 1) + 1, cnt.value
-    assert bad.value == 0, f"{bad.value} of {cnt.value} square roots differ from IEEE sqrt"
+def test_spec_normal_device_equals_oracle_on_every_word():
+    """spec_normal (csrc/nig_math.cuh: inverse-CDF table + cubic) on the device == the oracle's restatement for EVERY one of
+    the 2^32 input words: two wrapping checksums over the result bit patterns, computed on both sides."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import oracle as O
+    sums = (C.c_uint64 * 2)()
+    N.check(N.lib().nig_selftest_normal(0, 0, 1, 1 << 32, sums))
+    assert (sums[0], sums[1]) == O.selftest_normal(0, 1, 1 << 32)
+    N.check(N.lib().nig_selftest_normal(0, 12345, 2654435761, 1 << 20, sums))
+    assert (sums[0], sums[1]) == O.selftest_normal(12345, 2654435761, 1 << 20)

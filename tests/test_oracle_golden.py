@@ -157,6 +157,30 @@ def test_spec_normals_are_gaussian():
     assert abs(np.corrcoef(z[0::4], z[1::4])[0, 1]) < 0.03
 
 
+def test_spec_normal_is_the_inverse_cdf():
+    """spec_normal(w) == Phi^-1 of the word's probability level to fp32 rounding: the symmetric tail count
+    v = 2 (w mod 2^31) + 1 stands for p = v / 2^33, bit 31 is the sign (math spec). Checked against
+    scipy's ndtri over random words, every octave of the tail, and the end points; monotone in the tail count."""
+    from scipy.special import ndtri
+    from scipy import stats
+    rng = np.random.default_rng(11)
+    words = np.concatenate([rng.integers(0, 2 ** 32, 200_000, dtype=np.uint64),
+                            (rng.integers(0, 2 ** 32, 60_000, dtype=np.uint64) >> rng.integers(1, 31, 60_000).astype(np.uint64)),
+                            [0, 1, 2, 3, 2 ** 31 - 1, 2 ** 31, 2 ** 31 + 1, 2 ** 32 - 1]]).astype(np.uint64)
+    z = np.array([O.spec_normal(w) for w in words], np.float64)
+    v = 2 * (words & np.uint64(0x7FFFFFFF)).astype(np.float64) + 1
+    mag = -ndtri(np.float32(v).astype(np.float64) / 2.0 ** 33)          # the spec rounds the count to binary32 first
+    ref = np.where(words >> np.uint64(31), -mag, mag)
+    np.testing.assert_allclose(z, ref, rtol=0, atol=8e-7)
+    assert 6.3 < abs(O.spec_normal(0)) < 6.4 and abs(O.spec_normal(2 ** 31 - 1)) < 1e-6      # deepest tail / centre
+    assert O.spec_normal(5) == -O.spec_normal(5 + 2 ** 31)
+    order = np.argsort(words[:200_000] & np.uint64(0x7FFFFFFF))
+    m = np.abs(z[:200_000])[order]
+    assert (np.diff(m) <= 1e-6).all()                                    # |z| falls as the tail count grows
+    ks = stats.kstest(z[:200_000], "norm")
+    assert ks.pvalue > 1e-3, ks
+
+
 def test_oracle_auto_reset_and_latch():
     env = O.OracleEnv(O.GRID, 64, auto_reset=True, seed=9)
     env.reset()
