@@ -117,7 +117,7 @@ static inline float u_sym(uint32_t x) { return fmaf((float)x, 0x1.0p-31f, -1.0f)
 
 /* One standard normal from one 32-bit word (math spec): inverse CDF by a dyadic-segment table.
  * v = 2 (w mod 2^31) + 1 counts the tail (p = v / 2^33); the binary32 exponent of RN(v) and its top four mantissa
- * bits select the segment, a cubic in the mantissa t in [1,2) (explicit fmaf, Horner) gives |z|, bit 31 of w the sign.
+ * bits select the segment, a cubic in f (explicit fmaf, Horner; coefficients pre-scaled by powers of two) gives |z|, bit 31 of w the sign.
  * The table is data of the spec (tools/fit_normal_table.py writes the same numbers for the library and for this file). */
 #include "nig_normal_table.h"
 static const float normal_tab[NIG_NORMAL_TAB_N][4] = { NIG_NORMAL_TAB_VALUES };
@@ -125,10 +125,9 @@ static const float normal_tab[NIG_NORMAL_TAB_N][4] = { NIG_NORMAL_TAB_VALUES };
 static float spec_normal(uint32_t w)
 {
     const uint32_t v = (w << 1) | 1u;
-    const uint32_t b = f_bits((float)v);                       /* round-to-nearest conversion */
-    const float* c = normal_tab[(b >> 19) - 127u * 16u];
-    const float t = bits_f((b & 0x007fffffu) | 0x3f800000u);
-    const float z = fmaf(fmaf(fmaf(c[3], t, c[2]), t, c[1]), t, c[0]);
+    const float f = (float)v;                                  /* round-to-nearest conversion */
+    const float* c = normal_tab[(f_bits(f) >> 19) - 127u * 16u];
+    const float z = fmaf(fmaf(fmaf(c[3], f, c[2]), f, c[1]), f, c[0]);
     return bits_f(f_bits(z) ^ (w & 0x80000000u));
 }
 
