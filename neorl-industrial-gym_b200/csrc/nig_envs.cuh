@@ -46,7 +46,7 @@ struct Reactor {
     struct NoiseGen {
         float z[4];
         uint32_t block = 0xffffffffu;
-        __device__ __forceinline__ void get(const RngKey& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
+        __device__ __forceinline__ void get(const Rng& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
         {
             const uint32_t b = tick >> 1;
             if (b != block) { rng_normals4(key, env, b, STREAM_NOISE, 0u, z); block = b; }   // warp-uniform branch
@@ -56,12 +56,12 @@ struct Reactor {
             nz[1] = mul(500.0f, zb);    // np.random.normal(0, pressure_noise_std / 10)  (:159)
         }
         // the same two values for ONE tick (single-step kernel): only the Box-Muller pair of this tick's parity
-        __device__ static __forceinline__ void get_single(const RngKey& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
+        __device__ static __forceinline__ void get_single(const Rng& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
         {
             const uint4 w = rng_words(key, env, tick >> 1, STREAM_NOISE, 0u);
             float za, zb;
             // (the single-step kernels measured 6 % faster on freshly reset populations with the branchy IEEE sqrt here)
-            normal_pair((tick & 1u) ? w.z : w.x, (tick & 1u) ? w.w : w.y, za, zb);
+            normal_pair(key.tab, (tick & 1u) ? w.z : w.x, (tick & 1u) ? w.w : w.y, za, zb);
             nz[0] = mul(0.1f, za);
             nz[1] = mul(500.0f, zb);
         }
@@ -92,13 +92,13 @@ struct Reactor {
         s[11] = 0.0f;
     }
     // Box-Muller pair `pair` (0..3) of the 8: the unit of work of the warp-cooperative reset (one pair per lane)
-    __device__ static __forceinline__ void reset_pair(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t pair,
+    __device__ static __forceinline__ void reset_pair(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t pair,
                                                       float& z0, float& z1)
     {
         const uint4 w = rng_words(key, env, tick, STREAM_RESET, (epoch << 8) | (pair >> 1));
-        normal_pair((pair & 1u) ? w.z : w.x, (pair & 1u) ? w.w : w.y, z0, z1);
+        normal_pair(key.tab, (pair & 1u) ? w.z : w.x, (pair & 1u) ? w.w : w.y, z0, z1);
     }
-    __device__ static __forceinline__ void reset(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, float (&s)[S])
+    __device__ static __forceinline__ void reset(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, float (&s)[S])
     {
         float z[8];
         rng_normals4(key, env, tick, STREAM_RESET, (epoch << 8) | 0u, reinterpret_cast<float (&)[4]>(z[0]));
@@ -183,7 +183,7 @@ struct Reactor {
     }
 
     // get_dataset controller branch (:366-385): a_j = g0_j*(T-320)/50 + g1_j*(level-55)/50 + sigma_j*N(0,1)
-    __device__ static __forceinline__ void policy_ctrl(const RngKey& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
+    __device__ static __forceinline__ void policy_ctrl(const Rng& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
                                                        const float (&s)[S], float (&a)[A])
     {
         float z[4];
@@ -218,7 +218,7 @@ struct Grid {
 
     struct NoiseGen {
         // draw order V(8) sigma .005, load(8) sigma 1, flow(7) sigma 2  (:136, :140, :144)
-        __device__ __forceinline__ void get(const RngKey& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
+        __device__ __forceinline__ void get(const Rng& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
         {
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
@@ -230,7 +230,7 @@ struct Grid {
                     if (4 * j + q < NZ) nz[4 * j + q] = mul(sg, z[q]);
             }
         }
-        __device__ static __forceinline__ void get_single(const RngKey& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
+        __device__ static __forceinline__ void get_single(const Rng& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
         {
             NoiseGen g;
             g.get(key, env, tick, nz);
@@ -245,7 +245,7 @@ struct Grid {
     static constexpr int ROLLOUT_MIN_CTAS = 3;
     static constexpr int STEP_MIN_CTAS = 4;          // single step: 146 -> 128 registers, 3 -> 4 CTAs per SM, +11 % (5, 6: worse)
     static constexpr int COOP_BLOCKS = 8;
-    __device__ static __forceinline__ void reset_block(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t j, float (&v)[4])
+    __device__ static __forceinline__ void reset_block(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t j, float (&v)[4])
     {
         if (j == 4u || j == 5u) {
             const uint4 w = rng_words(key, env, tick, STREAM_RESET, (epoch << 8) | j);
@@ -263,7 +263,7 @@ struct Grid {
             if (i < 7) s[25 + i] = mul(10.0f, v[24 + i]);
         }
     }
-    __device__ static __forceinline__ void reset(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, float (&s)[S])
+    __device__ static __forceinline__ void reset(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, float (&s)[S])
     {
         float v[32];
 #pragma unroll
@@ -337,7 +337,7 @@ struct Grid {
     }
 
     // get_dataset heuristics (:216-232): a_j = g0_j*freq_dev + g1_j*(sum load - sum gen)/8 + sigma_j*N(0,1)
-    __device__ static __forceinline__ void policy_ctrl(const RngKey& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
+    __device__ static __forceinline__ void policy_ctrl(const Rng& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
                                                        const float (&s)[S], float (&a)[A])
     {
         float gen[8], load[8], z[8];
@@ -377,8 +377,8 @@ struct Robot {
     static constexpr double PI = 3.141592653589793;
 
     struct NoiseGen {
-        __device__ __forceinline__ void get(const RngKey&, uint32_t, uint32_t, float (&)[1]) {}
-        __device__ static __forceinline__ void get_single(const RngKey&, uint32_t, uint32_t, float (&)[1]) {}
+        __device__ __forceinline__ void get(const Rng&, uint32_t, uint32_t, float (&)[1]) {}
+        __device__ static __forceinline__ void get_single(const Rng&, uint32_t, uint32_t, float (&)[1]) {}
     };
 
     __device__ static __forceinline__ void fk(const double (&q)[7], double (&pos)[3])
@@ -394,7 +394,7 @@ struct Robot {
         pos[0] = x; pos[1] = y; pos[2] = z;
     }
 
-    __device__ static __forceinline__ void reset(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, float (&s)[S])
+    __device__ static __forceinline__ void reset(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, float (&s)[S])
     {   // _get_initial_state (:113-137): q ~ U(-pi/2, pi/2)
         double q[7], pos[3];
 #pragma unroll
@@ -499,7 +499,7 @@ struct Robot {
 
     // get_dataset controllers (:266-287): P-control of the end-effector error on the first three joints;
     // mode 0 (expert) damps joints 3..6, mode 1 (mixed) drives them with U(-sigma[3], sigma[3])
-    __device__ static __forceinline__ void policy_ctrl(const RngKey& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
+    __device__ static __forceinline__ void policy_ctrl(const Rng& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
                                                        const float (&s)[S], float (&a)[A])
     {
         a[0] = mul(pp.gain[0][0], sub(0.3f, s[0]));

@@ -218,7 +218,7 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
 // for one lane, every resetting lane in turn broadcasts its env id, lanes 0..3 each produce ONE Box-Muller pair of its
 // draw, and the 8 normals are shuffled back. Same counters, same values as Env::reset(). Must be called convergently.
 template <class Env>
-__device__ __forceinline__ void coop_reset(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, bool need, float (&s)[Env::S])
+__device__ __forceinline__ void coop_reset(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, bool need, float (&s)[Env::S])
 {
     unsigned m = __ballot_sync(0xffffffffu, need);
     const uint32_t lane = threadIdx.x & 31u;
@@ -246,7 +246,7 @@ template <class Env>
 struct CoopSmem { static constexpr int floats = Env::COOP_BLOCKS > 0 ? (kThreads / 32) * 32 * Env::COOP_BLOCKS * 4 : 1; };
 
 template <class Env>
-__device__ __forceinline__ void coop_reset_blocks(const RngKey& key, uint32_t env, uint32_t tick, uint32_t epoch, bool need,
+__device__ __forceinline__ void coop_reset_blocks(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, bool need,
                                                   float (&s)[Env::S], float* cta_buf)
 {
     constexpr int RB = Env::COOP_BLOCKS, NV = RB * 4;
@@ -456,6 +456,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
     BlockStats bs;
     bs.init(sstat);
     const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
+    const Rng key(p.key, g_normal_tab);        // one-tile CTA: the L1-cached global table
 
     const int64_t i0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
     unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0, c_con = 0;  // c_con: 4 bits/constraint
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
 #pragma unroll
                     for (int k = 0; k < NZA; ++k) nz[k] = nzv[k][e];
                 } else {
-                    Env::NoiseGen::get_single(p.key, env, tick0, nz);
+                    Env::NoiseGen::get_single(key, env, tick0, nz);
                 }
             } else nz[0] = 0.0f;
             acc_t r; uint32_t f, vm;
@@ -509,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
                         for (int k = 0; k < S; ++k) s[k] = rs[k][e];
                     } else {
                         if constexpr (Env::COOP_RESET || Env::COOP_BLOCKS > 0) need_reset = true;
-                        else Env::reset(p.key, env, tick0 + 1u, p.epoch, s);
+                        else Env::reset(key, env, tick0 + 1u, p.epoch, s);
                     }
                     w = 0u; f |= NIG_F_RESET;
                 } else {
@@ -521,8 +522,8 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
 #pragma unroll
                 for (int k = 0; k < S; ++k) s[k] = ns[k];
             }
-            if constexpr (Env::COOP_RESET) coop_reset<Env>(p.key, env, tick0 + 1u, p.epoch, need_reset, s);
-            else if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(p.key, env, tick0 + 1u, p.epoch, need_reset, s, coop_buf);
+            if constexpr (Env::COOP_RESET) coop_reset<Env>(key, env, tick0 + 1u, p.epoch, need_reset, s);
+            else if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(key, env, tick0 + 1u, p.epoch, need_reset, s, coop_buf);
 #pragma unroll
             for (int k = 0; k < S; ++k) sv[k][e] = s[k];
             wv[e] = __uint_as_float(w);
@@ -619,6 +620,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
     BlockStats bs;
     bs.init(sstat);
     const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
+    const Rng key(p.key, g_normal_tab);        // (a shared copy would cost the fourth resident CTA its stage ring)
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < kStepStages; ++k) mbar_init(&full[k], 1);
@@ -688,7 +690,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             for (int k = 0; k < A; ++k) a[k] = av[k][e];
             const bool valid = i < p.n;
             const bool active = valid && !(w >> 31);
-            if constexpr (NZ > 0) Env::NoiseGen::get_single(p.key, env, tick0, nz);
+            if constexpr (NZ > 0) Env::NoiseGen::get_single(key, env, tick0, nz);
             else nz[0] = 0.0f;
             acc_t r; uint32_t f, vm;
             step_core<Env, CONS>(p.cons, p.max_steps, s, a, nz, 0u, w, ns, r, f, vm);
@@ -702,11 +704,11 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             if (done) {
                 if (p.auto_reset) {
                     if constexpr (Env::COOP_RESET) need_reset = true;
-                    else Env::reset(p.key, env, tick0 + 1u, p.epoch, ns);
+                    else Env::reset(key, env, tick0 + 1u, p.epoch, ns);
                     w = 0u; f |= NIG_F_RESET;
                 } else w |= 0x80000000u;
             }
-            if constexpr (Env::COOP_RESET) coop_reset<Env>(p.key, env, tick0 + 1u, p.epoch, need_reset, ns);
+            if constexpr (Env::COOP_RESET) coop_reset<Env>(key, env, tick0 + 1u, p.epoch, need_reset, ns);
 #pragma unroll
             for (int k = 0; k < S; ++k) sv[k][e] = ns[k];
             wv[e] = __uint_as_float(w);
@@ -772,12 +774,13 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= p.n) return;
     if (p.mask && !p.mask[i]) return;
+    const Rng key(p.key, g_normal_tab);
     float s[Env::S];
     if (p.init_states) {
 #pragma unroll
         for (int k = 0; k < Env::S; ++k) s[k] = p.init_aos ? p.init_states[i * Env::S + k] : p.init_states[k * p.pitch + i];
     } else {
-        Env::reset(p.key, p.env0 + (uint32_t)i, load_tick(p.tick_dev, p.tick), p.epoch, s);
+        Env::reset(key, p.env0 + (uint32_t)i, load_tick(p.tick_dev, p.tick), p.epoch, s);
     }
 #pragma unroll
     for (int k = 0; k < Env::S; ++k) p.state[k * p.pitch + i] = s[k];
@@ -842,7 +845,7 @@ struct RolloutArgs {
 
 // in-kernel policies ---------------------------------------------------------------------------------
 template <class Env>
-__device__ __forceinline__ void policy_uniform(const RngKey& key, uint32_t env, uint32_t tick, float (&a)[Env::A])
+__device__ __forceinline__ void policy_uniform(const Rng& key, uint32_t env, uint32_t tick, float (&a)[Env::A])
 {
 #pragma unroll
     for (int j = 0; j < (Env::A + 3) / 4; ++j) {
@@ -858,7 +861,7 @@ __device__ __forceinline__ void policy_uniform(const RngKey& key, uint32_t env, 
 // block 0 word 0 of the POLICY stream is the np.random.random() coin; the controller branch gets 8
 // normals (blocks 1, 2) and 4 words (block 3); the random branch uses words 1..3 of block 0 and blocks 8..
 template <class Env>
-__device__ __forceinline__ void policy_pctrl(const RngKey& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
+__device__ __forceinline__ void policy_pctrl(const Rng& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
                                              const float (&s)[Env::S], float (&a)[Env::A])
 {
     const uint4 w0 = rng_words(key, env, tick, STREAM_POLICY, 0u);
@@ -886,7 +889,7 @@ __device__ __forceinline__ void policy_pctrl(const RngKey& key, const nig_policy
 
 // benchmarks/baseline_agents.py controllers in fp64 like numpy computes them; integ / prev are the PID agent's state
 template <class Env>
-__device__ __forceinline__ void policy_baseline(const RngKey& key, const nig_baseline_t& b, uint32_t env, uint32_t tick,
+__device__ __forceinline__ void policy_baseline(const Rng& key, const nig_baseline_t& b, uint32_t env, uint32_t tick,
                                                 const float (&s)[Env::S], float (&a)[Env::A],
                                                 double (&integ)[Env::A], double (&prev)[Env::A])
 {
@@ -948,13 +951,16 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
     __shared__ double sfl[4];
     __shared__ unsigned long long sext[2];       // extremum keys of the episodes this CTA finished
+    __shared__ float4 s_tab[NIG_NORMAL_TAB_N];   // this CTA's copy of the normal table (8 KB, read K * draws times)
     __shared__ alignas(8) uint64_t bars[2];
     __shared__ float coop_buf[CoopSmem<Env>::floats];
     extern __shared__ __align__(128) float act_smem[];     // [2][kTmaChunk][A][kThreads] when TMA
     BlockStats bs;
     if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
     if constexpr (EXTREMA) { if (threadIdx.x < 2) sext[threadIdx.x] = 0ull; }
-    bs.init(sstat);
+    normal_table_to_smem(s_tab);
+    const Rng key(p.key, s_tab);
+    bs.init(sstat);                              // (synchronises the CTA)
 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < p.n;
@@ -1044,11 +1050,11 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
                 for (int k = 0; k < A; ++k) a_pf[k] = __ldcs(p.actions + ((int64_t)tn * A + k) * p.pitch + ic);
             }
         } else if constexpr (POLICY == NIG_POLICY_UNIFORM) {
-            policy_uniform<Env>(p.key, env, tick, a);
+            policy_uniform<Env>(key, env, tick, a);
         } else if constexpr (POLICY == NIG_POLICY_PCTRL) {
-            policy_pctrl<Env>(p.key, p.pp, env, tick, s, a);
+            policy_pctrl<Env>(key, p.pp, env, tick, s, a);
         } else if constexpr (POLICY == NIG_POLICY_BASELINE) {
-            policy_baseline<Env>(p.key, p.pp.baseline, env, tick, s, a, pid_i, pid_e);
+            policy_baseline<Env>(key, p.pp.baseline, env, tick, s, a, pid_i, pid_e);
         } else {
 #pragma unroll
             for (int k = 0; k < A; ++k) a[k] = 0.0f;
@@ -1065,7 +1071,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
 #pragma unroll
                     for (int k = 0; k < NZA; ++k) nz[k] = __ldcs(p.noise + ((int64_t)t * NZA + k) * p.pitch + ic);
                 }
-            } else ng.get(p.key, env, tick, nz);
+            } else ng.get(key, env, tick, nz);
         } else nz[0] = 0.0f;
 
         const bool active = valid && !latched;
@@ -1098,7 +1104,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
                 if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
                 if (p.auto_reset) {
                     if constexpr (Env::COOP_BLOCKS > 0) need_reset = true;
-                    else Env::reset(p.key, env, tick + 1u, p.epoch, s);
+                    else Env::reset(key, env, tick + 1u, p.epoch, s);
                     ep_st = 0u; ep_vi = 0u; ep_ret = (acc_t)0;
                 } else {
 #pragma unroll
@@ -1110,7 +1116,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
                 for (int k = 0; k < S; ++k) s[k] = ns[k];
             }
         }
-        if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(p.key, env, tick + 1u, p.epoch, need_reset, s, coop_buf);
+        if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(key, env, tick + 1u, p.epoch, need_reset, s, coop_buf);
     }
 
     // fp32-reward envs (reactor): the reward statistic of this launch is the fp32 per-env sum (K <= a few hundred
@@ -1210,19 +1216,23 @@ __global__ void __launch_bounds__(kThreads) dataset_kernel(const __grid_constant
 {
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
     using acc_t = typename Env::acc_t;
+    __shared__ float4 s_tab[NIG_NORMAL_TAB_N];
+    normal_table_to_smem(s_tab);
+    __syncthreads();
+    const Rng key(p.key, s_tab);
     const int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (e >= p.n_episodes) return;
     const uint32_t env = p.env0 + (uint32_t)e;
     float s[S];
-    Env::reset(p.key, env, 0u, p.epoch, s);
+    Env::reset(key, env, 0u, p.epoch, s);
     typename Env::NoiseGen ng;
     uint32_t w = 0u;
     int64_t row = WRITE ? p.offsets[e] : 0;
     int32_t len = 0;
     for (int t = 0; t < p.n_steps; ++t) {
         float a[A], nz[NZA], ns[S];
-        if (p.policy == NIG_POLICY_UNIFORM) policy_uniform<Env>(p.key, env, (uint32_t)t, a);
-        else if (p.policy == NIG_POLICY_PCTRL) policy_pctrl<Env>(p.key, p.pp, env, (uint32_t)t, s, a);
+        if (p.policy == NIG_POLICY_UNIFORM) policy_uniform<Env>(key, env, (uint32_t)t, a);
+        else if (p.policy == NIG_POLICY_PCTRL) policy_pctrl<Env>(key, p.pp, env, (uint32_t)t, s, a);
         else {
 #pragma unroll
             for (int k = 0; k < A; ++k) a[k] = 0.0f;
@@ -1236,7 +1246,7 @@ __global__ void __launch_bounds__(kThreads) dataset_kernel(const __grid_constant
                 a[k] = v;
             }
         }
-        if (NZ > 0) ng.get(p.key, env, (uint32_t)t, nz); else nz[0] = 0.0f;
+        if (NZ > 0) ng.get(key, env, (uint32_t)t, nz); else nz[0] = 0.0f;
         acc_t r; uint32_t f, vm;
         step_core<Env, CONS>(p.cons, p.max_steps, s, a, nz, 0u, w, ns, r, f, vm);
         const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
@@ -1328,7 +1338,7 @@ static __global__ void __launch_bounds__(256) selftest_normal_kernel(uint32_t fi
     unsigned long long s0 = 0, s1 = 0;
     for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t w = first + (uint32_t)k * stride;
-        const unsigned long long bits = __float_as_uint(spec_normal(w));
+        const unsigned long long bits = __float_as_uint(spec_normal(g_normal_tab, w));
         s0 += bits;
         s1 += bits * (k + 1ull);
     }
