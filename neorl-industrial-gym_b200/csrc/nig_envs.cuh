@@ -77,6 +77,7 @@ struct Reactor {
     // resident CTAs per SM the fused rollout is compiled for (register cap): measured, more resident warps LOSE for
     // the reactor (7.0 -> 6.8 -> 6.3e10 env-steps/s at 1M envs for 4 / 6 / 8 CTAs)
     static constexpr int ROLLOUT_MIN_CTAS = 1;
+    static constexpr bool TAB_SMEM = false;          // 2 normals per step: the L1-cached global table is as fast, no staging prologue
     static constexpr int STEP_MIN_CTAS = 1;
     __device__ static __forceinline__ void reset_from_normals(const float (&z)[8], float (&s)[S])
     {
@@ -243,6 +244,7 @@ struct Grid {
     // 206 registers uncapped = 2 resident CTAs per SM; capped at 168 (3 CTAs, 24 B of spills): +15 % at 1M envs, 4 CTAs (128
     // registers) no better
     static constexpr int ROLLOUT_MIN_CTAS = 3;
+    static constexpr bool TAB_SMEM = true;           // 23 normals per step: shared-memory copy of the normal table (+7 %)
     static constexpr int STEP_MIN_CTAS = 4;          // single step: 146 -> 128 registers, 3 -> 4 CTAs per SM, +11 % (5, 6: worse)
     static constexpr int COOP_BLOCKS = 8;
     __device__ static __forceinline__ void reset_block(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t j, float (&v)[4])
@@ -365,6 +367,7 @@ struct Robot {
     static constexpr bool FAST_DIV = false;          // fp64 divisions only
     static constexpr bool COOP_RESET = false;
     static constexpr int COOP_BLOCKS = 0;
+    static constexpr bool TAB_SMEM = false;          // normals only in reset / policy draws
     static constexpr int ROLLOUT_MIN_CTAS = 4;       // 177 -> 128 registers: 1.76 -> 2.05e10 env-steps/s at 1M envs
     static constexpr int STEP_MIN_CTAS = 6;          // 104 -> 80 registers: 0.39 -> 0.47 of the HBM peak at 4M envs
     static constexpr uint32_t CRIT_MASK = 0x3;       // force_limits, collision_avoidance (:56-68)

@@ -951,15 +951,15 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
     __shared__ double sfl[4];
     __shared__ unsigned long long sext[2];       // extremum keys of the episodes this CTA finished
-    __shared__ float4 s_tab[NIG_NORMAL_TAB_N];   // this CTA's copy of the normal table (8 KB, read K * draws times)
+    __shared__ float4 s_tab[Env::TAB_SMEM ? NIG_NORMAL_TAB_N : 1];   // this CTA's copy of the normal table (8 KB, read K * draws times)
     __shared__ alignas(8) uint64_t bars[2];
     __shared__ float coop_buf[CoopSmem<Env>::floats];
     extern __shared__ __align__(128) float act_smem[];     // [2][kTmaChunk][A][kThreads] when TMA
     BlockStats bs;
     if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
     if constexpr (EXTREMA) { if (threadIdx.x < 2) sext[threadIdx.x] = 0ull; }
-    normal_table_to_smem(s_tab);
-    const Rng key(p.key, s_tab);
+    if constexpr (Env::TAB_SMEM) normal_table_to_smem(s_tab);
+    const Rng key(p.key, Env::TAB_SMEM ? s_tab : g_normal_tab);
     bs.init(sstat);                              // (synchronises the CTA)
 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1303,7 +1303,7 @@ static __global__ void __launch_bounds__(256) selftest_division_kernel(RngKey ke
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long bad = 0, acc = 0;
     for (int it = 0; it < iters; ++it) {
-        const uint4 w = philox4x32_10(tid, (uint32_t)it, 7u, 0u, key.k0, key.k1);
+        const uint4 w = philox4x32<10>(tid, (uint32_t)it, 7u, 0u, key.k0, key.k1);
         {   // mode 0
             DivFast d;
             const float x = __uint_as_float(w.x), y = __uint_as_float(w.y);

@@ -36,18 +36,28 @@ def generate_dataset_device(native, n_episodes: int, n_steps: int, policy: int, 
 
 
 def episodes_for_transitions(native, n_transitions: int, n_steps: int, policy: int, params) -> int:
-    """Smallest episode count found whose dataset holds >= n_transitions rows. Episodes are independent envs keyed by
-    their index, so the row count is monotone in the episode count; the length-probe pass (nig_dataset_size) of the
-    final count is cached by the library and not repeated by the write pass."""
+    """The smallest episode count whose dataset holds >= n_transitions rows (so the overshoot is less than one episode).
+    Episodes are independent envs keyed by their index, so the row count is monotone in the episode count: grow
+    geometrically until the target is reached, then bisect. Each probe is one length-only pass (nig_dataset_size); the
+    probe of the final count is cached by the library and not repeated by the write pass."""
     if n_transitions <= 0:
         raise ValueError("n_transitions must be positive")
-    n_ep = max(1, -(-n_transitions // n_steps))
+    lo, hi = 0, max(1, -(-n_transitions // n_steps))       # lo: too few (0 episodes = 0 rows); hi: candidate
     for _ in range(32):
-        m = native.dataset_size(n_ep, n_steps, policy, params)
+        m = native.dataset_size(hi, n_steps, policy, params)
         if m >= n_transitions:
-            return n_ep
-        n_ep = max(n_ep + 1, int(n_ep * (n_transitions / max(m, 1)) * 1.02) + 1)
-    raise RuntimeError("could not reach the requested number of transitions (episodes end immediately?)")
+            break
+        lo, hi = hi, max(hi + 1, int(hi * (n_transitions / max(m, 1)) * 1.02) + 1)
+    else:
+        raise RuntimeError("could not reach the requested number of transitions (episodes end immediately?)")
+    while hi - lo > 1:
+        mid = (lo + hi) // 2
+        if native.dataset_size(mid, n_steps, policy, params) >= n_transitions:
+            hi = mid
+        else:
+            lo = mid
+    native.dataset_size(hi, n_steps, policy, params)       # leave the final count as the cached probe
+    return hi
 
 
 def generate_dataset(env, n_episodes: int, n_steps: int, policy: int, params, *, terminals_include_truncation: bool,

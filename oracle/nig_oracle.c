@@ -97,9 +97,12 @@ static float spec_expf(float x)
     return (p * s1) * s2;
 }
 
-static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+/* Philox4x32-R (Salmon et al., SC'11). The spec's streams use R = 7, the fewest rounds the paper reports as passing
+ * BigCrush ("Crush-resistant"); R = 10 is kept for the published known-answer vectors. */
+#define SPEC_PHILOX_ROUNDS 7
+static void philox4x32(int rounds, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
 {
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -143,13 +146,13 @@ enum { STREAM_NOISE = 0, STREAM_RESET = 1, STREAM_POLICY = 2 };
 static void normals4(const orc_cfg_t* cfg, uint32_t env, uint32_t tick, uint32_t stream, uint32_t j, float z[4])
 {
     uint32_t w[4];
-    philox4x32_10(env, tick, stream, j, (uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32), w);
+    philox4x32(SPEC_PHILOX_ROUNDS, env, tick, stream, j, (uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32), w);
     box_muller(w[0], w[1], &z[0], &z[1]);
     box_muller(w[2], w[3], &z[2], &z[3]);
 }
 static void words4(const orc_cfg_t* cfg, uint32_t env, uint32_t tick, uint32_t stream, uint32_t j, uint32_t w[4])
 {
-    philox4x32_10(env, tick, stream, j, (uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32), w);
+    philox4x32(SPEC_PHILOX_ROUNDS, env, tick, stream, j, (uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32), w);
 }
 
 ORC_API void orc_spec_normals4(uint64_t seed, uint32_t env, uint32_t tick, uint32_t stream, uint32_t j, float* z)
@@ -170,8 +173,17 @@ ORC_API void orc_selftest_normal(uint32_t first, uint32_t stride, int64_t count,
     }
     sums2[0] = s0; sums2[1] = s1;
 }
-ORC_API void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out)
-{ philox4x32_10(c0, c1, c2, c3, k0, k1, out); }
+ORC_API void orc_philox(int rounds, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out)
+{ philox4x32(rounds, c0, c1, c2, c3, k0, k1, out); }
+ORC_API int orc_spec_philox_rounds(void) { return SPEC_PHILOX_ROUNDS; }
+/* the spec's words for a rectangle of (env, tick) counters: out[(e * n_tick + t) * 4 + q] (statistical tests) */
+ORC_API void orc_words_batch(uint64_t seed, uint32_t env0, int32_t n_env, uint32_t tick0, int32_t n_tick, uint32_t stream, uint32_t j, uint32_t* out)
+{
+    for (int32_t e = 0; e < n_env; ++e)
+        for (int32_t t = 0; t < n_tick; ++t)
+            philox4x32(SPEC_PHILOX_ROUNDS, env0 + (uint32_t)e, tick0 + (uint32_t)t, stream, j, (uint32_t)seed, (uint32_t)(seed >> 32),
+                       out + ((size_t)e * (size_t)n_tick + (size_t)t) * 4);
+}
 
 /* Python's max(lo, min(hi, v)) on a float: min(hi,v) = v if v < hi else hi; max(lo,m) = m if m > lo else lo */
 static inline float py_clamp(float v, float lo, float hi)

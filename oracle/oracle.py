@@ -233,9 +233,17 @@ def selftest_normal(first, stride, count):
     return int(out[0]), int(out[1])
 
 
-def philox(c, k):
+def philox(c, k, rounds=10):
     out = np.empty(4, np.uint32)
-    lib().orc_philox(*(C.c_uint32(int(x)) for x in c), *(C.c_uint32(int(x)) for x in k), _p(out))
+    lib().orc_philox(C.c_int(rounds), *(C.c_uint32(int(x)) for x in c), *(C.c_uint32(int(x)) for x in k), _p(out))
+    return out
+
+
+def words_batch(seed, env0, n_env, tick0, n_tick, stream=0, j=0):
+    """uint32 [n_env, n_tick, 4]: the spec's Philox words of a rectangle of (env, tick) counters."""
+    out = np.empty((n_env, n_tick, 4), np.uint32)
+    lib().orc_words_batch(C.c_uint64(seed), C.c_uint32(env0), C.c_int32(n_env), C.c_uint32(tick0), C.c_int32(n_tick),
+                          C.c_uint32(stream), C.c_uint32(j), _p(out))
     return out
 
 

@@ -142,7 +142,12 @@ def test_spec_exp_accuracy():
 
 
 def test_philox_known_answers():
-    """Random123 known-answer vectors for Philox4x32-10."""
+    """Random123 known-answer vectors for Philox4x32-10 and for Philox4x32-7 (the round count of the spec's streams)."""
+    assert O.lib().orc_spec_philox_rounds() == 7
+    assert [hex(x) for x in O.philox((0, 0, 0, 0), (0, 0), 7)] == ["0x5f6fb709", "0xd893f64", "0x4f121f81", "0x4f730a48"]
+    assert [hex(x) for x in O.philox((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, 7)] == ["0x5207ddc2", "0x45165e59", "0x4d8ee751", "0x8c52f662"]
+    assert [hex(x) for x in O.philox((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), 7)] == \
+        ["0x4dfccaba", "0x190a87f0", "0xc47362ba", "0xb6b5242a"]
     assert [hex(x) for x in O.philox((0, 0, 0, 0), (0, 0))] == ["0x6627e8d5", "0xe169c58d", "0xbc57ac4c", "0x9b00dbd8"]
     assert [hex(x) for x in O.philox((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2)] == ["0x408f276d", "0x41c83b0e", "0xa20bc7c6", "0x6d5451fd"]
     assert [hex(x) for x in O.philox((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0))] == \
@@ -155,6 +160,29 @@ def test_spec_normals_are_gaussian():
     kurt = ((z - z.mean()) ** 4).mean() / z.var() ** 2
     assert abs(kurt - 3) < 0.1
     assert abs(np.corrcoef(z[0::4], z[1::4])[0, 1]) < 0.03
+
+
+def test_spec_stream_words_look_uniform_and_independent():
+    """Sanity screen of the 7-round streams on the counters the kernels actually use (consecutive env ids x consecutive
+    ticks): byte histograms, correlation between neighbouring envs / ticks / words, bit balance, avalanche. (The
+    BigCrush evidence for 7 rounds is Salmon et al.; this only guards against a wiring mistake.)"""
+    from scipy import stats
+    w = O.words_batch(12345, 1000, 512, 77, 256)                    # 131,072 blocks, 524,288 words
+    flat = w.reshape(-1)
+    for shift in (0, 8, 16, 24):
+        hist = np.bincount((flat >> shift) & 0xFF, minlength=256)
+        assert stats.chisquare(hist).pvalue > 1e-4, shift
+    u = flat.astype(np.float64) / 2.0 ** 32
+    assert stats.kstest(u, "uniform").pvalue > 1e-4
+    x = w.astype(np.float64)
+    for a, b in ((x[:-1, :, 0], x[1:, :, 0]), (x[:, :-1, 0], x[:, 1:, 0]), (x[..., 0], x[..., 1]), (x[..., 2], x[..., 3])):
+        assert abs(np.corrcoef(a.ravel(), b.ravel())[0, 1]) < 0.01
+    bits = np.unpackbits(flat.view(np.uint8))
+    assert abs(bits.mean() - 0.5) < 2e-3
+    # avalanche: neighbouring counters differ in about half of their 128 output bits
+    d_env = np.unpackbits((w[:-1] ^ w[1:]).view(np.uint8)).mean()
+    d_tick = np.unpackbits((w[:, :-1] ^ w[:, 1:]).view(np.uint8)).mean()
+    assert abs(d_env - 0.5) < 2e-3 and abs(d_tick - 0.5) < 2e-3
 
 
 def test_spec_normal_is_the_inverse_cdf():
