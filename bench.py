@@ -44,6 +44,7 @@ METRIC = "env-steps/sec (ChemicalReactor-v0, 64K envs)"
 UNIT = "env-steps/s"
 ALG_BYTES_PER_STEP = 122  # 48 state r + 48 state w + 12 action + 4 reward + 2 flags + 8 counter r/w
 ALG_OPS_PER_STEP = 128    # dynamics 76 + reward 30 + step logic 22 (RNG / addressing excluded)
+ISSUED_PER_WARP_STEP = 301   # ncu: executed warp-instructions per warp per step of the fused reactor kernel (profiles/r01_g_*)
 WORKLOAD = ("ChemicalReactor-v0 batched 65,536 envs x 1,000 steps fp32 per GPU; fused K=64 rollout kernel "
             "(15x64+40), in-kernel uniform-random policy (= action_space.sample()), Philox process noise, auto-reset")
 
@@ -277,11 +278,13 @@ def run_gpu(args):
             "kernel": "rollout_kernel<Reactor, default constraints, POLICY_UNIFORM> (K=64 fused steps)",
             "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
             "traffic": ncu_traffic("rollout_kernel<Reactor"),
-            "ncu": "profiles/r01_e_rollout_kernel_ncu_table.txt: 383 issued warp-instructions per 32 env-steps (128 algorithmic), issue slots "
-                   "71 % busy while active, FMA pipe 38 %, ALU pipe 57 %, 3.5 warps per SM sub-partition (65,536 envs = 0.69 waves)",
-            "frac_with_rng_ops": (ALG_OPS_PER_STEP + 2 * 52) / ALG_OPS_PER_STEP * achieved / fp32_peak,
+            "ncu": "profiles/r01_g_reactor_rollout_kernel_ncu_table.txt: 301 issued warp-instructions per 32 env-steps (128 algorithmic), issue slots "
+                   "70 % busy while active, FMA pipe 37 %, ALU pipe 55 %, 3.5 warps per SM sub-partition (65,536 envs = 0.69 waves)",
+            # every instruction the kernel issues (ncu count, 301 per warp-step) against one warp-instruction per cycle
+            # per SM sub-partition at the peak the probe measured: how full the issue slots are over the whole launch
+            "issue_slot_frac": ISSUED_PER_WARP_STEP / ALG_OPS_PER_STEP * achieved / fp32_peak,
             "note": f"algorithmic {ALG_OPS_PER_STEP} fp32 ops/env-step (SURVEY 8d; RNG, IEEE-division expansion and addressing "
-                    "excluded) x env-steps per launch / mean launch time (frac_with_rng_ops adds the survey's 2 Gaussians x ~52 ops per step); peak = unfused FADD/FMUL issue rate measured live by "
+                    "excluded) x env-steps per launch / mean launch time (issue_slot_frac counts all 301 issued instructions per step, RNG included); peak = unfused FADD/FMUL issue rate measured live by "
                     "nig_fp32_probe (nominal 148 SM x 128 lanes x 1.965 GHz = 37.2 T op/s). Tensor cores do not apply: element-wise ODE.",
         }
         # ---- single-step kernel at 65,536 envs (launch-bound) and its HBM roofline at 4M envs (> L2)
