@@ -27,6 +27,7 @@ nat.rollout_device(K, N.POLICY_UNIFORM)
 view = allreduce_device_stats(nat)                     # in place on the device block, int64 counters + fp64 sums
 torch.cuda.synchronize()
 summed = nat.stats_dict()
+nat.rollout_device(512, N.POLICY_UNIFORM)              # past the 500-step truncation: every env finishes an episode
 ext = allreduce_extrema(nat)                           # one MAX all-reduce of the two int64 keys
 state = nat.get_state_host()[0]
 gathered = [None] * world
@@ -41,6 +42,7 @@ if rank == 0:
               "episode_length_sum", "violations_per_constraint"):
         assert summed[k] == ref[k], (k, summed[k], ref[k])
     assert abs(summed["return_sum"] - ref["return_sum"]) <= 1e-9 * abs(ref["return_sum"]) + 1e-6
+    w.rollout_device(512, N.POLICY_UNIFORM); torch.cuda.synchronize()
     assert ext == w.read_extrema() and ext[0] is not None and ext[0] < ext[1], (ext, w.read_extrema())
     ws = w.get_state_host()[0]
     assert np.array_equal(np.concatenate(gathered).view(np.uint32), ws.view(np.uint32))

@@ -20,5 +20,5 @@ def test_sharded_rollout_nccl_allreduce_matches_unsharded():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "_nccl_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-8000:]
     assert f"NCCL_SHARDED_OK {world}" in out.stdout, out.stdout[-2000:]
