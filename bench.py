@@ -206,11 +206,9 @@ def run_gpu(args):
     stats_view = env.stats_tensor()
 
     def one_pass():
-        done = 0
-        while done < HORIZON:
-            k = min(K, HORIZON - done)
-            env.rollout_device(k, N.POLICY_UNIFORM)
-            done += k
+        # 1,000 steps as 15 x K=64 + one K=40 fused launches per env slice (C ABI nig_rollout_steps: the slices advance on
+        # internal streams forked from / joined to the current stream, so the CUDA events below bracket all of them)
+        env.rollout_steps_device(HORIZON, K, N.POLICY_UNIFORM)
 
     def barrier():
         if dist is not None:
@@ -260,7 +258,9 @@ def run_gpu(args):
         if others is not None:
             extra["other_configs"] = others
         # ---- roofline of the dominant kernel of the timed region (fused rollout): fp32 pipe
-        kernel_ms = total_ms / (args.steps * launches_per_pass())        # average launch (15 x K=64 and one K=40)
+        # per whole-population K-step launch (15 x K=64 and one K=40 per bench step). The env slices of nig_rollout_steps
+        # run these launches concurrently on several streams, so the duration is the step time shared out over them
+        kernel_ms = total_ms / (args.steps * launches_per_pass())
         ops_per_launch = ALG_OPS_PER_STEP * n * HORIZON / launches_per_pass()
         import ctypes as C
         ops = C.c_double(0)
@@ -310,7 +310,9 @@ def run_gpu(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n, "steps_per_env_per_bench_step": HORIZON, "K": K,
-                   "launches_per_bench_step": launches_per_pass(), "parallelism": f"env-index shards x{world}, no data-path collective",
+                   "launches_per_bench_step": int(launches) // max(args.steps, 1),
+                   "env_slices_per_gpu": (int(launches) // max(args.steps, 1)) // launches_per_pass(),
+                   "parallelism": f"env-index shards x{world}, no data-path collective",
                    "l2": "256 MiB write between timed iterations (outside the CUDA-event brackets); state lives in registers across K steps"},
         "clocks": clocks, "gpu_launches": int(launches),
         "wall_s_timed_region": t_wall,

@@ -255,6 +255,12 @@ NIG_API int nig_step_host(nig_env_t* env, const nig_step_io_t* io);
 /* K fused steps with state in registers: the `for step: action = policy(obs); env.step(action)` loops of
  * performance_benchmark.py:106-133, utils.evaluate_with_safety (utils.py:82-125) and get_dataset */
 NIG_API int nig_rollout(nig_env_t* env, const nig_rollout_t* r, void* stream);
+/* total_steps steps of every env as ceil(total_steps / r->n_steps) fused launches (in-kernel policies only). On a large
+ * population the envs are split into slices that advance on internal streams forked from and joined back to `stream`
+ * (NIG_HOST_SLICES, default 8 here and 4 in nig_rollout_host, >= 8,192 envs per slice): a slice's next launch fills the SMs another slice's tail leaves
+ * idle, which a single sequence of whole-population launches cannot do. Results do not depend on the slicing. Per-env
+ * outputs cover the whole call (or add to the arrays with NIG_ROLLOUT_ACCUMULATE). Asynchronous like nig_rollout. */
+NIG_API int nig_rollout_steps(nig_env_t* env, const nig_rollout_t* r, int32_t total_steps, void* stream);
 
 /* The same loops with HOST buffers: what performance_benchmark.py:106-133 / utils.evaluate_with_safety do per env in
  * Python, for every env of the handle in one call. Host arrays are exact-size ([n] or [n][dim]); the call stages

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -68,6 +69,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 } // namespace
 
+constexpr int kMaxHostSlices = 8;
 struct nig_env {
     nig_config_t cfg;
     int kind, S, A, NZ;
@@ -89,6 +91,10 @@ struct nig_env {
     int32_t *h_i32a, *h_i32b;
     unsigned long long* extrema; // [2] min / max finished-episode return keys (outside the summable stats block)
     bool track_extrema;          // nig_track_extrema: rollouts run the EXTREMA kernel flavour
+    // nig_rollout_host over env slices: slice s runs H2D -> reset -> K-step launches -> D2H on its own stream, so the
+    // copies of one slice overlap the stepping of the others (and the slices' launches fill each other's tails)
+    cudaStream_t slice_stream[kMaxHostSlices];
+    cudaEvent_t slice_done[kMaxHostSlices], slice_begin;
     uint32_t* cons_masks;       // device copy of the NIG_CON_BOUND one-hot masks (ConsParams::masks)
     uint32_t* tick_dev;         // device-tick mode (CUDA-graph capture): [0] tick, [1] finished-CTA counter; null = host tick
     double* pid_state;          // [2][A][pitch] PID integral / previous error of NIG_POLICY_BASELINE (lazily allocated, zeroed)
@@ -257,6 +263,134 @@ int state_io(nig_env* e, float* ext_state, int layout, int32_t* st, int32_t* vi,
     return NIG_OK;
 }
 
+// envs [i0, i0 + ns) of the handle -> rows [i0, i0 + ns) of an AoS [n][S] device array
+int state_to_aos_range(nig_env* e, float* ext_aos, int64_t i0, int64_t ns, cudaStream_t s)
+{
+    StateIoArgs a{e->state + i0, e->ep_word + i0, ns, e->pitch, ext_aos + i0 * e->S, nullptr, nullptr, nullptr, e->S, 1, 1};
+    e->launches++;
+    NIG_CUDA(nig::launch_state_io(a, s));
+    return NIG_OK;
+}
+
+// IndustrialEnv.reset of envs [i0, i0 + ns) with an explicit epoch (the caller bumps e->epoch once for all slices)
+int reset_range(nig_env* e, const float* init_aos, int64_t i0, int64_t ns, uint32_t epoch, cudaStream_t s)
+{
+    ResetArgs a{e->state + i0, e->ep_word + i0, e->ep_return + i0, ns, e->pitch, (uint32_t)e->cfg.env_id_offset + (uint32_t)i0, e->tick, epoch,
+                e->tick_dev, e->key, nullptr, init_aos ? init_aos + i0 * e->S : nullptr, 1};
+    e->launches++;
+    NIG_CUDA(nig::launch_reset(e->kind, a, s));
+    return NIG_OK;
+}
+
+// argument checks of a fused rollout (shared by nig_rollout and the sliced nig_rollout_host); allocates the PID state
+int rollout_checks(nig_env* e, const nig_rollout_t* r)
+{
+    if (!r) return fail(NIG_ERR_INVALID, "nig_rollout: null descriptor");
+    if (r->n_steps <= 0) return fail(NIG_ERR_INVALID, "nig_rollout: n_steps must be positive (got %d)", r->n_steps);
+    if (r->policy == NIG_POLICY_ACTIONS && !r->actions) return fail(NIG_ERR_INVALID, "nig_rollout: NIG_POLICY_ACTIONS needs an actions tensor");
+    if (r->noise && e->NZ == 0) return fail(NIG_ERR_INVALID, "nig_rollout: env kind %d has no process noise", e->kind);
+    if (r->noise && r->policy != NIG_POLICY_ACTIONS)
+        return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: teacher-forced noise is only available together with teacher-forced actions (NIG_POLICY_ACTIONS)");
+    if (r->policy < NIG_POLICY_ACTIONS || r->policy > NIG_POLICY_BASELINE) return fail(NIG_ERR_INVALID, "unknown rollout policy %d", r->policy);
+    if (r->noise && e->track_extrema)
+        return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: teacher-forced noise has no return-extrema kernel flavour (nig_track_extrema(env, 0) first)");
+    if (r->policy == NIG_POLICY_BASELINE) {
+        const nig_baseline_t& b = r->pp.baseline;
+        if (b.kind < NIG_BASELINE_RANDOM || b.kind > NIG_BASELINE_CONSTANT) return fail(NIG_ERR_INVALID, "unknown baseline controller %d", b.kind);
+        if (b.kind == NIG_BASELINE_PID) {
+            const int prc = dev_alloc(&e->pid_state, (size_t)2 * e->A * e->pitch);      // zero-initialised = a fresh agent
+            if (prc != NIG_OK) return prc;
+        }
+    }
+    for (int k = 0; k < e->cons.n; ++k)
+        if (e->cons.c[k].kind == NIG_CON_HOSTMASK) return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: host-evaluated constraints cannot run inside a fused rollout");
+    return NIG_OK;
+}
+
+// how many env slices nig_rollout_host uses: 1 for teacher-forced inputs (their [T][D][n] chunks are already
+// double-buffered on a copy stream), for device-tick handles (graph capture) and for small populations; else
+// NIG_HOST_SLICES (default: 4 through the host-buffer call, 8 through the device call -- measured on B200 at 65,536 reactor
+// envs, bench.py: device 6.76 / 7.51 / 7.70 / 7.81e10 env-steps/s and host 5.69 / 6.38 / 6.58 / 6.26e10 for 1 / 2 / 4 / 8
+// slices), at least 8,192 envs per slice
+int host_slices(const nig_env* e, bool forced, int want = 4)
+{
+    if (forced || e->tick_dev) return 1;
+    if (const char* v = getenv("NIG_HOST_SLICES")) want = atoi(v);
+    if (want > kMaxHostSlices) want = kMaxHostSlices;
+    const int64_t fit = e->n / 8192;
+    if (want > fit) want = (int)fit;
+    return want < 1 ? 1 : want;
+}
+
+// one fused launch over envs [i0, i0 + ns) at an explicit tick (validation and e->tick bookkeeping are the callers')
+int rollout_range(nig_env* e, const nig_rollout_t* r, cudaStream_t stream, int64_t i0, int64_t ns, uint32_t tick)
+{
+    RolloutArgs a;
+    memset(&a, 0, sizeof a);
+    a.state = e->state + i0; a.ep_word = e->ep_word + i0; a.ep_return = e->ep_return + i0; a.n = ns; a.pitch = e->pitch;
+    a.env0 = (uint32_t)e->cfg.env_id_offset + (uint32_t)i0; a.tick = tick; a.epoch = e->epoch; a.key = e->key; a.tick_dev = e->tick_dev;
+    a.max_steps = e->max_steps; a.auto_reset = e->cfg.auto_reset; a.n_steps = r->n_steps;
+    a.actions = r->actions ? r->actions + i0 : nullptr; a.noise = r->noise ? r->noise + i0 : nullptr; a.pp = r->pp;
+    a.reward_sum = r->reward_sum ? r->reward_sum + i0 : nullptr;
+    a.viol_count = r->viol_count ? r->viol_count + i0 : nullptr;
+    a.done_count = r->done_count ? r->done_count + i0 : nullptr;
+    a.accumulate = (r->flags & NIG_ROLLOUT_ACCUMULATE) ? 1 : 0;
+    a.pid_state = e->pid_state ? e->pid_state + i0 : nullptr;
+    a.extrema = e->extrema;
+    a.stats = e->stats; a.cons = e->cons;
+    CUtensorMap map;
+    memset(&map, 0, sizeof map);
+    const bool tma = r->policy == NIG_POLICY_ACTIONS && (r->flags & NIG_ROLLOUT_USE_TMA) && !e->track_extrema && i0 == 0 && ns == e->n;
+    int rc;
+    if (tma && (rc = make_action_map(e, r->actions, r->n_steps, &map)) != NIG_OK) return rc;
+    RolloutLaunch cfg;
+    cfg.policy = r->policy; cfg.cons = e->cons.is_default; cfg.tma = tma; cfg.tf_noise = r->noise != nullptr;
+    cfg.block = e->rollout_block ? e->rollout_block : 128;
+    cfg.extrema = e->track_extrema;
+    e->launches++;
+    const int64_t extent = (ns + 127) / 128 * 128;          // launch extent; <= the rows' pitch because slices start at multiples of 128
+    NIG_CUDA(nig::launch_rollout(e->kind, cfg, extent, a, map, stream));
+    return NIG_OK;
+}
+
+// T steps of every env as ceil(T / K) fused launches per env slice, slice q on e->slice_stream[q] (already forked by
+// the caller). Launches are issued chunk-major so that every stream always has work queued; per-env outputs accumulate
+// from the second chunk on (or from the first, with NIG_ROLLOUT_ACCUMULATE in proto.flags).
+int sliced_launches(nig_env* e, const nig_rollout_t& proto, int32_t T, int32_t K, int slices, int64_t per)
+{
+    const uint32_t tick0 = e->tick;
+    int32_t done = 0;
+    for (int c = 0; done < T; ++c) {
+        nig_rollout_t d = proto;
+        d.n_steps = T - done < K ? T - done : K;
+        if (c > 0) d.flags |= NIG_ROLLOUT_ACCUMULATE;
+        if (c == 0) if (int rc = rollout_checks(e, &d)) return rc;
+        for (int q = 0; q < slices; ++q) {
+            const int64_t i0 = q * per, ns = std::min<int64_t>(per, e->n - i0);
+            if (ns <= 0) continue;
+            if (int rc = rollout_range(e, &d, e->slice_stream[q], i0, ns, tick0 + (uint32_t)done)) return rc;
+        }
+        done += d.n_steps;
+    }
+    e->tick = tick0 + (uint32_t)T;
+    return NIG_OK;
+}
+
+// create the slice streams / events on first use and make slices 0..slices-1 wait for the work queued on `st`
+int fork_slices(nig_env* e, int slices, cudaStream_t st)
+{
+    if (!e->slice_begin) NIG_CUDA(cudaEventCreateWithFlags(&e->slice_begin, cudaEventDisableTiming));
+    for (int k = 0; k < slices; ++k) {
+        if (!e->slice_stream[k]) NIG_CUDA(cudaStreamCreateWithFlags(&e->slice_stream[k], cudaStreamNonBlocking));
+        if (!e->slice_done[k]) NIG_CUDA(cudaEventCreateWithFlags(&e->slice_done[k], cudaEventDisableTiming));
+    }
+    NIG_CUDA(cudaEventRecord(e->slice_begin, st));
+    for (int k = 0; k < slices; ++k) NIG_CUDA(cudaStreamWaitEvent(e->slice_stream[k], e->slice_begin, 0));
+    return NIG_OK;
+}
+
+inline int64_t slice_size(int64_t n, int slices) { return ((n + slices - 1) / slices + 127) / 128 * 128; }
+
 } // namespace
 
 // =====================================================================================================
@@ -365,6 +499,11 @@ int nig_destroy(nig_env_t* e)
         if (e->r_ev_done[b]) cudaEventDestroy(e->r_ev_done[b]);
     }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int k = 0; k < kMaxHostSlices; ++k) {
+        if (e->slice_stream[k]) cudaStreamDestroy(e->slice_stream[k]);
+        if (e->slice_done[k]) cudaEventDestroy(e->slice_done[k]);
+    }
+    if (e->slice_begin) cudaEventDestroy(e->slice_begin);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return NIG_OK;
@@ -529,49 +668,41 @@ int nig_step_host(nig_env_t* e, const nig_step_io_t* io)
 int nig_rollout(nig_env_t* e, const nig_rollout_t* r, void* stream)
 {
     NIG_CHECK_ENV(e);
-    if (!r) return fail(NIG_ERR_INVALID, "nig_rollout: null descriptor");
-    if (r->n_steps <= 0) return fail(NIG_ERR_INVALID, "nig_rollout: n_steps must be positive (got %d)", r->n_steps);
-    if (r->policy == NIG_POLICY_ACTIONS && !r->actions) return fail(NIG_ERR_INVALID, "nig_rollout: NIG_POLICY_ACTIONS needs an actions tensor");
-    if (r->noise && e->NZ == 0) return fail(NIG_ERR_INVALID, "nig_rollout: env kind %d has no process noise", e->kind);
-    if (r->noise && r->policy != NIG_POLICY_ACTIONS)
-        return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: teacher-forced noise is only available together with teacher-forced actions (NIG_POLICY_ACTIONS)");
-    if (r->policy < NIG_POLICY_ACTIONS || r->policy > NIG_POLICY_BASELINE) return fail(NIG_ERR_INVALID, "unknown rollout policy %d", r->policy);
-    if (r->noise && e->track_extrema)
-        return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: teacher-forced noise has no return-extrema kernel flavour (nig_track_extrema(env, 0) first)");
-    if (r->policy == NIG_POLICY_BASELINE) {
-        const nig_baseline_t& b = r->pp.baseline;
-        if (b.kind < NIG_BASELINE_RANDOM || b.kind > NIG_BASELINE_CONSTANT) return fail(NIG_ERR_INVALID, "unknown baseline controller %d", b.kind);
-        if (b.kind == NIG_BASELINE_PID) {
-            const int prc = dev_alloc(&e->pid_state, (size_t)2 * e->A * e->pitch);      // zero-initialised = a fresh agent
-            if (prc != NIG_OK) return prc;
-        }
-    }
-    for (int k = 0; k < e->cons.n; ++k)
-        if (e->cons.c[k].kind == NIG_CON_HOSTMASK) return fail(NIG_ERR_UNSUPPORTED, "nig_rollout: host-evaluated constraints cannot run inside a fused rollout");
-    RolloutArgs a;
-    memset(&a, 0, sizeof a);
-    a.state = e->state; a.ep_word = e->ep_word; a.ep_return = e->ep_return; a.n = e->n; a.pitch = e->pitch;
-    a.env0 = (uint32_t)e->cfg.env_id_offset; a.tick = e->tick; a.epoch = e->epoch; a.key = e->key; a.tick_dev = e->tick_dev;
-    a.max_steps = e->max_steps; a.auto_reset = e->cfg.auto_reset; a.n_steps = r->n_steps;
-    a.actions = r->actions; a.noise = r->noise; a.pp = r->pp;
-    a.reward_sum = r->reward_sum; a.viol_count = r->viol_count; a.done_count = r->done_count;
-    a.accumulate = (r->flags & NIG_ROLLOUT_ACCUMULATE) ? 1 : 0;
-    a.pid_state = e->pid_state;
-    a.extrema = e->extrema;
-    a.stats = e->stats; a.cons = e->cons;
-    CUtensorMap map;
-    memset(&map, 0, sizeof map);
-    const bool tma = r->policy == NIG_POLICY_ACTIONS && (r->flags & NIG_ROLLOUT_USE_TMA) && !e->track_extrema;
-    int rc;
-    if (tma && (rc = make_action_map(e, r->actions, r->n_steps, &map)) != NIG_OK) return rc;
-    RolloutLaunch cfg;
-    cfg.policy = r->policy; cfg.cons = e->cons.is_default; cfg.tma = tma; cfg.tf_noise = r->noise != nullptr;
-    cfg.block = e->rollout_block ? e->rollout_block : 128;
-    cfg.extrema = e->track_extrema;
-    e->launches++;
+    if (int crc = rollout_checks(e, r)) return crc;
     note_device_work(e, (cudaStream_t)stream);
-    NIG_CUDA(nig::launch_rollout(e->kind, cfg, e->pitch, a, map, (cudaStream_t)stream));
+    if (int rc = rollout_range(e, r, (cudaStream_t)stream, 0, e->n, e->tick)) return rc;
     e->tick += (uint32_t)r->n_steps;
+    return NIG_OK;
+}
+
+int nig_rollout_steps(nig_env_t* e, const nig_rollout_t* r, int32_t total_steps, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    if (!r) return fail(NIG_ERR_INVALID, "nig_rollout_steps: null descriptor");
+    if (total_steps <= 0 || r->n_steps <= 0) return fail(NIG_ERR_INVALID, "nig_rollout_steps: total_steps and n_steps must be positive");
+    if (r->policy == NIG_POLICY_ACTIONS) return fail(NIG_ERR_UNSUPPORTED, "nig_rollout_steps: in-kernel policies only (teacher-forced actions: nig_rollout per chunk)");
+    cudaStream_t st = (cudaStream_t)stream;
+    note_device_work(e, st);
+    const int slices = host_slices(e, false, 8);
+    if (slices <= 1) {                       // small population / device tick: plain launch sequence on the caller's stream
+        int32_t done = 0;
+        for (int c = 0; done < total_steps; ++c) {
+            nig_rollout_t d = *r;
+            d.n_steps = total_steps - done < r->n_steps ? total_steps - done : r->n_steps;
+            if (c > 0) d.flags |= NIG_ROLLOUT_ACCUMULATE;
+            if (c == 0) if (int rc = rollout_checks(e, &d)) return rc;
+            if (int rc = rollout_range(e, &d, st, 0, e->n, e->tick)) return rc;
+            e->tick += (uint32_t)d.n_steps;
+            done += d.n_steps;
+        }
+        return NIG_OK;
+    }
+    if (int rc = fork_slices(e, slices, st)) return rc;
+    if (int rc = sliced_launches(e, *r, total_steps, r->n_steps, slices, slice_size(e->n, slices))) return rc;
+    for (int k = 0; k < slices; ++k) {
+        NIG_CUDA(cudaEventRecord(e->slice_done[k], e->slice_stream[k]));
+        NIG_CUDA(cudaStreamWaitEvent(st, e->slice_done[k], 0));
+    }
     return NIG_OK;
 }
 
@@ -621,18 +752,67 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
             e->r_cap = K;
         }
     }
+    if (r->reward_sum && (rc = dev_alloc(&e->h_reward, cap)) != NIG_OK) return rc;
+    if (r->viol_count && (rc = dev_alloc(&e->h_i32a, cap)) != NIG_OK) return rc;
+    if (r->done_count && (rc = dev_alloc(&e->h_i32b, cap)) != NIG_OK) return rc;
+    if (r->init_states && (rc = dev_alloc(&e->h_reset, cap * e->S)) != NIG_OK) return rc;
+    if (r->final_obs && (rc = dev_alloc(&e->h_obs, cap * e->S)) != NIG_OK) return rc;
+
+    // ---- in-kernel policies on a large population: env slices on their own streams. Slice s copies its initial states in,
+    // resets, runs its ceil(T / K) fused launches and copies its results out independently of the others, so the PCIe
+    // copies overlap the stepping, and a slice's next launch fills the SMs another slice's tail leaves idle. Trajectories
+    // do not depend on the slicing (random streams are keyed by global env id and tick).
+    const int slices = host_slices(e, forced);
+    if (slices > 1) {
+        const int64_t per = slice_size((int64_t)n, slices);
+        if ((rc = fork_slices(e, slices, st)) != NIG_OK) return rc;
+        const bool reset = r->reset_first || r->init_states;
+        if (reset) e->epoch += 1;
+        for (int k = 0; k < slices; ++k) {
+            const int64_t i0 = k * per, ns = std::min<int64_t>(per, (int64_t)n - i0);
+            if (ns <= 0) continue;
+            cudaStream_t ss = e->slice_stream[k];
+            if (r->init_states)
+                NIG_CUDA(cudaMemcpyAsync(e->h_reset + i0 * e->S, r->init_states + i0 * e->S, (size_t)ns * e->S * sizeof(float), cudaMemcpyHostToDevice, ss));
+            if (reset && (rc = reset_range(e, r->init_states ? e->h_reset : nullptr, i0, ns, e->epoch, ss)) != NIG_OK) return rc;
+        }
+        nig_rollout_t d;
+        memset(&d, 0, sizeof d);
+        d.policy = r->policy; d.pp = r->pp;
+        d.reward_sum = r->reward_sum ? e->h_reward : nullptr;
+        d.viol_count = r->viol_count ? e->h_i32a : nullptr;
+        d.done_count = r->done_count ? e->h_i32b : nullptr;
+        if ((rc = sliced_launches(e, d, T, K, slices, per)) != NIG_OK) return rc;
+        for (int k = 0; k < slices; ++k) {
+            const int64_t i0 = k * per, ns = std::min<int64_t>(per, (int64_t)n - i0);
+            if (ns <= 0) continue;
+            cudaStream_t ss = e->slice_stream[k];
+            if (r->final_obs) {
+                if ((rc = state_to_aos_range(e, e->h_obs, i0, ns, ss)) != NIG_OK) return rc;
+                NIG_CUDA(cudaMemcpyAsync(r->final_obs + i0 * e->S, e->h_obs + i0 * e->S, (size_t)ns * e->S * sizeof(float), cudaMemcpyDeviceToHost, ss));
+            }
+            if (r->reward_sum) NIG_CUDA(cudaMemcpyAsync(r->reward_sum + i0, e->h_reward + i0, (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, ss));
+            if (r->viol_count) NIG_CUDA(cudaMemcpyAsync(r->viol_count + i0, e->h_i32a + i0, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ss));
+            if (r->done_count) NIG_CUDA(cudaMemcpyAsync(r->done_count + i0, e->h_i32b + i0, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ss));
+            NIG_CUDA(cudaEventRecord(e->slice_done[k], ss));
+            NIG_CUDA(cudaStreamWaitEvent(st, e->slice_done[k], 0));
+        }
+        unsigned long long hs[NIG_STATS_SLOTS];
+        if (r->counters24 || r->sums8) NIG_CUDA(cudaMemcpyAsync(hs, e->stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+        NIG_CUDA(cudaStreamSynchronize(st));
+        if (r->counters24) for (int k = 0; k < 24; ++k) r->counters24[k] = (int64_t)hs[k];
+        if (r->sums8) memcpy(r->sums8, &hs[24], 8 * sizeof(double));
+        return NIG_OK;
+    }
+
     if (r->reset_first || r->init_states) {
         const float* dinit = nullptr;
         if (r->init_states) {
-            if ((rc = dev_alloc(&e->h_reset, cap * e->S)) != NIG_OK) return rc;
             NIG_CUDA(cudaMemcpyAsync(e->h_reset, r->init_states, n * e->S * sizeof(float), cudaMemcpyHostToDevice, st));
             dinit = e->h_reset;
         }
         if ((rc = nig_reset(e, nullptr, dinit, NIG_LAYOUT_AOS, st)) != NIG_OK) return rc;
     }
-    if (r->reward_sum && (rc = dev_alloc(&e->h_reward, cap)) != NIG_OK) return rc;
-    if (r->viol_count && (rc = dev_alloc(&e->h_i32a, cap)) != NIG_OK) return rc;
-    if (r->done_count && (rc = dev_alloc(&e->h_i32b, cap)) != NIG_OK) return rc;
     // rows of a [T][D][n] host tensor -> [K][D][pitch] device chunk
     auto copy_chunk = [&](float* dst, const float* src, int D, int32_t t0, int32_t k) -> cudaError_t {
         return cudaMemcpy2DAsync(dst, cap * sizeof(float), src + (size_t)t0 * D * n, n * sizeof(float), n * sizeof(float),
@@ -664,7 +844,6 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
         done += k;
     }
     if (r->final_obs) {
-        if ((rc = dev_alloc(&e->h_obs, cap * e->S)) != NIG_OK) return rc;
         if ((rc = state_io(e, e->h_obs, NIG_LAYOUT_AOS, nullptr, nullptr, nullptr, true, st)) != NIG_OK) return rc;
         NIG_CUDA(cudaMemcpyAsync(r->final_obs, e->h_obs, n * e->S * sizeof(float), cudaMemcpyDeviceToHost, st));
     }

@@ -109,6 +109,7 @@ SYMBOLS = {
     "nig_step": (C.c_int, [_VP, C.POINTER(StepIO), _VP]),
     "nig_step_host": (C.c_int, [_VP, C.POINTER(StepIO)]),
     "nig_rollout": (C.c_int, [_VP, C.POINTER(Rollout), _VP]),
+    "nig_rollout_steps": (C.c_int, [_VP, _VP, C.c_int32, _VP]),
     "nig_rollout_host": (C.c_int, [_VP, C.POINTER(RolloutHost)]),
     "nig_reset_policy_state": (C.c_int, [_VP, _VP]),
     "nig_dataset": (C.c_int, [_VP, _I64, _I32, _I32, C.POINTER(PolicyParams), C.POINTER(DatasetOut), C.POINTER(_I64), _VP]),

@@ -353,6 +353,18 @@ class NativeEnv:
         r.reward_sum, r.viol_count, r.done_count = N.ptr_of(reward_sum), N.ptr_of(viol_count), N.ptr_of(done_count)
         N.check(N.lib().nig_rollout(self._h, C.byref(r), self._stream(stream)))
 
+    def rollout_steps_device(self, total_steps: int, steps_per_launch: int = 64, policy: int = N.POLICY_UNIFORM, *, params=None,
+                             reward_sum=None, viol_count=None, done_count=None, accumulate: bool = False, stream=None):
+        """``total_steps`` steps of every env in ``steps_per_launch``-step fused launches with an in-kernel policy; large
+        populations advance as env slices on internal streams (nig_rollout_steps). Asynchronous on ``stream``."""
+        r = N.Rollout()
+        r.n_steps, r.policy = int(steps_per_launch), int(policy)
+        r.flags = N.ROLLOUT_ACCUMULATE if accumulate else 0
+        if params is not None:
+            r.pp = params
+        r.reward_sum, r.viol_count, r.done_count = N.ptr_of(reward_sum), N.ptr_of(viol_count), N.ptr_of(done_count)
+        N.check(N.lib().nig_rollout_steps(self._h, C.byref(r), int(total_steps), self._stream(stream)))
+
     def get_state_device(self, state=None, layout=N.LAYOUT_SOA, ep_step=None, ep_viol=None, done=None, stream=None):
         N.check(N.lib().nig_get_state(self._h, N.ptr_of(state), layout, N.ptr_of(ep_step), N.ptr_of(ep_viol),
                                       N.ptr_of(done), self._stream(stream)))

@@ -59,6 +59,79 @@ def test_rollout_host_random_policy_vs_oracle(mods, name):
     env.close()
 
 
+@pytest.mark.parametrize("name,policy", [("reactor", "random"), ("grid", "random"), ("reactor", "pid")])
+def test_rollout_host_env_slices_equal_one_launch_sequence(mods, name, policy, monkeypatch):
+    """nig_rollout_host splits a large population into env slices on separate streams (copies of one slice overlap the
+    stepping of the others). Every output must equal the unsliced call's bit for bit -- trajectories are keyed by global
+    env id and tick -- for a ragged last slice, initial states from the host, two consecutive calls, and the
+    stateful in-kernel PID controller."""
+    ni, N, O = mods
+    n, T, K = 3 * 8192 + 1000, 130, 64
+    cls = {"reactor": ni.ChemicalReactorEnv, "grid": ni.PowerGridEnv}[name]
+    out = {}
+    init = None
+    for slices in (1, 3):
+        monkeypatch.setenv("NIG_HOST_SLICES", str(slices))
+        env = cls(num_envs=n, seed=33, env_id_offset=7)
+        if policy == "pid":
+            from neorl_industrial.benchmarks.baseline_agents import PIDControllerAgent
+            policy = PIDControllerAgent(env.state_dim, env.action_dim, kp=0.01, ki=0.001, kd=0.001)
+        drawn = env.native.reset_host()                  # (every run: explicit resets advance the epoch that keys the reset draws)
+        if init is None:
+            init = drawn.copy()
+            init[:, 0] += np.float32(0.25)
+        a = env.rollout(T, policy, steps_per_launch=K, init_states=init)
+        b = env.rollout(40, policy, steps_per_launch=K)                   # continues without a reset
+        out[slices] = (a, b, env.native.launch_count)
+        env.close()
+    for x, y in zip(out[1][:2], out[3][:2]):
+        for key in ("obs", "reward_sum", "violations", "episodes"):
+            assert_bits_equal(x[key], y[key], f"{key} sliced vs unsliced")
+        for key in ("steps", "episodes", "terminated", "truncated", "critical_shutdowns", "violations", "successes",
+                    "episode_length_sum", "violations_per_constraint"):
+            assert x["stats"][key] == y["stats"][key], key
+        np.testing.assert_allclose(x["stats"]["return_sum"], y["stats"]["return_sum"], rtol=1e-12)
+    assert out[3][2] > out[1][2]                                           # the sliced calls really launched per slice
+
+
+@pytest.mark.parametrize("slices", [1, 3])
+def test_rollout_steps_device_equals_launch_sequence(mods, slices, monkeypatch):
+    """nig_rollout_steps (T steps as fused K-step launches, env slices on internal streams) == the same launches issued one
+    by one with nig_rollout on one stream: state, episode counters, per-env outputs, stats."""
+    import torch
+    ni, N, O = mods
+    monkeypatch.setenv("NIG_HOST_SLICES", str(slices))
+    n, T, K = 3 * 8192 + 1000, 150, 64
+    a = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=9, env_id_offset=3)
+    b = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=9, env_id_offset=3)
+    a.reset_host(); b.reset_host()
+    rs, vc, dc = a.empty(), a.empty(dtype=torch.int32), a.empty(dtype=torch.int32)
+    a.rollout_steps_device(T, K, N.POLICY_UNIFORM, reward_sum=rs, viol_count=vc, done_count=dc)
+    a.rollout_steps_device(20, K, N.POLICY_UNIFORM, reward_sum=rs, viol_count=vc, done_count=dc, accumulate=True)
+    ref_rs = np.zeros(n, np.float32); ref_vc = np.zeros(n, np.int64); ref_dc = np.zeros(n, np.int64)
+    r1, v1, d1 = b.empty(), b.empty(dtype=torch.int32), b.empty(dtype=torch.int32)
+    for c, k in enumerate((64, 64, 22, 20)):
+        b.rollout_device(k, N.POLICY_UNIFORM, reward_sum=r1, viol_count=v1, done_count=d1)
+        torch.cuda.synchronize()
+        part = r1[:n].cpu().numpy()
+        ref_rs = part.copy() if c == 0 else (ref_rs + part).astype(np.float32)
+        ref_vc += v1[:n].cpu().numpy(); ref_dc += d1[:n].cpu().numpy()
+    torch.cuda.synchronize()
+    for x, y, what in zip(a.get_state_host(), b.get_state_host(), ("state", "ep_step", "ep_viol", "done")):
+        assert_bits_equal(x, y, what)
+    assert_bits_equal(rs[:n].cpu().numpy(), ref_rs, "reward_sum")
+    assert np.array_equal(vc[:n].cpu().numpy(), ref_vc) and np.array_equal(dc[:n].cpu().numpy(), ref_dc)
+    sa, sb = a.stats_dict(), b.stats_dict()
+    for key in ("steps", "episodes", "terminated", "truncated", "violations", "successes", "episode_length_sum", "violations_per_constraint"):
+        assert sa[key] == sb[key], key
+    assert sa["steps"] == n * (T + 20)
+    with pytest.raises(NotImplementedError):
+        r = N.Rollout(); r.n_steps, r.policy = 8, N.POLICY_ACTIONS
+        import ctypes as C
+        N.check(N.lib().nig_rollout_steps(a._h, C.byref(r), 16, None))
+    a.close(); b.close()
+
+
 def test_rollout_host_teacher_forced_vs_reference_episodes(mods, golden_dir):
     """16 free-running 500-step reference episodes (initial state, actions and noise from the unmodified reference)
     replayed through the fused kernel with teacher-forced actions AND noise, in 64-step launches."""
