@@ -425,7 +425,7 @@ def other_configs(torch, ni, N, local, rank, world, dist, seed):
     off, cnt = shard_bounds(n_total, world, rank)
     env = ni.NativeEnv(N.ENV_POWER_GRID, cnt, device=local, seed=seed, env_id_offset=off)
     env.reset_device()
-    ms = timed(lambda: [env.rollout_device(64, N.POLICY_UNIFORM) for _ in range(4)], 3)
+    ms = timed(lambda: env.rollout_steps_device(256, 64, N.POLICY_UNIFORM), 3)
     acts = torch.rand((8, env.pitch), device=dev) * 2 - 1
     rew, fl, vm = env.empty(), env.empty(dtype=torch.uint8), env.empty(dtype=torch.uint8)
     ms1 = timed(lambda: env.step_device(acts, reward=rew, flags=fl, viol_mask=vm), 20)
@@ -444,7 +444,7 @@ def other_configs(torch, ni, N, local, rank, world, dist, seed):
     # ---- RobotAssembly-v0 (the third env implemented upstream), same sharding
     env = ni.NativeEnv(N.ENV_ROBOT_ASSEMBLY, cnt, device=local, seed=seed, env_id_offset=off)
     env.reset_device()
-    ms = timed(lambda: [env.rollout_device(64, N.POLICY_UNIFORM) for _ in range(4)], 3)
+    ms = timed(lambda: env.rollout_steps_device(256, 64, N.POLICY_UNIFORM), 3)
     acts = torch.rand((7, env.pitch), device=dev) * 2 - 1
     ms1 = timed(lambda: env.step_device(acts, reward=rew, flags=fl, viol_mask=vm), 20)
     out["robot_assembly_1m"] = {
@@ -463,7 +463,7 @@ def other_configs(torch, ni, N, local, rank, world, dist, seed):
     nat = wrapped.native
     nat.reset_device()
     nat.clear_stats()
-    ms = timed(lambda: [nat.rollout_device(64, N.POLICY_UNIFORM) for _ in range(4)], 5)
+    ms = timed(lambda: nat.rollout_steps_device(256, 64, N.POLICY_UNIFORM), 5)
     allreduce_device_stats(nat)
     torch.cuda.synchronize()
     st = nat.stats_dict()

@@ -49,11 +49,7 @@ def evaluate_policy_device(env, n_steps: int, policy: int = N.POLICY_UNIFORM, pa
     nat.clear_stats()
     nat.track_extrema(True)            # the kernel flavour that also keeps return_min / return_max
     try:
-        done = 0
-        while done < n_steps:
-            k = min(chunk, n_steps - done)
-            nat.rollout_device(k, policy, params=params)
-            done += k
+        nat.rollout_steps_device(n_steps, chunk, policy, params=params)    # chunk-step fused launches, env slices on streams
     finally:
         nat.track_extrema(False)
     counters, sums = nat.read_stats()
