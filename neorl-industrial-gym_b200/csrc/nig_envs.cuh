@@ -55,19 +55,18 @@ struct Reactor {
             nz[0] = mul(0.1f, za);      // np.random.normal(0, temp_noise_std / 10)      (:149)
             nz[1] = mul(500.0f, zb);    // np.random.normal(0, pressure_noise_std / 10)  (:159)
         }
-        // the same two values for ONE tick (single-step kernel): only the Box-Muller pair of this tick's parity
+        // the same two values for ONE tick (single-step kernel): only the pair of normals of this tick's parity
         __device__ static __forceinline__ void get_single(const Rng& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
         {
             const uint4 w = rng_words(key, env, tick >> 1, STREAM_NOISE, 0u);
             float za, zb;
-            // (the single-step kernels measured 6 % faster on freshly reset populations with the branchy IEEE sqrt here)
             normal_pair(key.tab, (tick & 1u) ? w.z : w.x, (tick & 1u) ? w.w : w.y, za, zb);
             nz[0] = mul(0.1f, za);
             nz[1] = mul(500.0f, zb);
         }
     };
 
-    // _get_initial_state (:89-107) drawn from the RESET stream: 8 standard normals = Box-Muller pairs 0..3 of
+    // _get_initial_state (:89-107) drawn from the RESET stream: 8 standard normals = word pairs 0..3 of
     // Philox blocks (epoch << 8) | {0, 1}
     // measured on B200 (tools/steady_step.py, tools/rollout_sweep.py): the single-step kernels gain 6 % at 16M envs
     // (0.86 -> 0.92 of the HBM peak), the fused rollout loses 2 % (one extra ballot per step) and keeps Env::reset()
@@ -92,7 +91,7 @@ struct Reactor {
         s[10] = add(60.0f, mul(5.0f, z[7]));
         s[11] = 0.0f;
     }
-    // Box-Muller pair `pair` (0..3) of the 8: the unit of work of the warp-cooperative reset (one pair per lane)
+    // pair of normals `pair` (0..3) of the 8: the unit of work of the warp-cooperative reset (one pair per lane)
     __device__ static __forceinline__ void reset_pair(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t pair,
                                                       float& z0, float& z1)
     {

@@ -213,9 +213,9 @@ __device__ __forceinline__ void step_core(const ConsParams& cp, int max_steps,
 }
 
 // ---- warp-cooperative auto-reset ---------------------------------------------------------------------------------
-// A finished env needs Env::RESET_NORMALS fresh Gaussians (reactor: 2 Philox blocks + 4 Box-Muller pairs, ~370
+// A finished env needs Env::RESET_NORMALS fresh Gaussians (reactor: 2 Philox blocks + 8 table normals, ~150
 // instructions) and on average only 1 lane in 12 warp-steps finishes: instead of the whole warp walking the full draw
-// for one lane, every resetting lane in turn broadcasts its env id, lanes 0..3 each produce ONE Box-Muller pair of its
+// for one lane, every resetting lane in turn broadcasts its env id, lanes 0..3 each produce ONE pair of normals of its
 // draw, and the 8 normals are shuffled back. Same counters, same values as Env::reset(). Must be called convergently.
 template <class Env>
 __device__ __forceinline__ void coop_reset(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, bool need, float (&s)[Env::S])

@@ -17,7 +17,7 @@
  *
  * Two things are NOT reference code but this project's documented spec, restated here
  * independently of the CUDA sources so that free-running runs can be compared bit-for-bit:
- *   - the counter-based RNG (Philox4x32-10 -> Box-Muller with fmaf polynomials), and
+ *   - the counter-based RNG (Philox4x32-7 -> inverse-CDF normals by a dyadic-segment table + fmaf cubic), and
  *   - spec_expf(), a <1 ulp fmaf-polynomial exp (exp_mode 1). exp_mode 0 uses libm expf and is
  *     what is compared against the reference goldens (numpy's own float32 exp is a SIMD routine
  *     that is not correctly rounded and is host-dependent, so conc' is a tolerance compare there).
@@ -134,7 +134,7 @@ static float spec_normal(uint32_t w)
     return bits_f(f_bits(z) ^ (w & 0x80000000u));
 }
 
-static void box_muller(uint32_t xa, uint32_t xb, float* z0, float* z1)   /* historical name: a pair of normals */
+static void normal_pair(uint32_t xa, uint32_t xb, float* z0, float* z1)
 {
     *z0 = spec_normal(xa);
     *z1 = spec_normal(xb);
@@ -147,8 +147,8 @@ static void normals4(const orc_cfg_t* cfg, uint32_t env, uint32_t tick, uint32_t
 {
     uint32_t w[4];
     philox4x32(SPEC_PHILOX_ROUNDS, env, tick, stream, j, (uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32), w);
-    box_muller(w[0], w[1], &z[0], &z[1]);
-    box_muller(w[2], w[3], &z[2], &z[3]);
+    normal_pair(w[0], w[1], &z[0], &z[1]);
+    normal_pair(w[2], w[3], &z[2], &z[3]);
 }
 static void words4(const orc_cfg_t* cfg, uint32_t env, uint32_t tick, uint32_t stream, uint32_t j, uint32_t w[4])
 {

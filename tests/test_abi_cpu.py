@@ -128,3 +128,21 @@ def test_extrema_keys_decode_in_order():
     lo, hi = ni.NativeEnv.decode_extrema(keys)
     assert np.isclose(lo, xs.min(), rtol=3e-16, atol=0) and np.isclose(hi, xs.max(), rtol=3e-16, atol=0)
     assert ni.NativeEnv.decode_extrema(np.zeros(2, np.int64)) == (None, None)
+
+
+def test_normal_table_headers_are_the_generators_output(tmp_path):
+    """csrc/nig_normal_table.h and oracle/nig_normal_table.h hold the same numbers, and they are what
+    tools/fit_normal_table.py produces today (the table is data of the math spec: library and oracle must not drift)."""
+    import importlib.util
+    a = open(os.path.join(ROOT, "neorl-industrial-gym_b200", "csrc", "nig_normal_table.h")).read()
+    b = open(os.path.join(ROOT, "oracle", "nig_normal_table.h")).read()
+    strip = lambda t: t.split("*/", 1)[1]
+    assert strip(a) == strip(b)
+    spec = importlib.util.spec_from_file_location("fit_normal_table", os.path.join(ROOT, "tools", "fit_normal_table.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    tab, err_abs, _ = mod.build()
+    out = tmp_path / "t.h"
+    mod.emit(tab, str(out), "CUDA library")
+    assert out.read_text() == a
+    assert tab.shape == (513, 4) and err_abs < 6e-7

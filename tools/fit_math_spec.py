@@ -2,8 +2,9 @@
 
 Run once; the printed constants are pasted (as hex floats) into csrc/nig_math.cuh and, independently,
 into oracle/nig_oracle.c. Both sides evaluate them with the same fmaf Horner order, so GPU and
-CPU oracle agree bit-for-bit. Accuracy targets: exp <= ~1 ulp; log/sincos ~1e-7 abs (they only
-shape the Gaussian process noise).
+CPU oracle agree bit-for-bit. Accuracy targets: exp <= ~1 ulp; log/sincos ~1e-7 abs.
+The log / sincos fits belonged to the Box-Muller normals of the first builds; the normals are now the table inverse CDF
+of tools/fit_normal_table.py and only the exp fit is still in use (the fp64 sin/cos of the robot were fitted separately).
 """
 import numpy as np
 from numpy.polynomial import chebyshev as C, polynomial as P
