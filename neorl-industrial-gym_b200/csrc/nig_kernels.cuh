@@ -617,10 +617,15 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
     extern __shared__ __align__(128) float stage_smem[];     // [kStepStages][ROWS][TILE]
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
     __shared__ alignas(8) uint64_t full[kStepStages];
+    __shared__ float coop_buf[CoopSmem<Env>::floats];
+    // persistent CTAs amortise a shared copy of the normal table where the env draws many normals per step (PowerGrid);
+    // for the reactor it would cost the fourth resident CTA its stage ring (measured: 0.90 -> 0.85 of the HBM peak)
+    __shared__ float4 s_tab[Env::TAB_SMEM ? NIG_NORMAL_TAB_N : 1];
+    if constexpr (Env::TAB_SMEM) normal_table_to_smem(s_tab);
     BlockStats bs;
     bs.init(sstat);
     const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
-    const Rng key(p.key, g_normal_tab);        // (a shared copy would cost the fourth resident CTA its stage ring)
+    const Rng key(p.key, Env::TAB_SMEM ? s_tab : g_normal_tab);
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < kStepStages; ++k) mbar_init(&full[k], 1);
@@ -703,12 +708,13 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             bool need_reset = false;
             if (done) {
                 if (p.auto_reset) {
-                    if constexpr (Env::COOP_RESET) need_reset = true;
+                    if constexpr (Env::COOP_RESET || Env::COOP_BLOCKS > 0) need_reset = true;
                     else Env::reset(key, env, tick0 + 1u, p.epoch, ns);
                     w = 0u; f |= NIG_F_RESET;
                 } else w |= 0x80000000u;
             }
             if constexpr (Env::COOP_RESET) coop_reset<Env>(key, env, tick0 + 1u, p.epoch, need_reset, ns);
+            else if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(key, env, tick0 + 1u, p.epoch, need_reset, ns, coop_buf);
 #pragma unroll
             for (int k = 0; k < S; ++k) sv[k][e] = ns[k];
             wv[e] = __uint_as_float(w);

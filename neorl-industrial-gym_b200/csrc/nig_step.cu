@@ -1,4 +1,5 @@
 // single-step kernels of the three envs (see nig_kernels.cuh)
+#include <cstdlib>
 #include "nig_launch.h"
 namespace nig {
 namespace {
@@ -72,9 +73,13 @@ cudaError_t launch_step_pipelined(int kind, int cons, int64_t pitch, const StepA
 {
     switch (kind) {
     case NIG_ENV_CHEMICAL_REACTOR: return go_pipe<Reactor, 2>(cons, pitch, a, st, used);
+    case NIG_ENV_ROBOT_ASSEMBLY:
+        // measured on B200 (tools/step_pipe_all_ab.py, steady-state episode mix): 92 -> 80 us at 1M envs, 328 -> 293 us
+        // at 4M (0.41 -> 0.47 and 0.46 -> 0.52 of the HBM peak). Two envs per thread spill at the 128-register cap (115 us).
+        return go_pipe<Robot, 1>(cons, pitch, a, st, used);
     default:
-        // PowerGrid (23 Gaussian draws per step) and RobotAssembly (fp64 kinematics) are issue-bound, not HBM-bound:
-        // measured on B200 the pipeline gains nothing there (tools/step_sweep_all.py), so they keep step_kernel.
+        // PowerGrid (23 Gaussian draws per step, block-cooperative reset buffer) is latency-bound at the pipeline's two
+        // resident CTAs per SM: 115 -> 136 us at 1M envs. It keeps step_kernel.
         *used = false;
         return cudaSuccess;
     }

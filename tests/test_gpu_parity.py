@@ -513,12 +513,12 @@ def test_full_size_rollout_property(mods):
     assert d["episodes"] > 100000
 
 
-@pytest.mark.parametrize("name", ["reactor", "grid"])
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
 def test_step_pipelined_kernel_bitexact_vs_oracle(mods, name, monkeypatch):
     """Populations with more tiles than resident CTAs take the persistent TMA-pipelined step kernel (bulk copies into a
     3-stage shared-memory ring); same results as the oracle, bit for bit, including truncation + in-kernel auto-reset,
-    a ragged last tile, and the statistics block; and identical to the one-tile-per-CTA kernel. (Only the reactor is
-    routed to the pipelined kernel -- the grid case checks the large-population dispatch of the plain kernel.)"""
+    a ragged last tile, and the statistics block; and identical to the one-tile-per-CTA kernel. (The reactor and the
+    robot are routed to the pipelined kernel -- the grid case checks the large-population dispatch of the plain kernel.)"""
     ni, N, O, torch = mods
     kind = KINDS[name]
     n = 300_007 if name == "reactor" else 160_003
