@@ -265,7 +265,9 @@ NIG_API int nig_rollout_steps(nig_env_t* env, const nig_rollout_t* r, int32_t to
 /* The same loops with HOST buffers: what performance_benchmark.py:106-133 / utils.evaluate_with_safety do per env in
  * Python, for every env of the handle in one call. Host arrays are exact-size ([n] or [n][dim]); the call stages
  * them through device buffers (cudaMemcpyAsync, true DMA when the host arrays are page-locked, see nig_host_alloc),
- * runs ceil(n_steps / steps_per_launch) fused launches and returns synchronised.
+ * runs ceil(n_steps / steps_per_launch) fused launches and returns synchronised. With an in-kernel policy and at least
+ * 16,384 envs the population is split into env slices (NIG_HOST_SLICES, default 4) that each copy in, step and copy out on
+ * their own stream, so the PCIe copies of one slice overlap the stepping of the others; results do not depend on it.
  * Teacher-forced inputs (optional): init_states [n][S]; actions [T][A][n] with policy == NIG_POLICY_ACTIONS and
  * noise [T][NZ][n] (time-major, SoA per step -- the layout the kernel consumes; copied chunk by chunk,
  * double-buffered so the copy of chunk c+1 overlaps the launch of chunk c). */
