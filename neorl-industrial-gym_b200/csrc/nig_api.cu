@@ -51,7 +51,8 @@ void builtin_constraints(int kind, nig_constraint_t* c)
 
 // how the kernels evaluate a constraint set: CONS_DEFAULT = exactly the env's three built-ins in registration order with
 // their default penalties (compile-time code); CONS_PREFIX = those three first, then extra descriptors (a SafetyWrapper
-// that appends constraints: built-ins stay compile-time code, a loop walks descriptors 3..n-1); CONS_GENERIC otherwise.
+// that appends constraints: built-ins stay compile-time code, a loop walks descriptors 3..n-1), or CONS_BOUNDS1 / 2 when
+// the extras are one / two pure state bounds (straight-line code in the fused rollout); CONS_GENERIC otherwise.
 int cons_mode(int kind, const nig_constraint_t* c, int n)
 {
     if (n < 3) return CONS_GENERIC;
@@ -60,7 +61,10 @@ int cons_mode(int kind, const nig_constraint_t* c, int n)
     for (int k = 0; k < 3; ++k)
         if (c[k].kind != NIG_CON_BUILTIN || c[k].id != k || c[k].penalty != d[k].penalty || (c[k].critical != 0) != (d[k].critical != 0))
             return CONS_GENERIC;
-    return n == 3 ? CONS_DEFAULT : CONS_PREFIX;
+    if (n == 3) return CONS_DEFAULT;
+    bool pure_bounds = n <= 5;              // one or two extras, each lo <= s[i] <= hi without an action term
+    for (int k = 3; k < n && pure_bounds; ++k) pure_bounds = c[k].kind == NIG_CON_BOUND && c[k].ai < 0;
+    return pure_bounds ? (n == 4 ? CONS_BOUNDS1 : CONS_BOUNDS2) : CONS_PREFIX;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -176,10 +180,10 @@ int launch_step(nig_env* e, const StepArgs& a, cudaStream_t st)
                        ((uintptr_t)a.actions & 15u) == 0 && e->step_pipe != 0 && e->step_vec == 0;
     if (plain) {
         bool used = false;
-        NIG_CUDA(nig::launch_step_pipelined(e->kind, e->cons.is_default, e->pitch, a, st, &used));
+        NIG_CUDA(nig::launch_step_pipelined(e->kind, cons_for_step(e->cons.is_default), e->pitch, a, st, &used));
         if (used) return NIG_OK;
     }
-    NIG_CUDA(nig::launch_step(e->kind, vec, e->cons.is_default, e->pitch, a, st));
+    NIG_CUDA(nig::launch_step(e->kind, vec, cons_for_step(e->cons.is_default), e->pitch, a, st));
     return NIG_OK;
 }
 

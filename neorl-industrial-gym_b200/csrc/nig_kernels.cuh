@@ -28,11 +28,17 @@ namespace nig {
 
 constexpr int kThreads = 128;
 // how a kernel instantiation evaluates the safety constraints (see step_core_impl)
-enum : int { CONS_GENERIC = 0, CONS_DEFAULT = 1, CONS_PREFIX = 2 };
+// CONS_BOUNDS1 / CONS_BOUNDS2: the built-ins plus exactly one / two pure state bounds (lo <= s[i] <= hi: the temperature /
+// pressure bands of a SafetyWrapper) as straight-line code -- fused rollout kernels only, everything else treats them as
+// CONS_PREFIX (cons_for_step). The guarded descriptor loop of CONS_PREFIX splits the step into several basic blocks and
+// measured +56 % for the first extra constraint (tools/wrapper_cost.py).
+enum : int { CONS_GENERIC = 0, CONS_DEFAULT = 1, CONS_PREFIX = 2, CONS_BOUNDS1 = 3, CONS_BOUNDS2 = 4 };
+__host__ __device__ constexpr int cons_fast_extras(int cons) { return cons == CONS_BOUNDS1 ? 1 : cons == CONS_BOUNDS2 ? 2 : 0; }
+inline int cons_for_step(int cons) { return cons > CONS_PREFIX ? CONS_PREFIX : cons; }
 
 struct ConsParams {
     int32_t n;
-    int32_t is_default;        // CONS_GENERIC / CONS_DEFAULT / CONS_PREFIX (host-side dispatch only)
+    int32_t is_default;        // CONS_GENERIC / CONS_DEFAULT / CONS_PREFIX / CONS_BOUNDS* (host-side dispatch only)
     nig_constraint_t c[NIG_MAX_CONSTRAINTS];
     // NIG_CON_BOUND one-hot masks in DEVICE memory (kept out of the kernel parameters: 1.3 KB of them made every launch
     // measurably slower): row k = [NIG_MAX_STATE_DIM words: all-ones at si][NIG_MAX_ACTION_DIM words: all-ones at ai >= 0]
@@ -131,7 +137,8 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
     // CONS_DEFAULT: exactly the env's built-ins with their default penalties (the env as registered upstream): compile-time
     // code, no loop. CONS_PREFIX: the built-ins first, then extra descriptors (a SafetyWrapper that ADDS constraints): the
     // built-ins stay compile-time code, the loop walks only the extras. CONS_GENERIC: every descriptor at run time.
-    constexpr bool DEFCONS = CONS != CONS_GENERIC, EXTRAS = CONS != CONS_DEFAULT;
+    constexpr bool DEFCONS = CONS != CONS_GENERIC, EXTRAS = CONS == CONS_GENERIC || CONS == CONS_PREFIX;
+    constexpr int NXF = cons_fast_extras(CONS);
     constexpr int K0 = DEFCONS ? Env::NB : 0;
     if constexpr (DEFCONS) {
 #pragma unroll
@@ -139,6 +146,15 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
             const bool ok = Env::builtin(k, s, a);
             vm |= ok ? 0u : (1u << k);
             if ((Env::CRIT_MASK >> k) & 1u) crit = crit || !ok;
+        }
+    }
+    if constexpr (NXF > 0) {                // exactly NXF pure state bounds after the built-ins: no guards, no kind dispatch
+#pragma unroll
+        for (int k = Env::NB; k < Env::NB + NXF; ++k) {
+            const float v = pick<Env::S>(s, cp.masks + k * kConsMaskRow);
+            const bool ok = (cp.c[k].lo <= v) && (v <= cp.c[k].hi);
+            vm |= ok ? 0u : (1u << k);
+            crit = crit || (!ok && cp.c[k].critical != 0);
         }
     }
     if constexpr (EXTRAS) {
@@ -157,6 +173,13 @@ __device__ __forceinline__ void step_core_impl(const ConsParams& cp, int max_ste
 #pragma unroll
         for (int k = 0; k < Env::NB; ++k)
             if ((vm >> k) & 1u) r = r + (acc_t)Env::penalty(k);
+    }
+    if constexpr (NXF > 0) {
+#pragma unroll
+        for (int k = Env::NB; k < Env::NB + NXF; ++k) {
+            const acc_t rp = r + (acc_t)cp.c[k].penalty;      // same sum as the guarded form, selected instead of branched
+            r = ((vm >> k) & 1u) ? rp : r;
+        }
     }
     if constexpr (EXTRAS) {
 #pragma unroll
@@ -1094,7 +1117,10 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
             c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
 #pragma unroll
             for (int k = 0; k < Env::NB; ++k) c_con[k] += (vm >> k) & 1u;
-            if constexpr (CONS != CONS_DEFAULT) {
+            if constexpr (cons_fast_extras(CONS) > 0) {
+#pragma unroll
+                for (int k = Env::NB; k < Env::NB + cons_fast_extras(CONS); ++k) c_con[k] += (vm >> k) & 1u;
+            } else if constexpr (CONS != CONS_DEFAULT) {
 #pragma unroll
                 for (int k = Env::NB; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] += (vm >> k) & 1u;
             }

@@ -52,9 +52,32 @@ cudaError_t rollout_policy_extrema(const RolloutLaunch& c, int64_t pitch, const 
     }
 }
 
-template <class Env>
-cudaError_t rollout_env(const RolloutLaunch& c, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
+// CONS_BOUNDS1 / CONS_BOUNDS2 (built-ins + one / two state bounds as straight-line code): the throughput flavours only
+// (in-kernel policies and register-prefetched action tensors); TMA staging, teacher-forced noise and the extrema flavour
+// take the CONS_PREFIX kernels for such a constraint set.
+template <class Env, int CONS>
+cudaError_t rollout_policy_bounds(const RolloutLaunch& c, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
 {
+    switch (c.policy) {
+    case NIG_POLICY_ACTIONS: return rollout_go<Env, CONS, NIG_POLICY_ACTIONS, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_UNIFORM: return rollout_go<Env, CONS, NIG_POLICY_UNIFORM, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_ZERO: return rollout_go<Env, CONS, NIG_POLICY_ZERO, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_PCTRL: return rollout_go<Env, CONS, NIG_POLICY_PCTRL, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_BASELINE: return rollout_go<Env, CONS, NIG_POLICY_BASELINE, false, false>(c, pitch, a, map, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <class Env>
+cudaError_t rollout_env(const RolloutLaunch& c0, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
+{
+    RolloutLaunch c = c0;
+    if (c.cons > CONS_PREFIX) {
+        if (!c.extrema && !c.tma && !c.tf_noise)
+            return c.cons == CONS_BOUNDS1 ? rollout_policy_bounds<Env, CONS_BOUNDS1>(c, pitch, a, map, st)
+                                          : rollout_policy_bounds<Env, CONS_BOUNDS2>(c, pitch, a, map, st);
+        c.cons = CONS_PREFIX;
+    }
     if (c.extrema)
         return c.cons == CONS_DEFAULT ? rollout_policy_extrema<Env, CONS_DEFAULT>(c, pitch, a, map, st)
              : c.cons == CONS_PREFIX  ? rollout_policy_extrema<Env, CONS_PREFIX>(c, pitch, a, map, st)

@@ -396,6 +396,57 @@ def test_constraint_descriptors_vs_oracle(mods):
     env.close()
 
 
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+@pytest.mark.parametrize("extras", ["one_bound", "two_bounds", "two_with_action_term", "three_bounds"])
+def test_rollout_with_wrapper_bounds_bitexact_vs_oracle(mods, name, extras):
+    """Fused rollout of an env whose SafetyWrapper appended declarative bounds == the oracle, bit for bit: one / two pure
+    state bounds take the straight-line CONS_BOUNDS1 / 2 kernels, an action term or a third bound the guarded descriptor
+    loop (CONS_PREFIX); TMA-staged actions and the extrema flavour fall back to CONS_PREFIX for the same constraint set."""
+    ni, N, O, torch = mods
+    from neorl_industrial.vector import make_constraint
+    kind, n, K = KINDS[name], 3000, 70
+    f32 = lambda x: float(np.float32(x))
+    spec = N.env_spec(kind)
+    builtins = [make_constraint(N.CON_BUILTIN, cid=k, penalty=spec.constraints[k].penalty, critical=bool(spec.constraints[k].critical))
+                for k in range(3)]
+    lo0, hi0 = (300.0, 325.0) if kind == 0 else (-0.4, 0.4)
+    lo1, hi1 = (1.2e5, 3.5e5) if kind == 0 else ((0.97, 1.03) if kind == 1 else (-0.3, 0.3))
+    b0 = make_constraint(N.CON_BOUND, si=0, lo=f32(lo0), hi=f32(hi0), penalty=-40.0)
+    b1 = make_constraint(N.CON_BOUND, si=1, lo=f32(lo1), hi=f32(hi1), penalty=-15.0, critical=True)
+    b0a = make_constraint(N.CON_BOUND, si=0, ai=0, coef=f32(0.1), lo=f32(lo0), hi=f32(hi0), penalty=-40.0)
+    b2 = make_constraint(N.CON_BOUND, si=2, lo=f32(-1e3), hi=f32(60.0 if kind == 0 else 1.0), penalty=-5.0)
+    cons = builtins + {"one_bound": [b0], "two_bounds": [b0, b1], "two_with_action_term": [b0a, b1], "three_bounds": [b0, b1, b2]}[extras]
+    env = _native_env(ni, kind, n, auto_reset=True, seed=31, constraints=cons)
+    ocons = [O.Con(c.kind, c.id, c.si, c.ai, c.coef, c.lo, c.hi, c.penalty, c.critical) for c in cons]
+    orc = O.OracleEnv(kind, n, auto_reset=True, seed=31, exp_mode=1, builtin=False, extra_cons=ocons)
+    assert_bits_equal(env.reset_host(), orc.reset(), "reset")
+    dev = env.torch_device()
+    rsum = env.empty()
+    env.rollout_device(K, N.POLICY_UNIFORM, reward_sum=rsum)
+    o_rs = O.rollout(orc, K, O.POLICY_UNIFORM, want_reward_sum=True)
+    torch.cuda.synchronize()
+    assert_bits_equal(rsum[:n].cpu().numpy(), o_rs, "reward sum with penalties")
+    # teacher-forced actions through TMA (falls back to the descriptor loop) and, with extrema tracking, the LDG flavour
+    rng = np.random.default_rng(2)
+    for use_tma, ext in ((True, False), (False, True)):
+        acts = rng.uniform(-1.3, 1.3, (16, n, env.A)).astype(np.float32)
+        d_act = torch.zeros((16, env.A, env.pitch), dtype=torch.float32, device=dev)
+        d_act[:, :, :n] = torch.from_numpy(np.ascontiguousarray(acts.transpose(0, 2, 1))).to(dev)
+        env.track_extrema(ext)
+        env.rollout_device(16, N.POLICY_ACTIONS, actions=d_act, use_tma=use_tma)
+        for t in range(16):
+            orc.step(acts[t], want_next_obs=False)
+    env.track_extrema(False)
+    torch.cuda.synchronize()
+    st, es, ev, dn = env.get_state_host()
+    assert_bits_equal(st, orc.state, "state"); assert_bits_equal(es, orc.ep_step, "ep_step"); assert_bits_equal(ev, orc.ep_viol, "ep_viol")
+    c, _ = env.read_stats()
+    assert c[:6].tolist() == orc.stats[:6].tolist()
+    assert c[8:8 + len(cons)].tolist() == orc.stats[8:8 + len(cons)].tolist()
+    assert c[8 + 3] > 0                                   # the first appended bound really fired
+    env.close()
+
+
 def test_safety_wrapper_api(mods):
     """README.md:126-139: SafetyWrapper(env, constraints=[fn], penalty=-100) with a Python callable and with the
     declarative BoundConstraint give identical results; penalties and violation counts follow base.py:179-183."""
