@@ -84,3 +84,17 @@ def allreduce_extrema(native, group=None):
     import torch
     torch.cuda.synchronize(native.torch_device())
     return native.decode_extrema(keys.cpu().numpy())
+
+
+def allreduce_extrema_keys(keys, group=None):
+    """Host-side flavour of :func:`allreduce_extrema`: ``keys`` = the two order-preserving int64 keys of this rank
+    (``NativeEnv.extrema_tensor().cpu()`` or any int64[2]); one MAX all-reduce on the process group's CPU path, then
+    decode. Returns (return_min, return_max) or (None, None)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from .vector import NativeEnv
+    k = torch.as_tensor(np.ascontiguousarray(keys, np.int64)).clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(k, op=dist.ReduceOp.MAX, group=group)
+    return NativeEnv.decode_extrema(k.numpy())

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from neorl_industrial.distributed import allreduce_stats, shard_bounds
+from neorl_industrial.distributed import allreduce_extrema_keys, allreduce_stats, shard_bounds
 
 
 def test_shard_bounds_tile_exactly():
@@ -41,7 +41,14 @@ def _worker(rank, world, port, n_total, T, q):
     counters = np.zeros(24, np.int64); counters[:16] = env.stats
     sums = np.zeros(8, np.float64); sums[2] = float(rs.astype(np.float64).sum())
     counters, sums = allreduce_stats(counters, sums)
-    q.put((rank, off, env.state.copy(), counters, sums))
+    # return extrema across ranks: each rank's two order-preserving keys (restated here the way the kernel builds them),
+    # one MAX all-reduce, decode
+    def key(x):
+        b = np.array(x, np.float64).view(np.uint64)
+        return ((np.where(b >> np.uint64(63), ~b, b | np.uint64(1 << 63))) >> np.uint64(1)).astype(np.int64)
+    ret = rs.astype(np.float64)
+    ext = allreduce_extrema_keys(np.array([key(-ret).max(), key(ret).max()], np.int64))
+    q.put((rank, off, env.state.copy(), counters, sums, ext))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -67,6 +74,7 @@ def test_two_rank_gloo_allreduce_matches_unsharded():
     for r in results:        # every rank holds the same global sums after the all-reduce
         assert r[3][:16].tolist() == whole.stats.tolist()
         np.testing.assert_allclose(r[4][2], float(rs.astype(np.float64).sum()), rtol=1e-12)
+        np.testing.assert_allclose(r[5], [float(rs.min()), float(rs.max())], rtol=3e-16)
     assert whole.stats[1] > n_total      # grid episodes are short: many auto-resets happened
 
 
