@@ -349,7 +349,9 @@ int rollout_range(nig_env* e, const nig_rollout_t* r, cudaStream_t stream, int64
     if (tma && (rc = make_action_map(e, r->actions, r->n_steps, &map)) != NIG_OK) return rc;
     RolloutLaunch cfg;
     cfg.policy = r->policy; cfg.cons = e->cons.is_default; cfg.tma = tma; cfg.tf_noise = r->noise != nullptr;
-    cfg.block = e->rollout_block ? e->rollout_block : 128;
+    // one-warp CTAs for small reactor launches (a slice, or a whole population of <= 16,384 envs): finer-grained placement
+    // on the SMs, measured 7.82 / 7.93 / 7.98e10 env-steps/s for 128 / 64 / 32 threads per CTA at 8 slices of 8,192 envs
+    cfg.block = e->rollout_block ? e->rollout_block : (e->kind == NIG_ENV_CHEMICAL_REACTOR && ns <= 16384 ? 32 : 128);
     cfg.extrema = e->track_extrema;
     e->launches++;
     const int64_t extent = (ns + 127) / 128 * 128;          // launch extent; <= the rows' pitch because slices start at multiples of 128
