@@ -53,17 +53,17 @@ cudaError_t rollout_policy_extrema(const RolloutLaunch& c, int64_t pitch, const 
 }
 
 // CONS_BOUNDS1 / CONS_BOUNDS2 (built-ins + one / two state bounds as straight-line code): the throughput flavours only
-// (in-kernel policies and register-prefetched action tensors); TMA staging, teacher-forced noise and the extrema flavour
-// take the CONS_PREFIX kernels for such a constraint set.
-template <class Env, int CONS>
+// (in-kernel policies and register-prefetched action tensors, with or without return extrema -- the evaluation of a wrapped
+// env); TMA staging and teacher-forced noise take the CONS_PREFIX kernels for such a constraint set.
+template <class Env, int CONS, bool EXTREMA>
 cudaError_t rollout_policy_bounds(const RolloutLaunch& c, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
 {
     switch (c.policy) {
-    case NIG_POLICY_ACTIONS: return rollout_go<Env, CONS, NIG_POLICY_ACTIONS, false, false>(c, pitch, a, map, st);
-    case NIG_POLICY_UNIFORM: return rollout_go<Env, CONS, NIG_POLICY_UNIFORM, false, false>(c, pitch, a, map, st);
-    case NIG_POLICY_ZERO: return rollout_go<Env, CONS, NIG_POLICY_ZERO, false, false>(c, pitch, a, map, st);
-    case NIG_POLICY_PCTRL: return rollout_go<Env, CONS, NIG_POLICY_PCTRL, false, false>(c, pitch, a, map, st);
-    case NIG_POLICY_BASELINE: return rollout_go<Env, CONS, NIG_POLICY_BASELINE, false, false>(c, pitch, a, map, st);
+    case NIG_POLICY_ACTIONS: return rollout_go<Env, CONS, NIG_POLICY_ACTIONS, false, false, EXTREMA>(c, pitch, a, map, st);
+    case NIG_POLICY_UNIFORM: return rollout_go<Env, CONS, NIG_POLICY_UNIFORM, false, false, EXTREMA>(c, pitch, a, map, st);
+    case NIG_POLICY_ZERO: return rollout_go<Env, CONS, NIG_POLICY_ZERO, false, false, EXTREMA>(c, pitch, a, map, st);
+    case NIG_POLICY_PCTRL: return rollout_go<Env, CONS, NIG_POLICY_PCTRL, false, false, EXTREMA>(c, pitch, a, map, st);
+    case NIG_POLICY_BASELINE: return rollout_go<Env, CONS, NIG_POLICY_BASELINE, false, false, EXTREMA>(c, pitch, a, map, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -73,9 +73,13 @@ cudaError_t rollout_env(const RolloutLaunch& c0, int64_t pitch, const RolloutArg
 {
     RolloutLaunch c = c0;
     if (c.cons > CONS_PREFIX) {
-        if (!c.extrema && !c.tma && !c.tf_noise)
-            return c.cons == CONS_BOUNDS1 ? rollout_policy_bounds<Env, CONS_BOUNDS1>(c, pitch, a, map, st)
-                                          : rollout_policy_bounds<Env, CONS_BOUNDS2>(c, pitch, a, map, st);
+        if (!c.tma && !c.tf_noise) {
+            if (c.extrema)
+                return c.cons == CONS_BOUNDS1 ? rollout_policy_bounds<Env, CONS_BOUNDS1, true>(c, pitch, a, map, st)
+                                              : rollout_policy_bounds<Env, CONS_BOUNDS2, true>(c, pitch, a, map, st);
+            return c.cons == CONS_BOUNDS1 ? rollout_policy_bounds<Env, CONS_BOUNDS1, false>(c, pitch, a, map, st)
+                                          : rollout_policy_bounds<Env, CONS_BOUNDS2, false>(c, pitch, a, map, st);
+        }
         c.cons = CONS_PREFIX;
     }
     if (c.extrema)

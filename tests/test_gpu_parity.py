@@ -445,6 +445,20 @@ def test_rollout_with_wrapper_bounds_bitexact_vs_oracle(mods, name, extras):
     assert c[8:8 + len(cons)].tolist() == orc.stats[8:8 + len(cons)].tolist()
     assert c[8 + 3] > 0                                   # the first appended bound really fired
     env.close()
+    # return extrema of a wrapped env: the straight-line flavour == the descriptor loop (forced by a third, never-violated
+    # bound with zero penalty, which leaves every reward unchanged)
+    if extras == "two_bounds":
+        neutral = make_constraint(N.CON_BOUND, si=2, lo=f32(-3e38), hi=f32(3e38), penalty=0.0)
+        got = []
+        for cs in (cons, cons + [neutral]):
+            e2 = _native_env(ni, kind, n, auto_reset=True, seed=31, constraints=cs)
+            e2.reset_host(); e2.track_extrema(True)
+            e2.rollout_steps_device(600 if kind == 0 else 60, 64, N.POLICY_UNIFORM)
+            torch.cuda.synchronize()
+            got.append((e2.read_extrema(), e2.stats_dict()["episodes"], e2.stats_dict()["return_sum"]))
+            e2.close()
+        assert got[0][0] == got[1][0] and got[0][0][0] is not None and got[0][1] == got[1][1] > 0
+        np.testing.assert_allclose(got[0][2], got[1][2], rtol=1e-12)
 
 
 def test_safety_wrapper_api(mods):
