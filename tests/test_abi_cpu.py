@@ -146,3 +146,20 @@ def test_normal_table_headers_are_the_generators_output(tmp_path):
     mod.emit(tab, str(out), "CUDA library")
     assert out.read_text() == a
     assert tab.shape == (513, 4) and err_abs < 6e-7
+
+
+def test_bench_reference_arm_runs_without_a_gpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) needs no GPU: one JSON line with the
+    contract's keys, the same metric / unit as the GPU arm, `impl: reference`, a cpu_baseline block and an e2e block."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("env-steps/sec (ChemicalReactor-v0") and line["value"] > 1e5
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["gpu_launches"] == 0 and line["vs_baseline"] is None
