@@ -353,6 +353,16 @@ NIG_API int nig_selftest_division(int device, int64_t n, uint64_t seed, int64_t*
  * oracle computes the same sums; the whole 2^32-word domain is (first 0, stride 1, count 2^32). */
 NIG_API int nig_selftest_normal(int device, uint32_t first, uint32_t stride, int64_t count, uint64_t* sums2);
 
+/* teacher-forced replay of the in-kernel policies (test hook): the get_dataset controller / random branches
+ * (chemical_reactor.py:364-390, power_grid.py:216-232, robot_assembly.py:266-291; policy = NIG_POLICY_PCTRL) and the
+ * benchmark baseline controllers (benchmarks/baseline_agents.py:46-114; NIG_POLICY_BASELINE) evaluated by the device code on
+ * HOST arrays of caller-supplied states and random inputs instead of the in-kernel draws: states [n_steps][n][S],
+ * coin [n_steps][n] (the np.random.random() of the mix, NULL = 0.5), z [n_steps][n][8] standard normals,
+ * u [n_steps][n][8] uniforms in [-1, 1] (NULL = zeros) -> actions [n_steps][n][A] as get_dataset stores them. Env i keeps
+ * its PID integral / previous error across the n_steps rows like one agent object does. */
+NIG_API int nig_selftest_policy(int device, int32_t env_kind, int32_t policy, const nig_policy_params_t* pp, int64_t n, int32_t n_steps,
+                                const float* states, const float* coin, const float* z, const float* u, float* actions);
+
 #ifdef __cplusplus
 }
 #endif

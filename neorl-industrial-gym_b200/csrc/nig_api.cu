@@ -1209,6 +1209,38 @@ int nig_selftest_normal(int device, uint32_t first, uint32_t stride, int64_t cou
     return NIG_OK;
 }
 
+int nig_selftest_policy(int device, int32_t env_kind, int32_t policy, const nig_policy_params_t* pp, int64_t n, int32_t n_steps,
+                         const float* states, const float* coin, const float* z, const float* u, float* actions)
+{
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    if (env_kind < 0 || env_kind > NIG_ENV_ROBOT_ASSEMBLY || !pp || !states || !actions || n <= 0 || n_steps <= 0)
+        return fail(NIG_ERR_INVALID, "nig_selftest_policy: bad env kind, null pointer or empty shape");
+    if (policy != NIG_POLICY_PCTRL && policy != NIG_POLICY_BASELINE)
+        return fail(NIG_ERR_INVALID, "nig_selftest_policy: policy must be NIG_POLICY_PCTRL or NIG_POLICY_BASELINE");
+    nig_env_spec_t spec;
+    nig_env_spec(env_kind, &spec);
+    const size_t rows = (size_t)n * (size_t)n_steps;
+    const size_t b_s = rows * spec.state_dim * sizeof(float), b_c = rows * sizeof(float), b_r = rows * 8 * sizeof(float),
+                 b_a = rows * spec.action_dim * sizeof(float);
+    char* d = nullptr;
+    NIG_CUDA(cudaMalloc((void**)&d, b_s + b_c + 2 * b_r + b_a));
+    float* d_s = (float*)d; float* d_c = (float*)(d + b_s); float* d_z = (float*)(d + b_s + b_c);
+    float* d_u = (float*)(d + b_s + b_c + b_r); float* d_a = (float*)(d + b_s + b_c + 2 * b_r);
+    cudaError_t ce = cudaMemcpy(d_s, states, b_s, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && coin) ce = cudaMemcpy(d_c, coin, b_c, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && z) ce = cudaMemcpy(d_z, z, b_r, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess && u) ce = cudaMemcpy(d_u, u, b_r, cudaMemcpyHostToDevice);
+    nig::PolicyTestArgs a{};
+    a.policy = policy; a.T = n_steps; a.n = n; a.pp = *pp;
+    a.states = d_s; a.coin = coin ? d_c : nullptr; a.z = z ? d_z : nullptr; a.u = u ? d_u : nullptr; a.actions = d_a;
+    if (ce == cudaSuccess) ce = nig::launch_selftest_policy(env_kind, a, nullptr);
+    if (ce == cudaSuccess) ce = cudaMemcpy(actions, d_a, b_a, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    NIG_CUDA(ce);
+    return NIG_OK;
+}
+
 int nig_fp32_probe(int device, int32_t iters, double* ops, void* stream)
 {
     DeviceGuard guard(device);

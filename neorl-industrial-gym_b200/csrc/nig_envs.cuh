@@ -183,17 +183,25 @@ struct Reactor {
     }
 
     // get_dataset controller branch (:366-385): a_j = g0_j*(T-320)/50 + g1_j*(level-55)/50 + sigma_j*N(0,1)
-    __device__ static __forceinline__ void policy_ctrl(const Rng& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
-                                                       const float (&s)[S], float (&a)[A])
+    // policy_ctrl_from: the arithmetic for given standard normals z (the draw is separated so that the reference's own
+    // get_dataset transitions can be replayed teacher-forced, tests/golden/policy_forced.npz)
+    __device__ static __forceinline__ void policy_ctrl_from(const nig_policy_params_t& pp, const float (&s)[S], const float (&z)[8],
+                                                            const float (&)[4], float (&a)[A])
     {
-        float z[4];
-        rng_normals4(key, env, tick, STREAM_POLICY, 1u, z);
         DivExact div;    // the controller branch is taken by a subset of the lanes: keep the IEEE division here
         const float te = NIG_CDIV(div, sub(s[0], 320.0f), 50.0f);
         const float le = NIG_CDIV(div, sub(s[10], 55.0f), 50.0f);
 #pragma unroll
         for (int k = 0; k < A; ++k)
             a[k] = add(add(mul(pp.gain[k][0], te), mul(pp.gain[k][1], le)), mul(pp.sigma[k], z[k]));
+    }
+    __device__ static __forceinline__ void policy_ctrl(const Rng& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
+                                                       const float (&s)[S], float (&a)[A])
+    {
+        float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const float u[4] = {0.f, 0.f, 0.f, 0.f};
+        rng_normals4(key, env, tick, STREAM_POLICY, 1u, reinterpret_cast<float (&)[4]>(z[0]));
+        policy_ctrl_from(pp, s, z, u, a);
     }
 };
 
@@ -338,23 +346,25 @@ struct Grid {
     }
 
     // get_dataset heuristics (:216-232): a_j = g0_j*freq_dev + g1_j*(sum load - sum gen)/8 + sigma_j*N(0,1)
-    __device__ static __forceinline__ void policy_ctrl(const Rng& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
-                                                       const float (&s)[S], float (&a)[A])
+    __device__ static __forceinline__ void policy_ctrl_from(const nig_policy_params_t& pp, const float (&s)[S], const float (&z)[8],
+                                                            const float (&)[4], float (&a)[A])
     {
-        float gen[8], load[8], z[8];
+        float gen[8], load[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { gen[i] = s[9 + i]; load[i] = s[17 + i]; }
         const float imb8 = fdiv(sub(pairwise8(load), pairwise8(gen)), 8.0f);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            float zz[4];
-            rng_normals4(key, env, tick, STREAM_POLICY, (uint32_t)(1 + j), zz);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) z[4 * j + q] = zz[q];
-        }
-#pragma unroll
         for (int k = 0; k < A; ++k)
             a[k] = add(add(mul(pp.gain[k][0], s[0]), mul(pp.gain[k][1], imb8)), mul(pp.sigma[k], z[k]));
+    }
+    __device__ static __forceinline__ void policy_ctrl(const Rng& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
+                                                       const float (&s)[S], float (&a)[A])
+    {
+        float z[8];
+        const float u[4] = {0.f, 0.f, 0.f, 0.f};
+        rng_normals4(key, env, tick, STREAM_POLICY, 1u, reinterpret_cast<float (&)[4]>(z[0]));
+        rng_normals4(key, env, tick, STREAM_POLICY, 2u, reinterpret_cast<float (&)[4]>(z[4]));
+        policy_ctrl_from(pp, s, z, u, a);
     }
 };
 
@@ -499,19 +509,27 @@ struct Robot {
         return d || !inside;
     }
 
-    // get_dataset controllers (:266-287): P-control of the end-effector error on the first three joints;
-    // mode 0 (expert) damps joints 3..6, mode 1 (mixed) drives them with U(-sigma[3], sigma[3])
+    // get_dataset controllers (:266-287): P-control of the end-effector error on the first three joints, in binary64
+    // like the reference (target_position is a float64 array, :83) and rounded to fp32 where the dataset stores it;
+    // mode 0 (expert) damps joints 3..6 (fp32: obs * Python float), mode 1 (mixed) drives them with U(-sigma[3], sigma[3])
+    __device__ static __forceinline__ void policy_ctrl_from(const nig_policy_params_t& pp, const float (&s)[S], const float (&)[8],
+                                                            const float (&u)[4], float (&a)[A])
+    {
+        const double kp = (double)pp.gain[0][0];
+        a[0] = (float)dmul(kp, dsub(0.3, (double)s[0]));
+        a[1] = (float)dmul(kp, dsub(0.0, (double)s[1]));
+        a[2] = (float)dmul(kp, dsub(0.4, (double)s[2]));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            a[3 + k] = pp.mode == 0 ? mul(pp.gain[3][0], s[10 + k]) : mul(pp.sigma[3], u[k]);
+    }
     __device__ static __forceinline__ void policy_ctrl(const Rng& key, const nig_policy_params_t& pp, uint32_t env, uint32_t tick,
                                                        const float (&s)[S], float (&a)[A])
     {
-        a[0] = mul(pp.gain[0][0], sub(0.3f, s[0]));
-        a[1] = mul(pp.gain[0][0], sub(0.0f, s[1]));
-        a[2] = mul(pp.gain[0][0], sub(0.4f, s[2]));
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const uint4 w = rng_words(key, env, tick, STREAM_POLICY, 3u);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            a[3 + k] = pp.mode == 0 ? mul(pp.gain[3][0], s[10 + k]) : mul(pp.sigma[3], u_sym(ww[k]));
+        const float u[4] = {u_sym(w.x), u_sym(w.y), u_sym(w.z), u_sym(w.w)};
+        policy_ctrl_from(pp, s, z, u, a);
     }
 };
 

@@ -916,6 +916,22 @@ __device__ __forceinline__ void policy_pctrl(const Rng& key, const nig_policy_pa
     }
 }
 
+// policy_pctrl with every random input supplied by the caller (coin in (0, 1], 8 standard normals, 8 uniforms in
+// [-1, 1]): the arithmetic of the get_dataset branches without the draws, for the teacher-forced replay of the
+// reference's own get_dataset transitions (selftest_policy_kernel, tests/golden/policy_forced.npz)
+template <class Env>
+__device__ __forceinline__ void policy_pctrl_forced(const nig_policy_params_t& pp, const float (&s)[Env::S], float coin,
+                                                    const float (&z)[8], const float (&u)[8], float (&a)[Env::A])
+{
+    if (coin <= pp.p_ctrl) {
+        const float u4[4] = {u[0], u[1], u[2], u[3]};
+        Env::policy_ctrl_from(pp, s, z, u4, a);
+    } else {
+#pragma unroll
+        for (int k = 0; k < Env::A; ++k) a[k] = mul(pp.uniform_scale, u[k]);
+    }
+}
+
 // benchmarks/baseline_agents.py controllers in fp64 like numpy computes them; integ / prev are the PID agent's state
 template <class Env>
 __device__ __forceinline__ void policy_baseline(const Rng& key, const nig_baseline_t& b, uint32_t env, uint32_t tick,
@@ -1376,6 +1392,50 @@ static __global__ void __launch_bounds__(256) selftest_normal_kernel(uint32_t fi
     }
     atomicAdd(&out[0], s0);
     atomicAdd(&out[1], s1);
+}
+
+// ---- teacher-forced policy replay: the in-kernel policies on caller-supplied states and random inputs ------------------
+// One thread = one env walking T steps (the PID controller's integral / previous error persist across the steps like the
+// agent object's, benchmarks/baseline_agents.py:58-60). Layouts: states [T][n][S], coin [T][n], z / u [T][n][8],
+// actions out [T][n][A] (the value the dataset stores: clipped to +-store_clip when that is positive).
+struct PolicyTestArgs {
+    int32_t policy, T;
+    int64_t n;
+    nig_policy_params_t pp;
+    const float* states; const float* coin; const float* z; const float* u;
+    float* actions;
+};
+template <class Env>
+__global__ void __launch_bounds__(kThreads) selftest_policy_kernel(const __grid_constant__ PolicyTestArgs p)
+{
+    constexpr int S = Env::S, A = Env::A;
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= p.n) return;
+    const Rng key(RngKey{0u, 0u}, g_normal_tab);
+    double pid_i[A], pid_e[A];
+#pragma unroll
+    for (int k = 0; k < A; ++k) { pid_i[k] = 0.0; pid_e[k] = 0.0; }
+    for (int t = 0; t < p.T; ++t) {
+        const int64_t row = (int64_t)t * p.n + i;
+        float s[S], a[A], z[8], u[8];
+#pragma unroll
+        for (int k = 0; k < S; ++k) s[k] = p.states[row * S + k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { z[k] = p.z ? p.z[row * 8 + k] : 0.0f; u[k] = p.u ? p.u[row * 8 + k] : 0.0f; }
+        if (p.policy == NIG_POLICY_PCTRL) policy_pctrl_forced<Env>(p.pp, s, p.coin ? p.coin[row] : 0.5f, z, u, a);
+        else policy_baseline<Env>(key, p.pp.baseline, (uint32_t)i, (uint32_t)t, s, a, pid_i, pid_e);
+        if (p.pp.store_clip > 0.0f) {
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                float v = a[k];
+                v = v < -p.pp.store_clip ? -p.pp.store_clip : v;
+                v = v > p.pp.store_clip ? p.pp.store_clip : v;
+                a[k] = v;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < A; ++k) p.actions[row * A + k] = a[k];
+    }
 }
 
 // ---- measured-peak probe: independent unfused FADD/FMUL chains (what the physics is made of) ------

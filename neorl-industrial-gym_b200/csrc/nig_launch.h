@@ -26,6 +26,7 @@ cudaError_t launch_state_io(const StateIoArgs& a, cudaStream_t st);
 cudaError_t launch_scan_lengths(const int64_t* len, int64_t* off, int64_t n, int64_t* total, cudaStream_t st);
 cudaError_t launch_fp32_probe(float* sink, int iters, int blocks, cudaStream_t st);
 cudaError_t launch_selftest_normal(uint32_t first, uint32_t stride, unsigned long long count, unsigned long long* out, cudaStream_t st);
+cudaError_t launch_selftest_policy(int kind, const PolicyTestArgs& a, cudaStream_t st);
 cudaError_t launch_selftest_division(RngKey key, int iters, int blocks, unsigned long long* out, cudaStream_t st);
 
 inline unsigned grid_for(int64_t items, int block = kThreads) { return (unsigned)((items + block - 1) / block); }

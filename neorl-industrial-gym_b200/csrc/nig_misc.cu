@@ -31,6 +31,16 @@ cudaError_t launch_selftest_division(RngKey key, int iters, int blocks, unsigned
     selftest_division_kernel<<<blocks, 256, 0, st>>>(key, iters, out);
     return cudaGetLastError();
 }
+cudaError_t launch_selftest_policy(int kind, const PolicyTestArgs& a, cudaStream_t st)
+{
+    const unsigned g = grid_for(a.n);
+    switch (kind) {
+    case NIG_ENV_CHEMICAL_REACTOR: selftest_policy_kernel<Reactor><<<g, kThreads, 0, st>>>(a); break;
+    case NIG_ENV_POWER_GRID: selftest_policy_kernel<Grid><<<g, kThreads, 0, st>>>(a); break;
+    default: selftest_policy_kernel<Robot><<<g, kThreads, 0, st>>>(a); break;
+    }
+    return cudaGetLastError();
+}
 cudaError_t launch_rollout(int kind, const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
 {
     switch (kind) {

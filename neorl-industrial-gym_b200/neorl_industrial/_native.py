@@ -137,6 +137,8 @@ SYMBOLS = {
     "nig_fp32_probe": (C.c_int, [C.c_int, _I32, C.POINTER(C.c_double), _VP]),
     "nig_selftest_division": (C.c_int, [C.c_int, _I64, _U64, C.POINTER(_I64), C.POINTER(_I64)]),
     "nig_selftest_normal": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_int64, C.POINTER(C.c_uint64)]),
+    "nig_selftest_policy": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_void_p, _I64, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -765,6 +765,24 @@ typedef struct {
     float sigma[8];
 } orc_pp_t;
 
+/* the controller branch for given random inputs: z = 8 standard normals, u = 4 uniforms in [-1, 1] */
+static void policy_ctrl_from(const orc_cfg_t* cfg, const orc_pp_t* pp, const float* s, const float* z, const float* u, float* a)
+{
+    if (cfg->kind == ORC_REACTOR) {                 /* chemical_reactor.py:366-385 */
+        const float te = (s[0] - 320.0f) / 50.0f, le = (s[10] - 55.0f) / 50.0f;
+        for (int k = 0; k < 3; ++k) a[k] = (pp->gain[k][0] * te + pp->gain[k][1] * le) + pp->sigma[k] * z[k];
+    } else if (cfg->kind == ORC_GRID) {             /* power_grid.py:216-229 */
+        const float imb8 = (pairwise8(s + 17) - pairwise8(s + 9)) / 8.0f;
+        for (int k = 0; k < 8; ++k) a[k] = (pp->gain[k][0] * s[0] + pp->gain[k][1] * imb8) + pp->sigma[k] * z[k];
+    } else {                                        /* robot_assembly.py:266-287: float64 target_position - float32 obs */
+        const double kp = (double)pp->gain[0][0];
+        a[0] = (float)(kp * (0.3 - (double)s[0]));
+        a[1] = (float)(kp * (0.0 - (double)s[1]));
+        a[2] = (float)(kp * (0.4 - (double)s[2]));
+        for (int k = 0; k < 4; ++k) a[3 + k] = pp->mode == 0 ? pp->gain[3][0] * s[10 + k] : pp->sigma[3] * u[k];
+    }
+}
+
 static void policy_one(const orc_cfg_t* cfg, int policy, const orc_pp_t* pp, uint32_t env, uint32_t tick, const float* s, float* a)
 {
     const int A = kA[cfg->kind];
@@ -782,30 +800,46 @@ static void policy_one(const orc_cfg_t* cfg, int policy, const orc_pp_t* pp, uin
     words4(cfg, env, tick, STREAM_POLICY, 0u, w0);
     const float coin = u_open(w0[0]);
     if (coin <= pp->p_ctrl) {
-        if (cfg->kind == ORC_REACTOR) {
-            float z[4];
-            normals4(cfg, env, tick, STREAM_POLICY, 1u, z);
-            const float te = (s[0] - 320.0f) / 50.0f, le = (s[10] - 55.0f) / 50.0f;
-            for (int k = 0; k < 3; ++k) a[k] = (pp->gain[k][0] * te + pp->gain[k][1] * le) + pp->sigma[k] * z[k];
-        } else if (cfg->kind == ORC_GRID) {
-            float z[8];
+        float z[8] = {0}, u[4] = {0};
+        if (cfg->kind == ORC_REACTOR) normals4(cfg, env, tick, STREAM_POLICY, 1u, z);
+        else if (cfg->kind == ORC_GRID) {
             normals4(cfg, env, tick, STREAM_POLICY, 1u, z);
             normals4(cfg, env, tick, STREAM_POLICY, 2u, z + 4);
-            const float imb8 = (pairwise8(s + 17) - pairwise8(s + 9)) / 8.0f;
-            for (int k = 0; k < 8; ++k) a[k] = (pp->gain[k][0] * s[0] + pp->gain[k][1] * imb8) + pp->sigma[k] * z[k];
         } else {
-            a[0] = pp->gain[0][0] * (0.3f - s[0]);
-            a[1] = pp->gain[0][0] * (0.0f - s[1]);
-            a[2] = pp->gain[0][0] * (0.4f - s[2]);
             words4(cfg, env, tick, STREAM_POLICY, 3u, w);
-            for (int k = 0; k < 4; ++k) a[3 + k] = pp->mode == 0 ? pp->gain[3][0] * s[10 + k] : pp->sigma[3] * u_sym(w[k]);
+            for (int k = 0; k < 4; ++k) u[k] = u_sym(w[k]);
         }
+        policy_ctrl_from(cfg, pp, s, z, u, a);
     } else {
         for (int k = 0; k < A && k < 3; ++k) a[k] = pp->uniform_scale * u_sym(w0[1 + k]);
         for (int j = 0; 3 + 4 * j < A; ++j) {
             words4(cfg, env, tick, STREAM_POLICY, (uint32_t)(8 + j), w);
             for (int q = 0; q < 4; ++q) if (3 + 4 * j + q < A) a[3 + 4 * j + q] = pp->uniform_scale * u_sym(w[q]);
         }
+    }
+}
+
+/* get_dataset's policy on caller-supplied random inputs (teacher-forced replay of the reference's own transitions):
+ * coin [n] or NULL (= 0.5), z [n][8] standard normals, u [n][8] uniforms in [-1, 1]; actions [n][A] as stored
+ * (clipped to +-store_clip when positive) */
+ORC_API void orc_policy_forced(const orc_cfg_t* cfg, const orc_pp_t* pp, int64_t n, const float* state, const float* coin,
+                               const float* z, const float* u, float* actions)
+{
+    const int S = kS[cfg->kind], A = kA[cfg->kind];
+    static const float zero8[8] = {0};
+    for (int64_t i = 0; i < n; ++i) {
+        const float* zi = z ? z + i * 8 : zero8;
+        const float* ui = u ? u + i * 8 : zero8;
+        float* a = actions + i * A;
+        if ((coin ? coin[i] : 0.5f) <= pp->p_ctrl) policy_ctrl_from(cfg, pp, state + i * S, zi, ui, a);
+        else for (int k = 0; k < A; ++k) a[k] = pp->uniform_scale * ui[k];
+        if (pp->store_clip > 0.0f)
+            for (int k = 0; k < A; ++k) {
+                float v = a[k];
+                v = v < -pp->store_clip ? -pp->store_clip : v;
+                v = v > pp->store_clip ? pp->store_clip : v;
+                a[k] = v;
+            }
     }
 }
 

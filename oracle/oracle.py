@@ -188,6 +188,18 @@ def policy_actions(env: "OracleEnv", policy, pp=None):
     return a
 
 
+def policy_forced(kind, pp, state, coin=None, z=None, u=None):
+    """get_dataset's policy arithmetic on supplied random inputs (coin [n], z [n, 8] normals, u [n, 8] in [-1, 1])."""
+    state = np.ascontiguousarray(state, np.float32)
+    n = state.shape[0]
+    f32 = lambda x: None if x is None else np.ascontiguousarray(x, np.float32)
+    coin, z, u = f32(coin), f32(z), f32(u)
+    a = np.empty((n, ACTION_DIM[kind]), np.float32)
+    cfg = make_cfg(kind)
+    lib().orc_policy_forced(C.byref(cfg), C.byref(pp), C.c_int64(n), _p(state), _p(coin), _p(z), _p(u), _p(a))
+    return a
+
+
 def dynamics(kind, s, a, nz=None, exp_mode=0):
     s = np.ascontiguousarray(s, np.float32)
     a = np.ascontiguousarray(a, np.float32)

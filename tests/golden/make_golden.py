@@ -10,7 +10,12 @@ Fixtures (all small, committed):
   <env>_trace.npz  : BASELINE config #1 -- one env, 1000 steps, random fp32 actions, reset on done; everything
                      needed to replay it teacher-forced (states, actions, noise, reset states, outputs).
   reactor_freerun.npz : 16 free-running 500-step episodes (actions + noise recorded) for the drift test.
-  reactor_dataset_stats.json : summary statistics of the reference's get_dataset('mixed'/'expert').
+  <env>_dataset_stats.json : summary statistics of the reference's get_dataset(quality) for every quality.
+  policy_forced.npz : get_dataset's POLICY, teacher-forced -- per env x quality ~2000 transitions of the reference's own
+                     get_dataset run: the observation the policy saw, every random value it drew (coin, normals,
+                     uniforms; recorded by interposing np.random.*), and the action it stored.
+  baseline_agents.npz : benchmarks/baseline_agents.py (loaded by file path, pure numpy) driven over state sequences:
+                     PID (integral / derivative state), MPC heuristic, Constant -> float64 actions.
 """
 from __future__ import annotations
 
@@ -260,11 +265,159 @@ def make_freerun(envs, n_ep, seed):
     print("reactor_freerun: lengths", length.tolist())
 
 
-def make_dataset_stats(envs, seed):
+class PolicyRecorder:
+    """Pass-through interposer on np.random.normal / uniform / random / rand that records, per transition of a running
+    get_dataset, the draws made by the POLICY (those outside env.reset / env.step) and the action handed to env.step."""
+
+    def __init__(self, env):
+        self.env, self.in_env, self.pending, self.rows = env, 0, [], []
+        self._orig = {k: getattr(np.random, k) for k in ("normal", "uniform", "random", "rand")}
+        self._step, self._reset = env.step, env.reset
+
+    def _wrap_draw(self, name):
+        orig = self._orig[name]
+
+        def f(*a, **kw):
+            v = orig(*a, **kw)
+            if not self.in_env:
+                self.pending.append((name, a, np.array(v, np.float64).copy()))
+            return v
+        return f
+
+    def __enter__(self):
+        for k in self._orig:
+            setattr(np.random, k, self._wrap_draw(k))
+
+        def step(action):
+            self.rows.append((self.env.state.copy(), self.pending, np.array(action, np.float64).copy()))
+            self.pending = []
+            self.in_env += 1
+            try:
+                return self._step(action)
+            finally:
+                self.in_env -= 1
+
+        def reset(*a, **kw):
+            assert not self.pending
+            self.in_env += 1
+            try:
+                return self._reset(*a, **kw)
+            finally:
+                self.in_env -= 1
+        self.env.step, self.env.reset = step, reset
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self._orig.items():
+            setattr(np.random, k, v)
+        del self.env.step, self.env.reset
+        return False
+
+
+def forced_inputs(name, draws):
+    """Recorded np.random calls of one transition -> (coin, z[8] = normal / scale, u[8] = uniform mapped to [-1, 1])."""
+    coin, z, u = np.nan, np.zeros(8), np.zeros(8)
+    nz = nu = 0
+    for fn, args, v in draws:
+        if fn in ("random", "rand"):
+            assert np.isnan(coin) and v.ndim == 0
+            coin = float(v)
+        elif fn == "normal":
+            assert args[0] == 0 and v.ndim == 0
+            z[nz] = float(v) / args[1]; nz += 1
+        else:
+            lo, hi = float(args[0]), float(args[1])
+            assert lo == -hi
+            for x in np.atleast_1d(v):
+                u[nu] = x / hi; nu += 1
+    return coin, z, u
+
+
+def make_policy_forced(envs, seed, per_case=2000):
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name in ("reactor", "grid", "robot"):
+        for quality in ("expert", "medium", "mixed", "random"):
+            np.random.seed(seed)
+            env = getattr(envs, ENV_CLASS[name])()
+            with PolicyRecorder(env) as rec:
+                d = env.get_dataset(quality)
+            rows = rec.rows
+            assert len(rows) == len(d["actions"])
+            stored = d["actions"]
+            for i in rng.choice(len(rows), 50, replace=False):    # the recorder sees what the dataset stores
+                assert np.array_equal(np.asarray(rows[i][2], np.float32), stored[i]), (name, quality, i)
+                assert np.array_equal(rows[i][0], d["observations"][i])
+            pick = np.sort(rng.choice(len(rows), min(per_case, len(rows)), replace=False))
+            obs = np.array([rows[i][0] for i in pick], np.float32)
+            fi = [forced_inputs(name, rows[i][1]) for i in pick]
+            key = f"{name}_{quality}"
+            out[key + "_obs"] = obs
+            out[key + "_coin"] = np.array([f[0] for f in fi], np.float64)
+            out[key + "_z"] = np.array([f[1] for f in fi], np.float32)
+            out[key + "_u"] = np.array([f[2] for f in fi], np.float32)
+            out[key + "_action"] = stored[pick].astype(np.float32)
+            c = out[key + "_coin"]
+            print(f"policy_forced {key}: {len(rows)} transitions recorded, {len(pick)} kept, coin drawn in "
+                  f"{np.isfinite(c).sum()}, normals in {(np.abs(out[key + '_z']).sum(1) > 0).sum()}, "
+                  f"uniforms in {(np.abs(out[key + '_u']).sum(1) > 0).sum()}")
+    np.savez_compressed(os.path.join(HERE, "policy_forced.npz"), **out)
+
+
+def make_baseline_goldens(seed):
+    """benchmarks/baseline_agents.py:28-114, imported by file path (pure numpy)."""
+    import importlib.util
+    path = os.path.join(ref_loader.REFERENCE_SRC, "neorl_industrial", "benchmarks", "baseline_agents.py")
+    spec = importlib.util.spec_from_file_location("_ref_baseline_agents", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(seed)
+    out = {}
+    T, n = 64, 48
+    for name, (S, A) in {"reactor": (12, 3), "grid": (32, 8), "robot": (24, 7)}.items():
+        tr = np.load(os.path.join(HERE, f"{name}_trace.npz"))["state"]
+        # n independent agents, each fed T consecutive states of the reference trace from a different offset,
+        # plus (last quarter) states scaled so that the clip at +-1 and the integral wind-up are both exercised
+        starts = rng.integers(0, len(tr) - T, n)
+        states = np.stack([tr[s0:s0 + T] for s0 in starts], 1).astype(np.float32)      # [T, n, S]
+        states[:, 3 * n // 4:, :A] *= 0.01
+        # setpoint near the mean of the process variables and gains scaled by their spread: O(1) actions, partly clipped
+        setpoint = tr[:, :A].astype(np.float64).mean(0) + rng.normal(0, 0.05, A)
+        spread = float(tr[:, :A].astype(np.float64).std(0).max()) + 1e-3
+        gains = np.array([0.8, 0.05, 0.02]) / spread
+        const = rng.uniform(-1, 1, A)
+        out[f"{name}_pid_gains"] = gains
+        cases = {
+            "pid": lambda: mod.PIDControllerAgent(S, A, kp=gains[0], ki=gains[1], kd=gains[2], setpoint=setpoint.copy()),
+            "pid_default": lambda: mod.PIDControllerAgent(S, A),
+            "mpc": lambda: mod.MPC_Agent(S, A),
+            "constant": lambda: mod.ConstantAgent(S, A, constant_action=const.copy()),
+        }
+        out[f"{name}_states"] = states
+        out[f"{name}_setpoint"] = setpoint
+        out[f"{name}_constant"] = const
+        for cname, mk in cases.items():
+            acts = np.zeros((T, n, A), np.float64)
+            for i in range(n):
+                agent = mk()
+                for t in range(T):
+                    acts[t, i] = agent.act(states[t, i])
+            out[f"{name}_{cname}_actions"] = acts
+        print(f"baseline_agents {name}: {T} x {n} states, |pid action| == 1 in "
+              f"{np.mean(np.abs(out[f'{name}_pid_actions']) == 1.0):.2f} of the entries")
+    # the factory and the random agent's range (distribution only: it draws from the global numpy stream)
+    np.random.seed(seed)
+    ra = mod.BaselineAgentFactory.create("random", 12, 3, action_low=-0.5, action_high=0.25)
+    draws = np.array([ra.act(np.zeros(12)) for _ in range(4000)])
+    out["random_low_high_mean_std"] = np.array([draws.min(), draws.max(), draws.mean(), draws.std()])
+    np.savez_compressed(os.path.join(HERE, "baseline_agents.npz"), **out)
+
+
+def make_dataset_stats(envs, seed, name="reactor"):
     out = {}
     for quality in ("mixed", "expert", "medium", "random"):
         np.random.seed(seed)
-        env = envs.ChemicalReactorEnv()
+        env = getattr(envs, ENV_CLASS[name])()
         d = env.get_dataset(quality)
         term = d["terminals"]
         ends = np.flatnonzero(term)
@@ -278,16 +431,17 @@ def make_dataset_stats(envs, seed):
             "action_mean": d["actions"].mean(0).tolist(), "action_std": d["actions"].std(0).tolist(),
             "obs_mean": d["observations"].mean(0).tolist(), "obs_std": d["observations"].std(0).tolist(),
             "frac_action_saturated": float(np.mean(np.abs(d["actions"]) >= 1.0)),
-            "timeouts_any": bool(d["timeouts"].any()),
+            "timeouts_any": bool(d["timeouts"].any()) if "timeouts" in d else False,
+            "episode_len_mean": float(len(term) / max(1, int(term.sum()))) if name != "reactor" else None,
         }
         print(quality, {k: out[quality][k] for k in ("n", "n_terminals", "reward_mean", "reward_std")})
-    with open(os.path.join(HERE, "reactor_dataset_stats.json"), "w") as f:
+    with open(os.path.join(HERE, f"{name}_dataset_stats.json"), "w") as f:
         json.dump(out, f, indent=1)
 
 
 if __name__ == "__main__":
     envs = ref_loader.load_reference_envs()
-    which = sys.argv[1:] or ["forced", "trace", "freerun", "dataset"]
+    which = sys.argv[1:] or ["forced", "trace", "freerun", "dataset", "dataset_all", "policy", "baselines"]
     if "forced" in which:
         make_forced(envs, "reactor", 6000, 1)
         make_forced(envs, "grid", 3000, 2)
@@ -300,3 +454,10 @@ if __name__ == "__main__":
         make_freerun(envs, 16, 5)
     if "dataset" in which:
         make_dataset_stats(envs, 0)
+    if "dataset_all" in which:
+        make_dataset_stats(envs, 0, "grid")
+        make_dataset_stats(envs, 0, "robot")
+    if "policy" in which:
+        make_policy_forced(envs, 11)
+    if "baselines" in which:
+        make_baseline_goldens(12)

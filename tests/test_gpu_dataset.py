@@ -121,6 +121,32 @@ def test_other_envs_dataset_contract(mods, name):
     env.close()
 
 
+@pytest.mark.parametrize("name", ["grid", "robot"])
+def test_other_envs_dataset_reference_statistics(mods, golden_dir, name):
+    """Distributional parity of PowerGrid / RobotAssembly get_dataset with the reference's own runs (goldens from
+    power_grid.py:194-249 / robot_assembly.py:246-308, every quality): the RNG streams necessarily differ, so mean episode
+    length, termination rate, reward level and the action moments are compared, from 10x the reference's episode count.
+    Tolerances are ~3 sigma of the reference sample (80 .. 250 episodes)."""
+    ni, N, O, torch = mods
+    gold = json.load(open(os.path.join(golden_dir, f"{name}_dataset_stats.json")))
+    env = ni.make(ENV_IDS[name], seed=3)
+    for quality, g in gold.items():
+        n_ep_ref, _, _, _ = type(env).dataset_policy(quality)
+        d = env.get_dataset(quality, n_episodes=10 * n_ep_ref)
+        n = len(d["rewards"])
+        assert d["observations"].dtype == np.float32 and d["actions"].dtype == np.float32 and d["terminals"].dtype == bool
+        ep_len, ep_len_ref = n / (10 * n_ep_ref), g["n"] / n_ep_ref
+        assert abs(ep_len - ep_len_ref) / ep_len_ref < 0.25, (quality, ep_len, ep_len_ref)
+        assert abs(d["terminals"].sum() / (10 * n_ep_ref) - g["n_terminals"] / n_ep_ref) < 0.08, quality
+        # reward level: per-transition rewards are dominated by the -1000 critical-shutdown step that ends most episodes
+        se = g["reward_std"] / np.sqrt(g["n_terminals"])
+        assert abs(d["rewards"].mean() - g["reward_mean"]) < 4 * se + 0.05 * abs(g["reward_mean"]), (quality, d["rewards"].mean(), g["reward_mean"])
+        a_std, a_std_ref = d["actions"].std(0), np.array(g["action_std"])
+        np.testing.assert_allclose(a_std, a_std_ref, rtol=0.15, atol=0.03, err_msg=quality)
+        np.testing.assert_allclose(d["actions"].mean(0), g["action_mean"], atol=0.12 * max(1.0, float(a_std_ref.max())), err_msg=quality)
+    env.close()
+
+
 def test_one_million_transition_dataset(mods):
     """BASELINE config #5: >= 1M 'mixed' ChemicalReactor transitions written on the device in D4RL layout."""
     ni, N, O, torch = mods
