@@ -18,7 +18,8 @@ Also measured in the same run and reported in the JSON line:
                    (state larger than L2), achieved GB/s vs MEASURED_PEAKS.json.
   e2e           -- env.rollout(1000, "random", init_states=host) -> host returns / violations / obs: the same workload
                    through the drop-in API with host buffers (nig_rollout_host); e2e_step_api = one env.step() per call.
-  cpu_baseline  -- the CPU oracle port (C, all host threads) on a bounded sample of the same workload.
+  cpu_baseline  -- the reference's own Python step loop (performance_benchmark.py:106-133, unmodified modules from
+                   oracle/_ref) on one core and on all host cores, plus the C oracle port, in the same run.
 """
 from __future__ import annotations
 
@@ -132,49 +133,100 @@ def cpu_rollout_rate(n_envs: int, horizon: int, threads: int, seed: int = 0):
     return n_envs * horizon / dt, dt
 
 
-def cpu_baseline(budget_s: float = 12.0):
-    """The oracle port (C, scalar per env, same workload incl. RNG) on the box's host cores; bounded sample."""
-    from oracle import oracle as O
+def bench_config(world: int):
+    """`config` of the JSON line -- the SAME object in the CUDA arm and the reference arm (what differs between the arms,
+    e.g. the reference arm's bounded sample or the CUDA arm's launch counts, is reported outside it)."""
+    return {"workload": WORKLOAD, "envs_per_gpu": ENVS_PER_GPU, "steps_per_env_per_bench_step": HORIZON, "K": K,
+            "parallelism": f"env-index shards x{world}, no data-path collective",
+            "l2": "256 MiB write between timed iterations (outside the CUDA-event brackets); state lives in registers across K steps"}
+
+
+def reference_loop(mode: str, procs: int = 0, repeats: int = 5, rounds: int = 1, timeout: float = 600.0):
+    """The reference's own step loop (performance_benchmark.py:106-133, unmodified modules from oracle/_ref) timed by
+    oracle/ref_bench.py in a process of its own; None when oracle/_ref did not travel to this machine."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py"), "--mode", mode, "--steps", str(HORIZON),
+           "--repeats", str(repeats), "--rounds", str(rounds)]
+    if procs:
+        cmd += ["--procs", str(procs)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def port_baseline(budget_s: float):
+    """The C oracle port (scalar per env, same workload incl. RNG) on all host threads; bounded sample."""
     threads = host_threads()
     r1, _ = cpu_rollout_rate(2048, 250, 1)                       # calibrate (single thread)
     n = int(min(ENVS_PER_GPU, max(1024, r1 * threads * 0.5 * budget_s / HORIZON))) // 256 * 256 or 256
     rate, dt = cpu_rollout_rate(n, HORIZON, threads)
     return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-            "reference_python_loop": {"value": 12177.0, "unit": UNIT, "cores": 1, "note": "the UNMODIFIED reference's own loop "
-                                      "(performance_benchmark.py:106-133) timed at survey time in the build container (BASELINE.md section 2); "
-                                      "the reference publishes 9,378 steps/s (hardware unstated). Not re-measured here: the tree is absent on the GPU box"},
-            "sample": f"C oracle port (oracle/nig_oracle.c, scalar per env, same policy/noise/auto-reset), {n} envs x {HORIZON} "
-                      f"steps in {dt:.2f} s on {threads} threads; single-thread rate {r1:.3g} env-steps/s. The reference itself is a "
-                      "pure-Python per-env loop with no jit/vmap batch path (published 9,378 steps/s, hardware unstated); "
-                      "its source tree is not on this box."}
+            "sample": f"C oracle port (oracle/nig_oracle.c, scalar per env, same policy / noise / auto-reset), {n} envs x {HORIZON} "
+                      f"steps in {dt:.2f} s on {threads} threads; single-thread rate {r1:.3g} env-steps/s"}
+
+
+def cpu_baseline(budget_s: float = 8.0):
+    """The reference's own CPU step loop on this box's host cores, in the same run: (i) one core, median of 5 x 1,000 steps;
+    (ii) P = all usable cores, P forked processes with one env each (the reference has no batched / jit / vmap path);
+    plus, labelled as ours, the C oracle port on all threads."""
+    threads = host_threads()
+    port = port_baseline(budget_s)
+    single = reference_loop("single", repeats=5)
+    if single is None:
+        port["note"] = "oracle/_ref (the reference's modules, oracle/make_ref.py) is not present on this machine: C port only"
+        return port
+    reps = max(1, int(round(single["steps_per_sec"] * 0.6 * budget_s / HORIZON)))
+    allc = reference_loop("all", procs=threads, repeats=reps, rounds=1)
+    return {"value": allc["steps_per_sec"], "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": f"the reference's own loop (performance_benchmark.py:106-133; unmodified environments/*.py + core/types.py "
+                      f"from oracle/_ref, gymnasium / jax stubbed, numpy {single['numpy']}): {threads} forked processes x 1 env x "
+                      f"{reps} x {HORIZON} steps in {allc['round_wall_s'][0]:.2f} s. The reference has no batched / jit / vmap path.",
+            "single_core": {"value": single["steps_per_sec"], "unit": UNIT, "cores": 1, "min": single["min"], "max": single["max"],
+                            "sample": f"median of {single['repeats']} x {HORIZON} steps, one env, one core"},
+            "port": port}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path. The reference is pure Python and does not travel
-    to the GPU box, so this times the oracle port with all host threads, on the same config / metric / unit."""
+    """--impl reference: the reference's own CPU implementation of the path -- its per-env Python step loop
+    (performance_benchmark.py:106-133) from oracle/_ref -- on all host cores (one forked process per core, one env each);
+    each bench step is a bounded sample of the 65,536 x 1,000 workload (~1 s). Falls back to the C port (kind "port")
+    only if oracle/_ref is absent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
     threads = host_threads()
-    r1, _ = cpu_rollout_rate(2048, 250, 1)
-    # each step: a bounded sample of the 65,536 x 1,000 workload sized to ~1 s
-    n = int(min(ENVS_PER_GPU, max(1024, r1 * threads * 0.5 * 1.0 / HORIZON))) // 256 * 256 or 256
-    for _ in range(args.warmup):
-        cpu_rollout_rate(n, HORIZON, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_rollout_rate(n, HORIZON, threads)
-    dt = time.perf_counter() - t0
-    value = n * HORIZON * args.steps / dt
+    single = reference_loop("single", repeats=3)
+    if single is not None:
+        reps = max(1, int(round(single["steps_per_sec"] * 0.6 * 1.0 / HORIZON)))
+        res = reference_loop("all", procs=threads, repeats=reps, rounds=args.warmup + args.steps)
+        walls = res["round_wall_s"][args.warmup:]
+        per_step = threads * reps * HORIZON
+        dt = sum(walls)
+        kind = "reference"
+        sample = (f"the reference's own loop (performance_benchmark.py:106-133, unmodified modules from oracle/_ref): per bench step "
+                  f"{threads} forked processes x 1 env x {reps} x {HORIZON} steps = {per_step} env-steps; single core "
+                  f"{single['steps_per_sec']:.0f} steps/s")
+    else:
+        r1, _ = cpu_rollout_rate(2048, 250, 1)
+        n = int(min(ENVS_PER_GPU, max(1024, r1 * threads * 0.5 * 1.0 / HORIZON))) // 256 * 256 or 256
+        for _ in range(args.warmup):
+            cpu_rollout_rate(n, HORIZON, threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_rollout_rate(n, HORIZON, threads)
+        dt = time.perf_counter() - t0
+        per_step = n * HORIZON
+        kind = "port"
+        sample = f"C oracle port, {n} envs x {HORIZON} steps per bench step, {threads} threads (oracle/_ref absent on this machine)"
+    value = per_step * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_envs_per_step": n, "steps_per_env_per_bench_step": HORIZON},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"C oracle port, {n} envs x {HORIZON} steps per bench step, {threads} threads "
-                                   "(reference = pure-Python per-env loop, not present on this box)"},
+        "config": bench_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                         "env_steps_per_bench_step": per_step},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -309,11 +361,9 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": n, "steps_per_env_per_bench_step": HORIZON, "K": K,
-                   "launches_per_bench_step": int(launches) // max(args.steps, 1),
-                   "env_slices_per_gpu": (int(launches) // max(args.steps, 1)) // launches_per_pass(),
-                   "parallelism": f"env-index shards x{world}, no data-path collective",
-                   "l2": "256 MiB write between timed iterations (outside the CUDA-event brackets); state lives in registers across K steps"},
+        "config": bench_config(world),
+        "launch_config": {"launches_per_bench_step": int(launches) // max(args.steps, 1),
+                          "env_slices_per_gpu": (int(launches) // max(args.steps, 1)) // launches_per_pass()},
         "clocks": clocks, "gpu_launches": int(launches),
         "wall_s_timed_region": t_wall,
         "counters": {"steps": int(counters[0]), "episodes": int(counters[1]), "violations": int(counters[5]),

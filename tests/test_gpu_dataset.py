@@ -135,12 +135,19 @@ def test_other_envs_dataset_reference_statistics(mods, golden_dir, name):
         d = env.get_dataset(quality, n_episodes=10 * n_ep_ref)
         n = len(d["rewards"])
         assert d["observations"].dtype == np.float32 and d["actions"].dtype == np.float32 and d["terminals"].dtype == bool
-        ep_len, ep_len_ref = n / (10 * n_ep_ref), g["n"] / n_ep_ref
-        assert abs(ep_len - ep_len_ref) / ep_len_ref < 0.25, (quality, ep_len, ep_len_ref)
-        assert abs(d["terminals"].sum() / (10 * n_ep_ref) - g["n_terminals"] / n_ep_ref) < 0.08, quality
+        # an episode either terminates or runs into the 1,000-step cap (a few % of the robot's do, and those few carry most
+        # of the transitions: the plain mean length varies 13 .. 54 between reference seeds) -> compare the termination
+        # rate and the mean length of the TERMINATED episodes, (n - 1000 * n_capped) / n_terminated
+        n_term, n_term_ref = int(d["terminals"].sum()), g["n_terminals"]
+        assert abs(n_term / (10 * n_ep_ref) - n_term_ref / n_ep_ref) < 0.08, quality
+        len_t = (n - 1000 * (10 * n_ep_ref - n_term)) / n_term
+        len_t_ref = (g["n"] - 1000 * (n_ep_ref - n_term_ref)) / n_term_ref
+        assert abs(len_t - len_t_ref) / len_t_ref < 0.25, (quality, len_t, len_t_ref)
         # reward level: per-transition rewards are dominated by the -1000 critical-shutdown step that ends most episodes
-        se = g["reward_std"] / np.sqrt(g["n_terminals"])
-        assert abs(d["rewards"].mean() - g["reward_mean"]) < 4 * se + 0.05 * abs(g["reward_mean"]), (quality, d["rewards"].mean(), g["reward_mean"])
+        # (only where no reference episode ran into the cap: a handful of capped episodes would carry most transitions)
+        if n_term_ref == n_ep_ref:
+            se = g["reward_std"] / np.sqrt(g["n_terminals"])
+            assert abs(d["rewards"].mean() - g["reward_mean"]) < 4 * se + 0.05 * abs(g["reward_mean"]), (quality, d["rewards"].mean(), g["reward_mean"])
         a_std, a_std_ref = d["actions"].std(0), np.array(g["action_std"])
         np.testing.assert_allclose(a_std, a_std_ref, rtol=0.15, atol=0.03, err_msg=quality)
         np.testing.assert_allclose(d["actions"].mean(0), g["action_mean"], atol=0.12 * max(1.0, float(a_std_ref.max())), err_msg=quality)
