@@ -36,7 +36,7 @@ extern "C" {
 #define NIG_API
 #endif
 
-#define NIG_ABI_VERSION 3
+#define NIG_ABI_VERSION 4
 #define NIG_MAX_CONSTRAINTS 8
 #define NIG_MAX_STATE_DIM 32
 #define NIG_MAX_ACTION_DIM 8
@@ -315,7 +315,8 @@ NIG_API int nig_set_tick(nig_env_t* env, uint32_t tick, uint32_t epoch);
  * be replayed any number of times and keeps drawing fresh noise (a host-side counter would be frozen into the graph).
  * Enable BEFORE capturing; nig_get_tick / nig_set_tick keep working (they synchronise). */
 NIG_API int nig_use_device_tick(nig_env_t* env, int32_t enable);
-/* reset(seed=...) made effective (the reference ignores it, base.py:135) */
+/* reset(seed=...) made effective (the reference ignores it, base.py:135): re-keys the random streams
+ * AND rewinds the handle's tick / epoch to 0, so that set_seed(s) + reset gives the same states and noise every time */
 NIG_API int nig_set_seed(nig_env_t* env, uint64_t seed);
 
 /* violation / return counters (info["violations"], info["total_violations"], evaluate_with_safety's
@@ -331,6 +332,13 @@ NIG_API int nig_clear_stats(nig_env_t* env, void* stream);
  * NIG_ERR_UNSUPPORTED). Two order-preserving int64 keys on the device (0 = none yet), kept outside the summable stats
  * block: ranks combine them with one MAX all-reduce, then decode. Accurate to the last mantissa bit of the fp64 return. */
 NIG_API int nig_track_extrema(nig_env_t* env, int32_t on);
+/* The running return of every env's current episode is kept in one fp64 accumulator per env, shared by nig_step and
+ * nig_rollout, so that the two can be mixed freely on one handle: finished-episode statistics (return / length sums,
+ * successes -- utils.py:128-152) count every episode whichever call ended it, and nig_set_state with an episode step
+ * counter restarts the accumulator. On by default. nig_track_returns(env, 0) makes the SINGLE-STEP kernels skip the
+ * accumulator (16 B less HBM traffic per env-step: the plain gym loop of performance_benchmark.py:106-133 keeps no
+ * returns either); statistics then cover only episodes that ran entirely inside nig_rollout calls. */
+NIG_API int nig_track_returns(nig_env_t* env, int32_t on);
 NIG_API int nig_extrema_ptr(nig_env_t* env, void** keys2_dev);
 NIG_API int nig_read_extrema(nig_env_t* env, double* ret_min, double* ret_max, int32_t* have);
 NIG_API int nig_decode_extrema(const int64_t* keys2, double* ret_min, double* ret_max, int32_t* have);

@@ -87,14 +87,17 @@ struct nig_env {
     double* ep_return;
     unsigned long long* stats;
     cudaStream_t stream;       // internal stream of the *_host calls
-    cudaStream_t dev_stream;   // stream of the last device-API call that was not on `stream` ...
-    bool dev_dirty;            // ... and whether a *_host call still has to wait for it
+    cudaStream_t dev_streams[4];   // caller streams device-API work was submitted on since the last *_host call ...
+    int n_dev_streams;             // ... (more than four distinct ones: dev_sync_all) ...
+    bool dev_sync_all;
+    bool dev_dirty;                // ... and whether a *_host call still has to wait for them
     // device staging of the *_host calls (lazily allocated)
     float *h_actions, *h_noise, *h_reset, *h_obs, *h_next_obs, *h_reward;
     uint8_t *h_hostmask, *h_flags, *h_viol, *h_mask;
     int32_t *h_i32a, *h_i32b;
     unsigned long long* extrema; // [2] min / max finished-episode return keys (outside the summable stats block)
     bool track_extrema;          // nig_track_extrema: rollouts run the EXTREMA kernel flavour
+    bool track_returns = true;   // nig_track_returns: the single-step kernels keep the episode-return accumulator too
     // nig_rollout_host over env slices: slice s runs H2D -> reset -> K-step launches -> D2H on its own stream, so the
     // copies of one slice overlap the stepping of the others (and the slices' launches fill each other's tails)
     cudaStream_t slice_stream[kMaxHostSlices];
@@ -148,13 +151,19 @@ struct DeviceGuard {
 // work submitted since the last one (no cost for loops of device calls; the *_host calls are synchronous anyway)
 inline void note_device_work(nig_env* e, cudaStream_t st)
 {
-    if (st != e->stream) { e->dev_stream = st; e->dev_dirty = true; }
+    if (st == e->stream) return;
+    e->dev_dirty = true;
+    for (int k = 0; k < e->n_dev_streams; ++k)
+        if (e->dev_streams[k] == st) return;
+    if (e->n_dev_streams < 4) e->dev_streams[e->n_dev_streams++] = st;
+    else e->dev_sync_all = true;
 }
 int host_entry(nig_env* e)
 {
     if (e->dev_dirty) {
-        NIG_CUDA(cudaStreamSynchronize(e->dev_stream));
-        e->dev_dirty = false;
+        if (e->dev_sync_all) NIG_CUDA(cudaDeviceSynchronize());
+        else for (int k = 0; k < e->n_dev_streams; ++k) NIG_CUDA(cudaStreamSynchronize(e->dev_streams[k]));
+        e->dev_dirty = false; e->dev_sync_all = false; e->n_dev_streams = 0;
     }
     return NIG_OK;
 }
@@ -261,6 +270,8 @@ int set_cons(nig_env* e, const nig_constraint_t* c, int n)
 int state_io(nig_env* e, float* ext_state, int layout, int32_t* st, int32_t* vi, uint8_t* dn, bool to_ext, cudaStream_t s)
 {
     StateIoArgs a{e->state, e->ep_word, e->n, e->pitch, ext_state, st, vi, dn, e->S, layout == NIG_LAYOUT_AOS ? 1 : 0, to_ext ? 1 : 0};
+    // importing an episode step counter re-bases the episode: its return accumulator restarts from zero
+    a.ep_return = (!to_ext && st) ? e->ep_return : nullptr;
     e->launches++;
     note_device_work(e, s);
     NIG_CUDA(nig::launch_state_io(a, s));
@@ -271,6 +282,7 @@ int state_io(nig_env* e, float* ext_state, int layout, int32_t* st, int32_t* vi,
 int state_to_aos_range(nig_env* e, float* ext_aos, int64_t i0, int64_t ns, cudaStream_t s)
 {
     StateIoArgs a{e->state + i0, e->ep_word + i0, ns, e->pitch, ext_aos + i0 * e->S, nullptr, nullptr, nullptr, e->S, 1, 1};
+    a.ep_return = nullptr;
     e->launches++;
     NIG_CUDA(nig::launch_state_io(a, s));
     return NIG_OK;
@@ -392,6 +404,17 @@ int fork_slices(nig_env* e, int slices, cudaStream_t st)
     }
     NIG_CUDA(cudaEventRecord(e->slice_begin, st));
     for (int k = 0; k < slices; ++k) NIG_CUDA(cudaStreamWaitEvent(e->slice_stream[k], e->slice_begin, 0));
+    return NIG_OK;
+}
+
+// the caller's stream waits for everything queued on the slice streams (also on the error paths: whatever a failed call
+// did launch must not be left running unordered with the caller's next work)
+int join_slices(nig_env* e, int slices, cudaStream_t st)
+{
+    for (int k = 0; k < slices; ++k) {
+        NIG_CUDA(cudaEventRecord(e->slice_done[k], e->slice_stream[k]));
+        NIG_CUDA(cudaStreamWaitEvent(st, e->slice_done[k], 0));
+    }
     return NIG_OK;
 }
 
@@ -577,6 +600,7 @@ int nig_step(nig_env_t* e, const nig_step_io_t* io, void* stream)
     StepArgs a;
     memset(&a, 0, sizeof a);
     a.state = e->state; a.ep_word = e->ep_word; a.n = e->n; a.pitch = e->pitch;
+    a.ep_return = e->track_returns ? e->ep_return : nullptr;
     a.env0 = (uint32_t)e->cfg.env_id_offset; a.tick = e->tick; a.epoch = e->epoch; a.key = e->key; a.tick_dev = e->tick_dev;
     a.max_steps = e->max_steps; a.auto_reset = e->cfg.auto_reset;
     a.actions = io->actions; a.noise = io->noise; a.reset_states = io->reset_states; a.hostmask = io->hostmask;
@@ -704,12 +728,9 @@ int nig_rollout_steps(nig_env_t* e, const nig_rollout_t* r, int32_t total_steps,
         return NIG_OK;
     }
     if (int rc = fork_slices(e, slices, st)) return rc;
-    if (int rc = sliced_launches(e, *r, total_steps, r->n_steps, slices, slice_size(e->n, slices))) return rc;
-    for (int k = 0; k < slices; ++k) {
-        NIG_CUDA(cudaEventRecord(e->slice_done[k], e->slice_stream[k]));
-        NIG_CUDA(cudaStreamWaitEvent(st, e->slice_done[k], 0));
-    }
-    return NIG_OK;
+    const int rc = sliced_launches(e, *r, total_steps, r->n_steps, slices, slice_size(e->n, slices));
+    const int jrc = join_slices(e, slices, st);
+    return rc ? rc : jrc;
 }
 
 int nig_reset_policy_state(nig_env_t* e, void* stream)
@@ -780,7 +801,7 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
             cudaStream_t ss = e->slice_stream[k];
             if (r->init_states)
                 NIG_CUDA(cudaMemcpyAsync(e->h_reset + i0 * e->S, r->init_states + i0 * e->S, (size_t)ns * e->S * sizeof(float), cudaMemcpyHostToDevice, ss));
-            if (reset && (rc = reset_range(e, r->init_states ? e->h_reset : nullptr, i0, ns, e->epoch, ss)) != NIG_OK) return rc;
+            if (reset && (rc = reset_range(e, r->init_states ? e->h_reset : nullptr, i0, ns, e->epoch, ss)) != NIG_OK) { join_slices(e, slices, st); return rc; }
         }
         nig_rollout_t d;
         memset(&d, 0, sizeof d);
@@ -788,13 +809,13 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
         d.reward_sum = r->reward_sum ? e->h_reward : nullptr;
         d.viol_count = r->viol_count ? e->h_i32a : nullptr;
         d.done_count = r->done_count ? e->h_i32b : nullptr;
-        if ((rc = sliced_launches(e, d, T, K, slices, per)) != NIG_OK) return rc;
+        if ((rc = sliced_launches(e, d, T, K, slices, per)) != NIG_OK) { join_slices(e, slices, st); return rc; }
         for (int k = 0; k < slices; ++k) {
             const int64_t i0 = k * per, ns = std::min<int64_t>(per, (int64_t)n - i0);
             if (ns <= 0) continue;
             cudaStream_t ss = e->slice_stream[k];
             if (r->final_obs) {
-                if ((rc = state_to_aos_range(e, e->h_obs, i0, ns, ss)) != NIG_OK) return rc;
+                if ((rc = state_to_aos_range(e, e->h_obs, i0, ns, ss)) != NIG_OK) { join_slices(e, slices, st); return rc; }
                 NIG_CUDA(cudaMemcpyAsync(r->final_obs + i0 * e->S, e->h_obs + i0 * e->S, (size_t)ns * e->S * sizeof(float), cudaMemcpyDeviceToHost, ss));
             }
             if (r->reward_sum) NIG_CUDA(cudaMemcpyAsync(r->reward_sum + i0, e->h_reward + i0, (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, ss));
@@ -1083,7 +1104,8 @@ int nig_set_seed(nig_env_t* e, uint64_t seed)
     if (!e) return fail(NIG_ERR_INVALID, "null env handle");
     e->cfg.seed = seed;
     e->key = RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)};
-    return NIG_OK;
+    // a new key starts its streams at their origin: reset(seed = s) is reproducible whatever the handle did before
+    return nig_set_tick(e, 0u, 0u);
 }
 
 int nig_stats_ptr(nig_env_t* e, void** p)
@@ -1109,6 +1131,13 @@ int nig_clear_stats(nig_env_t* e, void* stream)
     NIG_CHECK_ENV(e);
     NIG_CUDA(cudaMemsetAsync(e->stats, 0, NIG_STATS_SLOTS * sizeof(unsigned long long), (cudaStream_t)stream));
     NIG_CUDA(cudaMemsetAsync(e->extrema, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
+    return NIG_OK;
+}
+
+int nig_track_returns(nig_env_t* e, int32_t on)
+{
+    NIG_CHECK_ENV(e);
+    e->track_returns = on != 0;
     return NIG_OK;
 }
 
@@ -1245,8 +1274,10 @@ int nig_fp32_probe(int device, int32_t iters, double* ops, void* stream)
 {
     DeviceGuard guard(device);
     if (!guard.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    static float* sink = nullptr;
-    if (!sink) NIG_CUDA(cudaMalloc((void**)&sink, 256));
+    static float* sinks[64] = {nullptr};          // one scratch word per device (a pointer is only valid on its own device)
+    if (device < 0 || device >= 64) return fail(NIG_ERR_INVALID, "nig_fp32_probe: device ordinal %d out of range", device);
+    if (!sinks[device]) NIG_CUDA(cudaMalloc((void**)&sinks[device], 256));
+    float* sink = sinks[device];
     const int blocks = 148 * 8;
     NIG_CUDA(nig::launch_fp32_probe(sink, iters, blocks, (cudaStream_t)stream));
     if (ops) *ops = (double)blocks * 256.0 * (double)iters * 16.0;

@@ -31,6 +31,20 @@ __device__ __forceinline__ double pairwise8d(const double (&x)[8])
     return dadd(dadd(dadd(x[0], x[1]), dadd(x[2], x[3])), dadd(dadd(x[4], x[5]), dadd(x[6], x[7])));
 }
 
+// action_space.sample() of the envs without a fused noise / policy block: blocks 0.. of the POLICY stream, one word per action
+template <int A>
+__device__ __forceinline__ void uniform_actions_policy_stream(const Rng& key, uint32_t env, uint32_t tick, float (&a)[A])
+{
+#pragma unroll
+    for (int j = 0; j < (A + 3) / 4; ++j) {
+        const uint4 w = rng_words(key, env, tick, STREAM_POLICY, (uint32_t)j);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (4 * j + q < A) a[4 * j + q] = u_sym(ww[q]);
+    }
+}
+
 // ================================================================================================
 // ChemicalReactor-v0  (environments/chemical_reactor.py)
 // ================================================================================================
@@ -41,30 +55,41 @@ struct Reactor {
     using acc_t = float;                              // reward stays np.float32 upstream
     __device__ static constexpr float penalty(int k) { return k == 0 ? -100.0f : (k == 1 ? -50.0f : -25.0f); }
 
-    // process noise of step `tick`: pair (tick & 1) of Philox block (env, tick >> 1, NOISE, 0);
-    // the fused rollout kernel therefore needs one Philox call per TWO steps.
+    // ONE Philox block per step, (env, tick, NOISE, 0): words x, y -> the two process-noise normals of the step; words z, w
+    // are the action_space.sample() of the uniform-random policy (uniform_from_words). (The first builds used half a
+    // noise block + a whole policy block per step: 1.5 blocks; IMAD.WIDE issues at a quarter of the FMA-pipe rate on
+    // sm_100a -- tools/pipe_probe.cu -- so a Philox block is 56 pipe cycles, not 28 instructions.)
     struct NoiseGen {
-        float z[4];
-        uint32_t block = 0xffffffffu;
+        uint4 w;
         __device__ __forceinline__ void get(const Rng& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
         {
-            const uint32_t b = tick >> 1;
-            if (b != block) { rng_normals4(key, env, b, STREAM_NOISE, 0u, z); block = b; }   // warp-uniform branch
-            const float za = (tick & 1u) ? z[2] : z[0];
-            const float zb = (tick & 1u) ? z[3] : z[1];
+            w = rng_words(key, env, tick, STREAM_NOISE, 0u);
+            float za, zb;
+            normal_pair(key.tab, w.x, w.y, za, zb);
             nz[0] = mul(0.1f, za);      // np.random.normal(0, temp_noise_std / 10)      (:149)
             nz[1] = mul(500.0f, zb);    // np.random.normal(0, pressure_noise_std / 10)  (:159)
         }
-        // the same two values for ONE tick (single-step kernel): only the pair of normals of this tick's parity
         __device__ static __forceinline__ void get_single(const Rng& key, uint32_t env, uint32_t tick, float (&nz)[NZ])
         {
-            const uint4 w = rng_words(key, env, tick >> 1, STREAM_NOISE, 0u);
-            float za, zb;
-            normal_pair(key.tab, (tick & 1u) ? w.z : w.x, (tick & 1u) ? w.w : w.y, za, zb);
-            nz[0] = mul(0.1f, za);
-            nz[1] = mul(500.0f, zb);
+            NoiseGen g;
+            g.get(key, env, tick, nz);
         }
     };
+    // action_space.sample() (performance_benchmark.py:118) from words z, w of the step's block: a0 / a1 from bits 21..0 of
+    // z / w, a2 from the two 10-bit tops; the bits go straight into the mantissa of a float in [1, 2) (one LOP3 each, no
+    // int -> float conversion) and one exact fma maps it to [-1, 1): a0, a1 = v * 2^-21 - 1, a2 = v * 2^-19 - 1
+    __device__ static __forceinline__ void uniform_from_words(uint32_t wz, uint32_t ww, float (&a)[A])
+    {
+        a[0] = __fmaf_rn(__uint_as_float((wz & 0x3fffffu) | 0x3f800000u), 4.0f, -5.0f);
+        a[1] = __fmaf_rn(__uint_as_float((ww & 0x3fffffu) | 0x3f800000u), 4.0f, -5.0f);
+        const uint32_t v2 = __funnelshift_l(ww, wz >> 22, 10);          // (wz[31:22] << 10) | ww[31:22]
+        a[2] = __fmaf_rn(__uint_as_float(v2 | 0x3f800000u), 16.0f, -17.0f);
+    }
+    __device__ static __forceinline__ void uniform_actions(const Rng& key, uint32_t env, uint32_t tick, float (&a)[A])
+    {
+        const uint4 w = rng_words(key, env, tick, STREAM_NOISE, 0u);    // (the same block as NoiseGen::get: CSE'd when both are live)
+        uniform_from_words(w.z, w.w, a);
+    }
 
     // _get_initial_state (:89-107) drawn from the RESET stream: 8 standard normals = word pairs 0..3 of
     // Philox blocks (epoch << 8) | {0, 1}
@@ -245,6 +270,11 @@ struct Grid {
         }
     };
 
+    __device__ static __forceinline__ void uniform_actions(const Rng& key, uint32_t env, uint32_t tick, float (&a)[A])
+    {
+        uniform_actions_policy_stream<A>(key, env, tick, a);
+    }
+
     // _get_initial_state (:90-110): 8 Philox blocks of the RESET stream -- blocks 0,1 voltages ~ N(1, .01), 2,3
     // generation ~ N(base_load, 2), 4,5 loads = base_load * U(.8, 1.2), 6,7 line flows ~ N(0, 10). One block (4 raw
     // values) is the unit of work of the warp-cooperative reset.
@@ -392,6 +422,11 @@ struct Robot {
         __device__ __forceinline__ void get(const Rng&, uint32_t, uint32_t, float (&)[1]) {}
         __device__ static __forceinline__ void get_single(const Rng&, uint32_t, uint32_t, float (&)[1]) {}
     };
+
+    __device__ static __forceinline__ void uniform_actions(const Rng& key, uint32_t env, uint32_t tick, float (&a)[A])
+    {
+        uniform_actions_policy_stream<A>(key, env, tick, a);
+    }
 
     __device__ static __forceinline__ void fk(const double (&q)[7], double (&pos)[3])
     {   // _forward_kinematics (:94-111)

@@ -336,6 +336,13 @@ __device__ __forceinline__ unsigned long long extremum_key(double x)
     return k >> 1;                   // 0 only for a NaN bit pattern
 }
 
+template <class T> __device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // ---- block-level statistics: per-thread counts -> REDUX -> shared atomics -> one global atomic per slot
 struct BlockStats {
     unsigned int* sh;   // [NIG_STATS_SLOTS] shared counters
@@ -397,6 +404,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 struct StepArgs {
     float* state;            // [S][pitch]
     uint32_t* ep_word;       // [pitch]
+    double* ep_return;       // [pitch] running episode return (shared with the rollout kernel), or null: not tracked (nig_track_returns)
     int64_t n, pitch;
     uint32_t env0, tick, epoch;
     uint32_t* tick_dev;      // non-null: device-resident tick (graph capture), see load_tick()
@@ -417,6 +425,35 @@ struct StepArgs {
     unsigned long long* stats;
     ConsParams cons;
 };
+
+// finished-episode statistics of the single-step kernels (the same slots the fused rollout fills: evaluate_with_safety's
+// return / length aggregates, utils.py:128-152), so that a handle driven through nig_step reports them too and a
+// nig_rollout that follows continues every running episode's return from the right value
+struct StepEpisodeStats {
+    unsigned int c_succ = 0;
+    unsigned long long len_sum = 0, len_sq = 0;
+    double ret_sum = 0.0, ret_sq = 0.0;
+    __device__ __forceinline__ void episode(double ret, unsigned long long len)
+    {
+        c_succ += ret > 0.0 ? 1u : 0u;
+        len_sum += len; len_sq += len * len;
+        ret_sum += ret; ret_sq += ret * ret;
+    }
+};
+
+// finished-episode return / length sums of a warp -> the global stats block (rare: only warps that finished an episode)
+__device__ __forceinline__ void flush_episode_stats(BlockStats& bs, unsigned long long* stats, const StepEpisodeStats& eps)
+{
+    bs.warp_add(NIG_ST_SUCCESSES, eps.c_succ);
+    const unsigned long long ls = warp_sum(eps.len_sum), lq = warp_sum(eps.len_sq);
+    const double rs_ = warp_sum(eps.ret_sum), rq = warp_sum(eps.ret_sq);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats[NIG_ST_EP_LEN_SUM], ls);
+        atomicAdd(&stats[NIG_ST_EP_LEN_SQ], lq);
+        atomicAdd(reinterpret_cast<double*>(stats) + NIG_ST_F_RETURN_SUM, rs_);
+        atomicAdd(reinterpret_cast<double*>(stats) + NIG_ST_F_RETURN_SQ, rq);
+    }
+}
 
 template <int D, int VEC>
 __device__ __forceinline__ void load_rows(const float* base, int64_t pitch, int64_t n, int64_t i0, bool aos, float (&v)[D][VEC])
@@ -483,6 +520,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
 
     const int64_t i0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
     unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0, c_con = 0;  // c_con: 4 bits/constraint
+    StepEpisodeStats eps;
     if (i0 < p.pitch) {
         float sv[S][VEC], av[A][VEC], nzv[NZA][VEC], rs[S][VEC];
         load_rows<S, VEC>(p.state, p.pitch, p.n, i0, false, sv);
@@ -506,6 +544,8 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             for (int k = 0; k < A; ++k) a[k] = av[k][e];
             const bool valid = i < p.n;
             const bool active = valid && !(w >> 31);
+            acc_t er = (acc_t)0;                       // running episode return (the accumulator the fused rollout continues)
+            if (p.ep_return && active) er = (acc_t)p.ep_return[i];
             if (NZ > 0) {
                 if (p.noise) {
 #pragma unroll
@@ -524,6 +564,11 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             }
             const bool done = active && (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED));
             bool need_reset = false;
+            if (p.ep_return && active) {
+                er = er + r;
+                if (done) eps.episode((double)er, (unsigned long long)epw_step(w));
+                p.ep_return[i] = (done && p.auto_reset) ? 0.0 : (double)er;
+            }
 #pragma unroll
             for (int k = 0; k < S; ++k) nsv[k][e] = ns[k];     // s' of the transition (pre-reset)
             if (done) {
@@ -582,13 +627,16 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             if (p.obs) store_rows<S, VEC>(p.obs, p.pitch, p.n, i0, p.aux_aos != 0, sv);
             if (p.next_obs) store_rows<S, VEC>(p.next_obs, p.pitch, p.n, i0, p.aux_aos != 0, nsv);
         }
-        if (p.reward) stvec<VEC>(p.reward + i0, rw);
-        if (p.flags) {
+        // VEC == 1 serves the exact-size [n] arrays of the host-buffer (zero-copy) and torch APIs: no store past env n - 1
+        // (the vector flavours require pitch-capacity device arrays, include/nig_b200.h)
+        const bool in_n = VEC > 1 || i0 < p.n;
+        if (p.reward && in_n) stvec<VEC>(p.reward + i0, rw);
+        if (p.flags && in_n) {
             if constexpr (VEC == 4) *reinterpret_cast<uchar4*>(p.flags + i0) = make_uchar4(fl[0], fl[1], fl[2], fl[3]);
             else if constexpr (VEC == 2) *reinterpret_cast<uchar2*>(p.flags + i0) = make_uchar2(fl[0], fl[1]);
             else p.flags[i0] = (uint8_t)fl[0];
         }
-        if (p.viol_mask) {
+        if (p.viol_mask && in_n) {
             if constexpr (VEC == 4) *reinterpret_cast<uchar4*>(p.viol_mask + i0) = make_uchar4(vmk[0], vmk[1], vmk[2], vmk[3]);
             else if constexpr (VEC == 2) *reinterpret_cast<uchar2*>(p.viol_mask + i0) = make_uchar2(vmk[0], vmk[1]);
             else p.viol_mask[i0] = (uint8_t)vmk[0];
@@ -596,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
         if (p.terminated || p.truncated) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
-                if (i0 + e < p.pitch) {
+                if (i0 + e < (VEC == 1 ? p.n : p.pitch)) {
                     if (p.terminated) p.terminated[i0 + e] = (uint8_t)((fl[e] & NIG_F_TERMINATED) ? 1 : 0);
                     if (p.truncated) p.truncated[i0 + e] = (uint8_t)((fl[e] & NIG_F_TRUNCATED) ? 1 : 0);
                 }
@@ -611,6 +659,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
         bs.warp_add(NIG_ST_CRITICAL, c_crit);
         bs.warp_add(NIG_ST_VIOLATIONS, c_viol);
         for (int k = 0; k < p.cons.n; ++k) bs.warp_add(NIG_ST_CON0 + k, (c_con >> (4 * k)) & 0xfu);
+        if (p.ep_return && __any_sync(0xffffffffu, c_ep != 0u)) flush_episode_stats(bs, p.stats, eps);
     }
     bs.flush(p.stats);
     advance_device_tick(p.tick_dev, 1u);
@@ -681,6 +730,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
     unsigned int c_con[NIG_MAX_CONSTRAINTS];
 #pragma unroll
     for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] = 0;
+    StepEpisodeStats eps;
 
     for (int it = 0;; ++it) {
         const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -718,6 +768,8 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             for (int k = 0; k < A; ++k) a[k] = av[k][e];
             const bool valid = i < p.n;
             const bool active = valid && !(w >> 31);
+            acc_t er = (acc_t)0;                       // running episode return (plain LDG / STG beside the staged rows)
+            if (p.ep_return && active) er = (acc_t)p.ep_return[i];
             if constexpr (NZ > 0) Env::NoiseGen::get_single(key, env, tick0, nz);
             else nz[0] = 0.0f;
             acc_t r; uint32_t f, vm;
@@ -729,6 +781,11 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             }
             const bool done = active && (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED));
             bool need_reset = false;
+            if (p.ep_return && active) {
+                er = er + r;
+                if (done) eps.episode((double)er, (unsigned long long)epw_step(w));
+                p.ep_return[i] = (done && p.auto_reset) ? 0.0 : (double)er;
+            }
             if (done) {
                 if (p.auto_reset) {
                     if constexpr (Env::COOP_RESET || Env::COOP_BLOCKS > 0) need_reset = true;
@@ -778,6 +835,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k)
             if (k < p.cons.n) bs.warp_add(NIG_ST_CON0 + k, c_con[k]);
+        if (p.ep_return && __any_sync(0xffffffffu, c_ep != 0u)) flush_episode_stats(bs, p.stats, eps);
     }
     bs.flush(p.stats);
     advance_device_tick(p.tick_dev, 1u);
@@ -823,6 +881,7 @@ struct StateIoArgs {
     int64_t n, pitch;
     float* ext_state; int32_t* ext_step; int32_t* ext_viol; uint8_t* ext_done;
     int32_t S, aos, to_ext;
+    double* ep_return;       // import with an episode step counter: the episode's return accumulator restarts (else null)
 };
 static __global__ void __launch_bounds__(kThreads) state_io_kernel(const __grid_constant__ StateIoArgs p)
 {
@@ -846,6 +905,7 @@ static __global__ void __launch_bounds__(kThreads) state_io_kernel(const __grid_
         const uint32_t vi = p.ext_viol ? (uint32_t)p.ext_viol[i] : epw_viol(w);
         const uint32_t dn = p.ext_done ? (uint32_t)(p.ext_done[i] != 0) : (w >> 31);
         p.ep_word[i] = epw_make(st, vi, dn);
+        if (p.ep_return) p.ep_return[i] = 0.0;
     }
 }
 
@@ -876,14 +936,7 @@ struct RolloutArgs {
 template <class Env>
 __device__ __forceinline__ void policy_uniform(const Rng& key, uint32_t env, uint32_t tick, float (&a)[Env::A])
 {
-#pragma unroll
-    for (int j = 0; j < (Env::A + 3) / 4; ++j) {
-        const uint4 w = rng_words(key, env, tick, STREAM_POLICY, (uint32_t)j);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (4 * j + q < Env::A) a[4 * j + q] = u_sym(ww[q]);
-    }
+    Env::uniform_actions(key, env, tick, a);
 }
 
 // get_dataset mixes (chemical_reactor.py:364-390, power_grid.py:216-232, robot_assembly.py:266-291):
@@ -973,12 +1026,157 @@ __device__ __forceinline__ void policy_baseline(const Rng& key, const nig_baseli
     }
 }
 
-template <class T> __device__ __forceinline__ T warp_sum(T v)
+// ================================================================================================
+// ChemicalReactor-v0: the invariant-specialised step loop of the fused rollout (uniform-random policy, default
+// constraints, auto-reset -- BASELINE config #2, the loop of performance_benchmark.py:106-133)
+// ================================================================================================
+// Inside a free-running rollout almost everything step_core evaluates is decided before the step starts:
+//   * e-stop latch s8 is 0 at every step start -- a step that sets it (T' > 350 or P' > 506625, :199-201) ends the episode
+//     (_is_done, :283) and the env is re-initialised in the same step -> the PLC is always in manual mode (:126-129),
+//     `estop > 0.5` is simply "tripped this step";
+//   * for the same reason T <= 350 and P <= 506625 hold at every step start (fresh states are N(320, 2) / N(253312.5, 1e4)
+//     with |z| < 6.4) -> the two critical constraints (:292-299) are satisfied, only `level_limits` can be violated, no
+//     critical shutdown, no -1000;
+//   * the alarm latch s9 is 0 or 1 -> carried as a predicate; cat / 100 of the next step is this step's reward term.
+// The loop below carries these as invariants (checked once at entry by the caller, re-established by every step) and
+// drops the work they decide: 9 of 12 division-guard compares (the ranges are implied: |T' - 320| <= 120 is checked on the
+// value the exp argument needs anyway), the e-stop / alarm float selects and compares, the constraint mask, the penalty
+// and critical-shutdown logic of constraints 0 / 1. Every arithmetic operation that remains is the one step_core performs,
+// in the same order -> bit-identical results (tests/test_gpu_parity.py compares with the oracle, which knows nothing of
+// this). If a guard fails (never observed: it takes |T' - 320| > 120 K, a pressure outside [1e3, 1e7] Pa or a denormal
+// heat balance) the warp leaves the loop WITHOUT committing the step and the generic loop carries on from there.
+__device__ __forceinline__ float cdiv_noguard(float x, float c, float rc)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    const float q = __fmul_rn(x, rc);
+    const float r = __fmaf_rn(-q, c, x);
+    return __fmaf_rn(r, rc, q);
 }
+#define NIG_CDIV_NG(x, c) cdiv_noguard((x), (c), 1.0f / (c))
+
+struct RolloutAcc {            // episode / launch statistics of one thread (shared by the fast and the generic loop)
+    unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0, c_succ = 0, c_done = 0;
+    unsigned int c_con[NIG_MAX_CONSTRAINTS];
+    unsigned long long len_sum = 0, len_sq = 0;
+    double ret_sum = 0.0, ret_sq = 0.0, rew_sum = 0.0;
+};
+
+// returns the number of steps committed (== n_steps unless a guard failed)
+template <bool EXTREMA>
+__device__ __forceinline__ int reactor_fast_steps(const Rng& key, uint32_t env, uint32_t tick0, uint32_t epoch, int n_steps, int max_steps,
+                                                  float (&s)[Reactor::S], uint32_t& ep_st, uint32_t& ep_vi, float& ep_ret, float& rsum,
+                                                  RolloutAcc& acc, float& r_lo, float& r_hi)
+{
+    float T = s[0], P = s[1], cool = s[2], feed = s[3], conc = s[4], cat = s[5], hx = s[6], rv = s[7], level = s[10], bt = s[11];
+    bool alarm = __float_as_uint(s[9]) != 0u;
+    float catd = __fdiv_rn(cat, 100.0f);
+    int t_trunc = max_steps - (int)ep_st - 1;       // loop index of the step at which the running episode is truncated (base.py:191)
+    unsigned int c_lvl = 0;
+    int t = 0;
+#pragma unroll 1
+    for (; t < n_steps; ++t) {
+        const uint32_t tick = tick0 + (uint32_t)t;
+        const uint4 w = rng_words(key, env, tick, STREAM_NOISE, 0u);
+        float za, zb, a[Reactor::A];
+        normal_pair(key.tab, w.x, w.y, za, zb);
+        const float nz0 = mul(0.1f, za), nz1 = mul(500.0f, zb);                 // :149, :159
+        Reactor::uniform_from_words(w.z, w.w, a);
+        const bool lvl_bad = !((20.0f <= level) && (level <= 90.0f));           // :302-305 on the pre-step state
+        // _dynamics (:109-226), manual mode
+        const float hp = mul(a[0], 50000.0f), cadj = mul(a[1], 0.1f), fadj = mul(a[2], 0.1f);
+        const float kca = mul(mul(0.1f, conc), catd);
+        const float rh = mul(kca, 10000.0f);
+        const float ch = mul(mul(mul(cool, 100.0f), sub(T, hx)), 0.1f);
+        const float num = sub(add(hp, rh), ch);
+        bool ok = fabsf(num) >= 0x1.0p-120f;
+        const float dT = add(NIG_CDIV_NG(num, 418000.0f), nz0);
+        const float nT = add(T, mul(dT, 0.1f));
+        const float d = sub(nT, 320.0f);
+        ok = ok && (fabsf(d) <= 120.0f);                // 200 <= T' <= 440: T' / T and -(T' - 320) / 20 are in the proven domain
+        float y0;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(T));
+        const float e0 = __fmaf_rn(-T, y0, 1.0f);
+        const float y1 = __fmaf_rn(y0, e0, y0);
+        const float q0 = __fmaf_rn(nT, y1, 0.0f);
+        const float q = __fmaf_rn(y1, __fmaf_rn(-T, q0, nT), q0);               // == __fdiv_rn(nT, T) (DivFast::vdiv)
+        const float pfr = mul(mul(conc, 0.1f), 1000.0f);
+        float nP = add(add(mul(P, q), mul(pfr, 0.1f)), nz1);
+        const float nrv = py_clamp(add(rv, mul(sub(nP, 506625.0f), 0.001f)), 0.0f, 100.0f);
+        {
+            const float x = sub(nP, mul(mul(nrv, 0.01f), 10000.0f));
+            const float xr = (x > 101325.0f) ? x : 101325.0f;
+            nP = (nrv > 0.0f) ? xr : nP;
+        }
+        ok = ok && (fabsf(sub(nP, 5.0e6f)) <= 4.999e6f);        // 1e3 <= P' < 1e7: |P' - 253312.5| is 0 or >= 2^-14, finite
+        const float ncool = py_clamp(add(cool, cadj), 10.0f, 100.0f);
+        const float feed_v = add(feed, fadj);
+        const float nfeed = py_clamp(feed_v, 5.0f, 50.0f);
+        const float ex = spec_expf(NIG_CDIV_NG(-d, 20.0f));
+        const float rr = mul(kca, ex);
+        float fdil = mul(nfeed, 0.001f);
+        fdil = (feed_v > 5.0f) ? fdil : 0x1.47ae14p-8f;
+        fdil = (feed_v < 50.0f) ? fdil : 0x1.99999ap-5f;
+        const float cv = add(conc, mul(sub(rr, fdil), 0.1f));
+        const float nconc = (cv > 0.0f) ? cv : 0.0f;
+        const float catv = sub(cat, (nT > 340.0f) ? 0.001f : 0.0001f);
+        const float ncat = (catv > 50.0f) ? catv : 50.0f;
+        const float nhx = add(hx, mul(mul(0.1f, sub(add(290.0f, mul(cool, 0.1f)), hx)), 0.1f));
+        const bool trip = (nT > 350.0f) || (nP > 506625.0f);                   // :199 -> estop' = alarm' = 1
+        const bool nalarm = alarm || (nT > 345.0f) || (nP > 480000.0f);        // :197
+        const float nlevel = py_clamp(add(level, mul(mul(sub(nfeed, 20.0f), 0.1f), 0.1f)), 0.0f, 100.0f);
+        const float nbt = add(bt, 0.1f);
+        // _compute_reward (:228-270) on the new state, then the level penalty (base.py:179-183)
+        float r = add(0.0f, mul(nconc, 100.0f));
+        r = sub(r, mul(fabsf(d), 0.5f));
+        r = sub(r, mul(NIG_CDIV_NG(fabsf(sub(nP, 253312.5f)), 1000.0f), 0.1f));
+        const float ncatd = NIG_CDIV_NG(ncat, 100.0f);
+        r = add(r, mul(ncatd, 10.0f));
+        const bool band = (30.0f <= nlevel) && (nlevel <= 80.0f);
+        r = band ? add(r, 5.0f) : sub(r, mul(fabsf(sub(nlevel, 55.0f)), 0.2f));
+        if (nalarm) r = sub(r, 50.0f);
+        if (trip) r = sub(r, 200.0f);
+        r = sub(r, mul(add(add(fabsf(a[0]), fabsf(a[1])), fabsf(a[2])), 0.1f));
+        if (lvl_bad) r = add(r, -25.0f);
+        if (__builtin_expect(!__all_sync(0xffffffffu, ok), 0)) break;           // (uniform) redo this step in the generic loop
+        rsum = add(rsum, r);
+        ep_ret = ep_ret + r;
+        c_lvl += lvl_bad ? 1u : 0u;
+        ep_vi += lvl_bad ? 1u : 0u;
+        T = nT; P = nP; cool = ncool; feed = nfeed; conc = nconc; cat = ncat; hx = nhx; rv = nrv; level = nlevel; bt = nbt;
+        alarm = nalarm; catd = ncatd;
+        const bool term = trip || (nlevel < 5.0f) || (nlevel > 95.0f) || (nbt > 50.0f);   // _is_done (:272-290)
+        const bool trunc = t >= t_trunc;
+        if (__any_sync(0xffffffffu, term || trunc)) {
+            if (term || trunc) {
+                const unsigned long long len = (unsigned long long)(max_steps - (t_trunc - t));
+                acc.c_ep += 1; acc.c_done += 1;
+                acc.c_term += term ? 1u : 0u;
+                acc.c_trunc += trunc ? 1u : 0u;
+                acc.c_succ += (ep_ret > 0.0f) ? 1u : 0u;
+                acc.len_sum += len; acc.len_sq += len * len;
+                acc.ret_sum += (double)ep_ret; acc.ret_sq += (double)ep_ret * (double)ep_ret;
+                if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
+                float z[8];
+                rng_normals4(key, env, tick + 1u, STREAM_RESET, (epoch << 8) | 0u, reinterpret_cast<float (&)[4]>(z[0]));
+                rng_normals4(key, env, tick + 1u, STREAM_RESET, (epoch << 8) | 1u, reinterpret_cast<float (&)[4]>(z[4]));
+                float f[Reactor::S];
+                Reactor::reset_from_normals(z, f);
+                T = f[0]; P = f[1]; cool = f[2]; feed = f[3]; conc = f[4]; cat = f[5]; hx = f[6]; rv = f[7]; level = f[10]; bt = f[11];
+                alarm = false;
+                catd = __fdiv_rn(cat, 100.0f);
+                ep_vi = 0u; ep_ret = 0.0f;
+                t_trunc = t + max_steps;
+            }
+        }
+    }
+    s[0] = T; s[1] = P; s[2] = cool; s[3] = feed; s[4] = conc; s[5] = cat; s[6] = hx; s[7] = rv;
+    s[8] = 0.0f; s[9] = alarm ? 1.0f : 0.0f; s[10] = level; s[11] = bt;
+    ep_st = (uint32_t)(max_steps - (t_trunc - t + 1));
+    acc.c_steps += (unsigned int)t;
+    acc.c_viol += c_lvl;
+    acc.c_con[2] += c_lvl;
+    return t;
+}
+
 
 // TFNOISE: process noise teacher-forced from p.noise (POLICY_ACTIONS only). The LDG flavour of POLICY_ACTIONS
 // prefetches the next step's actions / noise into registers one step ahead, so the L2 latency of the loads is
@@ -1041,12 +1239,9 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     typename Env::NoiseGen ng;
 
     float rsum = 0.0f;
-    unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0, c_succ = 0, c_done = 0;
-    unsigned int c_con[NIG_MAX_CONSTRAINTS];
+    RolloutAcc acc;
 #pragma unroll
-    for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] = 0;
-    unsigned long long len_sum = 0, len_sq = 0;
-    double ret_sum = 0.0, ret_sq = 0.0, rew_sum = 0.0;
+    for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) acc.c_con[k] = 0;
     acc_t r_lo = (acc_t)INFINITY, r_hi = -(acc_t)INFINITY;     // extrema of this thread's finished-episode returns
 
     double pid_i[A], pid_e[A];             // POLICY_BASELINE: the PID agent's integral and previous error
@@ -1068,8 +1263,21 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
         }
     }
 
+    // ChemicalReactor-v0 under the benchmark's own configuration (uniform-random policy, the env's default constraints,
+    // auto-reset): warps whose envs all satisfy the loop invariants of reactor_fast_steps run the specialised loop; whatever
+    // it does not commit (nothing, normally) is left to the generic loop below
+    int t_begin = 0;
+    if constexpr (Env::KIND == NIG_ENV_CHEMICAL_REACTOR && CONS == CONS_DEFAULT && POLICY == NIG_POLICY_UNIFORM && !TMA && !TFNOISE) {
+        const bool inv = valid && !latched && p.auto_reset != 0 && __float_as_uint(s[8]) == 0u &&
+                         (__float_as_uint(s[9]) == 0u || __float_as_uint(s[9]) == 0x3f800000u) &&
+                         s[0] >= 200.0f && s[0] <= 350.0f && s[1] <= 506625.0f && s[5] >= 1e-30f && s[5] <= 1e30f &&
+                         ep_st < (uint32_t)p.max_steps;
+        if (__all_sync(0xffffffffu, inv))
+            t_begin = reactor_fast_steps<EXTREMA>(key, env, tick0, p.epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi);
+    }
+
 #pragma unroll 1      // measured: unrolling by 2 (to drop the 12 state moves per step) is 4 % slower
-    for (int t = 0; t < p.n_steps; ++t) {
+    for (int t = t_begin; t < p.n_steps; ++t) {
         const uint32_t tick = tick0 + (uint32_t)t;
         float a[A], nz[NZA], ns[S];
         if constexpr (POLICY == NIG_POLICY_ACTIONS) {
@@ -1128,27 +1336,27 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
             const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
             rsum = add(rsum, (float)r);
             ep_ret = ep_ret + r;
-            if constexpr (sizeof(acc_t) == 8) rew_sum += r;      // fp32-reward envs: derived from rsum after the loop
-            c_steps += 1; c_viol += __popc(vm);
-            c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
+            if constexpr (sizeof(acc_t) == 8) acc.rew_sum += r;      // fp32-reward envs: derived from rsum after the loop
+            acc.c_steps += 1; acc.c_viol += __popc(vm);
+            acc.c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
 #pragma unroll
-            for (int k = 0; k < Env::NB; ++k) c_con[k] += (vm >> k) & 1u;
+            for (int k = 0; k < Env::NB; ++k) acc.c_con[k] += (vm >> k) & 1u;
             if constexpr (cons_fast_extras(CONS) > 0) {
 #pragma unroll
-                for (int k = Env::NB; k < Env::NB + cons_fast_extras(CONS); ++k) c_con[k] += (vm >> k) & 1u;
+                for (int k = Env::NB; k < Env::NB + cons_fast_extras(CONS); ++k) acc.c_con[k] += (vm >> k) & 1u;
             } else if constexpr (CONS != CONS_DEFAULT) {
 #pragma unroll
-                for (int k = Env::NB; k < NIG_MAX_CONSTRAINTS; ++k) c_con[k] += (vm >> k) & 1u;
+                for (int k = Env::NB; k < NIG_MAX_CONSTRAINTS; ++k) acc.c_con[k] += (vm >> k) & 1u;
             }
             ep_st = st2; ep_vi = vi2;
             if (done) {
                 const unsigned long long len = st2;
-                c_ep += 1; c_done += 1;
-                c_term += (f & NIG_F_TERMINATED) ? 1u : 0u;
-                c_trunc += (f & NIG_F_TRUNCATED) ? 1u : 0u;
-                c_succ += (ep_ret > (acc_t)0) ? 1u : 0u;
-                len_sum += len; len_sq += len * len;
-                ret_sum += (double)ep_ret; ret_sq += (double)ep_ret * (double)ep_ret;
+                acc.c_ep += 1; acc.c_done += 1;
+                acc.c_term += (f & NIG_F_TERMINATED) ? 1u : 0u;
+                acc.c_trunc += (f & NIG_F_TRUNCATED) ? 1u : 0u;
+                acc.c_succ += (ep_ret > (acc_t)0) ? 1u : 0u;
+                acc.len_sum += len; acc.len_sq += len * len;
+                acc.ret_sum += (double)ep_ret; acc.ret_sq += (double)ep_ret * (double)ep_ret;
                 if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
                 if (p.auto_reset) {
                     if constexpr (Env::COOP_BLOCKS > 0) need_reset = true;
@@ -1169,7 +1377,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
 
     // fp32-reward envs (reactor): the reward statistic of this launch is the fp32 per-env sum (K <= a few hundred
     // terms) widened once, instead of an F2F + DADD per step on the XU / FP64 pipes
-    if constexpr (sizeof(acc_t) == 4) rew_sum = (double)rsum;
+    if constexpr (sizeof(acc_t) == 4) acc.rew_sum = (double)rsum;
     if (valid) {
 #pragma unroll
         for (int k = 0; k < S; ++k) p.state[k * p.pitch + i] = s[k];
@@ -1186,28 +1394,28 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
         }
         if (p.accumulate) {
             if (p.reward_sum) p.reward_sum[i] = add(p.reward_sum[i], rsum);
-            if (p.viol_count) p.viol_count[i] += (int32_t)c_viol;
-            if (p.done_count) p.done_count[i] += (int32_t)c_done;
+            if (p.viol_count) p.viol_count[i] += (int32_t)acc.c_viol;
+            if (p.done_count) p.done_count[i] += (int32_t)acc.c_done;
         } else {
             if (p.reward_sum) p.reward_sum[i] = rsum;
-            if (p.viol_count) p.viol_count[i] = (int32_t)c_viol;
-            if (p.done_count) p.done_count[i] = (int32_t)c_done;
+            if (p.viol_count) p.viol_count[i] = (int32_t)acc.c_viol;
+            if (p.done_count) p.done_count[i] = (int32_t)acc.c_done;
         }
     }
     // violation / episode statistics: warp REDUX + shuffle trees -> one global atomic per slot per block
-    bs.warp_add(NIG_ST_STEPS, c_steps);
-    bs.warp_add(NIG_ST_VIOLATIONS, c_viol);
-    bs.warp_add(NIG_ST_CRITICAL, c_crit);
+    bs.warp_add(NIG_ST_STEPS, acc.c_steps);
+    bs.warp_add(NIG_ST_VIOLATIONS, acc.c_viol);
+    bs.warp_add(NIG_ST_CRITICAL, acc.c_crit);
 #pragma unroll
     for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k)
-        if (k < p.cons.n) bs.warp_add(NIG_ST_CON0 + k, c_con[k]);
-    if (__any_sync(0xffffffffu, c_ep != 0u)) {
-        bs.warp_add(NIG_ST_EPISODES, c_ep);
-        bs.warp_add(NIG_ST_TERMINATED, c_term);
-        bs.warp_add(NIG_ST_TRUNCATED, c_trunc);
-        bs.warp_add(NIG_ST_SUCCESSES, c_succ);
-        const unsigned long long ls = warp_sum(len_sum), lq = warp_sum(len_sq);
-        const double rs_ = warp_sum(ret_sum), rq = warp_sum(ret_sq);
+        if (k < p.cons.n) bs.warp_add(NIG_ST_CON0 + k, acc.c_con[k]);
+    if (__any_sync(0xffffffffu, acc.c_ep != 0u)) {
+        bs.warp_add(NIG_ST_EPISODES, acc.c_ep);
+        bs.warp_add(NIG_ST_TERMINATED, acc.c_term);
+        bs.warp_add(NIG_ST_TRUNCATED, acc.c_trunc);
+        bs.warp_add(NIG_ST_SUCCESSES, acc.c_succ);
+        const unsigned long long ls = warp_sum(acc.len_sum), lq = warp_sum(acc.len_sq);
+        const double rs_ = warp_sum(acc.ret_sum), rq = warp_sum(acc.ret_sq);
         if constexpr (EXTREMA) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -1227,7 +1435,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
         }
     }
     {
-        const double rw_ = warp_sum(rew_sum);
+        const double rw_ = warp_sum(acc.rew_sum);
         if ((threadIdx.x & 31) == 0) atomicAdd(&sfl[2], rw_);
     }
     bs.flush(p.stats);

@@ -16,7 +16,7 @@ _ROOT = os.path.dirname(_PKG_DIR)                       # neorl-industrial-gym_b
 LIB_PATH = os.path.join(_ROOT, "libnig_b200.so")
 CSRC_DIR = os.path.join(_ROOT, "csrc")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_CONSTRAINTS = 8
 STATS_SLOTS = 32
 
@@ -127,6 +127,7 @@ SYMBOLS = {
     "nig_read_stats": (C.c_int, [_VP, _VP, _VP]),
     "nig_clear_stats": (C.c_int, [_VP, _VP]),
     "nig_track_extrema": (C.c_int, [_VP, C.c_int32]),
+    "nig_track_returns": (C.c_int, [_VP, C.c_int32]),
     "nig_extrema_ptr": (C.c_int, [_VP, C.POINTER(_VP)]),
     "nig_read_extrema": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I32)]),
     "nig_decode_extrema": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I32)]),

@@ -255,6 +255,12 @@ class NativeEnv:
         N.check(N.lib().nig_read_stats(self._h, N.ptr_of(counters), N.ptr_of(sums)))
         return counters, sums
 
+    def track_returns(self, on: bool = True):
+        """Whether the single-step kernels keep the per-env episode-return accumulator (on by default: finished-episode
+        return statistics stay correct when ``step`` and ``rollout`` calls are mixed). Off saves 16 B of HBM traffic per
+        env-step; the statistics then cover only episodes that ran entirely inside rollout calls."""
+        N.check(N.lib().nig_track_returns(self._h, int(bool(on))))
+
     def track_extrema(self, on: bool = True):
         """Rollouts of this handle also keep the smallest / largest finished-episode return (a 2 % slower kernel flavour)."""
         N.check(N.lib().nig_track_extrema(self._h, int(bool(on))))

@@ -323,14 +323,25 @@ static void reactor_reset(const orc_cfg_t* cfg, uint32_t env, uint32_t tick, uin
     s[11] = 0.0f;
 }
 
-/* process noise of step `tick`: pair (tick & 1) of block (env, tick >> 1, NOISE, 0) */
+/* ONE Philox block per reactor step, (env, tick, NOISE, 0): words 0, 1 -> the two process-noise normals of the step;
+ * words 2, 3 -> the uniform-random policy's action_space.sample() (reactor_uniform_actions) */
 static void reactor_noise(const orc_cfg_t* cfg, uint32_t env, uint32_t tick, float* nz)
 {
-    float z[4];
-    normals4(cfg, env, tick >> 1, STREAM_NOISE, 0u, z);
-    const float* p = (tick & 1u) ? z + 2 : z;
-    nz[0] = 0.1f * p[0];
-    nz[1] = 500.0f * p[1];
+    uint32_t w[4];
+    words4(cfg, env, tick, STREAM_NOISE, 0u, w);
+    nz[0] = 0.1f * spec_normal(w[0]);
+    nz[1] = 500.0f * spec_normal(w[1]);
+}
+/* a0 / a1 = v * 2^-21 - 1 from bits 21..0 of words 2 / 3, a2 = v * 2^-19 - 1 from their two 10-bit tops: the bits are the
+ * mantissa of a float in [1, 2) and one exact fma maps it to [-1, 1) */
+static void reactor_uniform_actions(const orc_cfg_t* cfg, uint32_t env, uint32_t tick, float* a)
+{
+    uint32_t w[4];
+    words4(cfg, env, tick, STREAM_NOISE, 0u, w);
+    a[0] = fmaf(bits_f((w[2] & 0x3fffffu) | 0x3f800000u), 4.0f, -5.0f);
+    a[1] = fmaf(bits_f((w[3] & 0x3fffffu) | 0x3f800000u), 4.0f, -5.0f);
+    const uint32_t v2 = ((w[2] >> 22) << 10) | (w[3] >> 22);
+    a[2] = fmaf(bits_f(v2 | 0x3f800000u), 16.0f, -17.0f);
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -789,6 +800,7 @@ static void policy_one(const orc_cfg_t* cfg, int policy, const orc_pp_t* pp, uin
     uint32_t w[4];
     if (policy == ORC_POLICY_ZERO) { for (int k = 0; k < A; ++k) a[k] = 0.0f; return; }
     if (policy == ORC_POLICY_UNIFORM) {
+        if (cfg->kind == ORC_REACTOR) { reactor_uniform_actions(cfg, env, tick, a); return; }
         for (int j = 0; j < (A + 3) / 4; ++j) {
             words4(cfg, env, tick, STREAM_POLICY, (uint32_t)j, w);
             for (int q = 0; q < 4; ++q) if (4 * j + q < A) a[4 * j + q] = u_sym(w[q]);

@@ -148,6 +148,15 @@ def test_normal_table_headers_are_the_generators_output(tmp_path):
     assert tab.shape == (513, 4) and err_abs < 6e-7
 
 
+def test_library_and_oracle_share_one_normal_table():
+    """csrc/nig_normal_table.h and oracle/nig_normal_table.h are two emissions of tools/fit_normal_table.py: the same
+    numbers (a silent divergence would show up as baffling bit-level parity failures)."""
+    strip = lambda t: [l for l in t.splitlines() if not l.lstrip().startswith(("//", "/*", "*"))]
+    a = open(os.path.join(ROOT, "neorl-industrial-gym_b200", "csrc", "nig_normal_table.h")).read()
+    b = open(os.path.join(ROOT, "oracle", "nig_normal_table.h")).read()
+    assert strip(a) == strip(b)
+
+
 def test_bench_reference_arm_runs_without_a_gpu():
     """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) needs no GPU: one JSON line with the
     contract's keys, the same metric / unit as the GPU arm, `impl: reference`, a cpu_baseline block and an e2e block."""

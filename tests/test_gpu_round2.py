@@ -1,0 +1,233 @@
+"""GPU tests added in round 2: the invariant-specialised reactor rollout loop against the oracle from adversarial entry
+states, the episode-return bookkeeping across mixed nig_step / nig_rollout use, the exact-size host outputs of the
+zero-copy step path, seeded resets."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import KINDS, assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    import neorl_industrial as ni
+    from neorl_industrial import _native as N
+    from oracle import oracle as O
+    return ni, N, O, torch
+
+
+def _compare(env, orc, N, what):
+    st, ep_step, ep_viol, done = env.get_state_host()
+    assert_bits_equal(st, orc.state, f"{what}: state")
+    assert_bits_equal(ep_step, orc.ep_step, f"{what}: episode step")
+    assert_bits_equal(ep_viol, orc.ep_viol, f"{what}: episode violations")
+    assert_bits_equal(done, orc.done_latch, f"{what}: done latch")
+    counters, _ = env.read_stats()
+    assert counters[:6].tolist() == orc.stats[:6].tolist(), (what, counters[:8], orc.stats[:8])
+    assert counters[N.ST_CON0:N.ST_CON0 + 3].tolist() == orc.stats[8:11].tolist(), what
+
+
+def test_reactor_fast_loop_from_adversarial_entry_states(mods):
+    """The specialised loop is entered per warp only when every env of the warp satisfies its invariants; these populations
+    mix warps that do with warps that do not (tripped e-stop, alarm set, fractional latch values, -0.0 flags, over-limit
+    temperature / pressure, odd catalyst values, episodes about to be truncated, a NaN) -- every result must still be the
+    oracle's, bit for bit, including the states the loop never saw."""
+    ni, N, O, torch = mods
+    rng = np.random.default_rng(5)
+    n, K = 4096 + 37, 48
+    env = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=21)
+    orc = O.OracleEnv(O.REACTOR, n, seed=21, exp_mode=1)
+    s0 = env.reset_host()
+    assert_bits_equal(s0, orc.reset(), "reset")
+    st = s0.copy()
+    ep_step = np.zeros(n, np.int32)
+    # warp-sized groups of special cases (one odd env spoils its whole warp; whole warps of them too)
+    def some(k):
+        return rng.choice(n, k, replace=False)
+    st[some(40), 8] = 1.0                      # e-stop already tripped
+    st[some(40), 9] = 1.0                      # alarm latched (still inside the invariant)
+    st[some(10), 8] = 0.3                      # fractional latch values the reference would carry along unchanged
+    st[some(10), 9] = 0.7
+    st[some(10), 8] = -0.0
+    st[some(10), 9] = -0.0
+    st[some(30), 0] = rng.uniform(350.0, 356.0, 30).astype(np.float32)     # over the temperature limit: critical shutdown
+    st[some(30), 1] = rng.uniform(5.0e5, 5.2e5, 30).astype(np.float32)     # around the pressure limit
+    st[some(10), 0] = 150.0                    # outside the loop's 200 .. 350 K entry range
+    st[some(10), 5] = rng.choice([0.0, 1e-35, 49.0, 50.0, 3e30], 10).astype(np.float32)
+    st[some(5), 4] = 0.0
+    st[some(3), 0] = np.nan
+    ep_step[some(200)] = rng.integers(440, 500, 200)                         # truncation inside the launch
+    st[32 * 5:32 * 6, 8] = 1.0                 # one whole warp outside the invariant
+    env.set_state_host(st, ep_step, np.zeros(n, np.int32), np.zeros(n, np.uint8))
+    orc.state[:] = st
+    orc.ep_step[:] = ep_step
+    for chunk in (K, 17, 1, 64):
+        env.rollout_device(chunk, N.POLICY_UNIFORM)
+        O.rollout(orc, chunk, O.POLICY_UNIFORM)
+        torch.cuda.synchronize()
+        _compare(env, orc, N, f"after a {chunk}-step launch")
+    env.close()
+
+
+def test_reactor_fast_loop_without_auto_reset_and_sharded(mods):
+    """auto_reset off never enters the specialised loop (latches instead); shards keyed by global env id agree with the
+    unsharded run whichever loop they took."""
+    ni, N, O, torch = mods
+    n, K = 2048, 96
+    env = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=4, auto_reset=False)
+    orc = O.OracleEnv(O.REACTOR, n, seed=4, exp_mode=1, auto_reset=False)
+    assert_bits_equal(env.reset_host(), orc.reset(), "reset")
+    env.rollout_device(K, N.POLICY_UNIFORM)
+    O.rollout(orc, K, O.POLICY_UNIFORM)
+    torch.cuda.synchronize()
+    _compare(env, orc, N, "no auto-reset")
+    env.close()
+    whole = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=9)
+    whole.reset_host()
+    whole.rollout_device(K, N.POLICY_UNIFORM)
+    ref = whole.get_state_host()[0]
+    for off, cnt in ((0, 700), (700, 1348)):
+        e = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, cnt, device=0, seed=9, env_id_offset=off)
+        e.reset_host()
+        e.rollout_device(K, N.POLICY_UNIFORM)
+        assert_bits_equal(e.get_state_host()[0], ref[off:off + cnt], f"shard at {off}")
+        e.close()
+    whole.close()
+
+
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+def test_episode_returns_across_mixed_step_and_rollout_calls(mods, name):
+    """One handle driven by alternating nig_step (host actions) and nig_rollout (the same actions drawn in-kernel) reports
+    the finished-episode statistics of the all-rollout run: the running return of every episode lives in one per-env
+    accumulator both kernels keep. Counters exact; fp64 sums to 1e-12 (atomics commute up to rounding)."""
+    ni, N, O, torch = mods
+    kind = KINDS[name]
+    n = 3000
+    # a 40-step episode cap so that every env finishes episodes inside the 106-step plan (reactor episodes run ~370 steps)
+    a_env = ni.NativeEnv(kind, n, device=0, seed=33, max_episode_steps=40)
+    b_env = ni.NativeEnv(kind, n, device=0, seed=33, max_episode_steps=40)
+    orc = O.OracleEnv(kind, n, seed=33, exp_mode=1, max_episode_steps=40)
+    a_env.reset_host(); b_env.reset_host(); orc.reset()
+    plan = [("rollout", 9), ("step", 7), ("rollout", 30), ("step", 12), ("rollout", 5), ("step", 3), ("rollout", 40)]
+    total = sum(k for _, k in plan)
+    a_env.rollout_device(total, N.POLICY_UNIFORM)
+    for how, k in plan:
+        if how == "rollout":
+            b_env.rollout_device(k, N.POLICY_UNIFORM)
+            O.rollout(orc, k, O.POLICY_UNIFORM)
+        else:
+            for _ in range(k):
+                act = O.policy_actions(orc, O.POLICY_UNIFORM)
+                b_env.step_host(act, want_obs=False)
+                orc.step(act, want_next_obs=False)
+    torch.cuda.synchronize()
+    assert_bits_equal(a_env.get_state_host()[0], b_env.get_state_host()[0], "final states")
+    ca, fa = a_env.read_stats()
+    cb, fb = b_env.read_stats()
+    assert ca[N.ST_EPISODES] >= 2 * n, "the plan must finish episodes"
+    assert ca[:6].tolist() == orc.stats[:6].tolist()
+    for slot in (N.ST_STEPS, N.ST_EPISODES, N.ST_TERMINATED, N.ST_TRUNCATED, N.ST_CRITICAL, N.ST_VIOLATIONS, N.ST_SUCCESSES,
+                 N.ST_EP_LEN_SUM, N.ST_EP_LEN_SQ):
+        assert ca[slot] == cb[slot], (slot, ca[slot], cb[slot])
+    np.testing.assert_allclose(fb[:2], fa[:2], rtol=1e-12)           # RETURN_SUM, RETURN_SQ
+    # and with tracking switched off the step kernels leave the accumulator alone (documented behaviour)
+    b_env.track_returns(False)
+    b_env.clear_stats()
+    act = O.policy_actions(orc, O.POLICY_UNIFORM)
+    b_env.step_host(act, want_obs=False)
+    cb2, fb2 = b_env.read_stats()
+    assert cb2[N.ST_STEPS] == n and cb2[N.ST_EP_LEN_SUM] == 0 and fb2[0] == 0.0
+    a_env.close(); b_env.close()
+
+
+def test_set_state_restarts_the_episode_return(mods):
+    ni, N, O, torch = mods
+    n = 512
+    env = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=1)
+    s0 = env.reset_host()
+    env.rollout_device(20, N.POLICY_UNIFORM)                 # leaves partial returns in the accumulators
+    env.set_state_host(s0, np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8))
+    env.clear_stats()
+    env.set_tick(0)
+    fresh = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=1)
+    fresh.reset_host()
+    fresh.set_state_host(s0, np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8))
+    fresh.set_tick(0, env.epoch)
+    env.rollout_device(500, N.POLICY_UNIFORM)
+    fresh.rollout_device(500, N.POLICY_UNIFORM)
+    ca, fa = env.read_stats()
+    cb, fb = fresh.read_stats()
+    assert ca[N.ST_EPISODES] == cb[N.ST_EPISODES] > 0
+    np.testing.assert_allclose(fa[:2], fb[:2], rtol=1e-12)
+    env.close(); fresh.close()
+
+
+@pytest.mark.parametrize("n", [1, 130])
+def test_zero_copy_step_writes_nothing_past_n(mods, n):
+    """nig_step_host with page-locked buffers runs the kernel directly on them: a C caller may pack reward[n], flags[n],
+    viol_mask[n], next_obs[n][S] back to back in ONE nig_host_alloc block -- nothing may be written past element n - 1 of
+    any of them (the padding lanes up to pitch used to store 0.0 rewards / INACTIVE flags over the neighbours)."""
+    ni, N, O, torch = mods
+    S, A = 12, 3
+    env = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=2)
+    env.reset_host()
+    lib = N.lib()
+    nbytes = 4 * n * A + 64 + 4 * n + 64 + n + 64 + n + 64 + 4 * n * S + 64 + 4 * n * S + 64
+    block = C.c_void_p()
+    N.check(lib.nig_host_alloc(nbytes, C.byref(block)))
+    buf = np.ctypeslib.as_array(C.cast(block, C.POINTER(C.c_uint8)), shape=(nbytes,))
+    buf[:] = 0xA5
+    off = [0]
+
+    def carve(count, dtype):
+        a = buf[off[0]:off[0] + count * np.dtype(dtype).itemsize].view(dtype)
+        off[0] += count * np.dtype(dtype).itemsize + 64            # 64 canary bytes after every array
+        return a
+    act, rew, fl, vm = carve(n * A, np.float32), carve(n, np.float32), carve(n, np.uint8), carve(n, np.uint8)
+    obs, nxt = carve(n * S, np.float32), carve(n * S, np.float32)
+    act[:] = np.random.default_rng(0).uniform(-1, 1, n * A).astype(np.float32)
+    io = N.StepIO()
+    io.actions, io.reward, io.flags, io.viol_mask = act.ctypes.data, rew.ctypes.data, fl.ctypes.data, vm.ctypes.data
+    io.obs, io.next_obs = obs.ctypes.data, nxt.ctypes.data
+    io.action_layout, io.aux_layout = N.LAYOUT_AOS, N.LAYOUT_AOS
+    launches0 = env.launch_count
+    for _ in range(3):
+        N.check(lib.nig_step_host(env._h, C.byref(io)))
+    assert env.launch_count - launches0 == 3                       # the zero-copy path: one launch per call, no staging kernels
+    used = np.zeros(nbytes, bool)
+    for a in (act, rew, fl, vm, obs, nxt):
+        start = a.ctypes.data - buf.ctypes.data
+        used[start:start + a.nbytes] = True
+    assert (buf[~used] == 0xA5).all(), "bytes outside the caller's arrays were overwritten"
+    assert np.isfinite(rew).all() and (fl != 0xA5).all()
+    N.check(lib.nig_host_free(block))
+    env.close()
+
+
+def test_seeded_reset_is_reproducible(mods):
+    """gym contract: reset(seed=s) twice gives the same first observation and the same noise afterwards."""
+    ni, N, O, torch = mods
+    env = ni.make("ChemicalReactor-v0", device="cuda:0")
+    o1, _ = env.reset(seed=42)
+    t1 = [env.step(np.array([0.1, -0.2, 0.3], np.float32))[0].copy() for _ in range(5)]
+    env.step(np.zeros(3, np.float32))
+    o2, _ = env.reset(seed=42)
+    t2 = [env.step(np.array([0.1, -0.2, 0.3], np.float32))[0].copy() for _ in range(5)]
+    assert_bits_equal(o1, o2, "first observation")
+    assert_bits_equal(np.stack(t1), np.stack(t2), "trajectory after the seeded reset")
+    o3, _ = env.reset(seed=43)
+    assert not np.array_equal(o1, o3)
+    o4, _ = env.reset()                   # unseeded resets keep drawing fresh states
+    assert not np.array_equal(o3, o4)
+    env.close()
+    venv = ni.TorchIndustrialEnv("ChemicalReactor-v0", 256, device="cuda:0", seed=1)
+    a, _ = venv.reset(seed=7)
+    a = a.clone()
+    venv.step(torch.zeros((256, 3), device=venv.device))
+    b, _ = venv.reset(seed=7)
+    assert torch.equal(a, b)
+    venv.close()
