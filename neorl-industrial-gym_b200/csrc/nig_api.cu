@@ -97,7 +97,7 @@ struct nig_env {
     int32_t *h_i32a, *h_i32b;
     unsigned long long* extrema; // [2] min / max finished-episode return keys (outside the summable stats block)
     bool track_extrema;          // nig_track_extrema: rollouts run the EXTREMA kernel flavour
-    bool track_returns = true;   // nig_track_returns: the single-step kernels keep the episode-return accumulator too
+    bool track_returns;          // nig_track_returns (default on, set in nig_create): the single-step kernels keep the episode-return accumulator too
     // nig_rollout_host over env slices: slice s runs H2D -> reset -> K-step launches -> D2H on its own stream, so the
     // copies of one slice overlap the stepping of the others (and the slices' launches fill each other's tails)
     cudaStream_t slice_stream[kMaxHostSlices];
@@ -476,6 +476,7 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     nig_env* e = new (std::nothrow) nig_env();
     if (!e) return fail(NIG_ERR_INVALID, "out of host memory");
     memset(e, 0, sizeof *e);
+    e->track_returns = true;
     e->cfg = *cfg;
     e->kind = cfg->env_kind;
     e->S = kS[e->kind]; e->A = kA[e->kind]; e->NZ = kNZ[e->kind];

@@ -102,6 +102,12 @@ struct Reactor {
     // the reactor (7.0 -> 6.8 -> 6.3e10 env-steps/s at 1M envs for 4 / 6 / 8 CTAs)
     static constexpr int ROLLOUT_MIN_CTAS = 1;
     static constexpr bool TAB_SMEM = false;          // 2 normals per step: the L1-cached global table is as fast, no staging prologue
+#ifndef NIG_REACTOR_ROLLOUT_TAB_SMEM
+#define NIG_REACTOR_ROLLOUT_TAB_SMEM 1
+#endif
+    // the fused rollout reads a shared-memory copy of the table: LEA.HI + LDS.128 [R.X16] instead of LEA.HI + IMAD.WIDE (a
+    // quarter-rate instruction) + LDG per normal; measured +5 % at 65,536 envs, +1.4 % at 1M (gpurun_out r2_ab1)
+    static constexpr bool ROLLOUT_TAB_SMEM = NIG_REACTOR_ROLLOUT_TAB_SMEM != 0;
     static constexpr int STEP_MIN_CTAS = 1;
     __device__ static __forceinline__ void reset_from_normals(const float (&z)[8], float (&s)[S])
     {
@@ -282,6 +288,7 @@ struct Grid {
     // registers) no better
     static constexpr int ROLLOUT_MIN_CTAS = 3;
     static constexpr bool TAB_SMEM = true;           // 23 normals per step: shared-memory copy of the normal table (+7 %)
+    static constexpr bool ROLLOUT_TAB_SMEM = true;
     static constexpr int STEP_MIN_CTAS = 4;          // single step: 146 -> 128 registers, 3 -> 4 CTAs per SM, +11 % (5, 6: worse)
     static constexpr int COOP_BLOCKS = 8;
     __device__ static __forceinline__ void reset_block(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t j, float (&v)[4])
@@ -407,6 +414,7 @@ struct Robot {
     static constexpr bool COOP_RESET = false;
     static constexpr int COOP_BLOCKS = 0;
     static constexpr bool TAB_SMEM = false;          // normals only in reset / policy draws
+    static constexpr bool ROLLOUT_TAB_SMEM = false;
     static constexpr int ROLLOUT_MIN_CTAS = 4;       // 177 -> 128 registers: 1.76 -> 2.05e10 env-steps/s at 1M envs
     static constexpr int STEP_MIN_CTAS = 6;          // 104 -> 80 registers: 0.39 -> 0.47 of the HBM peak at 4M envs
     static constexpr uint32_t CRIT_MASK = 0x3;       // force_limits, collision_avoidance (:56-68)

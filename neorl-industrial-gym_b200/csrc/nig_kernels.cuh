@@ -1045,6 +1045,10 @@ __device__ __forceinline__ void policy_baseline(const Rng& key, const nig_baseli
 // in the same order -> bit-identical results (tests/test_gpu_parity.py compares with the oracle, which knows nothing of
 // this). If a guard fails (never observed: it takes |T' - 320| > 120 K, a pressure outside [1e3, 1e7] Pa or a denormal
 // heat balance) the warp leaves the loop WITHOUT committing the step and the generic loop carries on from there.
+#ifndef NIG_FAST_UNROLL
+#define NIG_FAST_UNROLL 1
+#endif
+constexpr int kFastUnroll = NIG_FAST_UNROLL;
 __device__ __forceinline__ float cdiv_noguard(float x, float c, float rc)
 {
     const float q = __fmul_rn(x, rc);
@@ -1072,7 +1076,7 @@ __device__ __forceinline__ int reactor_fast_steps(const Rng& key, uint32_t env, 
     int t_trunc = max_steps - (int)ep_st - 1;       // loop index of the step at which the running episode is truncated (base.py:191)
     unsigned int c_lvl = 0;
     int t = 0;
-#pragma unroll 1
+#pragma unroll kFastUnroll
     for (; t < n_steps; ++t) {
         const uint32_t tick = tick0 + (uint32_t)t;
         const uint4 w = rng_words(key, env, tick, STREAM_NOISE, 0u);
@@ -1194,15 +1198,15 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
     __shared__ double sfl[4];
     __shared__ unsigned long long sext[2];       // extremum keys of the episodes this CTA finished
-    __shared__ float4 s_tab[Env::TAB_SMEM ? NIG_NORMAL_TAB_N : 1];   // this CTA's copy of the normal table (8 KB, read K * draws times)
+    __shared__ float4 s_tab[Env::ROLLOUT_TAB_SMEM ? NIG_NORMAL_TAB_N : 1];   // this CTA's copy of the normal table (8 KB, read K * draws times)
     __shared__ alignas(8) uint64_t bars[2];
     __shared__ float coop_buf[CoopSmem<Env>::floats];
     extern __shared__ __align__(128) float act_smem[];     // [2][kTmaChunk][A][kThreads] when TMA
     BlockStats bs;
     if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
     if constexpr (EXTREMA) { if (threadIdx.x < 2) sext[threadIdx.x] = 0ull; }
-    if constexpr (Env::TAB_SMEM) normal_table_to_smem(s_tab);
-    const Rng key(p.key, Env::TAB_SMEM ? s_tab : g_normal_tab);
+    if constexpr (Env::ROLLOUT_TAB_SMEM) normal_table_to_smem(s_tab);
+    const Rng key(p.key, Env::ROLLOUT_TAB_SMEM ? s_tab : g_normal_tab);
     bs.init(sstat);                              // (synchronises the CTA)
 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

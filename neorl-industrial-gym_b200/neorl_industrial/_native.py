@@ -13,7 +13,7 @@ import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG_DIR)                       # neorl-industrial-gym_b200/
-LIB_PATH = os.path.join(_ROOT, "libnig_b200.so")
+LIB_PATH = os.environ.get("NIG_LIB_PATH") or os.path.join(_ROOT, "libnig_b200.so")   # (override: A/B builds, tools/ab_build.sh)
 CSRC_DIR = os.path.join(_ROOT, "csrc")
 
 ABI_VERSION = 4
