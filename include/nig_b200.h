@@ -325,6 +325,18 @@ NIG_API int nig_stats_ptr(nig_env_t* env, void** stats_dev);
 NIG_API int nig_read_stats(nig_env_t* env, int64_t* counters24, double* sums8);
 NIG_API int nig_clear_stats(nig_env_t* env, void* stream);
 
+/* The path's only collective (the aggregation utils.py:128-152 does over one env, over every shard): sums the
+ * device stats block over the ranks of an NCCL communicator, in place, as ONE grouped launch on `stream` -- 24 int64
+ * counters (SUM: exact and order independent), 8 fp64 sums (SUM) and the two order-preserving return-extremum keys (MAX).
+ * `nccl_comm` is an ncclComm_t: any communicator whose ranks own the shards (torch.distributed's:
+ * ProcessGroupNCCL._comm_ptr(); or one made with the three helpers below, which need nothing but a way to hand rank 0's
+ * 128-byte id to the other ranks). NCCL is dlopen()ed on first use (libnccl.so.2); without it these four calls return
+ * NIG_ERR_UNSUPPORTED and everything else works. */
+NIG_API int nig_allreduce_stats(nig_env_t* env, void* nccl_comm, void* stream);
+NIG_API int nig_nccl_unique_id(void* id128);                                  /* rank 0: ncclGetUniqueId -> 128 bytes */
+NIG_API int nig_nccl_comm_init(void** nccl_comm, int32_t n_ranks, const void* id128, int32_t rank, int32_t device);
+NIG_API int nig_nccl_comm_destroy(void* nccl_comm);
+
 /* smallest / largest return among the episodes finished inside nig_rollout / nig_rollout_host since the last
  * nig_clear_stats (return_min / return_max of evaluate_with_safety, utils.py:131-132). Opt-in per handle with
  * nig_track_extrema(env, 1): the rollout then runs the kernel flavour that carries the two running extrema (measured

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <dlfcn.h>
 
 #include "nig_launch.h"
 
@@ -112,6 +113,7 @@ struct nig_env {
     int64_t launches;
     int step_vec;              // 0 = auto
     int rollout_block;         // 0 = 128
+    int rollout_ws;            // warp-specialised reactor rollout kernel (NIG_ROLLOUT_WS)
     int zero_copy;             // 1 (default): small-population *_host steps run in place on page-locked host buffers
     int step_pipe;             // 1 (default): large plain SoA steps take the persistent TMA-pipelined kernel
     PFN_encodeTiled encode_tiled;
@@ -365,6 +367,7 @@ int rollout_range(nig_env* e, const nig_rollout_t* r, cudaStream_t stream, int64
     // on the SMs, measured 7.82 / 7.93 / 7.98e10 env-steps/s for 128 / 64 / 32 threads per CTA at 8 slices of 8,192 envs
     cfg.block = e->rollout_block ? e->rollout_block : (e->kind == NIG_ENV_CHEMICAL_REACTOR && ns <= 16384 ? 32 : 128);
     cfg.extrema = e->track_extrema;
+    cfg.ws = e->rollout_ws != 0 && e->kind == NIG_ENV_CHEMICAL_REACTOR && e->cfg.auto_reset != 0;
     e->launches++;
     const int64_t extent = (ns + 127) / 128 * 128;          // launch extent; <= the rows' pitch because slices start at multiples of 128
     NIG_CUDA(nig::launch_rollout(e->kind, cfg, extent, a, map, stream));
@@ -486,6 +489,8 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     e->key = RngKey{(uint32_t)cfg->seed, (uint32_t)(cfg->seed >> 32)};
     if (const char* v = getenv("NIG_STEP_VEC")) e->step_vec = atoi(v);
     if (const char* v = getenv("NIG_ROLLOUT_BLOCK")) e->rollout_block = atoi(v);
+    e->rollout_ws = 0;
+    if (const char* v = getenv("NIG_ROLLOUT_WS")) e->rollout_ws = atoi(v);
     e->step_pipe = 1;
     if (const char* v = getenv("NIG_STEP_PIPE")) e->step_pipe = atoi(v);
     e->zero_copy = 1;
@@ -1124,6 +1129,104 @@ int nig_read_stats(nig_env_t* e, int64_t* counters24, double* sums8)
     NIG_CUDA(cudaMemcpy(h, e->stats, sizeof h, cudaMemcpyDeviceToHost));
     if (counters24) for (int k = 0; k < 24; ++k) counters24[k] = (int64_t)h[k];
     if (sums8) memcpy(sums8, &h[24], 8 * sizeof(double));
+    return NIG_OK;
+}
+
+// ---- the path's one collective, for callers that do not come through torch.distributed ------------------------------
+// NCCL is bound lazily with dlopen (libnccl.so.2: the copy already loaded into the process -- e.g. torch's -- wins, else
+// the system's), so the library has no link-time dependency on it and loads on machines without NCCL.
+namespace {
+struct nccl_id_t { char internal[128]; };            // == ncclUniqueId
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GetUniqueId)(nccl_id_t*) = nullptr;
+    int (*CommInitRank)(void**, int, nccl_id_t, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+};
+enum { kNcclInt64 = 4, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2 };   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+const NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+            api.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+            api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+            api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+            api.GetUniqueId = (int (*)(nccl_id_t*))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (int (*)(void**, int, nccl_id_t, int))dlsym(h, "ncclCommInitRank");
+            api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+            if (api.GroupStart && api.GroupEnd && api.AllReduce && api.GetUniqueId && api.CommInitRank && api.CommDestroy) api.lib = h;
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+int nccl_fail(const NcclApi* a, int rc, const char* what)
+{
+    return fail(NIG_ERR_CUDA, "%s failed: %s", what, a->GetErrorString ? a->GetErrorString(rc) : "NCCL error");
+}
+#define NIG_NCCL(api, call, what) do { const int nrc_ = (call); if (nrc_ != 0) return nccl_fail(api, nrc_, what); } while (0)
+} // namespace
+
+int nig_nccl_unique_id(void* id128)
+{
+    const NcclApi* a = nccl_api();
+    if (!a) return fail(NIG_ERR_UNSUPPORTED, "libnccl.so.2 not found (NCCL is only needed for nig_allreduce_stats)");
+    if (!id128) return fail(NIG_ERR_INVALID, "nig_nccl_unique_id: null buffer");
+    nccl_id_t id;
+    NIG_NCCL(a, a->GetUniqueId(&id), "ncclGetUniqueId");
+    memcpy(id128, &id, sizeof id);
+    return NIG_OK;
+}
+
+int nig_nccl_comm_init(void** comm, int32_t n_ranks, const void* id128, int32_t rank, int32_t device)
+{
+    const NcclApi* a = nccl_api();
+    if (!a) return fail(NIG_ERR_UNSUPPORTED, "libnccl.so.2 not found (NCCL is only needed for nig_allreduce_stats)");
+    if (!comm || !id128 || n_ranks <= 0 || rank < 0 || rank >= n_ranks) return fail(NIG_ERR_INVALID, "nig_nccl_comm_init: bad arguments");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(NIG_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    nccl_id_t id;
+    memcpy(&id, id128, sizeof id);
+    *comm = nullptr;
+    NIG_NCCL(a, a->CommInitRank(comm, n_ranks, id, rank), "ncclCommInitRank");
+    return NIG_OK;
+}
+
+int nig_nccl_comm_destroy(void* comm)
+{
+    const NcclApi* a = nccl_api();
+    if (!a) return fail(NIG_ERR_UNSUPPORTED, "libnccl.so.2 not found");
+    if (comm) NIG_NCCL(a, a->CommDestroy(comm), "ncclCommDestroy");
+    return NIG_OK;
+}
+
+int nig_allreduce_stats(nig_env_t* e, void* nccl_comm, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    const NcclApi* a = nccl_api();
+    if (!a) return fail(NIG_ERR_UNSUPPORTED, "libnccl.so.2 not found (NCCL is only needed for nig_allreduce_stats)");
+    if (!nccl_comm) return fail(NIG_ERR_INVALID, "nig_allreduce_stats: null communicator");
+    cudaStream_t st = (cudaStream_t)stream;
+    note_device_work(e, st);
+    // one group = one fused launch: 24 int64 counters (SUM: exact, order independent), 8 fp64 sums (SUM), and the two
+    // order-preserving return-extremum keys (MAX; zeros when nothing was tracked)
+    NIG_NCCL(a, a->GroupStart(), "ncclGroupStart");
+    int rc = a->AllReduce(e->stats, e->stats, 24, kNcclInt64, kNcclSum, nccl_comm, st);
+    if (rc == 0) rc = a->AllReduce(e->stats + 24, e->stats + 24, NIG_STATS_SLOTS - 24, kNcclFloat64, kNcclSum, nccl_comm, st);
+    if (rc == 0) rc = a->AllReduce(e->extrema, e->extrema, 2, kNcclInt64, kNcclMax, nccl_comm, st);
+    const int rc_end = a->GroupEnd();
+    if (rc != 0) return nccl_fail(a, rc, "ncclAllReduce");
+    NIG_NCCL(a, rc_end, "ncclGroupEnd");
     return NIG_OK;
 }
 

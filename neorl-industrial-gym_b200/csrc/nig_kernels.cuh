@@ -1064,9 +1064,34 @@ struct RolloutAcc {            // episode / launch statistics of one thread (sha
     double ret_sum = 0.0, ret_sq = 0.0, rew_sum = 0.0;
 };
 
+// The six values of a step that depend on nothing but the random streams: the manual-mode actuator commands
+// hp = a0 * 50000, cadj = a1 * 0.1, fadj = a2 * 0.1 (:127-129), the action penalty ((|a0| + |a1|) + |a2|) * 0.1 (:267-268)
+// and the two scaled process-noise normals (:149, :159).
+struct StepDraw { float hp, cadj, fadj, apen, nz0, nz1; };
+
+__device__ __forceinline__ StepDraw reactor_step_draw(const Rng& key, uint32_t env, uint32_t tick)
+{
+    const uint4 w = rng_words(key, env, tick, STREAM_NOISE, 0u);
+    float za, zb, a[Reactor::A];
+    normal_pair(key.tab, w.x, w.y, za, zb);
+    Reactor::uniform_from_words(w.z, w.w, a);
+    StepDraw d;
+    d.nz0 = mul(0.1f, za); d.nz1 = mul(500.0f, zb);
+    d.hp = mul(a[0], 50000.0f); d.cadj = mul(a[1], 0.1f); d.fadj = mul(a[2], 0.1f);
+    d.apen = mul(add(add(fabsf(a[0]), fabsf(a[1])), fabsf(a[2])), 0.1f);
+    return d;
+}
+
+// where the fast loop gets a step's draw from: computed in place ...
+struct DrawInKernel {
+    const Rng& key; uint32_t env, tick0;
+    __device__ __forceinline__ StepDraw get(int t) const { return reactor_step_draw(key, env, tick0 + (uint32_t)t); }
+    __device__ __forceinline__ void done(int, int) const {}
+};
+
 // returns the number of steps committed (== n_steps unless a guard failed)
-template <bool EXTREMA>
-__device__ __forceinline__ int reactor_fast_steps(const Rng& key, uint32_t env, uint32_t tick0, uint32_t epoch, int n_steps, int max_steps,
+template <bool EXTREMA, class Src>
+__device__ __forceinline__ int reactor_fast_steps(Src& src, const Rng& key, uint32_t env, uint32_t tick0, uint32_t epoch, int n_steps, int max_steps,
                                                   float (&s)[Reactor::S], uint32_t& ep_st, uint32_t& ep_vi, float& ep_ret, float& rsum,
                                                   RolloutAcc& acc, float& r_lo, float& r_hi)
 {
@@ -1079,14 +1104,10 @@ __device__ __forceinline__ int reactor_fast_steps(const Rng& key, uint32_t env, 
 #pragma unroll kFastUnroll
     for (; t < n_steps; ++t) {
         const uint32_t tick = tick0 + (uint32_t)t;
-        const uint4 w = rng_words(key, env, tick, STREAM_NOISE, 0u);
-        float za, zb, a[Reactor::A];
-        normal_pair(key.tab, w.x, w.y, za, zb);
-        const float nz0 = mul(0.1f, za), nz1 = mul(500.0f, zb);                 // :149, :159
-        Reactor::uniform_from_words(w.z, w.w, a);
+        const StepDraw dr = src.get(t);
+        const float nz0 = dr.nz0, nz1 = dr.nz1, hp = dr.hp, cadj = dr.cadj, fadj = dr.fadj;
         const bool lvl_bad = !((20.0f <= level) && (level <= 90.0f));           // :302-305 on the pre-step state
         // _dynamics (:109-226), manual mode
-        const float hp = mul(a[0], 50000.0f), cadj = mul(a[1], 0.1f), fadj = mul(a[2], 0.1f);
         const float kca = mul(mul(0.1f, conc), catd);
         const float rh = mul(kca, 10000.0f);
         const float ch = mul(mul(mul(cool, 100.0f), sub(T, hx)), 0.1f);
@@ -1138,9 +1159,10 @@ __device__ __forceinline__ int reactor_fast_steps(const Rng& key, uint32_t env, 
         r = band ? add(r, 5.0f) : sub(r, mul(fabsf(sub(nlevel, 55.0f)), 0.2f));
         if (nalarm) r = sub(r, 50.0f);
         if (trip) r = sub(r, 200.0f);
-        r = sub(r, mul(add(add(fabsf(a[0]), fabsf(a[1])), fabsf(a[2])), 0.1f));
+        r = sub(r, dr.apen);
         if (lvl_bad) r = add(r, -25.0f);
         if (__builtin_expect(!__all_sync(0xffffffffu, ok), 0)) break;           // (uniform) redo this step in the generic loop
+        src.done(t, n_steps);
         rsum = add(rsum, r);
         ep_ret = ep_ret + r;
         c_lvl += lvl_bad ? 1u : 0u;
@@ -1150,7 +1172,8 @@ __device__ __forceinline__ int reactor_fast_steps(const Rng& key, uint32_t env, 
         const bool term = trip || (nlevel < 5.0f) || (nlevel > 95.0f) || (nbt > 50.0f);   // _is_done (:272-290)
         const bool trunc = t >= t_trunc;
         if (__any_sync(0xffffffffu, term || trunc)) {
-            if (term || trunc) {
+            const bool fin = term || trunc;
+            if (fin) {
                 const unsigned long long len = (unsigned long long)(max_steps - (t_trunc - t));
                 acc.c_ep += 1; acc.c_done += 1;
                 acc.c_term += term ? 1u : 0u;
@@ -1159,11 +1182,12 @@ __device__ __forceinline__ int reactor_fast_steps(const Rng& key, uint32_t env, 
                 acc.len_sum += len; acc.len_sq += len * len;
                 acc.ret_sum += (double)ep_ret; acc.ret_sq += (double)ep_ret * (double)ep_ret;
                 if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
-                float z[8];
-                rng_normals4(key, env, tick + 1u, STREAM_RESET, (epoch << 8) | 0u, reinterpret_cast<float (&)[4]>(z[0]));
-                rng_normals4(key, env, tick + 1u, STREAM_RESET, (epoch << 8) | 1u, reinterpret_cast<float (&)[4]>(z[4]));
-                float f[Reactor::S];
-                Reactor::reset_from_normals(z, f);
+            }
+            // the fresh state (Reactor::reset: 2 Philox blocks, 8 table normals) drawn by the whole warp for its finished
+            // lane(s): one pair of normals per helper lane instead of the full draw under a one-lane mask
+            float f[Reactor::S];
+            coop_reset<Reactor>(key, env, tick + 1u, epoch, fin, f);
+            if (fin) {
                 T = f[0]; P = f[1]; cool = f[2]; feed = f[3]; conc = f[4]; cat = f[5]; hx = f[6]; rv = f[7]; level = f[10]; bt = f[11];
                 alarm = false;
                 catd = __fdiv_rn(cat, 100.0f);
@@ -1181,6 +1205,78 @@ __device__ __forceinline__ int reactor_fast_steps(const Rng& key, uint32_t env, 
     return t;
 }
 
+
+// ---- the common tail of the fused rollout kernels: state / episode word / return accumulator back to HBM, per-env
+// outputs, then the violation / episode statistics: warp REDUX + shuffle trees -> one global atomic per slot per block
+template <class Env, bool EXTREMA>
+__device__ __forceinline__ void rollout_epilogue(const RolloutArgs& p, BlockStats& bs, double* sfl, unsigned long long* sext,
+                                                 bool valid, int64_t i, const float (&s)[Env::S], uint32_t ep_st, uint32_t ep_vi, bool latched,
+                                                 typename Env::acc_t ep_ret, float rsum, RolloutAcc& acc,
+                                                 typename Env::acc_t r_lo, typename Env::acc_t r_hi)
+{
+    constexpr int S = Env::S;
+    using acc_t = typename Env::acc_t;
+    // fp32-reward envs (reactor): the reward statistic of this launch is the fp32 per-env sum (K <= a few hundred
+    // terms) widened once, instead of an F2F + DADD per step on the XU / FP64 pipes
+    if constexpr (sizeof(acc_t) == 4) acc.rew_sum = (double)rsum;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < S; ++k) p.state[k * p.pitch + i] = s[k];
+        p.ep_word[i] = epw_make(ep_st, ep_vi, latched ? 1u : 0u);
+        p.ep_return[i] = (double)ep_ret;
+        if (p.accumulate) {
+            if (p.reward_sum) p.reward_sum[i] = add(p.reward_sum[i], rsum);
+            if (p.viol_count) p.viol_count[i] += (int32_t)acc.c_viol;
+            if (p.done_count) p.done_count[i] += (int32_t)acc.c_done;
+        } else {
+            if (p.reward_sum) p.reward_sum[i] = rsum;
+            if (p.viol_count) p.viol_count[i] = (int32_t)acc.c_viol;
+            if (p.done_count) p.done_count[i] = (int32_t)acc.c_done;
+        }
+    }
+    bs.warp_add(NIG_ST_STEPS, acc.c_steps);
+    bs.warp_add(NIG_ST_VIOLATIONS, acc.c_viol);
+    bs.warp_add(NIG_ST_CRITICAL, acc.c_crit);
+#pragma unroll
+    for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k)
+        if (k < p.cons.n) bs.warp_add(NIG_ST_CON0 + k, acc.c_con[k]);
+    if (__any_sync(0xffffffffu, acc.c_ep != 0u)) {
+        bs.warp_add(NIG_ST_EPISODES, acc.c_ep);
+        bs.warp_add(NIG_ST_TERMINATED, acc.c_term);
+        bs.warp_add(NIG_ST_TRUNCATED, acc.c_trunc);
+        bs.warp_add(NIG_ST_SUCCESSES, acc.c_succ);
+        const unsigned long long ls = warp_sum(acc.len_sum), lq = warp_sum(acc.len_sq);
+        const double rs_ = warp_sum(acc.ret_sum), rq = warp_sum(acc.ret_sq);
+        if constexpr (EXTREMA) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const acc_t a_ = __shfl_xor_sync(0xffffffffu, r_lo, o), b_ = __shfl_xor_sync(0xffffffffu, r_hi, o);
+                r_lo = a_ < r_lo ? a_ : r_lo; r_hi = b_ > r_hi ? b_ : r_hi;
+            }
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&p.stats[NIG_ST_EP_LEN_SUM], ls);
+            atomicAdd(&p.stats[NIG_ST_EP_LEN_SQ], lq);
+            atomicAdd(&sfl[0], rs_);
+            atomicAdd(&sfl[1], rq);
+            if constexpr (EXTREMA) {
+                atomicMax(&sext[0], extremum_key(-(double)r_lo));
+                atomicMax(&sext[1], extremum_key((double)r_hi));
+            }
+        }
+    }
+    {
+        const double rw_ = warp_sum(acc.rew_sum);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sfl[2], rw_);
+    }
+    bs.flush(p.stats);
+    if (threadIdx.x < 3 && sfl[threadIdx.x] != 0.0)
+        atomicAdd(reinterpret_cast<double*>(p.stats) + NIG_ST_F_RETURN_SUM + threadIdx.x, sfl[threadIdx.x]);
+    if constexpr (EXTREMA) {
+        if (threadIdx.x < 2 && sext[threadIdx.x] != 0ull) atomicMax(&p.extrema[threadIdx.x], sext[threadIdx.x]);
+    }
+    advance_device_tick(p.tick_dev, (uint32_t)p.n_steps);
+}
 
 // TFNOISE: process noise teacher-forced from p.noise (POLICY_ACTIONS only). The LDG flavour of POLICY_ACTIONS
 // prefetches the next step's actions / noise into registers one step ahead, so the L2 latency of the loads is
@@ -1277,7 +1373,10 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
                          s[0] >= 200.0f && s[0] <= 350.0f && s[1] <= 506625.0f && s[5] >= 1e-30f && s[5] <= 1e30f &&
                          ep_st < (uint32_t)p.max_steps;
         if (__all_sync(0xffffffffu, inv))
-            t_begin = reactor_fast_steps<EXTREMA>(key, env, tick0, p.epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi);
+        {
+            DrawInKernel src{key, env, tick0};
+            t_begin = reactor_fast_steps<EXTREMA>(src, key, env, tick0, p.epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi);
+        }
     }
 
 #pragma unroll 1      // measured: unrolling by 2 (to drop the 12 state moves per step) is 4 % slower
@@ -1379,14 +1478,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
         if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(key, env, tick + 1u, p.epoch, need_reset, s, coop_buf);
     }
 
-    // fp32-reward envs (reactor): the reward statistic of this launch is the fp32 per-env sum (K <= a few hundred
-    // terms) widened once, instead of an F2F + DADD per step on the XU / FP64 pipes
-    if constexpr (sizeof(acc_t) == 4) acc.rew_sum = (double)rsum;
     if (valid) {
-#pragma unroll
-        for (int k = 0; k < S; ++k) p.state[k * p.pitch + i] = s[k];
-        p.ep_word[i] = epw_make(ep_st, ep_vi, latched ? 1u : 0u);
-        p.ep_return[i] = (double)ep_ret;
         if constexpr (POLICY == NIG_POLICY_BASELINE) {
             if (p.pp.baseline.kind == NIG_BASELINE_PID && p.pid_state != nullptr) {
 #pragma unroll
@@ -1396,59 +1488,215 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
                 }
             }
         }
-        if (p.accumulate) {
-            if (p.reward_sum) p.reward_sum[i] = add(p.reward_sum[i], rsum);
-            if (p.viol_count) p.viol_count[i] += (int32_t)acc.c_viol;
-            if (p.done_count) p.done_count[i] += (int32_t)acc.c_done;
-        } else {
-            if (p.reward_sum) p.reward_sum[i] = rsum;
-            if (p.viol_count) p.viol_count[i] = (int32_t)acc.c_viol;
-            if (p.done_count) p.done_count[i] = (int32_t)acc.c_done;
-        }
     }
-    // violation / episode statistics: warp REDUX + shuffle trees -> one global atomic per slot per block
-    bs.warp_add(NIG_ST_STEPS, acc.c_steps);
-    bs.warp_add(NIG_ST_VIOLATIONS, acc.c_viol);
-    bs.warp_add(NIG_ST_CRITICAL, acc.c_crit);
-#pragma unroll
-    for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k)
-        if (k < p.cons.n) bs.warp_add(NIG_ST_CON0 + k, acc.c_con[k]);
-    if (__any_sync(0xffffffffu, acc.c_ep != 0u)) {
-        bs.warp_add(NIG_ST_EPISODES, acc.c_ep);
-        bs.warp_add(NIG_ST_TERMINATED, acc.c_term);
-        bs.warp_add(NIG_ST_TRUNCATED, acc.c_trunc);
-        bs.warp_add(NIG_ST_SUCCESSES, acc.c_succ);
-        const unsigned long long ls = warp_sum(acc.len_sum), lq = warp_sum(acc.len_sq);
-        const double rs_ = warp_sum(acc.ret_sum), rq = warp_sum(acc.ret_sq);
-        if constexpr (EXTREMA) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const acc_t a_ = __shfl_xor_sync(0xffffffffu, r_lo, o), b_ = __shfl_xor_sync(0xffffffffu, r_hi, o);
-                r_lo = a_ < r_lo ? a_ : r_lo; r_hi = b_ > r_hi ? b_ : r_hi;
-            }
-        }
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&p.stats[NIG_ST_EP_LEN_SUM], ls);
-            atomicAdd(&p.stats[NIG_ST_EP_LEN_SQ], lq);
-            atomicAdd(&sfl[0], rs_);
-            atomicAdd(&sfl[1], rq);
-            if constexpr (EXTREMA) {
-                atomicMax(&sext[0], extremum_key(-(double)r_lo));
-                atomicMax(&sext[1], extremum_key((double)r_hi));
-            }
-        }
-    }
+    rollout_epilogue<Env, EXTREMA>(p, bs, sfl, sext, valid, i, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
+}
+
+// ================================================================================================
+// fused K-step rollout, warp-specialised flavour (ChemicalReactor-v0, the benchmark's configuration)
+// ================================================================================================
+// 65,536 envs are 2,048 warps on 592 SM sub-partitions: 3.5 warps each, every one a long dependent chain (Philox rounds ->
+// table normal -> heat balance -> T' -> T'/T -> P' -> relief valve -> reward sum), and the issue slots stay ~30 % empty.
+// The random inputs of a step depend on nothing but (env, tick), so they are split off: in every 96-thread CTA warp 0 is a
+// PRODUCER that draws, for the CTA's 64 envs (two per lane), the step's Philox block, the two table normals and the three
+// uniform actions and stores the six derived values (StepDraw) into a shared-memory ring; warps 1 and 2 are CONSUMERS that
+// run the invariant-specialised physics loop (reactor_fast_steps) with their draws read back from the ring (3 LDS.64 per
+// step). Producer and consumers meet at two mbarriers per ring slot (kWsG steps): `full` (32 producer lanes arrive after
+// their stores) and `empty` (the consumer lanes arrive after their loads). That makes 3,072 resident warps for the same
+// envs (5.2 per sub-partition), takes the longest-latency chain (Philox -> normals) off the consumers' critical path, and
+// the arithmetic is untouched: the same StepDraw values, bit for bit, reach the same instructions.
+// A consumer warp whose envs do not satisfy the loop invariants (or that leaves the loop on a failed guard) steps through
+// the generic path with its own in-place draws, like in rollout_kernel.
+constexpr int kWsG = 4;            // steps per ring slot
+constexpr int kWsSlots = 2;        // ring slots
+constexpr int kWsEnvs = 64;        // envs per CTA
+constexpr int kWsThreads = 96;     // producer warp + two consumer warps
+
+struct DrawFromRing {
+    const float2* lane_base;       // ring + this consumer lane's env index within the CTA; layout [slot][g][3][kWsEnvs]
+    uint64_t* full; uint64_t* empty;
+    __device__ __forceinline__ void wait_full(int t) const
     {
-        const double rw_ = warp_sum(acc.rew_sum);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sfl[2], rw_);
+        const int q = t / kWsG;
+        mbar_wait(&full[q % kWsSlots], (uint32_t)((q / kWsSlots) & 1));
     }
-    bs.flush(p.stats);
-    if (threadIdx.x < 3 && sfl[threadIdx.x] != 0.0)
-        atomicAdd(reinterpret_cast<double*>(p.stats) + NIG_ST_F_RETURN_SUM + threadIdx.x, sfl[threadIdx.x]);
-    if constexpr (EXTREMA) {
-        if (threadIdx.x < 2 && sext[threadIdx.x] != 0ull) atomicMax(&p.extrema[threadIdx.x], sext[threadIdx.x]);
+    __device__ __forceinline__ void arrive_empty(int t) const
+    {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[(t / kWsG) % kWsSlots])) : "memory");
     }
-    advance_device_tick(p.tick_dev, (uint32_t)p.n_steps);
+    __device__ __forceinline__ StepDraw get(int t) const
+    {
+        const int g = t % kWsG;
+        if (g == 0) wait_full(t);
+        const float2* b = lane_base + (((t / kWsG) % kWsSlots) * kWsG + g) * 3 * kWsEnvs;
+        const float2 v0 = b[0], v1 = b[kWsEnvs], v2 = b[2 * kWsEnvs];
+        StepDraw d;
+        d.hp = v0.x; d.cadj = v0.y; d.fadj = v1.x; d.apen = v1.y; d.nz0 = v2.x; d.nz1 = v2.y;
+        return d;
+    }
+    __device__ __forceinline__ void done(int t, int n_steps) const
+    {
+        if (t % kWsG == kWsG - 1 || t == n_steps - 1) arrive_empty(t);
+    }
+    // keep the handshake going without computing (a consumer that left the fast loop at step t_from, whose draw it had
+    // already fetched): the producer runs a fixed schedule and must not be left waiting for a slot
+    __device__ __forceinline__ void drain(int t_from, int n_steps) const
+    {
+        for (int t = t_from; t < n_steps; ++t) {
+            if (t != t_from && t % kWsG == 0) wait_full(t);
+            done(t, n_steps);
+        }
+    }
+};
+
+// one generic step of the uniform-random rollout with in-place draws: the loop body of rollout_kernel for POLICY_UNIFORM
+// (envs without a block-cooperative reset), used by the warp-specialised kernel where a warp cannot take the fast loop
+template <class Env, int CONS, bool EXTREMA>
+__device__ __forceinline__ void rollout_generic_uniform_step(const RolloutArgs& p, const Rng& key, uint32_t env, uint32_t tick, bool valid,
+                                                             float (&s)[Env::S], uint32_t& ep_st, uint32_t& ep_vi, bool& latched,
+                                                             typename Env::acc_t& ep_ret, float& rsum, RolloutAcc& acc,
+                                                             typename Env::acc_t& r_lo, typename Env::acc_t& r_hi)
+{
+    static_assert(Env::COOP_BLOCKS == 0, "block-cooperative resets go through rollout_kernel");
+    constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
+    using acc_t = typename Env::acc_t;
+    float a[A], nz[NZA], ns[S];
+    policy_uniform<Env>(key, env, tick, a);
+    if constexpr (NZ > 0) { typename Env::NoiseGen ng; ng.get(key, env, tick, nz); } else nz[0] = 0.0f;
+    const bool active = valid && !latched;
+    uint32_t st2, vi2, f, vm;
+    acc_t r;
+    step_core_unpacked<Env, CONS, false, true>(p.cons, p.max_steps, s, a, nz, 0u, ep_st, ep_vi, st2, vi2, ns, r, f, vm);
+    if (active) {
+        const bool done = (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED)) != 0;
+        rsum = add(rsum, (float)r);
+        ep_ret = ep_ret + r;
+        if constexpr (sizeof(acc_t) == 8) acc.rew_sum += r;
+        acc.c_steps += 1; acc.c_viol += __popc(vm);
+        acc.c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k)
+            if (k < Env::NB || CONS != CONS_DEFAULT) acc.c_con[k] += (vm >> k) & 1u;
+        ep_st = st2; ep_vi = vi2;
+        if (done) {
+            const unsigned long long len = st2;
+            acc.c_ep += 1; acc.c_done += 1;
+            acc.c_term += (f & NIG_F_TERMINATED) ? 1u : 0u;
+            acc.c_trunc += (f & NIG_F_TRUNCATED) ? 1u : 0u;
+            acc.c_succ += (ep_ret > (acc_t)0) ? 1u : 0u;
+            acc.len_sum += len; acc.len_sq += len * len;
+            acc.ret_sum += (double)ep_ret; acc.ret_sq += (double)ep_ret * (double)ep_ret;
+            if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
+            if (p.auto_reset) {
+                Env::reset(key, env, tick + 1u, p.epoch, s);
+                ep_st = 0u; ep_vi = 0u; ep_ret = (acc_t)0;
+            } else {
+#pragma unroll
+                for (int k = 0; k < S; ++k) s[k] = ns[k];
+                latched = true;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < S; ++k) s[k] = ns[k];
+        }
+    }
+}
+
+template <bool EXTREMA>
+__global__ void __launch_bounds__(kWsThreads, 7) rollout_reactor_ws_kernel(const __grid_constant__ RolloutArgs p)
+{
+    using Env = Reactor;
+    constexpr int S = Env::S;
+    __shared__ unsigned int sstat[NIG_STATS_SLOTS];
+    __shared__ double sfl[4];
+    __shared__ unsigned long long sext[2];
+    __shared__ float4 s_tab[NIG_NORMAL_TAB_N];
+    __shared__ alignas(16) float2 ring[kWsSlots * kWsG * 3 * kWsEnvs];
+    __shared__ alignas(8) uint64_t full[kWsSlots], empty[kWsSlots];
+    __shared__ int fast_warp[2];
+    BlockStats bs;
+    if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
+    if constexpr (EXTREMA) { if (threadIdx.x < 2) sext[threadIdx.x] = 0ull; }
+    normal_table_to_smem(s_tab);
+    const Rng key(p.key, s_tab);
+    bs.init(sstat);                              // (synchronises the CTA)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool producer = warp == 0;
+    const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
+    // consumer (warp 1, 2): env blockIdx * 64 + (warp - 1) * 32 + lane; the producer's values below are unused
+    const int64_t i = (int64_t)blockIdx.x * kWsEnvs + (producer ? 0 : (warp - 1) * 32) + lane;
+    const bool valid = !producer && i < p.n;
+    const int64_t ic = valid ? i : 0;
+    const uint32_t env = p.env0 + (uint32_t)ic;
+
+    float s[S];
+    uint32_t ep_st = 0, ep_vi = 0;
+    bool latched = false;
+    float ep_ret = 0.0f, rsum = 0.0f, r_lo = INFINITY, r_hi = -INFINITY;
+    RolloutAcc acc;
+#pragma unroll
+    for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) acc.c_con[k] = 0;
+    bool fast = false;
+    if (!producer) {
+#pragma unroll
+        for (int k = 0; k < S; ++k) s[k] = p.state[k * p.pitch + ic];
+        const uint32_t w0 = p.ep_word[ic];
+        ep_st = epw_step(w0); ep_vi = epw_viol(w0);
+        latched = (w0 >> 31) != 0u;
+        ep_ret = (float)p.ep_return[ic];
+        const bool inv = valid && !latched && p.auto_reset != 0 && __float_as_uint(s[8]) == 0u &&
+                         (__float_as_uint(s[9]) == 0u || __float_as_uint(s[9]) == 0x3f800000u) &&
+                         s[0] >= 200.0f && s[0] <= 350.0f && s[1] <= 506625.0f && s[5] >= 1e-30f && s[5] <= 1e30f &&
+                         ep_st < (uint32_t)p.max_steps;
+        fast = __all_sync(0xffffffffu, inv);
+        if (lane == 0) fast_warp[warp - 1] = fast ? 1 : 0;
+    } else {
+#pragma unroll
+        for (int k = 0; k < S; ++k) s[k] = 0.0f;
+    }
+    __syncthreads();
+    const int n_fast = fast_warp[0] + fast_warp[1];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < kWsSlots; ++k) { mbar_init(&full[k], 32); mbar_init(&empty[k], 32 * (n_fast > 0 ? n_fast : 1)); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (producer) {
+        if (n_fast > 0) {
+            const uint32_t env_a = p.env0 + (uint32_t)((int64_t)blockIdx.x * kWsEnvs + lane), env_b = env_a + 32u;
+            const int n_slots = (p.n_steps + kWsG - 1) / kWsG;
+#pragma unroll 1
+            for (int q = 0; q < n_slots; ++q) {
+                const int slot = q % kWsSlots;
+                if (q >= kWsSlots) mbar_wait(&empty[slot], (uint32_t)(((q / kWsSlots) - 1) & 1));
+#pragma unroll 1
+                for (int g = 0; g < kWsG; ++g) {
+                    const int t = q * kWsG + g;
+                    if (t >= p.n_steps) break;
+                    float2* b = ring + (slot * kWsG + g) * 3 * kWsEnvs + lane;
+                    const StepDraw da = reactor_step_draw(key, env_a, tick0 + (uint32_t)t);
+                    const StepDraw db = reactor_step_draw(key, env_b, tick0 + (uint32_t)t);
+                    b[0] = make_float2(da.hp, da.cadj); b[kWsEnvs] = make_float2(da.fadj, da.apen); b[2 * kWsEnvs] = make_float2(da.nz0, da.nz1);
+                    b[32] = make_float2(db.hp, db.cadj); b[kWsEnvs + 32] = make_float2(db.fadj, db.apen); b[2 * kWsEnvs + 32] = make_float2(db.nz0, db.nz1);
+                }
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[slot])) : "memory");
+            }
+        }
+    } else {
+        int t_begin = 0;
+        if (fast) {
+            DrawFromRing src{ring + (warp - 1) * 32 + lane, full, empty};
+            t_begin = reactor_fast_steps<EXTREMA>(src, key, env, tick0, p.epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi);
+            if (t_begin < p.n_steps) src.drain(t_begin, p.n_steps);
+        }
+#pragma unroll 1
+        for (int t = t_begin; t < p.n_steps; ++t)
+            rollout_generic_uniform_step<Env, CONS_DEFAULT, EXTREMA>(p, key, env, tick0 + (uint32_t)t, valid, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
+    }
+    rollout_epilogue<Env, EXTREMA>(p, bs, sfl, sext, valid, i, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
 }
 
 // ================================================================================================

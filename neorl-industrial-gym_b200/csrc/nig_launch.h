@@ -12,6 +12,7 @@ struct RolloutLaunch {
     bool tf_noise;     // teacher-forced process noise (POLICY_ACTIONS only)
     int block;         // threads per CTA: 32, 64 or 128
     bool extrema;      // nig_track_extrema: the kernel flavour that also keeps return_min / return_max
+    bool ws;           // ChemicalReactor-v0, uniform policy, default constraints: the warp-specialised kernel (producer / consumers)
 };
 
 cudaError_t launch_step(int kind, int vec, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st);

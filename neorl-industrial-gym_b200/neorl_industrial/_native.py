@@ -126,6 +126,10 @@ SYMBOLS = {
     "nig_stats_ptr": (C.c_int, [_VP, C.POINTER(_VP)]),
     "nig_read_stats": (C.c_int, [_VP, _VP, _VP]),
     "nig_clear_stats": (C.c_int, [_VP, _VP]),
+    "nig_allreduce_stats": (C.c_int, [_VP, _VP, _VP]),
+    "nig_nccl_unique_id": (C.c_int, [_VP]),
+    "nig_nccl_comm_init": (C.c_int, [C.POINTER(_VP), _I32, _VP, _I32, _I32]),
+    "nig_nccl_comm_destroy": (C.c_int, [_VP]),
     "nig_track_extrema": (C.c_int, [_VP, C.c_int32]),
     "nig_track_returns": (C.c_int, [_VP, C.c_int32]),
     "nig_extrema_ptr": (C.c_int, [_VP, C.POINTER(_VP)]),

@@ -63,14 +63,48 @@ def allreduce_stats(counters, sums, group=None):
     return counters, sums
 
 
-def allreduce_device_stats(native, group=None):
-    """In-place NCCL all-reduce of a NativeEnv's device stats block (no host staging): int64 counters and fp64 sums."""
+_own_comm = {}
+
+
+def nccl_comm(device_index: int, group=None) -> int:
+    """An ``ncclComm_t`` (as an int) over the ranks of ``group`` for ``nig_allreduce_stats``: a communicator of this
+    module's own (rank 0's NCCL id is handed round through the torch process group -- any backend --, then
+    ``ncclCommInitRank``), cached per (group, device). Being separate from torch's communicators, its collectives can be
+    queued on any stream without interfering with torch's."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import _native as N
+    key = (id(group), int(device_index))
+    if key not in _own_comm:
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = [None]
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            N.check(N.lib().nig_nccl_unique_id(C.cast(buf, C.c_void_p)))
+            ident = [bytes(buf)]
+        dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        comm = C.c_void_p()
+        N.check(N.lib().nig_nccl_comm_init(C.byref(comm), world, C.c_char_p(ident[0]), rank, int(device_index)))
+        _own_comm[key] = comm.value
+    return _own_comm[key]
+
+
+def allreduce_device_stats(native, group=None, stream=None):
+    """In-place all-reduce of a NativeEnv's device stats block over the ranks (no host staging): int64 counters and fp64
+    sums (SUM) and the return-extremum keys (MAX). On NCCL process groups this is ONE grouped launch through the C ABI
+    (``nig_allreduce_stats``) on the current torch stream; otherwise one ``torch.distributed`` all-reduce per part."""
     import torch
     import torch.distributed as dist
+    from . import _native as N
     view = native.stats_tensor()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(view[:24], group=group)
-        dist.all_reduce(view[24:].view(torch.float64), group=group)
+        if dist.get_backend(group) == "nccl":
+            st = native._stream(stream)
+            N.check(N.lib().nig_allreduce_stats(native._h, nccl_comm(native.device, group), st))
+        else:
+            dist.all_reduce(view[:24], group=group)
+            dist.all_reduce(view[24:].view(torch.float64), group=group)
+            dist.all_reduce(native.extrema_tensor(), op=dist.ReduceOp.MAX, group=group)
     return view
 
 

@@ -253,3 +253,33 @@ def test_seeded_reset_is_reproducible(mods):
     b, _ = venv.reset(seed=7)
     assert torch.equal(a, b)
     venv.close()
+
+
+def test_allreduce_stats_through_the_c_abi_single_rank(mods):
+    """nig_allreduce_stats with a communicator made by the C ABI's own helpers (ncclGetUniqueId / ncclCommInitRank through
+    the dlopen()ed libnccl): on a one-rank communicator the grouped all-reduce (int64 SUM, fp64 SUM, extrema MAX) must leave
+    the block unchanged. (World sizes > 1: tests/_nccl_worker.py under torchrun.)"""
+    ni, N, O, torch = mods
+    lib = N.lib()
+    ident = (C.c_char * 128)()
+    N.check(lib.nig_nccl_unique_id(C.cast(ident, C.c_void_p)))
+    comm = C.c_void_p()
+    N.check(lib.nig_nccl_comm_init(C.byref(comm), 1, C.cast(ident, C.c_void_p), 0, 0))
+    env = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, 4096, device=0, seed=3, max_episode_steps=30)
+    env.reset_device()
+    env.track_extrema(True)
+    env.rollout_device(100, N.POLICY_UNIFORM)
+    torch.cuda.synchronize()
+    before_c, before_f = env.read_stats()
+    before_x = env.read_extrema()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        N.check(lib.nig_allreduce_stats(env._h, comm, st))
+    torch.cuda.synchronize()
+    after_c, after_f = env.read_stats()
+    assert before_c.tolist() == after_c.tolist() and before_f.tolist() == after_f.tolist() and before_c[N.ST_EPISODES] > 0
+    assert env.read_extrema() == before_x and before_x[0] is not None
+    with pytest.raises(ValueError):
+        N.check(lib.nig_allreduce_stats(env._h, None, st))
+    N.check(lib.nig_nccl_comm_destroy(comm))
+    env.close()

@@ -9,5 +9,5 @@ mkdir -p ../_ab
 NV="/usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC,-fvisibility=hidden"
 $NV "$@" -c -o ../_ab/nig_rollout_reactor_$name.o nig_rollout_reactor.cu
 objs=$(ls ../build/*.o | grep -v nig_rollout_reactor.o)
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -Xcompiler -fPIC -o ../_ab/libnig_b200_$name.so $objs ../_ab/nig_rollout_reactor_$name.o
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -cudart static -Xcompiler -fPIC -o ../_ab/libnig_b200_$name.so $objs ../_ab/nig_rollout_reactor_$name.o -ldl
 echo built ../_ab/libnig_b200_$name.so
