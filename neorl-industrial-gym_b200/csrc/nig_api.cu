@@ -103,6 +103,18 @@ struct nig_env {
     // copies of one slice overlap the stepping of the others (and the slices' launches fill each other's tails)
     cudaStream_t slice_stream[kMaxHostSlices];
     cudaEvent_t slice_done[kMaxHostSlices], slice_begin;
+    // ... and that whole pipeline captured once in a CUDA graph and replayed (one driver call per nig_rollout_host instead
+    // of ~25 per slice): the kernels of a captured pipeline take tick / epoch as offsets from d_tickbase, which the graph's
+    // first node refreshes from the pinned word h_tickbase
+    cudaGraphExec_t host_graph;
+    struct HostGraphKey {
+        const void* ptr[5]; int32_t T, K, policy, reset, slices; int64_t launches; uint64_t config; nig_policy_params_t pp;
+    } host_graph_key;
+    uint32_t *d_tickbase, *h_tickbase;
+    bool graph_mode;            // set while a pipeline is being captured: rollout_range / reset_range emit base-relative counters
+    uint32_t graph_tick0;       // tick at the start of the call being captured
+    uint64_t config_version;    // bumped by every setter whose value is baked into kernel arguments (invalidates host_graph)
+    int host_graph_enable;      // NIG_HOST_GRAPH (default 1)
     uint32_t* cons_masks;       // device copy of the NIG_CON_BOUND one-hot masks (ConsParams::masks)
     uint32_t* tick_dev;         // device-tick mode (CUDA-graph capture): [0] tick, [1] finished-CTA counter; null = host tick
     double* pid_state;          // [2][A][pitch] PID integral / previous error of NIG_POLICY_BASELINE (lazily allocated, zeroed)
@@ -294,7 +306,8 @@ int state_to_aos_range(nig_env* e, float* ext_aos, int64_t i0, int64_t ns, cudaS
 int reset_range(nig_env* e, const float* init_aos, int64_t i0, int64_t ns, uint32_t epoch, cudaStream_t s)
 {
     ResetArgs a{e->state + i0, e->ep_word + i0, e->ep_return + i0, ns, e->pitch, (uint32_t)e->cfg.env_id_offset + (uint32_t)i0, e->tick, epoch,
-                e->tick_dev, e->key, nullptr, init_aos ? init_aos + i0 * e->S : nullptr, 1};
+                e->tick_dev, e->key, nullptr, init_aos ? init_aos + i0 * e->S : nullptr, 1, nullptr};
+    if (e->graph_mode) { a.tick = 0u; a.epoch = 0u; a.tick_base = e->d_tickbase; }
     e->launches++;
     NIG_CUDA(nig::launch_reset(e->kind, a, s));
     return NIG_OK;
@@ -356,6 +369,7 @@ int rollout_range(nig_env* e, const nig_rollout_t* r, cudaStream_t stream, int64
     a.pid_state = e->pid_state ? e->pid_state + i0 : nullptr;
     a.extrema = e->extrema;
     a.stats = e->stats; a.cons = e->cons;
+    if (e->graph_mode) { a.tick = tick - e->graph_tick0; a.epoch = 0u; a.tick_base = e->d_tickbase; }
     CUtensorMap map;
     memset(&map, 0, sizeof map);
     const bool tma = r->policy == NIG_POLICY_ACTIONS && (r->flags & NIG_ROLLOUT_USE_TMA) && !e->track_extrema && i0 == 0 && ns == e->n;
@@ -397,14 +411,11 @@ int sliced_launches(nig_env* e, const nig_rollout_t& proto, int32_t T, int32_t K
     return NIG_OK;
 }
 
+int prepare_slices(nig_env* e, int slices);
 // create the slice streams / events on first use and make slices 0..slices-1 wait for the work queued on `st`
 int fork_slices(nig_env* e, int slices, cudaStream_t st)
 {
-    if (!e->slice_begin) NIG_CUDA(cudaEventCreateWithFlags(&e->slice_begin, cudaEventDisableTiming));
-    for (int k = 0; k < slices; ++k) {
-        if (!e->slice_stream[k]) NIG_CUDA(cudaStreamCreateWithFlags(&e->slice_stream[k], cudaStreamNonBlocking));
-        if (!e->slice_done[k]) NIG_CUDA(cudaEventCreateWithFlags(&e->slice_done[k], cudaEventDisableTiming));
-    }
+    if (int rc = prepare_slices(e, slices)) return rc;
     NIG_CUDA(cudaEventRecord(e->slice_begin, st));
     for (int k = 0; k < slices; ++k) NIG_CUDA(cudaStreamWaitEvent(e->slice_stream[k], e->slice_begin, 0));
     return NIG_OK;
@@ -419,6 +430,70 @@ int join_slices(nig_env* e, int slices, cudaStream_t st)
         NIG_CUDA(cudaStreamWaitEvent(st, e->slice_done[k], 0));
     }
     return NIG_OK;
+}
+
+// create the slice streams / events (outside any capture)
+int prepare_slices(nig_env* e, int slices)
+{
+    if (!e->slice_begin) NIG_CUDA(cudaEventCreateWithFlags(&e->slice_begin, cudaEventDisableTiming));
+    for (int k = 0; k < slices; ++k) {
+        if (!e->slice_stream[k]) NIG_CUDA(cudaStreamCreateWithFlags(&e->slice_stream[k], cudaStreamNonBlocking));
+        if (!e->slice_done[k]) NIG_CUDA(cudaEventCreateWithFlags(&e->slice_done[k], cudaEventDisableTiming));
+    }
+    return NIG_OK;
+}
+
+static bool is_pinned_or_null(const void* p)
+{
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost) return true;
+    (void)cudaGetLastError();
+    return false;
+}
+bool host_buffers_pinned(const nig_rollout_host_t* r)
+{
+    return is_pinned_or_null(r->init_states) && is_pinned_or_null(r->reward_sum) && is_pinned_or_null(r->viol_count) &&
+           is_pinned_or_null(r->done_count) && is_pinned_or_null(r->final_obs);
+}
+
+// nig_rollout_host over env slices, enqueued on st and the slice streams (forked from / joined back to st): slice s copies its
+// initial states in, resets, runs its ceil(T / K) fused launches and copies its results out independently of the others, so
+// the PCIe copies overlap the stepping and a slice's next launch fills the SMs another slice's tail leaves idle. Trajectories
+// do not depend on the slicing (random streams are keyed by global env id and tick). Capturable (no synchronisation inside).
+int enqueue_sliced_host(nig_env* e, const nig_rollout_host_t* r, int slices, int64_t per, int32_t T, int32_t K, bool reset, cudaStream_t st)
+{
+    const int64_t n = e->n;
+    int rc;
+    if ((rc = fork_slices(e, slices, st)) != NIG_OK) return rc;
+    for (int k = 0; k < slices; ++k) {
+        const int64_t i0 = k * per, ns = std::min<int64_t>(per, n - i0);
+        if (ns <= 0) continue;
+        cudaStream_t ss = e->slice_stream[k];
+        if (r->init_states)
+            NIG_CUDA(cudaMemcpyAsync(e->h_reset + i0 * e->S, r->init_states + i0 * e->S, (size_t)ns * e->S * sizeof(float), cudaMemcpyHostToDevice, ss));
+        if (reset && (rc = reset_range(e, r->init_states ? e->h_reset : nullptr, i0, ns, e->epoch, ss)) != NIG_OK) { join_slices(e, slices, st); return rc; }
+    }
+    nig_rollout_t d;
+    memset(&d, 0, sizeof d);
+    d.policy = r->policy; d.pp = r->pp;
+    d.reward_sum = r->reward_sum ? e->h_reward : nullptr;
+    d.viol_count = r->viol_count ? e->h_i32a : nullptr;
+    d.done_count = r->done_count ? e->h_i32b : nullptr;
+    if ((rc = sliced_launches(e, d, T, K, slices, per)) != NIG_OK) { join_slices(e, slices, st); return rc; }
+    for (int k = 0; k < slices; ++k) {
+        const int64_t i0 = k * per, ns = std::min<int64_t>(per, n - i0);
+        if (ns <= 0) continue;
+        cudaStream_t ss = e->slice_stream[k];
+        if (r->final_obs) {
+            if ((rc = state_to_aos_range(e, e->h_obs, i0, ns, ss)) != NIG_OK) { join_slices(e, slices, st); return rc; }
+            NIG_CUDA(cudaMemcpyAsync(r->final_obs + i0 * e->S, e->h_obs + i0 * e->S, (size_t)ns * e->S * sizeof(float), cudaMemcpyDeviceToHost, ss));
+        }
+        if (r->reward_sum) NIG_CUDA(cudaMemcpyAsync(r->reward_sum + i0, e->h_reward + i0, (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, ss));
+        if (r->viol_count) NIG_CUDA(cudaMemcpyAsync(r->viol_count + i0, e->h_i32a + i0, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ss));
+        if (r->done_count) NIG_CUDA(cudaMemcpyAsync(r->done_count + i0, e->h_i32b + i0, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ss));
+    }
+    return join_slices(e, slices, st);
 }
 
 inline int64_t slice_size(int64_t n, int slices) { return ((n + slices - 1) / slices + 127) / 128 * 128; }
@@ -491,6 +566,8 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     if (const char* v = getenv("NIG_ROLLOUT_BLOCK")) e->rollout_block = atoi(v);
     e->rollout_ws = 0;
     if (const char* v = getenv("NIG_ROLLOUT_WS")) e->rollout_ws = atoi(v);
+    e->host_graph_enable = 1;
+    if (const char* v = getenv("NIG_HOST_GRAPH")) e->host_graph_enable = atoi(v);
     e->step_pipe = 1;
     if (const char* v = getenv("NIG_STEP_PIPE")) e->step_pipe = atoi(v);
     e->zero_copy = 1;
@@ -524,6 +601,9 @@ int nig_destroy(nig_env_t* e)
 {
     if (!e) return NIG_OK;
     DeviceGuard guard(e->cfg.device);
+    if (e->host_graph) cudaGraphExecDestroy(e->host_graph);
+    if (e->h_tickbase) cudaFreeHost(e->h_tickbase);
+    cudaFree(e->d_tickbase);
     cudaFree(e->state); cudaFree(e->ep_word); cudaFree(e->ep_return); cudaFree(e->stats);
     cudaFree(e->h_actions); cudaFree(e->h_noise); cudaFree(e->h_reset); cudaFree(e->h_obs); cudaFree(e->h_next_obs);
     cudaFree(e->h_reward); cudaFree(e->h_hostmask); cudaFree(e->h_flags); cudaFree(e->h_viol); cudaFree(e->h_mask);
@@ -550,6 +630,7 @@ int64_t nig_launch_count(const nig_env_t* e) { return e ? e->launches : 0; }
 
 int nig_set_constraints(nig_env_t* e, const nig_constraint_t* cons, int32_t n)
 {
+    if (e) e->config_version++;
     if (!e) return fail(NIG_ERR_INVALID, "null env handle");
     if (n > 0 && !cons) return fail(NIG_ERR_INVALID, "null constraint array");
     const int rc = validate_constraints(e->kind, cons, n);
@@ -795,40 +876,58 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
     // resets, runs its ceil(T / K) fused launches and copies its results out independently of the others, so the PCIe
     // copies overlap the stepping, and a slice's next launch fills the SMs another slice's tail leaves idle. Trajectories
     // do not depend on the slicing (random streams are keyed by global env id and tick).
-    const int slices = host_slices(e, forced);
+    const bool use_graph = e->host_graph_enable != 0 && !forced && !e->tick_dev && host_buffers_pinned(r);
+    const int slices = host_slices(e, forced, 4);      // (8 measured slower than 4 with and without the graph: tools/host_path_breakdown.py)
     if (slices > 1) {
         const int64_t per = slice_size((int64_t)n, slices);
-        if ((rc = fork_slices(e, slices, st)) != NIG_OK) return rc;
         const bool reset = r->reset_first || r->init_states;
         if (reset) e->epoch += 1;
-        for (int k = 0; k < slices; ++k) {
-            const int64_t i0 = k * per, ns = std::min<int64_t>(per, (int64_t)n - i0);
-            if (ns <= 0) continue;
-            cudaStream_t ss = e->slice_stream[k];
-            if (r->init_states)
-                NIG_CUDA(cudaMemcpyAsync(e->h_reset + i0 * e->S, r->init_states + i0 * e->S, (size_t)ns * e->S * sizeof(float), cudaMemcpyHostToDevice, ss));
-            if (reset && (rc = reset_range(e, r->init_states ? e->h_reset : nullptr, i0, ns, e->epoch, ss)) != NIG_OK) { join_slices(e, slices, st); return rc; }
-        }
-        nig_rollout_t d;
-        memset(&d, 0, sizeof d);
-        d.policy = r->policy; d.pp = r->pp;
-        d.reward_sum = r->reward_sum ? e->h_reward : nullptr;
-        d.viol_count = r->viol_count ? e->h_i32a : nullptr;
-        d.done_count = r->done_count ? e->h_i32b : nullptr;
-        if ((rc = sliced_launches(e, d, T, K, slices, per)) != NIG_OK) { join_slices(e, slices, st); return rc; }
-        for (int k = 0; k < slices; ++k) {
-            const int64_t i0 = k * per, ns = std::min<int64_t>(per, (int64_t)n - i0);
-            if (ns <= 0) continue;
-            cudaStream_t ss = e->slice_stream[k];
-            if (r->final_obs) {
-                if ((rc = state_to_aos_range(e, e->h_obs, i0, ns, ss)) != NIG_OK) { join_slices(e, slices, st); return rc; }
-                NIG_CUDA(cudaMemcpyAsync(r->final_obs + i0 * e->S, e->h_obs + i0 * e->S, (size_t)ns * e->S * sizeof(float), cudaMemcpyDeviceToHost, ss));
+        if (use_graph) {
+            // ---- the whole sliced pipeline as ONE graph launch: captured on first use (and again whenever a buffer address,
+            // the horizon, the policy or a baked-in setting changes), replayed afterwards with fresh tick / epoch words
+            nig_env::HostGraphKey key;
+            memset(&key, 0, sizeof key);
+            key.ptr[0] = r->init_states; key.ptr[1] = r->reward_sum; key.ptr[2] = r->viol_count; key.ptr[3] = r->done_count; key.ptr[4] = r->final_obs;
+            key.T = T; key.K = K; key.policy = r->policy; key.reset = reset ? 1 : 0; key.slices = slices;
+            key.config = e->config_version; key.pp = r->pp;
+            if (!e->h_tickbase) {
+                NIG_CUDA(cudaHostAlloc((void**)&e->h_tickbase, 2 * sizeof(uint32_t), cudaHostAllocPortable));
+                NIG_CUDA(cudaMalloc((void**)&e->d_tickbase, 2 * sizeof(uint32_t)));
             }
-            if (r->reward_sum) NIG_CUDA(cudaMemcpyAsync(r->reward_sum + i0, e->h_reward + i0, (size_t)ns * sizeof(float), cudaMemcpyDeviceToHost, ss));
-            if (r->viol_count) NIG_CUDA(cudaMemcpyAsync(r->viol_count + i0, e->h_i32a + i0, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ss));
-            if (r->done_count) NIG_CUDA(cudaMemcpyAsync(r->done_count + i0, e->h_i32b + i0, (size_t)ns * sizeof(int32_t), cudaMemcpyDeviceToHost, ss));
-            NIG_CUDA(cudaEventRecord(e->slice_done[k], ss));
-            NIG_CUDA(cudaStreamWaitEvent(st, e->slice_done[k], 0));
+            key.launches = e->host_graph ? e->host_graph_key.launches : 0;
+            if (!e->host_graph || memcmp(&key, &e->host_graph_key, sizeof key) != 0) {
+                if (e->host_graph) { cudaGraphExecDestroy(e->host_graph); e->host_graph = nullptr; }
+                if ((rc = prepare_slices(e, slices)) != NIG_OK) return rc;
+                {   // argument checks and lazy allocations (PID controller state) happen before the capture starts
+                    nig_rollout_t probe;
+                    memset(&probe, 0, sizeof probe);
+                    probe.policy = r->policy; probe.pp = r->pp; probe.n_steps = K;
+                    if ((rc = rollout_checks(e, &probe)) != NIG_OK) return rc;
+                }
+                const uint32_t tick0 = e->tick;
+                const int64_t launches0 = e->launches;
+                cudaGraph_t graph = nullptr;
+                NIG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+                e->graph_mode = true; e->graph_tick0 = tick0;
+                cudaError_t ce = cudaMemcpyAsync(e->d_tickbase, e->h_tickbase, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+                rc = ce == cudaSuccess ? enqueue_sliced_host(e, r, slices, per, T, K, reset, st) : fail(NIG_ERR_CUDA, "capturing the tick copy failed: %s", cudaGetErrorString(ce));
+                e->graph_mode = false;
+                ce = cudaStreamEndCapture(st, &graph);
+                key.launches = e->launches - launches0;
+                e->tick = tick0; e->launches = launches0;
+                if (rc != NIG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess) return fail(NIG_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&e->host_graph, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) { e->host_graph = nullptr; return fail(NIG_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce)); }
+                e->host_graph_key = key;
+            }
+            e->h_tickbase[0] = e->tick; e->h_tickbase[1] = e->epoch;
+            NIG_CUDA(cudaGraphLaunch(e->host_graph, st));
+            e->tick += (uint32_t)T;
+            e->launches += e->host_graph_key.launches;
+        } else {
+            if ((rc = enqueue_sliced_host(e, r, slices, per, T, K, reset, st)) != NIG_OK) return rc;
         }
         unsigned long long hs[NIG_STATS_SLOTS];
         if (r->counters24 || r->sums8) NIG_CUDA(cudaMemcpyAsync(hs, e->stats, sizeof hs, cudaMemcpyDeviceToHost, st));
@@ -1090,6 +1189,7 @@ int nig_set_tick(nig_env_t* e, uint32_t tick, uint32_t epoch)
 
 int nig_use_device_tick(nig_env_t* e, int32_t enable)
 {
+    if (e) e->config_version++;
     NIG_CHECK_ENV(e);
     NIG_CUDA(cudaDeviceSynchronize());
     if (enable && !e->tick_dev) {
@@ -1109,6 +1209,7 @@ int nig_set_seed(nig_env_t* e, uint64_t seed)
 {
     if (!e) return fail(NIG_ERR_INVALID, "null env handle");
     e->cfg.seed = seed;
+    e->config_version++;
     e->key = RngKey{(uint32_t)seed, (uint32_t)(seed >> 32)};
     // a new key starts its streams at their origin: reset(seed = s) is reproducible whatever the handle did before
     return nig_set_tick(e, 0u, 0u);
@@ -1240,6 +1341,7 @@ int nig_clear_stats(nig_env_t* e, void* stream)
 
 int nig_track_returns(nig_env_t* e, int32_t on)
 {
+    if (e) e->config_version++;
     NIG_CHECK_ENV(e);
     e->track_returns = on != 0;
     return NIG_OK;
@@ -1247,6 +1349,7 @@ int nig_track_returns(nig_env_t* e, int32_t on)
 
 int nig_track_extrema(nig_env_t* e, int32_t on)
 {
+    if (e) e->config_version++;
     NIG_CHECK_ENV(e);
     e->track_extrema = on != 0;
     return NIG_OK;

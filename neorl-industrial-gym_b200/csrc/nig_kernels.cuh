@@ -311,6 +311,11 @@ __device__ __forceinline__ uint32_t load_tick(const uint32_t* tick_dev, uint32_t
 {
     return tick_dev ? *reinterpret_cast<const volatile uint32_t*>(tick_dev) : host_tick;
 }
+// Third way of supplying the counters (captured host-buffer pipelines, nig_rollout_host): tick_base -> {tick, epoch} in device
+// memory, refreshed by the graph's first node from a pinned host word on every replay; the kernel arguments then hold
+// OFFSETS from that base (the slices of one call run concurrently, so the device tick above cannot serve them).
+__device__ __forceinline__ uint32_t base_tick(const uint32_t* tick_base) { return tick_base ? __ldg(tick_base) : 0u; }
+__device__ __forceinline__ uint32_t base_epoch(const uint32_t* tick_base) { return tick_base ? __ldg(tick_base + 1) : 0u; }
 __device__ __forceinline__ void advance_device_tick(uint32_t* tick_dev, uint32_t by)
 {
     if (tick_dev == nullptr) return;                // uniform
@@ -441,17 +446,33 @@ struct StepEpisodeStats {
     }
 };
 
-// finished-episode return / length sums of a warp -> the global stats block (rare: only warps that finished an episode)
-__device__ __forceinline__ void flush_episode_stats(BlockStats& bs, unsigned long long* stats, const StepEpisodeStats& eps)
+// finished-episode return / length sums of a warp -> per-CTA shared staging (EpisodeStaging) -> one global atomic per slot
+// per CTA (PowerGrid finishes an episode in ~18 % of its envs every step: per-warp global atomics on four addresses cost the
+// 1M-env single step 48 us)
+struct EpisodeStaging {
+    unsigned long long len[2];      // EP_LEN_SUM, EP_LEN_SQ
+    double ret[2];                  // RETURN_SUM, RETURN_SQ
+};
+__device__ __forceinline__ void episode_staging_init(EpisodeStaging* st)
+{
+    if (threadIdx.x < 2) { st->len[threadIdx.x] = 0ull; st->ret[threadIdx.x] = 0.0; }      // (before a __syncthreads of the caller)
+}
+__device__ __forceinline__ void stage_episode_stats(BlockStats& bs, EpisodeStaging* st, const StepEpisodeStats& eps)
 {
     bs.warp_add(NIG_ST_SUCCESSES, eps.c_succ);
     const unsigned long long ls = warp_sum(eps.len_sum), lq = warp_sum(eps.len_sq);
     const double rs_ = warp_sum(eps.ret_sum), rq = warp_sum(eps.ret_sq);
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&stats[NIG_ST_EP_LEN_SUM], ls);
-        atomicAdd(&stats[NIG_ST_EP_LEN_SQ], lq);
-        atomicAdd(reinterpret_cast<double*>(stats) + NIG_ST_F_RETURN_SUM, rs_);
-        atomicAdd(reinterpret_cast<double*>(stats) + NIG_ST_F_RETURN_SQ, rq);
+        atomicAdd(&st->len[0], ls); atomicAdd(&st->len[1], lq);
+        atomicAdd(&st->ret[0], rs_); atomicAdd(&st->ret[1], rq);
+    }
+}
+// after a __syncthreads that follows the last stage_episode_stats of the CTA (BlockStats::flush has one)
+__device__ __forceinline__ void flush_episode_staging(unsigned long long* stats, const EpisodeStaging* st)
+{
+    if (threadIdx.x < 2) {
+        if (st->len[threadIdx.x]) atomicAdd(&stats[threadIdx.x == 0 ? NIG_ST_EP_LEN_SUM : NIG_ST_EP_LEN_SQ], st->len[threadIdx.x]);
+        if (st->ret[threadIdx.x] != 0.0) atomicAdd(reinterpret_cast<double*>(stats) + NIG_ST_F_RETURN_SUM + threadIdx.x, st->ret[threadIdx.x]);
     }
 }
 
@@ -510,17 +531,24 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
     using acc_t = typename Env::acc_t;
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
+    __shared__ EpisodeStaging estage;
     __shared__ float coop_buf[CoopSmem<Env>::floats];
     __shared__ float aos_tile[VEC == 1 ? (kThreads / 32) * 32 * (S + 1) : 1];      // AoS transposes (VEC == 1 only)
     float* my_tile = aos_tile + (VEC == 1 ? (threadIdx.x >> 5) * 32 * (S + 1) : 0);
     BlockStats bs;
+    episode_staging_init(&estage);
     bs.init(sstat);
     const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
     const Rng key(p.key, g_normal_tab);        // one-tile CTA: the L1-cached global table
 
     const int64_t i0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
     unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0, c_con = 0;  // c_con: 4 bits/constraint
-    StepEpisodeStats eps;
+    // an env finishes at most one episode per launch: its return / length are kept per element and only summed in the
+    // epilogue, where nothing else is live (a running StepEpisodeStats cost PowerGrid 40 B of spills and 30 % of its rate)
+    double fin_ret[VEC];
+    uint32_t fin_len[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { fin_ret[e] = 0.0; fin_len[e] = 0u; }
     if (i0 < p.pitch) {
         float sv[S][VEC], av[A][VEC], nzv[NZA][VEC], rs[S][VEC];
         load_rows<S, VEC>(p.state, p.pitch, p.n, i0, false, sv);
@@ -566,7 +594,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             bool need_reset = false;
             if (p.ep_return && active) {
                 er = er + r;
-                if (done) eps.episode((double)er, (unsigned long long)epw_step(w));
+                if (done) { fin_ret[e] = (double)er; fin_len[e] = epw_step(w); }
                 p.ep_return[i] = (done && p.auto_reset) ? 0.0 : (double)er;
             }
 #pragma unroll
@@ -659,9 +687,16 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
         bs.warp_add(NIG_ST_CRITICAL, c_crit);
         bs.warp_add(NIG_ST_VIOLATIONS, c_viol);
         for (int k = 0; k < p.cons.n; ++k) bs.warp_add(NIG_ST_CON0 + k, (c_con >> (4 * k)) & 0xfu);
-        if (p.ep_return && __any_sync(0xffffffffu, c_ep != 0u)) flush_episode_stats(bs, p.stats, eps);
+        if (p.ep_return && __any_sync(0xffffffffu, c_ep != 0u)) {
+            StepEpisodeStats eps;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                if (fin_len[e]) eps.episode(fin_ret[e], (unsigned long long)fin_len[e]);
+            stage_episode_stats(bs, &estage, eps);
+        }
     }
     bs.flush(p.stats);
+    if (p.ep_return) flush_episode_staging(p.stats, &estage);
     advance_device_tick(p.tick_dev, 1u);
 }
 
@@ -688,6 +723,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
     using acc_t = typename Env::acc_t;
     extern __shared__ __align__(128) float stage_smem[];     // [kStepStages][ROWS][TILE]
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
+    __shared__ EpisodeStaging estage;
     __shared__ alignas(8) uint64_t full[kStepStages];
     __shared__ float coop_buf[CoopSmem<Env>::floats];
     // persistent CTAs amortise a shared copy of the normal table where the env draws many normals per step (PowerGrid);
@@ -695,6 +731,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
     __shared__ float4 s_tab[Env::TAB_SMEM ? NIG_NORMAL_TAB_N : 1];
     if constexpr (Env::TAB_SMEM) normal_table_to_smem(s_tab);
     BlockStats bs;
+    episode_staging_init(&estage);
     bs.init(sstat);
     const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
     const Rng key(p.key, Env::TAB_SMEM ? s_tab : g_normal_tab);
@@ -835,9 +872,10 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k)
             if (k < p.cons.n) bs.warp_add(NIG_ST_CON0 + k, c_con[k]);
-        if (p.ep_return && __any_sync(0xffffffffu, c_ep != 0u)) flush_episode_stats(bs, p.stats, eps);
+        if (p.ep_return && __any_sync(0xffffffffu, c_ep != 0u)) stage_episode_stats(bs, &estage, eps);
     }
     bs.flush(p.stats);
+    if (p.ep_return) flush_episode_staging(p.stats, &estage);
     advance_device_tick(p.tick_dev, 1u);
 }
 
@@ -853,6 +891,7 @@ struct ResetArgs {
     const uint8_t* mask;
     const float* init_states;
     int32_t init_aos;
+    const uint32_t* tick_base;      // see base_tick(): tick / epoch above are offsets from it when non-null
 };
 
 template <class Env>
@@ -867,7 +906,7 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < Env::S; ++k) s[k] = p.init_aos ? p.init_states[i * Env::S + k] : p.init_states[k * p.pitch + i];
     } else {
-        Env::reset(key, p.env0 + (uint32_t)i, load_tick(p.tick_dev, p.tick), p.epoch, s);
+        Env::reset(key, p.env0 + (uint32_t)i, load_tick(p.tick_dev, p.tick) + base_tick(p.tick_base), p.epoch + base_epoch(p.tick_base), s);
     }
 #pragma unroll
     for (int k = 0; k < Env::S; ++k) p.state[k * p.pitch + i] = s[k];
@@ -929,6 +968,7 @@ struct RolloutArgs {
     unsigned long long* extrema;   // [2] keys of the min / max finished-episode return (see extremum_key); EXTREMA kernels
     double* pid_state;         // [2][A][pitch] fp64: PID integral rows, then previous-error rows (POLICY_BASELINE / PID)
     unsigned long long* stats;
+    const uint32_t* tick_base; // see base_tick(): tick / epoch are offsets from it when non-null
     ConsParams cons;
 };
 
@@ -1309,7 +1349,8 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     const bool valid = i < p.n;
     const int64_t ic = valid ? i : 0;      // padding lanes shadow env 0 without side effects
     const uint32_t env = p.env0 + (uint32_t)ic;
-    const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
+    const uint32_t tick0 = load_tick(p.tick_dev, p.tick) + base_tick(p.tick_base);
+    const uint32_t epoch = p.epoch + base_epoch(p.tick_base);
 
     constexpr uint32_t kChunkBytes = kTmaChunk * A * kThreads * sizeof(float);
     int n_chunks = 0;
@@ -1375,7 +1416,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
         if (__all_sync(0xffffffffu, inv))
         {
             DrawInKernel src{key, env, tick0};
-            t_begin = reactor_fast_steps<EXTREMA>(src, key, env, tick0, p.epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi);
+            t_begin = reactor_fast_steps<EXTREMA>(src, key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi);
         }
     }
 
@@ -1463,7 +1504,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
                 if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
                 if (p.auto_reset) {
                     if constexpr (Env::COOP_BLOCKS > 0) need_reset = true;
-                    else Env::reset(key, env, tick + 1u, p.epoch, s);
+                    else Env::reset(key, env, tick + 1u, epoch, s);
                     ep_st = 0u; ep_vi = 0u; ep_ret = (acc_t)0;
                 } else {
 #pragma unroll
@@ -1475,7 +1516,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
                 for (int k = 0; k < S; ++k) s[k] = ns[k];
             }
         }
-        if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(key, env, tick + 1u, p.epoch, need_reset, s, coop_buf);
+        if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(key, env, tick + 1u, epoch, need_reset, s, coop_buf);
     }
 
     if (valid) {
@@ -1552,7 +1593,7 @@ struct DrawFromRing {
 // one generic step of the uniform-random rollout with in-place draws: the loop body of rollout_kernel for POLICY_UNIFORM
 // (envs without a block-cooperative reset), used by the warp-specialised kernel where a warp cannot take the fast loop
 template <class Env, int CONS, bool EXTREMA>
-__device__ __forceinline__ void rollout_generic_uniform_step(const RolloutArgs& p, const Rng& key, uint32_t env, uint32_t tick, bool valid,
+__device__ __forceinline__ void rollout_generic_uniform_step(const RolloutArgs& p, const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, bool valid,
                                                              float (&s)[Env::S], uint32_t& ep_st, uint32_t& ep_vi, bool& latched,
                                                              typename Env::acc_t& ep_ret, float& rsum, RolloutAcc& acc,
                                                              typename Env::acc_t& r_lo, typename Env::acc_t& r_hi)
@@ -1588,7 +1629,7 @@ __device__ __forceinline__ void rollout_generic_uniform_step(const RolloutArgs& 
             acc.ret_sum += (double)ep_ret; acc.ret_sq += (double)ep_ret * (double)ep_ret;
             if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
             if (p.auto_reset) {
-                Env::reset(key, env, tick + 1u, p.epoch, s);
+                Env::reset(key, env, tick + 1u, epoch, s);
                 ep_st = 0u; ep_vi = 0u; ep_ret = (acc_t)0;
             } else {
 #pragma unroll
@@ -1623,7 +1664,8 @@ __global__ void __launch_bounds__(kWsThreads, 7) rollout_reactor_ws_kernel(const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool producer = warp == 0;
-    const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
+    const uint32_t tick0 = load_tick(p.tick_dev, p.tick) + base_tick(p.tick_base);
+    const uint32_t epoch = p.epoch + base_epoch(p.tick_base);
     // consumer (warp 1, 2): env blockIdx * 64 + (warp - 1) * 32 + lane; the producer's values below are unused
     const int64_t i = (int64_t)blockIdx.x * kWsEnvs + (producer ? 0 : (warp - 1) * 32) + lane;
     const bool valid = !producer && i < p.n;
@@ -1689,12 +1731,12 @@ __global__ void __launch_bounds__(kWsThreads, 7) rollout_reactor_ws_kernel(const
         int t_begin = 0;
         if (fast) {
             DrawFromRing src{ring + (warp - 1) * 32 + lane, full, empty};
-            t_begin = reactor_fast_steps<EXTREMA>(src, key, env, tick0, p.epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi);
+            t_begin = reactor_fast_steps<EXTREMA>(src, key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi);
             if (t_begin < p.n_steps) src.drain(t_begin, p.n_steps);
         }
 #pragma unroll 1
         for (int t = t_begin; t < p.n_steps; ++t)
-            rollout_generic_uniform_step<Env, CONS_DEFAULT, EXTREMA>(p, key, env, tick0 + (uint32_t)t, valid, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
+            rollout_generic_uniform_step<Env, CONS_DEFAULT, EXTREMA>(p, key, env, tick0 + (uint32_t)t, epoch, valid, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
     }
     rollout_epilogue<Env, EXTREMA>(p, bs, sfl, sext, valid, i, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
 }
