@@ -74,7 +74,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 } // namespace
 
-constexpr int kMaxHostSlices = 8;
+constexpr int kMaxHostSlices = 16;
 struct nig_env {
     nig_config_t cfg;
     int kind, S, A, NZ;
@@ -126,6 +126,7 @@ struct nig_env {
     int step_vec;              // 0 = auto
     int rollout_block;         // 0 = 128
     int rollout_ws;            // warp-specialised reactor rollout kernel (NIG_ROLLOUT_WS)
+    int rollout_pair;          // two envs per thread + packed f32x2 (NIG_ROLLOUT_PAIR)
     int zero_copy;             // 1 (default): small-population *_host steps run in place on page-locked host buffers
     int step_pipe;             // 1 (default): large plain SoA steps take the persistent TMA-pipelined kernel
     PFN_encodeTiled encode_tiled;
@@ -199,14 +200,14 @@ int launch_step(nig_env* e, const StepArgs& a, cudaStream_t st)
     e->launches++;
     note_device_work(e, st);
     // plain SoA step (no teacher forcing, no observation copies, no host-evaluated constraints): persistent TMA pipeline
-    const bool plain = !a.action_aos && !a.noise && !a.reset_states && !a.hostmask && !a.obs && !a.next_obs && !a.terminated && !a.truncated &&
-                       ((uintptr_t)a.actions & 15u) == 0 && e->step_pipe != 0 && e->step_vec == 0;
+    const bool plain_args = !a.action_aos && !a.aux_aos && !a.noise && !a.reset_states && !a.hostmask && !a.obs && !a.next_obs && !a.terminated && !a.truncated;
+    const bool plain = plain_args && ((uintptr_t)a.actions & 15u) == 0 && e->step_pipe != 0 && e->step_vec == 0;
     if (plain) {
         bool used = false;
         NIG_CUDA(nig::launch_step_pipelined(e->kind, cons_for_step(e->cons.is_default), e->pitch, a, st, &used));
         if (used) return NIG_OK;
     }
-    NIG_CUDA(nig::launch_step(e->kind, vec, cons_for_step(e->cons.is_default), e->pitch, a, st));
+    NIG_CUDA(nig::launch_step(e->kind, vec, cons_for_step(e->cons.is_default), e->pitch, a, st, plain_args));
     return NIG_OK;
 }
 
@@ -348,7 +349,9 @@ int host_slices(const nig_env* e, bool forced, int want = 4)
     if (forced || e->tick_dev) return 1;
     if (const char* v = getenv("NIG_HOST_SLICES")) want = atoi(v);
     if (want > kMaxHostSlices) want = kMaxHostSlices;
-    const int64_t fit = e->n / 8192;
+    int64_t min_slice = 8192;
+    if (const char* v = getenv("NIG_MIN_SLICE")) min_slice = atoll(v) > 0 ? atoll(v) : min_slice;
+    const int64_t fit = e->n / min_slice;
     if (want > fit) want = (int)fit;
     return want < 1 ? 1 : want;
 }
@@ -382,6 +385,10 @@ int rollout_range(nig_env* e, const nig_rollout_t* r, cudaStream_t stream, int64
     cfg.block = e->rollout_block ? e->rollout_block : (e->kind == NIG_ENV_CHEMICAL_REACTOR && ns <= 16384 ? 32 : 128);
     cfg.extrema = e->track_extrema;
     cfg.ws = e->rollout_ws != 0 && e->kind == NIG_ENV_CHEMICAL_REACTOR && e->cfg.auto_reset != 0;
+    // two envs per thread + packed f32x2 arithmetic: measured +7 .. 8 % from 262,144 envs per launch up, -11 % at 65,536
+    // (half the warps: profiles/r02_e_pair_f32x2_ab.txt); NIG_ROLLOUT_PAIR = 0 / 1 forces it off / on
+    cfg.pair = (e->rollout_pair == 1 || (e->rollout_pair < 0 && ns >= 131072)) && e->kind == NIG_ENV_CHEMICAL_REACTOR &&
+               e->cfg.auto_reset != 0 && (i0 % 2) == 0;
     e->launches++;
     const int64_t extent = (ns + 127) / 128 * 128;          // launch extent; <= the rows' pitch because slices start at multiples of 128
     NIG_CUDA(nig::launch_rollout(e->kind, cfg, extent, a, map, stream));
@@ -566,6 +573,8 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     if (const char* v = getenv("NIG_ROLLOUT_BLOCK")) e->rollout_block = atoi(v);
     e->rollout_ws = 0;
     if (const char* v = getenv("NIG_ROLLOUT_WS")) e->rollout_ws = atoi(v);
+    e->rollout_pair = -1;            // auto
+    if (const char* v = getenv("NIG_ROLLOUT_PAIR")) e->rollout_pair = atoi(v);
     e->host_graph_enable = 1;
     if (const char* v = getenv("NIG_HOST_GRAPH")) e->host_graph_enable = atoi(v);
     e->step_pipe = 1;

@@ -369,7 +369,7 @@ struct Grid {
             cg[i] = dmul(gen_cost(i), (double)ns[9 + i]);                        // :169
         }
         const float vr = mul(-50.0f, pairwise8(d2));
-        const double ec = __ddiv_rn(-pairwise8d(cg), 1000.0);                    // :170
+        const double ec = ddiv_const(-pairwise8d(cg), 1000.0, 1.0 / 1000.0);     // :170
         const float ap = mul(-5.0f, pairwise8(a2));
         return dadd(dadd((double)add(fr, vr), ec), (double)ap);                  // :175
     }

@@ -525,19 +525,38 @@ __device__ __forceinline__ void store_aos_warp(float* base, int64_t n, int64_t i
     }
     __syncwarp();
 }
-template <class Env, int VEC, int CONS>
-__global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) step_kernel(const __grid_constant__ StepArgs p)
+// PLAIN: the caller guarantees the plain SoA step (no teacher-forced noise / reset states, no host-evaluated constraint mask,
+// no observation copies, no unpacked flag arrays, SoA actions): every run-time-uniform option branch below folds away at
+// compile time -- ~400 of PowerGrid's 1,923 issued instructions per step were those branches and their address arithmetic.
+template <class Env, int VEC, int CONS, bool PLAIN = false>
+__global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) step_kernel(const __grid_constant__ StepArgs p0)
 {
+    // (a by-value copy of the option fields with the PLAIN ones pinned to "absent"; everything else is read from p0 directly)
+    struct Opt {
+        const float* noise; const float* reset_states; const uint8_t* hostmask; float* obs; float* next_obs;
+        uint8_t* terminated; uint8_t* truncated; int32_t action_aos, aux_aos;
+    };
+    const Opt o = PLAIN ? Opt{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0}
+                        : Opt{p0.noise, p0.reset_states, p0.hostmask, p0.obs, p0.next_obs, p0.terminated, p0.truncated, p0.action_aos, p0.aux_aos};
+    const StepArgs& p = p0;
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
     using acc_t = typename Env::acc_t;
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
     __shared__ EpisodeStaging estage;
     __shared__ float coop_buf[CoopSmem<Env>::floats];
-    __shared__ float aos_tile[VEC == 1 ? (kThreads / 32) * 32 * (S + 1) : 1];      // AoS transposes (VEC == 1 only)
-    float* my_tile = aos_tile + (VEC == 1 ? (threadIdx.x >> 5) * 32 * (S + 1) : 0);
+    __shared__ float aos_tile[(VEC == 1 && !PLAIN) ? (kThreads / 32) * 32 * (S + 1) : 1];      // AoS transposes (VEC == 1 only)
+    float* my_tile = aos_tile + ((VEC == 1 && !PLAIN) ? (threadIdx.x >> 5) * 32 * (S + 1) : 0);
     BlockStats bs;
     episode_staging_init(&estage);
     bs.init(sstat);
+    if constexpr (PLAIN) {
+        // programmatic dependent launch (the launcher sets cudaLaunchAttributeProgrammaticStreamSerialization on this flavour):
+        // the CTAs of step t + 1 are scheduled while step t drains, set up their shared memory above, and wait HERE until
+        // step t has completed and flushed -- before the first read of anything it writes (tick, state, episode words).
+        // Their own dependents may be scheduled at once: they will wait in the same place.
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
     const Rng key(p.key, g_normal_tab);        // one-tile CTA: the L1-cached global table
 
@@ -552,11 +571,11 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
     if (i0 < p.pitch) {
         float sv[S][VEC], av[A][VEC], nzv[NZA][VEC], rs[S][VEC];
         load_rows<S, VEC>(p.state, p.pitch, p.n, i0, false, sv);
-        load_rows<A, VEC>(p.actions, p.pitch, p.n, i0, p.action_aos != 0, av);   // (a transposed AoS load measured 5 % slower)
+        load_rows<A, VEC>(p.actions, p.pitch, p.n, i0, o.action_aos != 0, av);   // (a transposed AoS load measured 5 % slower)
         float wv[VEC];
         ldvec<VEC>(reinterpret_cast<const float*>(p.ep_word) + i0, wv);
-        if (NZ > 0 && p.noise) load_rows<NZA, VEC>(p.noise, p.pitch, p.n, i0, p.aux_aos != 0, nzv);
-        if (p.reset_states) load_rows<S, VEC>(p.reset_states, p.pitch, p.n, i0, p.aux_aos != 0, rs);
+        if (NZ > 0 && o.noise) load_rows<NZA, VEC>(o.noise, p.pitch, p.n, i0, o.aux_aos != 0, nzv);
+        if (o.reset_states) load_rows<S, VEC>(o.reset_states, p.pitch, p.n, i0, o.aux_aos != 0, rs);
 
         float nsv[S][VEC], rw[VEC];
         uint32_t fl[VEC], vmk[VEC];
@@ -575,7 +594,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             acc_t er = (acc_t)0;                       // running episode return (the accumulator the fused rollout continues)
             if (p.ep_return && active) er = (acc_t)p.ep_return[i];
             if (NZ > 0) {
-                if (p.noise) {
+                if (o.noise) {
 #pragma unroll
                     for (int k = 0; k < NZA; ++k) nz[k] = nzv[k][e];
                 } else {
@@ -583,7 +602,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
                 }
             } else nz[0] = 0.0f;
             acc_t r; uint32_t f, vm;
-            const uint32_t hm = p.hostmask && valid ? p.hostmask[i] : 0u;
+            const uint32_t hm = o.hostmask && valid ? o.hostmask[i] : 0u;
             step_core<Env, CONS>(p.cons, p.max_steps, s, a, nz, hm, w, ns, r, f, vm);
             if (!active) {            // finished env without auto-reset (or padding lane): nothing happens
 #pragma unroll
@@ -601,7 +620,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             for (int k = 0; k < S; ++k) nsv[k][e] = ns[k];     // s' of the transition (pre-reset)
             if (done) {
                 if (p.auto_reset) {
-                    if (p.reset_states) {
+                    if (o.reset_states) {
 #pragma unroll
                         for (int k = 0; k < S; ++k) s[k] = rs[k][e];
                     } else {
@@ -635,25 +654,25 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
         store_rows<S, VEC>(p.state, p.pitch, p.n, i0, false, sv);
         stvec<VEC>(reinterpret_cast<float*>(p.ep_word) + i0, wv);
         if constexpr (VEC == 1) {
-            if (p.aux_aos) {
+            if (o.aux_aos) {
                 float row[S];
-                if (p.obs) {
+                if (o.obs) {
 #pragma unroll
                     for (int k = 0; k < S; ++k) row[k] = sv[k][0];
-                    store_aos_warp<S>(p.obs, p.n, i0, row, my_tile);
+                    store_aos_warp<S>(o.obs, p.n, i0, row, my_tile);
                 }
-                if (p.next_obs) {
+                if (o.next_obs) {
 #pragma unroll
                     for (int k = 0; k < S; ++k) row[k] = nsv[k][0];
-                    store_aos_warp<S>(p.next_obs, p.n, i0, row, my_tile);
+                    store_aos_warp<S>(o.next_obs, p.n, i0, row, my_tile);
                 }
             } else {
-                if (p.obs) store_rows<S, VEC>(p.obs, p.pitch, p.n, i0, false, sv);
-                if (p.next_obs) store_rows<S, VEC>(p.next_obs, p.pitch, p.n, i0, false, nsv);
+                if (o.obs) store_rows<S, VEC>(o.obs, p.pitch, p.n, i0, false, sv);
+                if (o.next_obs) store_rows<S, VEC>(o.next_obs, p.pitch, p.n, i0, false, nsv);
             }
         } else {
-            if (p.obs) store_rows<S, VEC>(p.obs, p.pitch, p.n, i0, p.aux_aos != 0, sv);
-            if (p.next_obs) store_rows<S, VEC>(p.next_obs, p.pitch, p.n, i0, p.aux_aos != 0, nsv);
+            if (o.obs) store_rows<S, VEC>(o.obs, p.pitch, p.n, i0, o.aux_aos != 0, sv);
+            if (o.next_obs) store_rows<S, VEC>(o.next_obs, p.pitch, p.n, i0, o.aux_aos != 0, nsv);
         }
         // VEC == 1 serves the exact-size [n] arrays of the host-buffer (zero-copy) and torch APIs: no store past env n - 1
         // (the vector flavours require pitch-capacity device arrays, include/nig_b200.h)
@@ -669,12 +688,12 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             else if constexpr (VEC == 2) *reinterpret_cast<uchar2*>(p.viol_mask + i0) = make_uchar2(vmk[0], vmk[1]);
             else p.viol_mask[i0] = (uint8_t)vmk[0];
         }
-        if (p.terminated || p.truncated) {
+        if (o.terminated || o.truncated) {
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 if (i0 + e < (VEC == 1 ? p.n : p.pitch)) {
-                    if (p.terminated) p.terminated[i0 + e] = (uint8_t)((fl[e] & NIG_F_TERMINATED) ? 1 : 0);
-                    if (p.truncated) p.truncated[i0 + e] = (uint8_t)((fl[e] & NIG_F_TRUNCATED) ? 1 : 0);
+                    if (o.terminated) o.terminated[i0 + e] = (uint8_t)((fl[e] & NIG_F_TERMINATED) ? 1 : 0);
+                    if (o.truncated) o.truncated[i0 + e] = (uint8_t)((fl[e] & NIG_F_TRUNCATED) ? 1 : 0);
                 }
             }
         }
@@ -1125,129 +1144,311 @@ __device__ __forceinline__ StepDraw reactor_step_draw(const Rng& key, uint32_t e
 // where the fast loop gets a step's draw from: computed in place ...
 struct DrawInKernel {
     const Rng& key; uint32_t env, tick0;
-    __device__ __forceinline__ StepDraw get(int t) const { return reactor_step_draw(key, env, tick0 + (uint32_t)t); }
+    __device__ __forceinline__ StepDraw get(int t, int) const { return reactor_step_draw(key, env, tick0 + (uint32_t)t); }
+    __device__ __forceinline__ void done(int, int) const {}
+};
+struct DrawInKernel2 {         // two envs per thread: lane 0 / 1 of the value type
+    const Rng& key; uint32_t env[2], tick0;
+    __device__ __forceinline__ StepDraw get(int t, int lane) const { return reactor_step_draw(key, env[lane], tick0 + (uint32_t)t); }
     __device__ __forceinline__ void done(int, int) const {}
 };
 
-// returns the number of steps committed (== n_steps unless a guard failed)
+// ---- one or two envs per thread -------------------------------------------------------------------------------------
+// The loop below is written once over a value type V: float (one env per thread) or F2 (two envs per thread, every
+// add / mul / fma of the physics issued as ONE packed instruction -- add.rn.f32x2 / mul.rn.f32x2 / fma.rn.f32x2, SASS FADD2 /
+// FMUL2 / FFMA2, IEEE round-to-nearest per lane, so the results are the scalar ones bit for bit). Compares, selects, min / max
+// and conversions have no packed form and stay per lane; so do the RNG and the table normals.
+struct F2 { float x, y; };
+struct B2 { bool x, y; };
+__device__ __forceinline__ float2 f2v(F2 a) { return make_float2(a.x, a.y); }
+__device__ __forceinline__ F2 v2f(float2 a) { return F2{a.x, a.y}; }
+template <class V> struct VT;
+template <> struct VT<float> {
+    static constexpr int N = 1; using M = bool;
+    __device__ static __forceinline__ float bc(float c) { return c; }
+    __device__ static __forceinline__ float get(float v, int) { return v; }
+    __device__ static __forceinline__ void set(float& v, int, float x) { v = x; }
+    __device__ static __forceinline__ bool getm(bool m, int) { return m; }
+    __device__ static __forceinline__ void setm(bool& m, int, bool x) { m = x; }
+};
+template <> struct VT<F2> {
+    static constexpr int N = 2; using M = B2;
+    __device__ static __forceinline__ F2 bc(float c) { return F2{c, c}; }
+    __device__ static __forceinline__ float get(F2 v, int k) { return k ? v.y : v.x; }
+    __device__ static __forceinline__ void set(F2& v, int k, float x) { if (k) v.y = x; else v.x = x; }
+    __device__ static __forceinline__ bool getm(B2 m, int k) { return k ? m.y : m.x; }
+    __device__ static __forceinline__ void setm(B2& m, int k, bool x) { if (k) m.y = x; else m.x = x; }
+};
+// packed arithmetic (the scalar add / mul / sub are in nig_envs.cuh).
+// TOOLCHAIN: ptxas 12.9 contracts `mul.rn.f32x2` followed by `add.rn.f32x2` into ONE FFMA2 -- despite the explicit .rn on
+// both (the PTX is right: cicc keeps them apart) and despite -fmad=false, also when the add is written fma(m, 1, c) or the
+// product fma(a, b, -0), and through an empty asm volatile on the halves (scalar mul.rn + add.rn are never contracted). A
+// single rounding instead of two changes the last bit: the first packed build differed from the oracle in 12 % of the
+// pressure / concentration values after 70 steps. Work-around: packed sums are written a * ONE + b and b * MINUS_ONE + a with
+// the +-1 read from constant memory, which ptxas cannot fold (FFMA2 R, R, UR.F32, R: same issue cost as FADD2, exact: RN(a+b)).
+static __device__ __constant__ float g_f2_one = 1.0f, g_f2_mone = -1.0f;
+__device__ __forceinline__ F2 add(F2 a, F2 b) { const float o = g_f2_one; return v2f(__ffma2_rn(f2v(a), make_float2(o, o), f2v(b))); }
+__device__ __forceinline__ F2 mul(F2 a, F2 b) { return v2f(__fmul2_rn(f2v(a), f2v(b))); }
+__device__ __forceinline__ F2 sub(F2 a, F2 b) { const float o = g_f2_mone; return v2f(__ffma2_rn(f2v(b), make_float2(o, o), f2v(a))); }
+__device__ __forceinline__ float vfma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ F2 vfma(F2 a, F2 b, F2 c) { return v2f(__ffma2_rn(f2v(a), f2v(b), f2v(c))); }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+__device__ __forceinline__ F2 vneg(F2 a) { return F2{-a.x, -a.y}; }
+__device__ __forceinline__ float vabs(float a) { return fabsf(a); }
+__device__ __forceinline__ F2 vabs(F2 a) { return F2{fabsf(a.x), fabsf(a.y)}; }
+__device__ __forceinline__ float rcp_approx(float a) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a)); return y; }
+__device__ __forceinline__ F2 rcp_approx(F2 a) { return F2{rcp_approx(a.x), rcp_approx(a.y)}; }
+// comparisons against a constant / selects, per lane
+#define NIG_CMP(name, op) \
+    __device__ __forceinline__ bool name(float a, float c) { return a op c; } \
+    __device__ __forceinline__ B2 name(F2 a, float c) { return B2{a.x op c, a.y op c}; }
+NIG_CMP(vgt, >) NIG_CMP(vlt, <) NIG_CMP(vge, >=) NIG_CMP(vle, <=)
+__device__ __forceinline__ bool mand(bool a, bool b) { return a && b; }
+__device__ __forceinline__ B2 mand(B2 a, B2 b) { return B2{a.x && b.x, a.y && b.y}; }
+__device__ __forceinline__ bool mor(bool a, bool b) { return a || b; }
+__device__ __forceinline__ B2 mor(B2 a, B2 b) { return B2{a.x || b.x, a.y || b.y}; }
+__device__ __forceinline__ bool mnot(bool a) { return !a; }
+__device__ __forceinline__ B2 mnot(B2 a) { return B2{!a.x, !a.y}; }
+__device__ __forceinline__ bool mall(bool a) { return a; }
+__device__ __forceinline__ bool mall(B2 a) { return a.x && a.y; }
+__device__ __forceinline__ bool many(bool a) { return a; }
+__device__ __forceinline__ bool many(B2 a) { return a.x || a.y; }
+__device__ __forceinline__ float vsel(bool m, float a, float b) { return m ? a : b; }
+__device__ __forceinline__ F2 vsel(B2 m, F2 a, F2 b) { return F2{m.x ? a.x : b.x, m.y ? a.y : b.y}; }
+__device__ __forceinline__ float vselc(bool m, float a, float b) { return m ? a : b; }                 // constants
+__device__ __forceinline__ F2 vselc(B2 m, float a, float b) { return F2{m.x ? a : b, m.y ? a : b}; }
+__device__ __forceinline__ F2 py_clamp(F2 v, float lo, float hi) { return F2{py_clamp(v.x, lo, hi), py_clamp(v.y, lo, hi)}; }
+
+template <class V>
+__device__ __forceinline__ V cdiv_noguard_v(V x, float c, float rc)
+{
+    using T = VT<V>;
+    const V q = mul(x, T::bc(rc));
+    const V r = vfma(vneg(q), T::bc(c), x);
+    return vfma(r, T::bc(rc), q);
+}
+#define NIG_CDIV_V(x, c) cdiv_noguard_v((x), (c), 1.0f / (c))
+
+// spec_expf (nig_math.cuh) over V: the same operations in the same order, the fma chain packed
+template <class V>
+__device__ __forceinline__ V spec_expf_v(V x)
+{
+    using T = VT<V>;
+    V xc = x, n, s1, s2;
+#pragma unroll
+    for (int k = 0; k < T::N; ++k) {
+        float c = T::get(x, k);
+        c = c < -104.0f ? -104.0f : c;
+        c = c > 89.0f ? 89.0f : c;
+        T::set(xc, k, c);
+    }
+    const V t = mul(xc, T::bc(0x1.715476p+0f));
+#pragma unroll
+    for (int k = 0; k < T::N; ++k) T::set(n, k, rintf(T::get(t, k)));
+    V r = vfma(n, T::bc(-0x1.62e4p-1f), xc);
+    r = vfma(n, T::bc(-0x1.7f7d1cp-20f), r);
+    V p = T::bc(0x1.a17e08p-13f);
+    p = vfma(p, r, T::bc(0x1.6d7548p-10f));
+    p = vfma(p, r, T::bc(0x1.1110a6p-7f));
+    p = vfma(p, r, T::bc(0x1.5554acp-5f));
+    p = vfma(p, r, T::bc(0x1.555556p-3f));
+    p = vfma(p, r, T::bc(0x1.0p-1f));
+    p = vfma(p, r, T::bc(1.0f));
+    p = vfma(p, r, T::bc(1.0f));
+#pragma unroll
+    for (int k = 0; k < T::N; ++k) {
+        const int ni = __float2int_rn(T::get(n, k));
+        const int n1 = ni >> 1, n2 = ni - n1;
+        T::set(s1, k, __int_as_float((n1 + 127) << 23));
+        T::set(s2, k, __int_as_float((n2 + 127) << 23));
+    }
+    return mul(mul(p, s1), s2);
+}
+
+// returns the number of steps committed (== n_steps unless a guard failed). V = float: one env (env[0]); V = F2: two envs.
+template <class V, bool EXTREMA, class Src>
+__device__ __forceinline__ int reactor_fast_steps_v(Src& src, const Rng& key, const uint32_t (&env)[VT<V>::N], uint32_t tick0, uint32_t epoch,
+                                                    int n_steps, int max_steps, float (&s)[VT<V>::N][Reactor::S],
+                                                    uint32_t (&ep_st)[VT<V>::N], uint32_t (&ep_vi)[VT<V>::N], float (&ep_ret_)[VT<V>::N],
+                                                    float (&rsum_)[VT<V>::N], RolloutAcc (&acc)[VT<V>::N], float& r_lo, float& r_hi)
+{
+    using T_ = VT<V>;
+    using M = typename T_::M;
+    constexpr int N = T_::N;
+    V T, P, cool, feed, conc, cat, hx, rv, level, bt, catd, ep_ret, rsum;
+    M alarm;
+    int t_trunc[N];
+    unsigned int c_lvl[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        T_::set(T, k, s[k][0]); T_::set(P, k, s[k][1]); T_::set(cool, k, s[k][2]); T_::set(feed, k, s[k][3]); T_::set(conc, k, s[k][4]);
+        T_::set(cat, k, s[k][5]); T_::set(hx, k, s[k][6]); T_::set(rv, k, s[k][7]); T_::set(level, k, s[k][10]); T_::set(bt, k, s[k][11]);
+        T_::setm(alarm, k, __float_as_uint(s[k][9]) != 0u);
+        T_::set(catd, k, __fdiv_rn(s[k][5], 100.0f));
+        T_::set(ep_ret, k, ep_ret_[k]); T_::set(rsum, k, rsum_[k]);
+        t_trunc[k] = max_steps - (int)ep_st[k] - 1;      // loop index of the step at which the running episode is truncated (base.py:191)
+        c_lvl[k] = 0u;
+    }
+    int t = 0;
+#pragma unroll kFastUnroll
+    for (; t < n_steps; ++t) {
+        const uint32_t tick = tick0 + (uint32_t)t;
+        V nz0, nz1, hp, cadj, fadj, apen;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const StepDraw dr = src.get(t, k);
+            T_::set(nz0, k, dr.nz0); T_::set(nz1, k, dr.nz1); T_::set(hp, k, dr.hp); T_::set(cadj, k, dr.cadj); T_::set(fadj, k, dr.fadj);
+            T_::set(apen, k, dr.apen);
+        }
+        const M lvl_bad = mnot(mand(vge(level, 20.0f), vle(level, 90.0f)));     // :302-305 on the pre-step state
+        // _dynamics (:109-226), manual mode
+        const V c01 = mul(T_::bc(0.1f), conc);
+        const V kca = mul(c01, catd);
+        const V rh = mul(kca, T_::bc(10000.0f));
+        const V ch = mul(mul(mul(cool, T_::bc(100.0f)), sub(T, hx)), T_::bc(0.1f));
+        const V num = sub(add(hp, rh), ch);
+        M ok = vge(vabs(num), 0x1.0p-120f);
+        const V dT = add(NIG_CDIV_V(num, 418000.0f), nz0);
+        const V nT = add(T, mul(dT, T_::bc(0.1f)));
+        const V d = sub(nT, T_::bc(320.0f));
+        ok = mand(ok, vle(vabs(d), 120.0f));            // 200 <= T' <= 440: T' / T and -(T' - 320) / 20 are in the proven domain
+        const V y0 = rcp_approx(T);
+        const V e0 = vfma(vneg(T), y0, T_::bc(1.0f));
+        const V y1 = vfma(y0, e0, y0);
+        const V q0 = vfma(nT, y1, T_::bc(0.0f));
+        const V q = vfma(y1, vfma(vneg(T), q0, nT), q0);                        // == __fdiv_rn(nT, T) (DivFast::vdiv)
+        const V pfr = mul(c01, T_::bc(1000.0f));                               // mul(mul(conc, 0.1f), 1000.0f)
+        V nP = add(add(mul(P, q), mul(pfr, T_::bc(0.1f))), nz1);
+        const V nrv = py_clamp(add(rv, mul(sub(nP, T_::bc(506625.0f)), T_::bc(0.001f))), 0.0f, 100.0f);
+        {
+            const V x = sub(nP, mul(mul(nrv, T_::bc(0.01f)), T_::bc(10000.0f)));
+            const V xr = vsel(vgt(x, 101325.0f), x, T_::bc(101325.0f));
+            nP = vsel(vgt(nrv, 0.0f), xr, nP);
+        }
+        ok = mand(ok, vle(vabs(sub(nP, T_::bc(5.0e6f))), 4.999e6f));   // 1e3 <= P' < 1e7: |P' - 253312.5| is 0 or >= 2^-14, finite
+        const V ncool = py_clamp(add(cool, cadj), 10.0f, 100.0f);
+        const V feed_v = add(feed, fadj);
+        const V nfeed = py_clamp(feed_v, 5.0f, 50.0f);
+        const V ex = spec_expf_v(NIG_CDIV_V(vneg(d), 20.0f));
+        const V rr = mul(kca, ex);
+        V fdil = mul(nfeed, T_::bc(0.001f));
+        fdil = vsel(vgt(feed_v, 5.0f), fdil, T_::bc(0x1.47ae14p-8f));
+        fdil = vsel(vlt(feed_v, 50.0f), fdil, T_::bc(0x1.99999ap-5f));
+        const V cv = add(conc, mul(sub(rr, fdil), T_::bc(0.1f)));
+        const V nconc = vsel(vgt(cv, 0.0f), cv, T_::bc(0.0f));
+        const V catv = sub(cat, vselc(vgt(nT, 340.0f), 0.001f, 0.0001f));
+        const V ncat = vsel(vgt(catv, 50.0f), catv, T_::bc(50.0f));
+        const V nhx = add(hx, mul(mul(T_::bc(0.1f), sub(add(T_::bc(290.0f), mul(cool, T_::bc(0.1f))), hx)), T_::bc(0.1f)));
+        const M trip = mor(vgt(nT, 350.0f), vgt(nP, 506625.0f));                // :199 -> estop' = alarm' = 1
+        const M nalarm = mor(alarm, mor(vgt(nT, 345.0f), vgt(nP, 480000.0f)));  // :197
+        const V nlevel = py_clamp(add(level, mul(mul(sub(nfeed, T_::bc(20.0f)), T_::bc(0.1f)), T_::bc(0.1f))), 0.0f, 100.0f);
+        const V nbt = add(bt, T_::bc(0.1f));
+        // _compute_reward (:228-270) on the new state, then the level penalty (base.py:179-183)
+        V r = add(T_::bc(0.0f), mul(nconc, T_::bc(100.0f)));
+        r = sub(r, mul(vabs(d), T_::bc(0.5f)));
+        r = sub(r, mul(NIG_CDIV_V(vabs(sub(nP, T_::bc(253312.5f))), 1000.0f), T_::bc(0.1f)));
+        const V ncatd = NIG_CDIV_V(ncat, 100.0f);
+        r = add(r, mul(ncatd, T_::bc(10.0f)));
+        const M band = mand(vge(nlevel, 30.0f), vle(nlevel, 80.0f));
+        r = vsel(band, add(r, T_::bc(5.0f)), sub(r, mul(vabs(sub(nlevel, T_::bc(55.0f))), T_::bc(0.2f))));
+        r = vsel(nalarm, sub(r, T_::bc(50.0f)), r);
+        r = vsel(trip, sub(r, T_::bc(200.0f)), r);
+        r = sub(r, apen);
+        r = vsel(lvl_bad, add(r, T_::bc(-25.0f)), r);
+        if (__builtin_expect(!__all_sync(0xffffffffu, mall(ok)), 0)) break;     // (uniform) redo this step in the generic loop
+        src.done(t, n_steps);
+        rsum = add(rsum, r);
+        ep_ret = add(ep_ret, r);
+        T = nT; P = nP; cool = ncool; feed = nfeed; conc = nconc; cat = ncat; hx = nhx; rv = nrv; level = nlevel; bt = nbt;
+        alarm = nalarm; catd = ncatd;
+        const M term = mor(mor(trip, vlt(nlevel, 5.0f)), mor(vgt(nlevel, 95.0f), vgt(nbt, 50.0f)));   // _is_done (:272-290)
+        M fin;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const unsigned int bad = T_::getm(lvl_bad, k) ? 1u : 0u;
+            c_lvl[k] += bad; ep_vi[k] += bad;
+            T_::setm(fin, k, T_::getm(term, k) || t >= t_trunc[k]);
+        }
+        if (__any_sync(0xffffffffu, many(fin))) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+                const bool fk = T_::getm(fin, k);
+                if (fk) {
+                    const float ret = T_::get(ep_ret, k);
+                    const unsigned long long len = (unsigned long long)(max_steps - (t_trunc[k] - t));
+                    acc[k].c_ep += 1; acc[k].c_done += 1;
+                    acc[k].c_term += T_::getm(term, k) ? 1u : 0u;
+                    acc[k].c_trunc += (t >= t_trunc[k]) ? 1u : 0u;
+                    acc[k].c_succ += (ret > 0.0f) ? 1u : 0u;
+                    acc[k].len_sum += len; acc[k].len_sq += len * len;
+                    acc[k].ret_sum += (double)ret; acc[k].ret_sq += (double)ret * (double)ret;
+                    if constexpr (EXTREMA) { r_lo = ret < r_lo ? ret : r_lo; r_hi = ret > r_hi ? ret : r_hi; }
+                }
+                // the fresh state (Reactor::reset: 2 Philox blocks, 8 table normals) drawn by the whole warp for its finished
+                // lane(s): one pair of normals per helper lane instead of the full draw under a one-lane mask
+                float f[Reactor::S];
+                coop_reset<Reactor>(key, env[k], tick + 1u, epoch, fk, f);
+                if (fk) {
+                    T_::set(T, k, f[0]); T_::set(P, k, f[1]); T_::set(cool, k, f[2]); T_::set(feed, k, f[3]); T_::set(conc, k, f[4]);
+                    T_::set(cat, k, f[5]); T_::set(hx, k, f[6]); T_::set(rv, k, f[7]); T_::set(level, k, f[10]); T_::set(bt, k, f[11]);
+                    T_::setm(alarm, k, false);
+                    T_::set(catd, k, __fdiv_rn(f[5], 100.0f));
+                    ep_vi[k] = 0u; T_::set(ep_ret, k, 0.0f);
+                    t_trunc[k] = t + max_steps;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        s[k][0] = T_::get(T, k); s[k][1] = T_::get(P, k); s[k][2] = T_::get(cool, k); s[k][3] = T_::get(feed, k); s[k][4] = T_::get(conc, k);
+        s[k][5] = T_::get(cat, k); s[k][6] = T_::get(hx, k); s[k][7] = T_::get(rv, k);
+        s[k][8] = 0.0f; s[k][9] = T_::getm(alarm, k) ? 1.0f : 0.0f; s[k][10] = T_::get(level, k); s[k][11] = T_::get(bt, k);
+        ep_st[k] = (uint32_t)(max_steps - (t_trunc[k] - t + 1));
+        ep_ret_[k] = T_::get(ep_ret, k); rsum_[k] = T_::get(rsum, k);
+        acc[k].c_steps += (unsigned int)t;
+        acc[k].c_viol += c_lvl[k];
+        acc[k].c_con[2] += c_lvl[k];
+    }
+    return t;
+}
+
+// one env per thread: the scalar instantiation behind the interface the one-env kernels use
 template <bool EXTREMA, class Src>
 __device__ __forceinline__ int reactor_fast_steps(Src& src, const Rng& key, uint32_t env, uint32_t tick0, uint32_t epoch, int n_steps, int max_steps,
                                                   float (&s)[Reactor::S], uint32_t& ep_st, uint32_t& ep_vi, float& ep_ret, float& rsum,
                                                   RolloutAcc& acc, float& r_lo, float& r_hi)
 {
-    float T = s[0], P = s[1], cool = s[2], feed = s[3], conc = s[4], cat = s[5], hx = s[6], rv = s[7], level = s[10], bt = s[11];
-    bool alarm = __float_as_uint(s[9]) != 0u;
-    float catd = __fdiv_rn(cat, 100.0f);
-    int t_trunc = max_steps - (int)ep_st - 1;       // loop index of the step at which the running episode is truncated (base.py:191)
-    unsigned int c_lvl = 0;
-    int t = 0;
-#pragma unroll kFastUnroll
-    for (; t < n_steps; ++t) {
-        const uint32_t tick = tick0 + (uint32_t)t;
-        const StepDraw dr = src.get(t);
-        const float nz0 = dr.nz0, nz1 = dr.nz1, hp = dr.hp, cadj = dr.cadj, fadj = dr.fadj;
-        const bool lvl_bad = !((20.0f <= level) && (level <= 90.0f));           // :302-305 on the pre-step state
-        // _dynamics (:109-226), manual mode
-        const float kca = mul(mul(0.1f, conc), catd);
-        const float rh = mul(kca, 10000.0f);
-        const float ch = mul(mul(mul(cool, 100.0f), sub(T, hx)), 0.1f);
-        const float num = sub(add(hp, rh), ch);
-        bool ok = fabsf(num) >= 0x1.0p-120f;
-        const float dT = add(NIG_CDIV_NG(num, 418000.0f), nz0);
-        const float nT = add(T, mul(dT, 0.1f));
-        const float d = sub(nT, 320.0f);
-        ok = ok && (fabsf(d) <= 120.0f);                // 200 <= T' <= 440: T' / T and -(T' - 320) / 20 are in the proven domain
-        float y0;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(T));
-        const float e0 = __fmaf_rn(-T, y0, 1.0f);
-        const float y1 = __fmaf_rn(y0, e0, y0);
-        const float q0 = __fmaf_rn(nT, y1, 0.0f);
-        const float q = __fmaf_rn(y1, __fmaf_rn(-T, q0, nT), q0);               // == __fdiv_rn(nT, T) (DivFast::vdiv)
-        const float pfr = mul(mul(conc, 0.1f), 1000.0f);
-        float nP = add(add(mul(P, q), mul(pfr, 0.1f)), nz1);
-        const float nrv = py_clamp(add(rv, mul(sub(nP, 506625.0f), 0.001f)), 0.0f, 100.0f);
-        {
-            const float x = sub(nP, mul(mul(nrv, 0.01f), 10000.0f));
-            const float xr = (x > 101325.0f) ? x : 101325.0f;
-            nP = (nrv > 0.0f) ? xr : nP;
-        }
-        ok = ok && (fabsf(sub(nP, 5.0e6f)) <= 4.999e6f);        // 1e3 <= P' < 1e7: |P' - 253312.5| is 0 or >= 2^-14, finite
-        const float ncool = py_clamp(add(cool, cadj), 10.0f, 100.0f);
-        const float feed_v = add(feed, fadj);
-        const float nfeed = py_clamp(feed_v, 5.0f, 50.0f);
-        const float ex = spec_expf(NIG_CDIV_NG(-d, 20.0f));
-        const float rr = mul(kca, ex);
-        float fdil = mul(nfeed, 0.001f);
-        fdil = (feed_v > 5.0f) ? fdil : 0x1.47ae14p-8f;
-        fdil = (feed_v < 50.0f) ? fdil : 0x1.99999ap-5f;
-        const float cv = add(conc, mul(sub(rr, fdil), 0.1f));
-        const float nconc = (cv > 0.0f) ? cv : 0.0f;
-        const float catv = sub(cat, (nT > 340.0f) ? 0.001f : 0.0001f);
-        const float ncat = (catv > 50.0f) ? catv : 50.0f;
-        const float nhx = add(hx, mul(mul(0.1f, sub(add(290.0f, mul(cool, 0.1f)), hx)), 0.1f));
-        const bool trip = (nT > 350.0f) || (nP > 506625.0f);                   // :199 -> estop' = alarm' = 1
-        const bool nalarm = alarm || (nT > 345.0f) || (nP > 480000.0f);        // :197
-        const float nlevel = py_clamp(add(level, mul(mul(sub(nfeed, 20.0f), 0.1f), 0.1f)), 0.0f, 100.0f);
-        const float nbt = add(bt, 0.1f);
-        // _compute_reward (:228-270) on the new state, then the level penalty (base.py:179-183)
-        float r = add(0.0f, mul(nconc, 100.0f));
-        r = sub(r, mul(fabsf(d), 0.5f));
-        r = sub(r, mul(NIG_CDIV_NG(fabsf(sub(nP, 253312.5f)), 1000.0f), 0.1f));
-        const float ncatd = NIG_CDIV_NG(ncat, 100.0f);
-        r = add(r, mul(ncatd, 10.0f));
-        const bool band = (30.0f <= nlevel) && (nlevel <= 80.0f);
-        r = band ? add(r, 5.0f) : sub(r, mul(fabsf(sub(nlevel, 55.0f)), 0.2f));
-        if (nalarm) r = sub(r, 50.0f);
-        if (trip) r = sub(r, 200.0f);
-        r = sub(r, dr.apen);
-        if (lvl_bad) r = add(r, -25.0f);
-        if (__builtin_expect(!__all_sync(0xffffffffu, ok), 0)) break;           // (uniform) redo this step in the generic loop
-        src.done(t, n_steps);
-        rsum = add(rsum, r);
-        ep_ret = ep_ret + r;
-        c_lvl += lvl_bad ? 1u : 0u;
-        ep_vi += lvl_bad ? 1u : 0u;
-        T = nT; P = nP; cool = ncool; feed = nfeed; conc = nconc; cat = ncat; hx = nhx; rv = nrv; level = nlevel; bt = nbt;
-        alarm = nalarm; catd = ncatd;
-        const bool term = trip || (nlevel < 5.0f) || (nlevel > 95.0f) || (nbt > 50.0f);   // _is_done (:272-290)
-        const bool trunc = t >= t_trunc;
-        if (__any_sync(0xffffffffu, term || trunc)) {
-            const bool fin = term || trunc;
-            if (fin) {
-                const unsigned long long len = (unsigned long long)(max_steps - (t_trunc - t));
-                acc.c_ep += 1; acc.c_done += 1;
-                acc.c_term += term ? 1u : 0u;
-                acc.c_trunc += trunc ? 1u : 0u;
-                acc.c_succ += (ep_ret > 0.0f) ? 1u : 0u;
-                acc.len_sum += len; acc.len_sq += len * len;
-                acc.ret_sum += (double)ep_ret; acc.ret_sq += (double)ep_ret * (double)ep_ret;
-                if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
-            }
-            // the fresh state (Reactor::reset: 2 Philox blocks, 8 table normals) drawn by the whole warp for its finished
-            // lane(s): one pair of normals per helper lane instead of the full draw under a one-lane mask
-            float f[Reactor::S];
-            coop_reset<Reactor>(key, env, tick + 1u, epoch, fin, f);
-            if (fin) {
-                T = f[0]; P = f[1]; cool = f[2]; feed = f[3]; conc = f[4]; cat = f[5]; hx = f[6]; rv = f[7]; level = f[10]; bt = f[11];
-                alarm = false;
-                catd = __fdiv_rn(cat, 100.0f);
-                ep_vi = 0u; ep_ret = 0.0f;
-                t_trunc = t + max_steps;
-            }
-        }
-    }
-    s[0] = T; s[1] = P; s[2] = cool; s[3] = feed; s[4] = conc; s[5] = cat; s[6] = hx; s[7] = rv;
-    s[8] = 0.0f; s[9] = alarm ? 1.0f : 0.0f; s[10] = level; s[11] = bt;
-    ep_st = (uint32_t)(max_steps - (t_trunc - t + 1));
-    acc.c_steps += (unsigned int)t;
-    acc.c_viol += c_lvl;
-    acc.c_con[2] += c_lvl;
-    return t;
+    const uint32_t envs[1] = {env};
+    auto& s1 = reinterpret_cast<float (&)[1][Reactor::S]>(s);
+    auto& st1 = reinterpret_cast<uint32_t (&)[1]>(ep_st);
+    auto& vi1 = reinterpret_cast<uint32_t (&)[1]>(ep_vi);
+    auto& er1 = reinterpret_cast<float (&)[1]>(ep_ret);
+    auto& rs1 = reinterpret_cast<float (&)[1]>(rsum);
+    auto& ac1 = reinterpret_cast<RolloutAcc (&)[1]>(acc);
+    return reactor_fast_steps_v<float, EXTREMA>(src, key, envs, tick0, epoch, n_steps, max_steps, s1, st1, vi1, er1, rs1, ac1, r_lo, r_hi);
 }
-
 
 // ---- the common tail of the fused rollout kernels: state / episode word / return accumulator back to HBM, per-env
 // outputs, then the violation / episode statistics: warp REDUX + shuffle trees -> one global atomic per slot per block
+// per-env outputs of a launch (reward sum, violation / finished-episode counts)
+__device__ __forceinline__ void rollout_env_outputs(const RolloutArgs& p, int64_t i, float rsum, const RolloutAcc& acc)
+{
+    if (p.accumulate) {
+        if (p.reward_sum) p.reward_sum[i] = add(p.reward_sum[i], rsum);
+        if (p.viol_count) p.viol_count[i] += (int32_t)acc.c_viol;
+        if (p.done_count) p.done_count[i] += (int32_t)acc.c_done;
+    } else {
+        if (p.reward_sum) p.reward_sum[i] = rsum;
+        if (p.viol_count) p.viol_count[i] = (int32_t)acc.c_viol;
+        if (p.done_count) p.done_count[i] = (int32_t)acc.c_done;
+    }
+}
+
+template <class Env, bool EXTREMA>
+__device__ __forceinline__ void rollout_stats_flush(const RolloutArgs& p, BlockStats& bs, double* sfl, unsigned long long* sext, RolloutAcc& acc,
+                                                    typename Env::acc_t r_lo, typename Env::acc_t r_hi);
+
 template <class Env, bool EXTREMA>
 __device__ __forceinline__ void rollout_epilogue(const RolloutArgs& p, BlockStats& bs, double* sfl, unsigned long long* sext,
                                                  bool valid, int64_t i, const float (&s)[Env::S], uint32_t ep_st, uint32_t ep_vi, bool latched,
@@ -1264,16 +1465,16 @@ __device__ __forceinline__ void rollout_epilogue(const RolloutArgs& p, BlockStat
         for (int k = 0; k < S; ++k) p.state[k * p.pitch + i] = s[k];
         p.ep_word[i] = epw_make(ep_st, ep_vi, latched ? 1u : 0u);
         p.ep_return[i] = (double)ep_ret;
-        if (p.accumulate) {
-            if (p.reward_sum) p.reward_sum[i] = add(p.reward_sum[i], rsum);
-            if (p.viol_count) p.viol_count[i] += (int32_t)acc.c_viol;
-            if (p.done_count) p.done_count[i] += (int32_t)acc.c_done;
-        } else {
-            if (p.reward_sum) p.reward_sum[i] = rsum;
-            if (p.viol_count) p.viol_count[i] = (int32_t)acc.c_viol;
-            if (p.done_count) p.done_count[i] = (int32_t)acc.c_done;
-        }
+        rollout_env_outputs(p, i, rsum, acc);
     }
+    rollout_stats_flush<Env, EXTREMA>(p, bs, sfl, sext, acc, r_lo, r_hi);
+}
+
+template <class Env, bool EXTREMA>
+__device__ __forceinline__ void rollout_stats_flush(const RolloutArgs& p, BlockStats& bs, double* sfl, unsigned long long* sext, RolloutAcc& acc,
+                                                    typename Env::acc_t r_lo, typename Env::acc_t r_hi)
+{
+    using acc_t = typename Env::acc_t;
     bs.warp_add(NIG_ST_STEPS, acc.c_steps);
     bs.warp_add(NIG_ST_VIOLATIONS, acc.c_viol);
     bs.warp_add(NIG_ST_CRITICAL, acc.c_crit);
@@ -1565,7 +1766,7 @@ struct DrawFromRing {
     {
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[(t / kWsG) % kWsSlots])) : "memory");
     }
-    __device__ __forceinline__ StepDraw get(int t) const
+    __device__ __forceinline__ StepDraw get(int t, int) const
     {
         const int g = t % kWsG;
         if (g == 0) wait_full(t);
@@ -1742,6 +1943,92 @@ __global__ void __launch_bounds__(kWsThreads, 7) rollout_reactor_ws_kernel(const
 }
 
 // ================================================================================================
+// fused K-step rollout, two envs per thread with packed f32x2 arithmetic (ChemicalReactor-v0, the benchmark's configuration)
+// ================================================================================================
+// Thread j owns envs 2j and 2j + 1 (adjacent: 64-bit loads / stores of the SoA rows) and runs reactor_fast_steps_v<F2>: the
+// add / mul / fma instructions of the physics are issued once for both envs (FADD2 / FMUL2 / FFMA2), the per-lane rest twice.
+// Warps whose 64 envs do not all satisfy the loop invariants step both envs through the generic path.
+template <bool EXTREMA>
+__global__ void __launch_bounds__(kThreads, 1) rollout_reactor_pair_kernel(const __grid_constant__ RolloutArgs p)
+{
+    using Env = Reactor;
+    constexpr int S = Env::S;
+    __shared__ unsigned int sstat[NIG_STATS_SLOTS];
+    __shared__ double sfl[4];
+    __shared__ unsigned long long sext[2];
+    __shared__ float4 s_tab[NIG_NORMAL_TAB_N];
+    BlockStats bs;
+    if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
+    if constexpr (EXTREMA) { if (threadIdx.x < 2) sext[threadIdx.x] = 0ull; }
+    normal_table_to_smem(s_tab);
+    const Rng key(p.key, s_tab);
+    bs.init(sstat);                              // (synchronises the CTA)
+
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i0 = 2 * j;
+    const bool valid[2] = {i0 < p.n, i0 + 1 < p.n};
+    const int64_t ib = valid[0] ? i0 : 0;           // (pitch is even: a valid first env has an in-bounds partner row slot)
+    const uint32_t env[2] = {p.env0 + (uint32_t)ib, p.env0 + (uint32_t)ib + 1u};
+    const uint32_t tick0 = load_tick(p.tick_dev, p.tick) + base_tick(p.tick_base);
+    const uint32_t epoch = p.epoch + base_epoch(p.tick_base);
+
+    float s[2][S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) {
+        const float2 v = *reinterpret_cast<const float2*>(p.state + k * p.pitch + ib);
+        s[0][k] = v.x; s[1][k] = v.y;
+    }
+    const uint2 w0 = *reinterpret_cast<const uint2*>(p.ep_word + ib);
+    uint32_t ep_st[2] = {epw_step(w0.x), epw_step(w0.y)}, ep_vi[2] = {epw_viol(w0.x), epw_viol(w0.y)};
+    bool latched[2] = {(w0.x >> 31) != 0u, (w0.y >> 31) != 0u};
+    const double2 er0 = *reinterpret_cast<const double2*>(p.ep_return + ib);
+    float ep_ret[2] = {(float)er0.x, (float)er0.y}, rsum[2] = {0.0f, 0.0f};
+    float r_lo = INFINITY, r_hi = -INFINITY;
+    RolloutAcc acc[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) acc[e].c_con[k] = 0;
+
+    bool inv = p.auto_reset != 0;
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+        inv = inv && valid[e] && !latched[e] && __float_as_uint(s[e][8]) == 0u &&
+              (__float_as_uint(s[e][9]) == 0u || __float_as_uint(s[e][9]) == 0x3f800000u) &&
+              s[e][0] >= 200.0f && s[e][0] <= 350.0f && s[e][1] <= 506625.0f && s[e][5] >= 1e-30f && s[e][5] <= 1e30f &&
+              ep_st[e] < (uint32_t)p.max_steps;
+    int t_begin = 0;
+    if (__all_sync(0xffffffffu, inv)) {
+        DrawInKernel2 src{key, {env[0], env[1]}, tick0};
+        t_begin = reactor_fast_steps_v<F2, EXTREMA>(src, key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi);
+    }
+#pragma unroll 1
+    for (int t = t_begin; t < p.n_steps; ++t) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+            rollout_generic_uniform_step<Env, CONS_DEFAULT, EXTREMA>(p, key, env[e], tick0 + (uint32_t)t, epoch, valid[e], s[e], ep_st[e], ep_vi[e],
+                                                                     latched[e], ep_ret[e], rsum[e], acc[e], r_lo, r_hi);
+    }
+    if (valid[0]) {                                  // rows are written pairwise; an invalid partner (odd n) keeps what it loaded
+#pragma unroll
+        for (int k = 0; k < S; ++k) *reinterpret_cast<float2*>(p.state + k * p.pitch + i0) = make_float2(s[0][k], s[1][k]);
+        *reinterpret_cast<uint2*>(p.ep_word + i0) = make_uint2(epw_make(ep_st[0], ep_vi[0], latched[0] ? 1u : 0u),
+                                                               valid[1] ? epw_make(ep_st[1], ep_vi[1], latched[1] ? 1u : 0u) : w0.y);
+        *reinterpret_cast<double2*>(p.ep_return + i0) = make_double2((double)ep_ret[0], valid[1] ? (double)ep_ret[1] : er0.y);
+        rollout_env_outputs(p, i0, rsum[0], acc[0]);
+        if (valid[1]) rollout_env_outputs(p, i0 + 1, rsum[1], acc[1]);
+    }
+    // one statistics flush for both envs of the thread
+    acc[0].rew_sum = (double)rsum[0] + (double)rsum[1];
+    acc[0].c_steps += acc[1].c_steps; acc[0].c_ep += acc[1].c_ep; acc[0].c_term += acc[1].c_term; acc[0].c_trunc += acc[1].c_trunc;
+    acc[0].c_crit += acc[1].c_crit; acc[0].c_viol += acc[1].c_viol; acc[0].c_succ += acc[1].c_succ; acc[0].c_done += acc[1].c_done;
+#pragma unroll
+    for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) acc[0].c_con[k] += acc[1].c_con[k];
+    acc[0].len_sum += acc[1].len_sum; acc[0].len_sq += acc[1].len_sq; acc[0].ret_sum += acc[1].ret_sum; acc[0].ret_sq += acc[1].ret_sq;
+    rollout_stats_flush<Env, EXTREMA>(p, bs, sfl, sext, acc[0], r_lo, r_hi);
+}
+
+// ================================================================================================
 // dataset writer (get_dataset: chemical_reactor.py:324-420, power_grid.py:194-249, robot_assembly.py:246-308)
 // ================================================================================================
 // One thread = one episode (an independent env with global id env0 + e): reset, then up to n_steps
@@ -1876,6 +2163,12 @@ static __global__ void __launch_bounds__(256) selftest_division_kernel(RngKey ke
                 const float q = d(x, cs[k], 1.0f / cs[k]);
                 if (d.ok()) { acc++; bad += __float_as_uint(q) != __float_as_uint(__fdiv_rn(x, cs[k])); }
             }
+        }
+        {   // mode 3: the binary64 constant division of PowerGrid's cost term (ddiv_const), operands across +-2^+-40
+            const double m = (double)(int)w.y + (double)w.z * 0x1.0p-32;
+            const double x = ldexp(m, (int)(w.w % 81u) - 40);
+            const double q = ddiv_const(x, 1000.0, 1.0 / 1000.0);
+            acc++; bad += __double_as_longlong(q) != __double_as_longlong(__ddiv_rn(x, 1000.0));
         }
     }
     atomicAdd(&out[0], bad);

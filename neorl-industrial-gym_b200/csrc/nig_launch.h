@@ -12,10 +12,11 @@ struct RolloutLaunch {
     bool tf_noise;     // teacher-forced process noise (POLICY_ACTIONS only)
     int block;         // threads per CTA: 32, 64 or 128
     bool extrema;      // nig_track_extrema: the kernel flavour that also keeps return_min / return_max
+    bool pair;         // ChemicalReactor-v0, uniform policy, default constraints: two envs per thread, packed f32x2 arithmetic
     bool ws;           // ChemicalReactor-v0, uniform policy, default constraints: the warp-specialised kernel (producer / consumers)
 };
 
-cudaError_t launch_step(int kind, int vec, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st);
+cudaError_t launch_step(int kind, int vec, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool plain);
 cudaError_t launch_step_pipelined(int kind, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used);
 cudaError_t launch_rollout(int kind, const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st);
 cudaError_t launch_rollout_reactor(const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st);

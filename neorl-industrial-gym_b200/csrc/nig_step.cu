@@ -4,9 +4,24 @@
 namespace nig {
 namespace {
 template <class Env, int VEC>
-cudaError_t go(int cons, int64_t pitch, const StepArgs& a, cudaStream_t st)
+cudaError_t go(int cons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool plain = false)
 {
     const unsigned g = grid_for((pitch + VEC - 1) / VEC);
+    if constexpr (VEC == 1) {
+        // the plain SoA step with the env's default constraints: the flavour with every option branch compiled out
+        if (plain && cons == CONS_DEFAULT) {
+            // launched with programmatic stream serialisation: back-to-back steps (a captured graph of them above all) overlap
+            // the launch latency and prologue of step t + 1 with the tail of step t (griddepcontrol.wait in the kernel)
+            static const bool pdl = [] { const char* v = getenv("NIG_STEP_PDL"); return v ? atoi(v) != 0 : true; }();
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(g); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            return cudaLaunchKernelEx(&cfg, step_kernel<Env, 1, CONS_DEFAULT, true>, a);
+        }
+    }
     if (cons == CONS_DEFAULT) step_kernel<Env, VEC, CONS_DEFAULT><<<g, kThreads, 0, st>>>(a);
     else if (cons == CONS_PREFIX) step_kernel<Env, VEC, CONS_PREFIX><<<g, kThreads, 0, st>>>(a);
     else step_kernel<Env, VEC, CONS_GENERIC><<<g, kThreads, 0, st>>>(a);
@@ -57,13 +72,13 @@ cudaError_t go_pipe(int cons, int64_t pitch, const StepArgs& a, cudaStream_t st,
 }
 } // namespace
 
-cudaError_t launch_step(int kind, int vec, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st)
+cudaError_t launch_step(int kind, int vec, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool plain)
 {
     switch (kind) {
     case NIG_ENV_CHEMICAL_REACTOR:
-        return vec == 4 ? go<Reactor, 4>(cons, pitch, a, st) : vec == 2 ? go<Reactor, 2>(cons, pitch, a, st) : go<Reactor, 1>(cons, pitch, a, st);
-    case NIG_ENV_POWER_GRID: return vec >= 2 ? go<Grid, 2>(cons, pitch, a, st) : go<Grid, 1>(cons, pitch, a, st);
-    default: return vec >= 2 ? go<Robot, 2>(cons, pitch, a, st) : go<Robot, 1>(cons, pitch, a, st);
+        return vec == 4 ? go<Reactor, 4>(cons, pitch, a, st) : vec == 2 ? go<Reactor, 2>(cons, pitch, a, st) : go<Reactor, 1>(cons, pitch, a, st, plain);
+    case NIG_ENV_POWER_GRID: return vec >= 2 ? go<Grid, 2>(cons, pitch, a, st) : go<Grid, 1>(cons, pitch, a, st, plain);
+    default: return vec >= 2 ? go<Robot, 2>(cons, pitch, a, st) : go<Robot, 1>(cons, pitch, a, st, plain);
     }
 }
 

@@ -56,6 +56,8 @@ class SafetyConstraint:
     description: str = ""
     # ("builtin", id) | ("bound", si, ai, coef, lo, hi) | None (host-evaluated callable)
     _native: Optional[tuple] = field(default=None, repr=False, compare=False)
+    # batched envs: check_fn takes (states [n, S], actions [n, A]) and returns bool [n] (one call per step instead of n)
+    vectorized: bool = field(default=False, compare=False)
 
 
 @dataclass

@@ -95,20 +95,37 @@ class IndustrialEnv:
         self.safety_constraints = [c for c in self.safety_constraints if c.name != name]
         self.native.set_constraints(self._native_constraints())
 
+    # callable check_fns are evaluated on the host, one Python call per env and constraint and step: fine for the single-env
+    # gym API, hopeless for a large batch -- above this many envs only vectorised callables (SafetyConstraint(...,
+    # vectorized=True): check_fn(states [n, S], actions [n, A]) -> bool [n]) or declarative BoundConstraints are accepted
+    HOSTMASK_LOOP_LIMIT = 4096
+
     def _hostmask(self, actions: np.ndarray) -> Optional[np.ndarray]:
         host = self._host_constraints()
         if not host:
             return None
         a = np.clip(actions, self.action_space.low, self.action_space.high)
-        mask = np.zeros(self.num_envs, np.uint8)
-        for i in range(self.num_envs):
-            for bit, c in enumerate(host):
+        n = self.num_envs
+        mask = np.zeros(n, np.uint8)
+        for bit, c in enumerate(host):
+            if getattr(c, "vectorized", False):
                 try:
-                    ok = bool(c.check_fn(self._state[i], a[i]))
+                    ok = np.asarray(c.check_fn(self._state, a)).astype(bool).reshape(n)
                 except Exception:          # base.py:109-113: an exception counts as a violation
-                    ok = False
-                if not ok:
-                    mask[i] |= np.uint8(1 << bit)
+                    ok = np.zeros(n, bool)
+            else:
+                if n > self.HOSTMASK_LOOP_LIMIT:
+                    raise ValueError(
+                        f"constraint {c.name!r} is a Python callable evaluated per env on the host ({n} envs x every step); "
+                        f"above {self.HOSTMASK_LOOP_LIMIT} envs use safety.BoundConstraint (evaluated in-kernel) or a "
+                        "vectorised callable: SafetyConstraint(..., vectorized=True)")
+                ok = np.ones(n, bool)
+                for i in range(n):
+                    try:
+                        ok[i] = bool(c.check_fn(self._state[i], a[i]))
+                    except Exception:
+                        ok[i] = False
+            mask[~ok] |= np.uint8(1 << bit)
         return mask
 
     # ------------------------------------------------------------------ reference attributes

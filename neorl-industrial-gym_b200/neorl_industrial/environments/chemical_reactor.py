@@ -40,7 +40,9 @@ class ChemicalReactorEnv(IndustrialEnv):
             SafetyConstraint("level_safety", self._level_constraint, -25.0, False,
                              "Reactor level must stay between 20-90%", _native=("builtin", 2)),
         ]
-        super().__init__(state_dim=12, action_dim=3, safety_constraints=constraints, max_episode_steps=500, dt=0.1, **kwargs)
+        kwargs.setdefault("max_episode_steps", 500)        # chemical_reactor.py:66 (overridable here, like the other envs)
+        kwargs.setdefault("dt", 0.1)
+        super().__init__(state_dim=12, action_dim=3, safety_constraints=constraints, **kwargs)
 
     # host-callable forms of the built-in checks (API parity: tests call constraint.check_fn(obs, action))
     def _temperature_constraint(self, state, action) -> bool:

@@ -63,34 +63,44 @@ def evaluate_policy_device(env, n_steps: int, policy: int = N.POLICY_UNIFORM, pa
 
 
 def evaluate_agent_batched(agent: Any, env: Any, n_episodes: int = 100) -> Dict[str, Any]:
-    """utils.py:82-154 with a batched env: every env runs episodes until ``n_episodes`` have finished in total."""
+    """utils.py:82-154 with a batched env. The reference runs ``n_episodes`` episodes one after the other, each from a fresh
+    reset to its end; here the episodes are dealt out to the envs as QUOTAS -- env i runs its first
+    ``n_episodes // num_envs`` (+1 for the first ``n_episodes % num_envs`` envs) episodes to the end and only those count,
+    every step of them and nothing else. (Keeping "the first n_episodes to finish across all envs" instead would favour
+    short episodes: the sample would be biased towards early terminations.)"""
     if not getattr(env, "auto_reset", False):
         raise ValueError("batched evaluation needs an auto-resetting env (ni.make(..., num_envs=N))")
     n = env.num_envs
+    quota = np.full(n, n_episodes // n, np.int64)
+    quota[: n_episodes % n] += 1
+    finished = np.zeros(n, np.int64)
     obs, _ = env.reset()
     ep_ret = np.zeros(n, np.float64)
     ep_len = np.zeros(n, np.int64)
-    returns, lengths, sat = [], [], []
+    returns, lengths = [], []
     viol = crit = shut = 0
-    while len(returns) < n_episodes:
+    sat_sum, sat_n = 0.0, 0
+    while np.any(finished < quota):
+        live = finished < quota                      # envs still inside their quota: only their steps are counted
         action = np.asarray(agent.predict(obs, deterministic=True), np.float32).reshape(n, env.action_dim)
         obs, reward, terminated, truncated, info = env.step(action)
         ep_ret += reward
         ep_len += 1
         sm = info["safety_metrics"]
-        viol += int(sm.violation_count.sum()); crit += int(sm.critical_violations.sum())
-        sat.append(float(np.mean(sm.satisfaction_rate)))
-        shut += int(np.sum(info["critical_shutdown"]))
-        done = terminated | truncated
-        for i in np.flatnonzero(done):
+        viol += int(np.asarray(sm.violation_count)[live].sum()); crit += int(np.asarray(sm.critical_violations)[live].sum())
+        sat_sum += float(np.asarray(sm.satisfaction_rate, np.float64)[live].sum()); sat_n += int(live.sum())
+        shut += int(np.sum(np.asarray(info["critical_shutdown"])[live]))
+        done = (terminated | truncated)
+        for i in np.flatnonzero(done & live):
             returns.append(float(ep_ret[i])); lengths.append(int(ep_len[i]))
+        finished[done & live] += 1
         ep_ret[done] = 0.0; ep_len[done] = 0
-    returns, lengths = np.array(returns[:n_episodes]), np.array(lengths[:n_episodes])
+    returns, lengths = np.array(returns), np.array(lengths)
     succ = int(np.sum(returns > 0))
     return {
         "return_mean": returns.mean(), "return_std": returns.std(), "return_min": returns.min(), "return_max": returns.max(),
         "length_mean": lengths.mean(), "length_std": lengths.std(),
         "safety_violations": viol, "safety_violations_per_episode": viol / n_episodes, "critical_violations": crit,
-        "emergency_shutdowns": shut, "constraint_satisfaction_rate": float(np.mean(sat)) if sat else 1.0,
+        "emergency_shutdowns": shut, "constraint_satisfaction_rate": (sat_sum / sat_n) if sat_n else 1.0,
         "successful_episodes": succ, "success_rate": succ / n_episodes,
     }

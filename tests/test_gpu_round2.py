@@ -283,3 +283,75 @@ def test_allreduce_stats_through_the_c_abi_single_rank(mods):
         N.check(lib.nig_allreduce_stats(env._h, None, st))
     N.check(lib.nig_nccl_comm_destroy(comm))
     env.close()
+
+
+class _BangBang:
+    """deterministic policy that ends reactor episodes at very different lengths (heats hard when cold)"""
+    is_trained = True
+
+    def predict(self, obs, deterministic=True):
+        obs = np.atleast_2d(obs)
+        a = np.zeros((obs.shape[0], 3), np.float32)
+        a[:, 0] = np.where(obs[:, 0] < 321.0, 1.0, -0.2)
+        return a
+
+
+def test_batched_evaluation_uses_per_env_episode_quotas(mods):
+    """evaluate_with_safety on a batched env runs, per env, a fixed quota of episodes to their end (utils.py:82-125 runs its
+    n_episodes one after the other): exactly n_episodes are counted, env i contributes its FIRST quota_i episodes, and the
+    result equals replaying those episodes one env at a time."""
+    ni, N, O, torch = mods
+    n, n_ep = 8, 21                                   # quotas 3,3,3,3,3,2,2,2
+    env = ni.make("ChemicalReactor-v0", num_envs=n, seed=5, max_episode_steps=60)
+    res = ni.evaluate_with_safety(_BangBang(), env, n_episodes=n_ep)
+    env.close()
+    # the same episodes, one env at a time (global env ids key the random streams, so env i alone reproduces shard i)
+    rets, lens, viol = [], [], 0
+    for i in range(n):
+        e1 = ni.make("ChemicalReactor-v0", num_envs=1, batched=True, seed=5, max_episode_steps=60, env_id_offset=i)
+        obs, _ = e1.reset()
+        quota = n_ep // n + (1 if i < n_ep % n else 0)
+        ep_r, ep_l = 0.0, 0
+        while quota:
+            obs, r, te, tr, info = e1.step(_BangBang().predict(obs))
+            ep_r += float(r[0]); ep_l += 1
+            viol += int(info["safety_metrics"].violation_count[0])
+            if te[0] or tr[0]:
+                rets.append(ep_r); lens.append(ep_l); ep_r, ep_l = 0.0, 0; quota -= 1
+        e1.close()
+    assert len(rets) == n_ep
+    np.testing.assert_allclose(res["return_mean"], np.mean(rets), rtol=1e-12)
+    np.testing.assert_allclose(res["length_mean"], np.mean(lens), rtol=1e-12)
+    assert res["return_min"] == min(rets) and res["return_max"] == max(rets) and res["safety_violations"] == viol
+
+
+def test_host_evaluated_constraints_vectorised_or_bounded(mods):
+    """callable check_fns run on the host: a vectorised one costs one call per step; a per-env one is refused above
+    HOSTMASK_LOOP_LIMIT envs instead of silently looping num_envs x constraints times in Python."""
+    ni, N, O, torch = mods
+    from neorl_industrial.core.types import SafetyConstraint
+    n = 6000
+    calls = []
+
+    def hot(states, actions):
+        calls.append(states.shape)
+        return states[:, 0] <= 321.0
+
+    env = ni.make("ChemicalReactor-v0", num_envs=n, seed=2)
+    env.add_safety_constraint(SafetyConstraint("hot_vec", hot, -7.0, False, vectorized=True))
+    obs, _ = env.reset()
+    a = np.zeros((n, 3), np.float32)
+    _, r1, _, _, info = env.step(a)
+    assert calls == [(n, 12)]
+    want = (obs[:, 0] > 321.0)
+    assert np.array_equal((info["violation_mask"] >> 3) & 1, want.astype(np.uint8)) and want.any() and not want.all()
+    env.add_safety_constraint(SafetyConstraint("hot_scalar", lambda s, a: s[0] <= 321.0, -7.0, False))
+    with pytest.raises(ValueError, match="vectorised callable"):
+        env.step(a)
+    env.close()
+    small = ni.make("ChemicalReactor-v0", num_envs=64, seed=2)
+    small.add_safety_constraint(SafetyConstraint("hot_scalar", lambda s, a: s[0] <= 321.0, -7.0, False))
+    o, _ = small.reset()
+    _, _, _, _, info = small.step(np.zeros((64, 3), np.float32))
+    assert np.array_equal((info["violation_mask"] >> 3) & 1, (o[:, 0] > 321.0).astype(np.uint8))
+    small.close()
