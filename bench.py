@@ -438,11 +438,12 @@ def single_step_section(torch, ni, N, local, dev, flush, hbm_peak, peak_src, arg
                        "note": "1,000 back-to-back launches; 8 MB working set is L2-resident, launch-latency bound"}
     # the same 1,000 launches as 10 replays of a captured 100-launch CUDA graph (device-resident tick: fresh noise each step)
     try:
-        env.use_device_tick(True)
+        env.use_device_tick(2)                   # device base + per-launch sequence offsets (nig_use_device_tick mode 2)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for _ in range(100):
                 env.step_device(acts, reward=rew, flags=fl, viol_mask=vm)
+            env.commit_ticks()                   # last node: the base moves on by 100 per replay
         g.replay()
         torch.cuda.synchronize()
         e0.record()
@@ -453,7 +454,7 @@ def single_step_section(torch, ni, N, local, dev, flush, hbm_peak, peak_src, arg
         msg = e0.elapsed_time(e1)
         out["envs_64k_cuda_graph"] = {"value": ENVS_PER_GPU * HORIZON / (msg * 1e-3), "unit": UNIT, "us_per_launch": msg * 1e3 / HORIZON,
                                       "hbm_frac": frac64(msg * 1e3 / HORIZON),
-                                      "note": "10 replays of a 100-launch CUDA graph (nig_use_device_tick)"}
+                                      "note": "10 replays of a 100-launch CUDA graph (nig_use_device_tick mode 2 + nig_commit_ticks; programmatic dependent launch)"}
     except Exception as ex:                                   # graph capture is an optimisation, never a requirement
         out["envs_64k_cuda_graph"] = {"error": repr(ex)}
     env.close()

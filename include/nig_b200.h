@@ -310,11 +310,19 @@ NIG_API int nig_set_state_host(nig_env_t* env, const float* state_aos, const int
 NIG_API int nig_state_ptr(nig_env_t* env, float** state_dev_soa, uint32_t** ep_word_dev);
 NIG_API int nig_get_tick(const nig_env_t* env, uint32_t* tick, uint32_t* epoch);
 NIG_API int nig_set_tick(nig_env_t* env, uint32_t tick, uint32_t epoch);
-/* CUDA-graph capture: with the device tick enabled the batched-step counter that keys the random streams lives in
- * device memory and the kernels advance it themselves, so a captured sequence of nig_step / nig_rollout launches can
- * be replayed any number of times and keeps drawing fresh noise (a host-side counter would be frozen into the graph).
- * Enable BEFORE capturing; nig_get_tick / nig_set_tick keep working (they synchronise). */
-NIG_API int nig_use_device_tick(nig_env_t* env, int32_t enable);
+/* CUDA-graph capture: a captured graph replays the SAME kernel arguments, so the batched-step counter that keys the random
+ * streams must not be one. Two device-resident modes (enable BEFORE capturing; nig_get_tick / nig_set_tick keep working,
+ * they synchronise):
+ *   1  every launch reads the counter from device memory and its last CTA advances it. Simple, any captured sequence
+ *      replays correctly; costs a fence + an atomic round trip at the end of every launch.
+ *   2  the device word is a BASE; every launch carries its offset from it (the launches since the last commit) as an
+ *      argument, nothing is advanced per launch, and the tick is known before the previous launch has finished (the
+ *      single-step kernel draws its noise while the previous step drains: programmatic dependent launch). The captured
+ *      sequence must END with nig_commit_ticks(env, stream), which moves the base on by the sequence's length; without it
+ *      every replay would repeat the same draws.
+ *   0  back to the host-side counter. */
+NIG_API int nig_use_device_tick(nig_env_t* env, int32_t mode);
+NIG_API int nig_commit_ticks(nig_env_t* env, void* stream);
 /* reset(seed=...) made effective (the reference ignores it, base.py:135): re-keys the random streams
  * AND rewinds the handle's tick / epoch to 0, so that set_seed(s) + reset gives the same states and noise every time */
 NIG_API int nig_set_seed(nig_env_t* env, uint64_t seed);
@@ -322,6 +330,10 @@ NIG_API int nig_set_seed(nig_env_t* env, uint64_t seed);
 /* violation / return counters (info["violations"], info["total_violations"], evaluate_with_safety's
  * aggregates utils.py:128-152). The device block can be all-reduced in place (NCCL sum over int64/fp64). */
 NIG_API int nig_stats_ptr(nig_env_t* env, void** stats_dev);
+/* The plain single-step kernel adds its counters to 128 shard copies of the block (one hot block serialised ~1,600
+ * reductions per launch in L2 at 65,536 envs); nig_read_stats, nig_allreduce_stats and the *_host calls fold the shards in
+ * first. A caller that reads the raw device block of nig_stats_ptr itself queues nig_fold_stats on its stream before. */
+NIG_API int nig_fold_stats(nig_env_t* env, void* stream);
 NIG_API int nig_read_stats(nig_env_t* env, int64_t* counters24, double* sums8);
 NIG_API int nig_clear_stats(nig_env_t* env, void* stream);
 

@@ -96,6 +96,8 @@ struct nig_env {
     float *h_actions, *h_noise, *h_reset, *h_obs, *h_next_obs, *h_reward;
     uint8_t *h_hostmask, *h_flags, *h_viol, *h_mask;
     int32_t *h_i32a, *h_i32b;
+    unsigned long long* stats_shards;   // kStatsShards x NIG_STATS_SLOTS: where the PLAIN single-step kernel adds (folded into stats on read)
+    bool shards_dirty;
     unsigned long long* extrema; // [2] min / max finished-episode return keys (outside the summable stats block)
     bool track_extrema;          // nig_track_extrema: rollouts run the EXTREMA kernel flavour
     bool track_returns;          // nig_track_returns (default on, set in nig_create): the single-step kernels keep the episode-return accumulator too
@@ -116,7 +118,9 @@ struct nig_env {
     uint64_t config_version;    // bumped by every setter whose value is baked into kernel arguments (invalidates host_graph)
     int host_graph_enable;      // NIG_HOST_GRAPH (default 1)
     uint32_t* cons_masks;       // device copy of the NIG_CON_BOUND one-hot masks (ConsParams::masks)
-    uint32_t* tick_dev;         // device-tick mode (CUDA-graph capture): [0] tick, [1] finished-CTA counter; null = host tick
+    uint32_t* tick_dev;         // device-tick modes (CUDA-graph capture): [0] tick, [1] finished-CTA counter; null = host tick
+    int tick_mode;              // 0 host tick; 1 device tick advanced by every launch; 2 device BASE + per-launch sequence offsets
+    uint32_t tick_commit;       // mode 2: host tick at the last nig_commit_ticks (launch offset = tick - tick_commit)
     double* pid_state;          // [2][A][pitch] PID integral / previous error of NIG_POLICY_BASELINE (lazily allocated, zeroed)
     float *r_act[2], *r_nz[2];  // nig_rollout_host: double-buffered action / noise chunks
     int32_t r_cap;              // steps each chunk buffer holds
@@ -180,6 +184,25 @@ int host_entry(nig_env* e)
         else for (int k = 0; k < e->n_dev_streams; ++k) NIG_CUDA(cudaStreamSynchronize(e->dev_streams[k]));
         e->dev_dirty = false; e->dev_sync_all = false; e->n_dev_streams = 0;
     }
+    return NIG_OK;
+}
+
+// how a launch at host tick `tick` gets its counters (see nig_use_device_tick): kernel argument, device tick, or base + offset
+template <class Args>
+void fill_tick(const nig_env* e, Args& a, uint32_t tick)
+{
+    if (e->graph_mode) { a.tick = tick - e->graph_tick0; a.tick_dev = nullptr; a.tick_base = e->d_tickbase; }
+    else if (e->tick_mode == 2) { a.tick = tick - e->tick_commit; a.tick_dev = nullptr; a.tick_base = e->tick_dev; }
+    else { a.tick = tick; a.tick_dev = e->tick_dev; a.tick_base = nullptr; }
+}
+
+// the PLAIN single-step kernel adds its counters to shard copies of the stats block: fold them in before the block is read
+int fold_stats(nig_env* e, cudaStream_t st)
+{
+    if (!e->shards_dirty) return NIG_OK;
+    e->launches++;
+    NIG_CUDA(nig::launch_fold_stats(e->stats_shards, e->stats, st));
+    e->shards_dirty = false;
     return NIG_OK;
 }
 
@@ -308,7 +331,8 @@ int reset_range(nig_env* e, const float* init_aos, int64_t i0, int64_t ns, uint3
 {
     ResetArgs a{e->state + i0, e->ep_word + i0, e->ep_return + i0, ns, e->pitch, (uint32_t)e->cfg.env_id_offset + (uint32_t)i0, e->tick, epoch,
                 e->tick_dev, e->key, nullptr, init_aos ? init_aos + i0 * e->S : nullptr, 1, nullptr};
-    if (e->graph_mode) { a.tick = 0u; a.epoch = 0u; a.tick_base = e->d_tickbase; }
+    fill_tick(e, a, e->tick);
+    if (e->graph_mode) a.epoch = 0u;
     e->launches++;
     NIG_CUDA(nig::launch_reset(e->kind, a, s));
     return NIG_OK;
@@ -372,7 +396,8 @@ int rollout_range(nig_env* e, const nig_rollout_t* r, cudaStream_t stream, int64
     a.pid_state = e->pid_state ? e->pid_state + i0 : nullptr;
     a.extrema = e->extrema;
     a.stats = e->stats; a.cons = e->cons;
-    if (e->graph_mode) { a.tick = tick - e->graph_tick0; a.epoch = 0u; a.tick_base = e->d_tickbase; }
+    fill_tick(e, a, tick);
+    if (e->graph_mode) a.epoch = 0u;
     CUtensorMap map;
     memset(&map, 0, sizeof map);
     const bool tma = r->policy == NIG_POLICY_ACTIONS && (r->flags & NIG_ROLLOUT_USE_TMA) && !e->track_extrema && i0 == 0 && ns == e->n;
@@ -597,6 +622,7 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     if (rc == NIG_OK) rc = dev_alloc(&e->ep_word, (size_t)e->pitch);
     if (rc == NIG_OK) rc = dev_alloc(&e->ep_return, (size_t)e->pitch);
     if (rc == NIG_OK) rc = dev_alloc(&e->stats, (size_t)NIG_STATS_SLOTS);
+    if (rc == NIG_OK) rc = dev_alloc(&e->stats_shards, (size_t)nig::kStatsShards * NIG_STATS_SLOTS);
     if (rc == NIG_OK) rc = dev_alloc(&e->extrema, (size_t)2);
     if (rc == NIG_OK && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess)
         rc = fail(NIG_ERR_CUDA, "cudaStreamCreate failed");
@@ -613,7 +639,7 @@ int nig_destroy(nig_env_t* e)
     if (e->host_graph) cudaGraphExecDestroy(e->host_graph);
     if (e->h_tickbase) cudaFreeHost(e->h_tickbase);
     cudaFree(e->d_tickbase);
-    cudaFree(e->state); cudaFree(e->ep_word); cudaFree(e->ep_return); cudaFree(e->stats);
+    cudaFree(e->state); cudaFree(e->ep_word); cudaFree(e->ep_return); cudaFree(e->stats); cudaFree(e->stats_shards);
     cudaFree(e->h_actions); cudaFree(e->h_noise); cudaFree(e->h_reset); cudaFree(e->h_obs); cudaFree(e->h_next_obs);
     cudaFree(e->h_reward); cudaFree(e->h_hostmask); cudaFree(e->h_flags); cudaFree(e->h_viol); cudaFree(e->h_mask);
     cudaFree(e->h_i32a); cudaFree(e->h_i32b); cudaFree(e->pid_state); cudaFree(e->tick_dev); cudaFree(e->cons_masks); cudaFree(e->extrema); cudaFree(e->d_len); cudaFree(e->d_off); cudaFree(e->d_total);
@@ -655,6 +681,7 @@ int nig_reset(nig_env_t* e, const uint8_t* mask, const float* init_states, int32
     e->epoch += 1;     // explicit resets draw with a fresh epoch; auto-resets reuse the current one
     ResetArgs a{e->state, e->ep_word, e->ep_return, e->n, e->pitch, (uint32_t)e->cfg.env_id_offset, e->tick, e->epoch, e->tick_dev,
                 e->key, mask, init_states, layout == NIG_LAYOUT_AOS ? 1 : 0};
+    fill_tick(e, a, e->tick);
     e->launches++;
     note_device_work(e, (cudaStream_t)stream);
     NIG_CUDA(nig::launch_reset(e->kind, a, (cudaStream_t)stream));
@@ -703,7 +730,9 @@ int nig_step(nig_env_t* e, const nig_step_io_t* io, void* stream)
     a.obs = io->obs; a.next_obs = io->next_obs; a.reward = io->reward; a.flags = io->flags; a.viol_mask = io->viol_mask;
     a.terminated = io->terminated; a.truncated = io->truncated;
     a.action_aos = io->action_layout == NIG_LAYOUT_AOS; a.aux_aos = io->aux_layout == NIG_LAYOUT_AOS;
-    a.stats = e->stats; a.cons = e->cons;
+    a.stats = e->stats; a.stats_shards = e->stats_shards; a.cons = e->cons;
+    e->shards_dirty = true;
+    fill_tick(e, a, e->tick);
     const int rc = launch_step(e, a, (cudaStream_t)stream);
     if (rc == NIG_OK) e->tick += 1;
     return rc;
@@ -939,7 +968,10 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
             if ((rc = enqueue_sliced_host(e, r, slices, per, T, K, reset, st)) != NIG_OK) return rc;
         }
         unsigned long long hs[NIG_STATS_SLOTS];
-        if (r->counters24 || r->sums8) NIG_CUDA(cudaMemcpyAsync(hs, e->stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+        if (r->counters24 || r->sums8) {
+            if ((rc = fold_stats(e, st)) != NIG_OK) return rc;
+            NIG_CUDA(cudaMemcpyAsync(hs, e->stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+        }
         NIG_CUDA(cudaStreamSynchronize(st));
         if (r->counters24) for (int k = 0; k < 24; ++k) r->counters24[k] = (int64_t)hs[k];
         if (r->sums8) memcpy(r->sums8, &hs[24], 8 * sizeof(double));
@@ -992,7 +1024,10 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
     if (r->viol_count) NIG_CUDA(cudaMemcpyAsync(r->viol_count, e->h_i32a, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (r->done_count) NIG_CUDA(cudaMemcpyAsync(r->done_count, e->h_i32b, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     unsigned long long hs[NIG_STATS_SLOTS];
-    if (r->counters24 || r->sums8) NIG_CUDA(cudaMemcpyAsync(hs, e->stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+    if (r->counters24 || r->sums8) {
+        if ((rc = fold_stats(e, st)) != NIG_OK) return rc;
+        NIG_CUDA(cudaMemcpyAsync(hs, e->stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+    }
     NIG_CUDA(cudaStreamSynchronize(st));
     if (r->counters24) for (int k = 0; k < 24; ++k) r->counters24[k] = (int64_t)hs[k];
     if (r->sums8) memcpy(r->sums8, &hs[24], 8 * sizeof(double));
@@ -1174,10 +1209,11 @@ int nig_get_tick(const nig_env_t* e, uint32_t* tick, uint32_t* epoch)
     if (!e) return fail(NIG_ERR_INVALID, "null env handle");
     if (tick) {
         *tick = e->tick;
-        if (e->tick_dev) {          // device-tick mode: the counter lives on the device (graph replays advance it)
+        if (e->tick_dev) {          // device-tick modes: the counter lives on the device (graph replays advance it)
             DeviceGuard guard(e->cfg.device);
             NIG_CUDA(cudaDeviceSynchronize());
             NIG_CUDA(cudaMemcpy(tick, e->tick_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            if (e->tick_mode == 2) *tick += e->tick - e->tick_commit;      // launches since the last commit
         }
     }
     if (epoch) *epoch = e->epoch;
@@ -1186,7 +1222,7 @@ int nig_get_tick(const nig_env_t* e, uint32_t* tick, uint32_t* epoch)
 int nig_set_tick(nig_env_t* e, uint32_t tick, uint32_t epoch)
 {
     if (!e) return fail(NIG_ERR_INVALID, "null env handle");
-    e->tick = tick; e->epoch = epoch;
+    e->tick = tick; e->epoch = epoch; e->tick_commit = tick;
     if (e->tick_dev) {
         DeviceGuard guard(e->cfg.device);
         NIG_CUDA(cudaDeviceSynchronize());
@@ -1200,17 +1236,32 @@ int nig_use_device_tick(nig_env_t* e, int32_t enable)
 {
     if (e) e->config_version++;
     NIG_CHECK_ENV(e);
+    if (enable < 0 || enable > 2) return fail(NIG_ERR_INVALID, "nig_use_device_tick: mode must be 0, 1 or 2");
+    uint32_t now = 0;
+    if (int rc = nig_get_tick(e, &now, nullptr)) return rc;      // (synchronises in the device modes)
     NIG_CUDA(cudaDeviceSynchronize());
-    if (enable && !e->tick_dev) {
-        NIG_CUDA(cudaMalloc((void**)&e->tick_dev, 2 * sizeof(uint32_t)));
-        const uint32_t init[2] = {e->tick, 0u};
+    if (enable && !e->tick_dev) NIG_CUDA(cudaMalloc((void**)&e->tick_dev, 2 * sizeof(uint32_t)));
+    if (!enable && e->tick_dev) { cudaFree(e->tick_dev); e->tick_dev = nullptr; }
+    e->tick = now; e->tick_commit = now; e->tick_mode = enable;
+    if (e->tick_dev) {
+        const uint32_t init[2] = {now, 0u};
         NIG_CUDA(cudaMemcpy(e->tick_dev, init, sizeof init, cudaMemcpyHostToDevice));
         NIG_CUDA(cudaDeviceSynchronize());
-    } else if (!enable && e->tick_dev) {
-        NIG_CUDA(cudaMemcpy(&e->tick, e->tick_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost));
-        cudaFree(e->tick_dev);
-        e->tick_dev = nullptr;
     }
+    return NIG_OK;
+}
+
+int nig_commit_ticks(nig_env_t* e, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    if (e->tick_mode != 2) return NIG_OK;                        // nothing to commit in the other modes
+    const uint32_t by = e->tick - e->tick_commit;
+    if (by) {
+        e->launches++;
+        note_device_work(e, (cudaStream_t)stream);
+        NIG_CUDA(nig::launch_commit_ticks(e->tick_dev, by, (cudaStream_t)stream));
+    }
+    e->tick_commit = e->tick;
     return NIG_OK;
 }
 
@@ -1231,11 +1282,19 @@ int nig_stats_ptr(nig_env_t* e, void** p)
     return NIG_OK;
 }
 
+int nig_fold_stats(nig_env_t* e, void* stream)
+{
+    NIG_CHECK_ENV(e);
+    note_device_work(e, (cudaStream_t)stream);
+    return fold_stats(e, (cudaStream_t)stream);
+}
+
 int nig_read_stats(nig_env_t* e, int64_t* counters24, double* sums8)
 {
     NIG_CHECK_ENV(e);
     unsigned long long h[NIG_STATS_SLOTS];
     NIG_CUDA(cudaDeviceSynchronize());
+    if (int rc = fold_stats(e, nullptr)) return rc;
     NIG_CUDA(cudaMemcpy(h, e->stats, sizeof h, cudaMemcpyDeviceToHost));
     if (counters24) for (int k = 0; k < 24; ++k) counters24[k] = (int64_t)h[k];
     if (sums8) memcpy(sums8, &h[24], 8 * sizeof(double));
@@ -1330,6 +1389,7 @@ int nig_allreduce_stats(nig_env_t* e, void* nccl_comm, void* stream)
     note_device_work(e, st);
     // one group = one fused launch: 24 int64 counters (SUM: exact, order independent), 8 fp64 sums (SUM), and the two
     // order-preserving return-extremum keys (MAX; zeros when nothing was tracked)
+    if (int frc = fold_stats(e, st)) return frc;
     NIG_NCCL(a, a->GroupStart(), "ncclGroupStart");
     int rc = a->AllReduce(e->stats, e->stats, 24, kNcclInt64, kNcclSum, nccl_comm, st);
     if (rc == 0) rc = a->AllReduce(e->stats + 24, e->stats + 24, NIG_STATS_SLOTS - 24, kNcclFloat64, kNcclSum, nccl_comm, st);
@@ -1344,6 +1404,8 @@ int nig_clear_stats(nig_env_t* e, void* stream)
 {
     NIG_CHECK_ENV(e);
     NIG_CUDA(cudaMemsetAsync(e->stats, 0, NIG_STATS_SLOTS * sizeof(unsigned long long), (cudaStream_t)stream));
+    NIG_CUDA(cudaMemsetAsync(e->stats_shards, 0, (size_t)nig::kStatsShards * NIG_STATS_SLOTS * sizeof(unsigned long long), (cudaStream_t)stream));
+    e->shards_dirty = false;
     NIG_CUDA(cudaMemsetAsync(e->extrema, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
     return NIG_OK;
 }

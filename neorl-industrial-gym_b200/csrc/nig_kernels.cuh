@@ -413,6 +413,7 @@ struct StepArgs {
     int64_t n, pitch;
     uint32_t env0, tick, epoch;
     uint32_t* tick_dev;      // non-null: device-resident tick (graph capture), see load_tick()
+    const uint32_t* tick_base;   // non-null: tick / epoch above are offsets from tick_base[0] (sequence-tick graphs, see base_tick())
     RngKey key;
     int32_t max_steps, auto_reset;
     const float* actions;
@@ -428,8 +429,13 @@ struct StepArgs {
     uint8_t* truncated;
     int32_t action_aos, aux_aos;
     unsigned long long* stats;
+    // PLAIN flavour: kStatsShards copies of the stats block; CTA b adds to copy b % kStatsShards. At 65,536 envs the 512
+    // CTAs' ~1,600 reductions on the three hot addresses of ONE block kept every launch waiting 1.25 us for the L2 atomic unit
+    // (4.07 -> 2.82 us per replayed launch without them); the copies are folded into `stats` whenever it is read (fold_stats_kernel)
+    unsigned long long* stats_shards;
     ConsParams cons;
 };
+constexpr int kStatsShards = 128;
 
 // finished-episode statistics of the single-step kernels (the same slots the fused rollout fills: evaluate_with_safety's
 // return / length aggregates, utils.py:128-152), so that a handle driven through nig_step reports them too and a
@@ -549,16 +555,26 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
     BlockStats bs;
     episode_staging_init(&estage);
     bs.init(sstat);
+    const Rng key(p.key, g_normal_tab);        // one-tile CTA: the L1-cached global table
+    // PLAIN + a tick that does not depend on the previous launch (a kernel argument, or base + sequence offset): this step's
+    // process noise is a function of (env, tick) alone and is drawn BEFORE waiting for the previous step (below)
+    const bool early = PLAIN && VEC == 1 && NZ > 0 && p.tick_dev == nullptr && (p.tick_base == nullptr || p.tick != 0u);
+    float nz_pre[NZA];
+    uint32_t tick_pre = 0u;
+    if (early) {
+        tick_pre = p.tick + base_tick(p.tick_base);
+        const int64_t ie = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+        Env::NoiseGen::get_single(key, p.env0 + (uint32_t)ie, tick_pre, nz_pre);
+    }
     if constexpr (PLAIN) {
         // programmatic dependent launch (the launcher sets cudaLaunchAttributeProgrammaticStreamSerialization on this flavour):
-        // the CTAs of step t + 1 are scheduled while step t drains, set up their shared memory above, and wait HERE until
-        // step t has completed and flushed -- before the first read of anything it writes (tick, state, episode words).
-        // Their own dependents may be scheduled at once: they will wait in the same place.
+        // the CTAs of step t + 1 are scheduled while step t drains, set up their shared memory and (see above) draw their
+        // noise, and wait HERE until step t has completed and flushed -- before the first read of anything it writes (device
+        // tick, state, episode words). Their own dependents may be scheduled at once: they will wait in the same place.
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
-    const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
-    const Rng key(p.key, g_normal_tab);        // one-tile CTA: the L1-cached global table
+    const uint32_t tick0 = early ? tick_pre : load_tick(p.tick_dev, p.tick) + base_tick(p.tick_base);
 
     const int64_t i0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
     unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0, c_con = 0;  // c_con: 4 bits/constraint
@@ -597,6 +613,9 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
                 if (o.noise) {
 #pragma unroll
                     for (int k = 0; k < NZA; ++k) nz[k] = nzv[k][e];
+                } else if (early) {
+#pragma unroll
+                    for (int k = 0; k < NZA; ++k) nz[k] = nz_pre[k];
                 } else {
                     Env::NoiseGen::get_single(key, env, tick0, nz);
                 }
@@ -698,6 +717,42 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             }
         }
     }
+    if constexpr (PLAIN) {
+        if (p.stats_shards) {
+            // per-WARP flush straight into a shard copy of the stats block: no CTA barrier and no shared staging, so the
+            // reductions leave right behind the warp's stores instead of one L2 round trip after the slowest warp of the CTA
+            // (the kernel cannot retire before they are acknowledged: 3.97 -> see DESIGN 3.1 us per replayed 65,536-env launch)
+            unsigned long long* const row = p.stats_shards +
+                (size_t)((blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kStatsShards) * NIG_STATS_SLOTS;
+            const bool lead = (threadIdx.x & 31) == 0;
+            auto red = [&](int slot, unsigned int v) {
+                const unsigned int t = __reduce_add_sync(0xffffffffu, v);
+                if (lead && t) atomicAdd(&row[slot], (unsigned long long)t);
+            };
+            red(NIG_ST_STEPS, c_steps);
+            if (__any_sync(0xffffffffu, (c_ep | c_viol | c_crit) != 0u)) {
+                red(NIG_ST_EPISODES, c_ep); red(NIG_ST_TERMINATED, c_term); red(NIG_ST_TRUNCATED, c_trunc);
+                red(NIG_ST_CRITICAL, c_crit); red(NIG_ST_VIOLATIONS, c_viol);
+                for (int k = 0; k < p.cons.n; ++k) red(NIG_ST_CON0 + k, (c_con >> (4 * k)) & 0xfu);
+                if (p.ep_return && __any_sync(0xffffffffu, c_ep != 0u)) {
+                    StepEpisodeStats eps;
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e)
+                        if (fin_len[e]) eps.episode(fin_ret[e], (unsigned long long)fin_len[e]);
+                    red(NIG_ST_SUCCESSES, eps.c_succ);
+                    const unsigned long long ls = warp_sum(eps.len_sum), lq = warp_sum(eps.len_sq);
+                    const double rs_ = warp_sum(eps.ret_sum), rq = warp_sum(eps.ret_sq);
+                    if (lead) {
+                        atomicAdd(&row[NIG_ST_EP_LEN_SUM], ls); atomicAdd(&row[NIG_ST_EP_LEN_SQ], lq);
+                        atomicAdd(reinterpret_cast<double*>(row) + NIG_ST_F_RETURN_SUM, rs_);
+                        atomicAdd(reinterpret_cast<double*>(row) + NIG_ST_F_RETURN_SQ, rq);
+                    }
+                }
+            }
+            advance_device_tick(p.tick_dev, 1u);
+            return;
+        }
+    }
     bs.warp_add(NIG_ST_STEPS, c_steps);
     if (__any_sync(0xffffffffu, (c_ep | c_viol | c_crit) != 0u)) {
         bs.warp_add(NIG_ST_EPISODES, c_ep);
@@ -714,8 +769,9 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             stage_episode_stats(bs, &estage, eps);
         }
     }
-    bs.flush(p.stats);
-    if (p.ep_return) flush_episode_staging(p.stats, &estage);
+    unsigned long long* const stats_out = (PLAIN && p.stats_shards) ? p.stats_shards + (blockIdx.x % kStatsShards) * NIG_STATS_SLOTS : p.stats;
+    bs.flush(stats_out);
+    if (p.ep_return) flush_episode_staging(stats_out, &estage);
     advance_device_tick(p.tick_dev, 1u);
 }
 
@@ -752,7 +808,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
     BlockStats bs;
     episode_staging_init(&estage);
     bs.init(sstat);
-    const uint32_t tick0 = load_tick(p.tick_dev, p.tick);
+    const uint32_t tick0 = load_tick(p.tick_dev, p.tick) + base_tick(p.tick_base);
     const Rng key(p.key, Env::TAB_SMEM ? s_tab : g_normal_tab);
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -932,6 +988,27 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(const __grid_constant__
     p.ep_word[i] = 0u;
     p.ep_return[i] = 0.0;
 }
+
+// stats[k] += sum over the shard copies, shards zeroed (slots 0..23 int64 counters, 24.. fp64 sums); one warp
+static __global__ void __launch_bounds__(32) fold_stats_kernel(unsigned long long* __restrict__ shards, unsigned long long* __restrict__ stats)
+{
+    const int k = threadIdx.x;
+    if (k >= NIG_STATS_SLOTS) return;
+    if (k < 24) {
+        unsigned long long sum = 0;
+        for (int r = 0; r < kStatsShards; ++r) { sum += shards[r * NIG_STATS_SLOTS + k]; shards[r * NIG_STATS_SLOTS + k] = 0ull; }
+        stats[k] += sum;
+    } else {
+        double* sh = reinterpret_cast<double*>(shards);
+        double sum = 0.0;
+        for (int r = 0; r < kStatsShards; ++r) { sum += sh[r * NIG_STATS_SLOTS + k]; sh[r * NIG_STATS_SLOTS + k] = 0.0; }
+        reinterpret_cast<double*>(stats)[k] += sum;
+    }
+}
+
+// sequence-tick mode: the launches of a captured sequence carry tick offsets 0 .. n-1 from tick_base[0]; this one-thread
+// kernel, captured at the end of the sequence, moves the base on by n so that the next replay draws fresh noise
+static __global__ void commit_ticks_kernel(uint32_t* tick_base, uint32_t by) { tick_base[0] += by; }
 
 // SoA <-> AoS / ep_word <-> (step, viol, done) conversion for get/set_state
 struct StateIoArgs {

@@ -16,6 +16,16 @@ cudaError_t launch_state_io(const StateIoArgs& a, cudaStream_t st)
     state_io_kernel<<<grid_for(a.n), kThreads, 0, st>>>(a);
     return cudaGetLastError();
 }
+cudaError_t launch_fold_stats(unsigned long long* shards, unsigned long long* stats, cudaStream_t st)
+{
+    fold_stats_kernel<<<1, 32, 0, st>>>(shards, stats);
+    return cudaGetLastError();
+}
+cudaError_t launch_commit_ticks(uint32_t* tick_base, uint32_t by, cudaStream_t st)
+{
+    commit_ticks_kernel<<<1, 1, 0, st>>>(tick_base, by);
+    return cudaGetLastError();
+}
 cudaError_t launch_fp32_probe(float* sink, int iters, int blocks, cudaStream_t st)
 {
     fp32_probe_kernel<<<blocks, 256, 0, st>>>(sink, iters);

@@ -122,8 +122,10 @@ SYMBOLS = {
     "nig_get_tick": (C.c_int, [_VP, C.POINTER(_U32), C.POINTER(_U32)]),
     "nig_set_tick": (C.c_int, [_VP, _U32, _U32]),
     "nig_use_device_tick": (C.c_int, [_VP, _I32]),
+    "nig_commit_ticks": (C.c_int, [_VP, _VP]),
     "nig_set_seed": (C.c_int, [_VP, _U64]),
     "nig_stats_ptr": (C.c_int, [_VP, C.POINTER(_VP)]),
+    "nig_fold_stats": (C.c_int, [_VP, _VP]),
     "nig_read_stats": (C.c_int, [_VP, _VP, _VP]),
     "nig_clear_stats": (C.c_int, [_VP, _VP]),
     "nig_allreduce_stats": (C.c_int, [_VP, _VP, _VP]),

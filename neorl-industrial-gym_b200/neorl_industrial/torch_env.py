@@ -73,16 +73,18 @@ class TorchIndustrialEnv:
         graph-capturable torch code). Returns ``replay()``; every replay advances the env by ``n_steps`` with fresh
         process noise (device-resident tick, nig_use_device_tick). Results of the last step stay in the env's buffers."""
         import torch
-        self.native.use_device_tick(True)
+        self.native.use_device_tick(2)                      # base + sequence offsets: see nig_use_device_tick
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):                       # warm-up outside capture
             out = self.step(policy(self._obs))
         torch.cuda.current_stream(self.device).wait_stream(side)
+        self.native.commit_ticks()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             for _ in range(n_steps):
                 out = self.step(policy(self._obs))
+            self.native.commit_ticks()                      # last node: the base moves on by n_steps per replay
         self._graph_out = out
 
         def replay():

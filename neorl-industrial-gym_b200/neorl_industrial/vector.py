@@ -136,10 +136,15 @@ class NativeEnv:
     def set_tick(self, tick: int, epoch: Optional[int] = None):
         N.check(N.lib().nig_set_tick(self._h, int(tick), self.epoch if epoch is None else int(epoch)))
 
-    def use_device_tick(self, enable: bool = True):
-        """Keep the step counter that keys the random streams on the device so that step / rollout launches can be
-        captured in a CUDA graph (torch.cuda.graph) and replayed: every replay advances the counter in-kernel."""
-        N.check(N.lib().nig_use_device_tick(self._h, int(bool(enable))))
+    def use_device_tick(self, enable=True):
+        """Device-resident step counter for CUDA-graph capture (nig_use_device_tick): ``True`` / 1 = advanced by every launch;
+        2 = base + per-launch sequence offsets (lowest launch latency; end the captured sequence with ``commit_ticks()``);
+        ``False`` / 0 = back to the host counter."""
+        N.check(N.lib().nig_use_device_tick(self._h, int(enable)))
+
+    def commit_ticks(self, stream=None):
+        """Mode-2 device tick: move the base on by the launches made since the last commit (capture this as the last node)."""
+        N.check(N.lib().nig_commit_ticks(self._h, self._stream(stream)))
 
     def reset_policy_state(self, stream=None):
         """Zero the device-resident PID controller state (= constructing a new PIDControllerAgent)."""
@@ -320,9 +325,11 @@ class NativeEnv:
         return torch.as_tensor(_CudaView(sp.value, (self.S, self.pitch), "<f4", self), device=self.torch_device())
 
     def stats_tensor(self):
-        """Zero-copy torch view of the device stats block as int64[32] (slots >= 24 hold fp64 bit patterns)."""
+        """Zero-copy torch view of the device stats block as int64[32] (slots >= 24 hold fp64 bit patterns); the shard copies
+        the plain single-step kernel adds to are folded in on the current stream first (nig_fold_stats)."""
         import torch
         p = C.c_void_p()
+        N.check(N.lib().nig_fold_stats(self._h, self._stream()))
         N.check(N.lib().nig_stats_ptr(self._h, C.byref(p)))
         return torch.as_tensor(_CudaView(p.value, (N.STATS_SLOTS,), "<i8", self), device=self.torch_device())
 

@@ -8,7 +8,10 @@ from util import assert_bits_equal
 pytestmark = pytest.mark.gpu
 
 
-def test_graph_replay_matches_eager_stepping():
+@pytest.mark.parametrize("mode", [1, 2])
+def test_graph_replay_matches_eager_stepping(mode):
+    """mode 1: the device tick is advanced by every launch; mode 2: base + per-launch sequence offsets, the captured
+    sequence ends with commit_ticks() (and the single-step kernel draws its noise before the previous launch has finished)."""
     import torch
     import neorl_industrial as ni
     from neorl_industrial import _native as N
@@ -27,16 +30,18 @@ def test_graph_replay_matches_eager_stepping():
         e.rollout_device(16, N.POLICY_UNIFORM)
         e.step_device(acts, reward=b[0], flags=b[1], viol_mask=b[2])
 
-    graph_env.use_device_tick(True)
+    graph_env.use_device_tick(mode)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):           # warm-up outside capture (lazy allocations, function attributes)
         body(graph_env, bufs[0])
     torch.cuda.current_stream().wait_stream(side)
+    graph_env.commit_ticks()                # (mode 2: the warm-up's launches; a no-op in mode 1)
     body(eager_env, bufs[1])
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         body(graph_env, bufs[0])
+        graph_env.commit_ticks()
     body(eager_env, bufs[1])                # the capture itself does not execute: replay once for it
     g.replay()
     for _ in range(3):
