@@ -1506,6 +1506,245 @@ __device__ __forceinline__ int reactor_fast_steps(Src& src, const Rng& key, uint
     return reactor_fast_steps_v<float, EXTREMA>(src, key, envs, tick0, epoch, n_steps, max_steps, s1, st1, vi1, er1, rs1, ac1, r_lo, r_hi);
 }
 
+// ================================================================================================
+// PowerGrid-v0: the lean step loop of the fused rollout (uniform-random policy, default constraints, auto-reset --
+// BASELINE config #3). The generic loop costs 1,390 instructions per step for 228 algorithmic operations; 200 of them
+// are register moves (ns -> s under the `active` / `done` selects), 100 are compares. This loop
+//   * updates the 32 state values IN PLACE, block of noise by block of noise (a Philox block's four normals are consumed
+//     as soon as they are drawn: no ns[32], no nz[23]);
+//   * carries, like the reactor loop above, the invariants a free-running env satisfies at every step start -- the
+//     frequency deviation is finite with |f| <= 1 and the voltages are in [0.9, 1.1] (else the previous step ended the
+//     episode and the state is fresh: V = 1 + 0.01 z with |z| < 6.4), generation is in [+0, 100] (a clamp result or
+//     N(base, 2)), loads are finite and >= +0 -- checked once per warp at entry, re-established by every step. Under them
+//       - V' - 1 is exact (Sterbenz), so the sixteen range compares of `voltage_limits` (:17-21) and the sixteen of `_is_done`
+//         (:179-192) become min / max trees (FMNMX3) of e_i = V_i - 1 compared with the exactly representable
+//         0.95f - 1, 1.05f - 1, 0.9f - 1, 1.1f - 1; the reward's |V' - 1| is the same e_i;
+//       - np.clip(gen + a, 0, 100) is max(min(g, 100), 0) (finite g, never -0.0), `generation_limits` (:24-30) is
+//         "the clamp changed nothing"; the load clamp is max(l, +0) (finite l);
+//       - frequency_stability / voltage_limits violations are critical: they end the episode, so their counters (and the
+//         critical-shutdown counter) are bumped in the episode-end branch, only generation_limits counts per step;
+//   * checks the one division guard (|f_dot numerator| in [2^-120, 2^100]) BEFORE anything is committed: a warp whose
+//     guard fails leaves the loop and the generic loop redoes the step with the IEEE division.
+// Every arithmetic operation that remains is the one step_core performs, in the same order -> bit-identical results
+// (tests/test_gpu_parity.py, tests/test_gpu_round2.py compare with the oracle, which knows nothing of this).
+// ================================================================================================
+__device__ __forceinline__ bool grid_fast_invariants(const float (&s)[Grid::S])
+{
+    bool inv = fabsf(s[0]) <= 1.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        inv = inv && s[1 + i] >= 0.9f && s[1 + i] <= 1.1f;
+        inv = inv && __float_as_uint(s[9 + i]) <= 0x42c80000u;       // +0 <= gen <= 100, not -0, not NaN
+        inv = inv && __float_as_uint(s[17 + i]) <= 0x7f7fffffu;      // load finite, >= +0
+    }
+    return inv;
+}
+
+// ---- the normal table, replicated 8 x in shared memory ---------------------------------------------------------------
+// 23 table normals per step (+ 4 per step for the resets) are 39 LDS.128 per warp-step; the draws concentrate on the ~50 rows
+// of the first octaves of p, so the lanes of a quarter-warp hit different rows of the same four banks all the time: ncu counts
+// 8.4 shared-memory wavefronts per LDS.128 (4 is the minimum for 32 x 16 B) and the SM's shared-memory data pipe 64 % busy --
+// at 1.8e10 env-steps/s; it would saturate at 2.9e10. The dedicated PowerGrid kernel therefore keeps EIGHT interleaved copies of
+// the table, row r of copy c at float4 index 8 r + c, and lane l reads copy l mod 8: the eight lanes of a quarter-warp always
+// touch eight different bank groups -> exactly 4 wavefronts per LDS.128, whatever the rows. 65.7 KB per CTA (dynamic).
+constexpr int kTabRep = 8;
+__device__ __forceinline__ void normal_table_to_smem_rep8(float4* dst)
+{
+    for (int i = threadIdx.x; i < NIG_NORMAL_TAB_N * kTabRep; i += blockDim.x) dst[i] = g_normal_tab[i >> 3];
+}
+// spec_normal with the replicated table; tab8l = table base + (lane & 7)
+__device__ __forceinline__ float spec_normal_rep8(const float4* tab8l, uint32_t w)
+{
+    const uint32_t v = w * 2u + 1u;
+    const float f = __uint2float_rn(v);
+    const float4 c = tab8l[((__float_as_uint(f) >> 16) & 0xfff8u) - 2032u * kTabRep];
+    const float z = __fmaf_rn(__fmaf_rn(__fmaf_rn(c.w, f, c.z), f, c.y), f, c.x);
+    return __uint_as_float(__float_as_uint(z) ^ (w & 0x80000000u));
+}
+__device__ __forceinline__ void rng_normals4_rep8(const Rng& key, const float4* tab8l, uint32_t env, uint32_t tick, uint32_t stream, uint32_t j, float (&z)[4])
+{
+    const uint4 w = rng_words(key, env, tick, stream, j);
+    z[0] = spec_normal_rep8(tab8l, w.x); z[1] = spec_normal_rep8(tab8l, w.y);
+    z[2] = spec_normal_rep8(tab8l, w.z); z[3] = spec_normal_rep8(tab8l, w.w);
+}
+
+// ---- block-granular cooperative reset of the dedicated PowerGrid kernel (same draws as coop_reset_blocks / Grid::reset) ----
+// The lanes of a warp own consecutive envs. Resetting lanes publish their lane index in rank order (list), the (rank, block)
+// work items are dealt four ranks per round to the four quarter-warps -- lane l always draws block l mod 8 --, each producer
+// stores its four raw values with one STS.128 into row `rank` of the warp's buffer (rows padded to 36 floats: the owners'
+// LDS.128 of different rows fall into different banks), the owners rebuild their state from their row.
+constexpr int kGridResetRow = 36;
+__device__ __forceinline__ void grid_coop_reset(const Rng& key, const float4* tab8l, uint32_t env, uint32_t tick, uint32_t epoch, bool need,
+                                                float (&s)[Grid::S], float* wbuf, uint32_t* list)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    const uint32_t lane = threadIdx.x & 31u;
+    const int cnt = __popc(m);
+    const int rk = __popc(m & ((1u << lane) - 1u));
+    if (need) list[rk] = lane;
+    __syncwarp();
+    const uint32_t j = lane & 7u;
+    const uint32_t env_w = env - lane;                               // env id of lane 0
+    const bool uni = (j == 4u) || (j == 5u);
+    for (int r0 = 0; r0 < cnt; r0 += 4) {
+        const int r = r0 + (int)(lane >> 3);
+        const bool live = r < cnt;
+        const uint32_t src = list[live ? r : 0];
+        const uint4 w = rng_words(key, env_w + src, tick, STREAM_RESET, (epoch << 8) | j);
+        float4 v;
+        v.x = uni ? u_sym(w.x) : spec_normal_rep8(tab8l, w.x);
+        v.y = uni ? u_sym(w.y) : spec_normal_rep8(tab8l, w.y);
+        v.z = uni ? u_sym(w.z) : spec_normal_rep8(tab8l, w.z);
+        v.w = uni ? u_sym(w.w) : spec_normal_rep8(tab8l, w.w);
+        if (live) *reinterpret_cast<float4*>(wbuf + r * kGridResetRow + (int)j * 4) = v;
+    }
+    __syncwarp();
+    if (need) {
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 x = *reinterpret_cast<const float4*>(wbuf + rk * kGridResetRow + q * 4);
+            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        }
+        Grid::reset_from_values(v, s);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// returns the number of steps committed (== n_steps unless the division guard failed)
+template <bool EXTREMA>
+__device__ __forceinline__ int grid_fast_steps(const Rng& key, uint32_t env, uint32_t tick0, uint32_t epoch, int n_steps, int max_steps,
+                                               float (&s)[Grid::S], uint32_t& ep_st, uint32_t& ep_vi, double& ep_ret, float& rsum,
+                                               RolloutAcc& acc, double& r_lo, double& r_hi, const float4* tab8l, float* wbuf, uint32_t* list)
+{
+    constexpr float kE90 = (float)((double)0.9f - 1.0), kE95 = (float)((double)0.95f - 1.0);
+    constexpr float kE105 = (float)((double)1.05f - 1.0), kE110 = (float)((double)1.1f - 1.0);
+    static_assert((double)kE90 == (double)0.9f - 1.0 && (double)kE95 == (double)0.95f - 1.0 &&
+                  (double)kE105 == (double)1.05f - 1.0 && (double)kE110 == (double)1.1f - 1.0, "thresholds must be exact in binary32");
+    int t_trunc = max_steps - (int)ep_st - 1;      // loop index of the step at which the running episode is truncated (base.py:191)
+    unsigned int c_gen = 0u, vi = ep_vi;
+    const double ret_sum0 = acc.ret_sum, ep_ret0 = ep_ret;
+    const unsigned int con0_0 = acc.c_con[0], con1_0 = acc.c_con[1];
+    int t = 0;
+#pragma unroll 1
+    for (; t < n_steps; ++t) {
+        const uint32_t tick = tick0 + (uint32_t)t;
+        // action_space.sample(); np.clip(gen + a, 0, 100) (:124); generation_limits on the pre-step state (:24-30)
+        float gen[8], ap;
+        bool gen_bad = false;
+        {
+            float a[8], a2[8];
+            Grid::uniform_actions(key, env, tick, a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a2[i] = mul(a[i], a[i]);                                         // :173
+                const float g = add(s[9 + i], a[i]);
+                gen[i] = fmaxf(fminf(g, 100.0f), 0.0f);
+                gen_bad = gen_bad || (gen[i] != g);
+            }
+            ap = mul(-5.0f, pairwise8(a2));
+        }
+        float sum_load;
+        {
+            const float ld[8] = {s[17], s[18], s[19], s[20], s[21], s[22], s[23], s[24]};
+            sum_load = pairwise8(ld);
+        }
+        const float imb = sub(pairwise8(gen), sum_load);                          // :127-129
+        const float x = add(-s[0], imb);                                          // mul(-1.0f, f) == -f
+        const bool ok = fabsf(x) >= 0x1.0p-120f && fabsf(x) <= 0x1.0p+100f;
+        if (__builtin_expect(!__all_sync(0xffffffffu, ok), 0)) break;             // (uniform) nothing committed yet
+        // frequency_stability (:10-14), voltage_limits (:17-21) on the pre-step state
+        const bool f_bad = !(fabsf(s[0]) < 0.5f);
+        bool v_bad;
+        {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = sub(s[1 + i], 1.0f);
+            const float emax = fmax3(fmax3(e[0], e[1], e[2]), fmax3(e[3], e[4], e[5]), fmaxf(e[6], e[7]));
+            const float emin = fmin3(fmin3(e[0], e[1], e[2]), fmin3(e[3], e[4], e[5]), fminf(e[6], e[7]));
+            v_bad = emin < kE95 || emax > kE105;
+        }
+        // _dynamics (:112-153), in place
+        s[0] = add(s[0], mul(NIG_CDIV_NG(x, 5.0f), 0.1f));                        // :132-133
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[9 + i] = gen[i];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {                                             // V(8) sigma .005, load(8) sigma 1, flow(7) sigma 2
+            float z[4];
+            rng_normals4_rep8(key, tab8l, env, tick, STREAM_NOISE, (uint32_t)j, z);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = 4 * j + q;
+                if (k < 8) s[1 + k] = add(s[1 + k], mul(0.005f, z[q]));           // :136-137
+                else if (k < 16) s[9 + k] = fmaxf(add(s[9 + k], z[q]), 0.0f);     // :140-141 (mul(1.0f, z) == z)
+                else if (k < 23) s[9 + k] = add(s[9 + k], mul(2.0f, z[q]));       // :144
+            }
+        }
+        // _compute_reward (:155-177) on the new state; _is_done (:179-192)
+        const float fr = mul(-100.0f, mul(s[0], s[0]));
+        float vr;
+        bool term;
+        {
+            float e[8], d2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { e[i] = sub(s[1 + i], 1.0f); d2[i] = mul(e[i], e[i]); }
+            vr = mul(-50.0f, pairwise8(d2));
+            const float emax = fmax3(fmax3(e[0], e[1], e[2]), fmax3(e[3], e[4], e[5]), fmaxf(e[6], e[7]));
+            const float emin = fmin3(fmin3(e[0], e[1], e[2]), fmin3(e[3], e[4], e[5]), fminf(e[6], e[7]));
+            term = fabsf(s[0]) > 1.0f || emin < kE90 || emax > kE110;
+        }
+        double cg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cg[i] = dmul(Grid::gen_cost(i), (double)gen[i]);   // :169
+        const double ec = ddiv_const(-pairwise8d(cg), 1000.0, 1.0 / 1000.0);     // :170
+        double r = dadd(dadd((double)add(fr, vr), ec), (double)ap);              // :175
+        if (f_bad) r = r + (double)Grid::penalty(0);                              // base.py:179-183, in constraint order
+        if (v_bad) r = r + (double)Grid::penalty(1);
+        if (gen_bad) r = r + (double)Grid::penalty(2);
+        const bool crit = f_bad || v_bad;
+        if (crit) r = r - 1000.0;                                                 // base.py:195-198
+        term = term || crit;
+        rsum = add(rsum, (float)r);
+        ep_ret = ep_ret + r;
+        c_gen += gen_bad ? 1u : 0u;
+        vi += gen_bad ? 1u : 0u;
+        const bool fin = term || t >= t_trunc;
+        if (__any_sync(0xffffffffu, fin)) {
+            if (fin) {
+                const unsigned long long len = (unsigned long long)(max_steps - (t_trunc - t));
+                acc.c_ep += 1; acc.c_done += 1;
+                acc.c_term += term ? 1u : 0u;
+                acc.c_trunc += (t >= t_trunc) ? 1u : 0u;
+                acc.c_succ += (ep_ret > 0.0) ? 1u : 0u;
+                acc.c_crit += crit ? 1u : 0u;
+                acc.c_con[0] += f_bad ? 1u : 0u;
+                acc.c_con[1] += v_bad ? 1u : 0u;
+                acc.len_sq += len * len;
+                acc.ret_sum += ep_ret; acc.ret_sq += ep_ret * ep_ret;
+                if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
+                ep_ret = 0.0; vi = 0u;
+                t_trunc = t + max_steps;
+            }
+            grid_coop_reset(key, tab8l, env, tick + 1u, epoch, fin, s, wbuf, list);
+        }
+    }
+    // every step belongs to an episode: the lengths of the episodes finished here add up to the steps taken, plus the part of
+    // the first episode that was there at entry, minus the part of the running one
+    const uint32_t ep_st_exit = (uint32_t)(max_steps - (t_trunc - t + 1));
+    acc.len_sum += (unsigned long long)((uint32_t)t + ep_st - ep_st_exit);
+    ep_st = ep_st_exit;
+    ep_vi = vi;
+    acc.c_steps += (unsigned int)t;
+    acc.c_con[2] += c_gen;
+    acc.c_viol += c_gen + (acc.c_con[0] - con0_0) + (acc.c_con[1] - con1_0);
+    // per-launch reward statistic: (returns of the episodes finished here) + (running return at exit - at entry)
+    acc.rew_sum += (acc.ret_sum - ret_sum0) + (ep_ret - ep_ret0);
+    return t;
+}
+
 // ---- the common tail of the fused rollout kernels: state / episode word / return accumulator back to HBM, per-env
 // outputs, then the violation / episode statistics: warp REDUX + shuffle trees -> one global atomic per slot per block
 // per-env outputs of a launch (reward sum, violation / finished-episode counts)
@@ -1876,7 +2115,7 @@ __device__ __forceinline__ void rollout_generic_uniform_step(const RolloutArgs& 
                                                              typename Env::acc_t& ep_ret, float& rsum, RolloutAcc& acc,
                                                              typename Env::acc_t& r_lo, typename Env::acc_t& r_hi)
 {
-    static_assert(Env::COOP_BLOCKS == 0, "block-cooperative resets go through rollout_kernel");
+    // (envs with a block-cooperative reset -- PowerGrid -- reset per lane here: this is their fallback path only)
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
     using acc_t = typename Env::acc_t;
     float a[A], nz[NZA], ns[S];
@@ -2016,6 +2255,69 @@ __global__ void __launch_bounds__(kWsThreads, 7) rollout_reactor_ws_kernel(const
         for (int t = t_begin; t < p.n_steps; ++t)
             rollout_generic_uniform_step<Env, CONS_DEFAULT, EXTREMA>(p, key, env, tick0 + (uint32_t)t, epoch, valid, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
     }
+    rollout_epilogue<Env, EXTREMA>(p, bs, sfl, sext, valid, i, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
+}
+
+// ================================================================================================
+// fused K-step rollout of PowerGrid-v0 under the benchmark's configuration (uniform-random policy, default constraints,
+// auto-reset): grid_fast_steps with the 8 x replicated normal table. THREADS x CTAS resident threads per SM share
+// CTAS x (65.7 KB table + 4.6 KB of reset buffer per warp) of dynamic shared memory. Warps whose envs do not all satisfy
+// the loop invariants (and warps whose division guard failed) step through the generic path (global-memory table).
+// ================================================================================================
+template <int THREADS> constexpr size_t grid_rollout_smem()
+{
+    return (size_t)NIG_NORMAL_TAB_N * kTabRep * sizeof(float4) + (size_t)(THREADS / 32) * (32 * kGridResetRow * sizeof(float) + 32 * sizeof(uint32_t));
+}
+template <bool EXTREMA, int THREADS, int MAXREG>
+__global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) rollout_grid_kernel(const __grid_constant__ RolloutArgs p)
+{
+    using Env = Grid;
+    constexpr int S = Env::S;
+    __shared__ unsigned int sstat[NIG_STATS_SLOTS];
+    __shared__ double sfl[4];
+    __shared__ unsigned long long sext[2];
+    extern __shared__ __align__(128) float4 dyn_smem4[];
+    float4* tab8 = dyn_smem4;
+    float* wbuf_all = reinterpret_cast<float*>(tab8 + NIG_NORMAL_TAB_N * kTabRep);
+    uint32_t* list_all = reinterpret_cast<uint32_t*>(wbuf_all + (THREADS / 32) * 32 * kGridResetRow);
+    BlockStats bs;
+    if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
+    if constexpr (EXTREMA) { if (threadIdx.x < 2) sext[threadIdx.x] = 0ull; }
+    normal_table_to_smem_rep8(tab8);
+    const Rng key(p.key, g_normal_tab);          // (the generic fallback and nothing else reads the table through `key`)
+    bs.init(sstat);                              // (synchronises the CTA)
+
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < p.n;
+    const int64_t ic = valid ? i : 0;
+    const uint32_t env = p.env0 + (uint32_t)ic;
+    const uint32_t tick0 = load_tick(p.tick_dev, p.tick) + base_tick(p.tick_base);
+    const uint32_t epoch = p.epoch + base_epoch(p.tick_base);
+    float s[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) s[k] = p.state[k * p.pitch + ic];
+    const uint32_t w0 = p.ep_word[ic];
+    uint32_t ep_st = epw_step(w0), ep_vi = epw_viol(w0);
+    bool latched = (w0 >> 31) != 0u;
+    double ep_ret = p.ep_return[ic];
+    float rsum = 0.0f;
+    double r_lo = INFINITY, r_hi = -INFINITY;
+    RolloutAcc acc;
+#pragma unroll
+    for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k) acc.c_con[k] = 0;
+
+    int t_begin = 0;
+    {
+        const bool inv = valid && !latched && p.auto_reset != 0 && ep_st < (uint32_t)p.max_steps && grid_fast_invariants(s);
+        if (__all_sync(0xffffffffu, inv)) {
+            const int warp = threadIdx.x >> 5;
+            t_begin = grid_fast_steps<EXTREMA>(key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi,
+                                               tab8 + (threadIdx.x & 7), wbuf_all + warp * 32 * kGridResetRow, list_all + warp * 32);
+        }
+    }
+#pragma unroll 1
+    for (int t = t_begin; t < p.n_steps; ++t)
+        rollout_generic_uniform_step<Env, CONS_DEFAULT, EXTREMA>(p, key, env, tick0 + (uint32_t)t, epoch, valid, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
     rollout_epilogue<Env, EXTREMA>(p, bs, sfl, sext, valid, i, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
 }
 

@@ -14,6 +14,7 @@ struct RolloutLaunch {
     bool extrema;      // nig_track_extrema: the kernel flavour that also keeps return_min / return_max
     bool pair;         // ChemicalReactor-v0, uniform policy, default constraints: two envs per thread, packed f32x2 arithmetic
     bool ws;           // ChemicalReactor-v0, uniform policy, default constraints: the warp-specialised kernel (producer / consumers)
+    int grid_fast;     // PowerGrid-v0, uniform policy, default constraints, auto-reset: 0 = generic kernel, 1 + shape = rollout_grid_kernel
 };
 
 cudaError_t launch_step(int kind, int vec, int cons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool plain);

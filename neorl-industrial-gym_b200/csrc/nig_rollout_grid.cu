@@ -1,8 +1,36 @@
 // fused K-step rollout kernels of Grid (see nig_kernels.cuh)
 #include "nig_rollout_launch.cuh"
+#include <cstdlib>
 namespace nig {
+template <bool EXTREMA, int THREADS, int MAXREG>
+static cudaError_t grid_fast_go(int64_t pitch, const RolloutArgs& a, cudaStream_t st)
+{
+    auto kern = rollout_grid_kernel<EXTREMA, THREADS, MAXREG>;
+    constexpr size_t smem = grid_rollout_smem<THREADS>();
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // (per device: set on every launch)
+    if (e != cudaSuccess) return e;
+    kern<<<grid_for(pitch, THREADS), THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <bool EXTREMA>
+static cudaError_t grid_fast(int shape, int64_t pitch, const RolloutArgs& a, cudaStream_t st)
+{
+    switch (shape) {                              // (threads per CTA, registers per thread): resident CTAs follow from both
+    case 1: return grid_fast_go<EXTREMA, 512, 128>(pitch, a, st);
+    case 2: return grid_fast_go<EXTREMA, 384, 168>(pitch, a, st);
+    case 3: return grid_fast_go<EXTREMA, 192, 168>(pitch, a, st);
+    case 4: return grid_fast_go<EXTREMA, 448, 144>(pitch, a, st);
+    case 5: return grid_fast_go<EXTREMA, 224, 144>(pitch, a, st);
+    case 6: return grid_fast_go<EXTREMA, 416, 152>(pitch, a, st);
+    case 7: return grid_fast_go<EXTREMA, 480, 136>(pitch, a, st);
+    case 8: return grid_fast_go<EXTREMA, 160, 136>(pitch, a, st);
+    default: return grid_fast_go<EXTREMA, 256, 128>(pitch, a, st);
+    }
+}
 cudaError_t launch_rollout_grid(const RolloutLaunch& cfg, int64_t pitch, const RolloutArgs& a, const CUtensorMap& map, cudaStream_t st)
 {
+    if (cfg.grid_fast && cfg.policy == NIG_POLICY_UNIFORM && cfg.cons == CONS_DEFAULT && !cfg.tma && !cfg.tf_noise)
+        return cfg.extrema ? grid_fast<true>(cfg.grid_fast - 1, pitch, a, st) : grid_fast<false>(cfg.grid_fast - 1, pitch, a, st);
     return rollout_env<Grid>(cfg, pitch, a, map, st);
 }
 } // namespace nig

@@ -73,6 +73,52 @@ def test_reactor_fast_loop_from_adversarial_entry_states(mods):
     env.close()
 
 
+@pytest.mark.parametrize("shape", ["1", "2", "3", "4", "5", "0"])
+def test_grid_fast_loop_from_adversarial_entry_states(mods, monkeypatch, shape):
+    """PowerGrid-v0: the dedicated lean rollout kernel (in-place step, min / max trees for the voltage ranges, max / min
+    clamps, 8 x replicated normal table, rank-dealt cooperative reset) enters its loop per warp only when every env of the
+    warp satisfies the invariants; these populations mix such warps with warps holding out-of-range / non-finite / signed-zero
+    states and episodes about to be truncated. Everything must be the oracle's, bit for bit, for every CTA shape and for the
+    generic kernel (NIG_GRID_FAST=0) alike; per-env sums, counters and episode statistics included."""
+    ni, N, O, torch = mods
+    monkeypatch.setenv("NIG_GRID_FAST", shape)
+    rng = np.random.default_rng(11)
+    n, K = 4096 + 37, 40
+    env = ni.NativeEnv(N.ENV_POWER_GRID, n, device=0, seed=33, env_id_offset=96)
+    orc = O.OracleEnv(O.GRID, n, seed=33, env_id0=96, exp_mode=1)
+    s0 = env.reset_host()
+    assert_bits_equal(s0, orc.reset(), "reset")
+    st = s0.copy()
+    ep_step = np.zeros(n, np.int32)
+    def some(k):
+        return rng.choice(n, k, replace=False)
+    st[some(40), 0] = rng.uniform(-1.2, 1.2, 40).astype(np.float32)       # frequency: inside, at and beyond both limits
+    st[some(6), 0] = np.array([0.5, -0.5, 1.0, -1.0, -0.0, 0.49999997], np.float32)
+    i = some(40); st[i, 1 + rng.integers(0, 8, 40)] = rng.uniform(0.88, 1.12, 40).astype(np.float32)   # voltages around every threshold
+    i = some(8); st[i, 1 + rng.integers(0, 8, 8)] = np.array([0.9, 0.95, 1.05, 1.1, 0.94999999, 1.0500001, 0.3, 2.5], np.float32)
+    i = some(30); st[i, 9 + rng.integers(0, 8, 30)] = rng.choice([0.0, -0.0, 100.0, 99.5, 0.4, 100.5, -3.0, 1e-30], 30).astype(np.float32)
+    i = some(20); st[i, 17 + rng.integers(0, 8, 20)] = rng.choice([0.0, -0.0, 1e-20, 0.3, 1e30, 3e38, -2.0], 20).astype(np.float32)
+    i = some(10); st[i, 25 + rng.integers(0, 7, 10)] = rng.choice([0.0, -0.0, 3e38, -3e38, np.inf], 10).astype(np.float32)
+    i = some(6); st[i, rng.integers(0, 32, 6)] = np.nan
+    i = some(4); st[i, 17 + rng.integers(0, 8, 4)] = np.inf
+    w = 32 * 7                                    # one warp with zero imbalance and zero frequency: the division guard fails
+    st[w:w + 32, 0] = 0.0; st[w:w + 32, 9:17] = 50.0; st[w:w + 32, 17:25] = 50.0
+    ep_step[some(300)] = rng.integers(950, 1000, 300)                      # truncation inside the launch
+    env.set_state_host(st, ep_step, np.zeros(n, np.int32), np.zeros(n, np.uint8))
+    orc.state[:] = st
+    orc.ep_step[:] = ep_step
+    rsum, vcnt, dcnt = env.empty(), env.empty(dtype=torch.int32), env.empty(dtype=torch.int32)
+    for chunk in (K, 17, 1, 64):
+        env.rollout_device(chunk, N.POLICY_UNIFORM, reward_sum=rsum, viol_count=vcnt, done_count=dcnt)
+        o_rs = O.rollout(orc, chunk, O.POLICY_UNIFORM, want_reward_sum=True)
+        torch.cuda.synchronize()
+        _compare(env, orc, N, f"after a {chunk}-step launch")
+        g_rs = rsum[:n].cpu().numpy()
+        both_nan = np.isnan(g_rs) & np.isnan(o_rs)       # (NaN states injected above: the payload / sign of a NaN sum is not specified)
+        assert_bits_equal(np.where(both_nan, 0, g_rs), np.where(both_nan, 0, o_rs), f"per-env reward sum of a {chunk}-step launch")
+    env.close()
+
+
 def test_reactor_fast_loop_without_auto_reset_and_sharded(mods):
     """auto_reset off never enters the specialised loop (latches instead); shards keyed by global env id agree with the
     unsharded run whichever loop they took."""

@@ -18,28 +18,32 @@ enum Op : int {
     FADD_IMM, FADD_RR, FMUL_RR, FFMA_RRR, FFMA_RRI, FADD2, FMUL2, FFMA2,
     FMNMX, FSEL, FSETP, LOP3, IMADW, I2FP, MUFU, IADD3,
     MIX_FMUL_LOP3, MIX_2FMUL_LOP3, MIX_FFMA2_LOP3, MIX_FMUL2_FSETP, MIX_FMUL_FSETP, MIX_FMUL_FMNMX, MIX_IMADW_LOP3,
-    MIX_FADD2_FMNMX_LOP3, MIX_FMUL_IMADW, N_OPS
+    MIX_FADD2_FMNMX_LOP3, MIX_FMUL_IMADW,
+    DADD_, DMUL_, DFMA_, F2F_64_32, F2F_32_64, FMNMX3_, IMAD_LO, IMAD_HI, SHF_, LDS128_, SHFL_, MIX_DFMA_FMUL, MIX_F2F_FMUL, N_OPS
 };
 static const char* kNames[N_OPS] = {
     "FADD r,imm", "FADD r,r", "FMUL r,r", "FFMA r,r,r", "FFMA r,r,imm", "FADD2 (f32x2)", "FMUL2 (f32x2)", "FFMA2 (f32x2)",
     "FMNMX", "FSEL", "FSETP (and-chain)", "LOP3 r,r,r", "IMAD.WIDE.U32", "I2FP.U32", "MUFU.RCP", "IADD3",
     "mix 1 FMUL + 1 LOP3", "mix 2 FMUL + 1 LOP3", "mix 1 FFMA2 + 1 LOP3", "mix 1 FMUL2 + 1 FSETP", "mix 1 FMUL + 1 FSETP", "mix 1 FMUL + 1 FMNMX",
-    "mix 1 IMAD.WIDE + 1 LOP3", "mix 1 FADD2 + 1 FMNMX + 1 LOP3", "mix 1 FMUL + 1 IMAD.WIDE"
+    "mix 1 IMAD.WIDE + 1 LOP3", "mix 1 FADD2 + 1 FMNMX + 1 LOP3", "mix 1 FMUL + 1 IMAD.WIDE",
+    "DADD", "DMUL", "DFMA", "F2F.F64.F32 (+F2F back)", "F2F.F32.F64 only (see prev)", "FMNMX3", "IMAD lo32", "IMAD.HI", "SHF.R", "LDS.128", "SHFL.IDX", "mix 1 DFMA + 1 FMUL", "mix 1 F2F pair + 2 FMUL"
 };
 // warp-instructions per chain per unrolled slot
-static const int kOpsPerSlot[N_OPS] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 3, 2, 2, 2, 2, 2, 3, 2};
+static const int kOpsPerSlot[N_OPS] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 3, 2, 2, 2, 2, 2, 3, 2, 1, 1, 1, 2, 1, 1, 1, 1, 1, 1, 1, 2, 4};
 
 template <int OP, int CH>
 __global__ void __launch_bounds__(1024, 1) probe(float* out, long long* cyc, int iters, float yv, float zv)
 {
-    float x[CH];
+    __shared__ float smem[2048];
+    for (int q = threadIdx.x; q < 2048; q += blockDim.x) smem[q] = (float)q;
+    float x[CH], y2[CH];
     unsigned u[CH];
     unsigned long long d[CH];
     float y = yv, z = zv;
     unsigned uy = __float_as_uint(yv) | 1u, uz = __float_as_uint(zv) | 3u;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-        x[c] = 1.0f + 1e-3f * (float)(threadIdx.x + c);
+        x[c] = 1.0f + 1e-3f * (float)(threadIdx.x + c); y2[c] = x[c];
         u[c] = threadIdx.x * 2654435761u + c;
         d[c] = ((unsigned long long)__float_as_uint(x[c]) << 32) | __float_as_uint(x[c] + 0.5f);
     }
@@ -69,6 +73,25 @@ __global__ void __launch_bounds__(1024, 1) probe(float* out, long long* cyc, int
                 else if constexpr (OP == I2FP) asm volatile("{.reg .f32 t; cvt.rn.f32.u32 t, %0; mov.b32 %0, t;}" : "+r"(u[c]));
                 else if constexpr (OP == MUFU) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(x[c]));
                 else if constexpr (OP == IADD3) asm volatile("add.u32 %0, %0, %1;" : "+r"(u[c]) : "r"(uy));
+                else if constexpr (OP == DADD_) asm volatile("{.reg .f64 t, s; mov.b64 t, %0; mov.b64 s, %1; add.rn.f64 t, t, s; mov.b64 %0, t;}" : "+l"(d[c]) : "l"(dy));
+                else if constexpr (OP == DMUL_) asm volatile("{.reg .f64 t, s; mov.b64 t, %0; mov.b64 s, %1; mul.rn.f64 t, t, s; mov.b64 %0, t;}" : "+l"(d[c]) : "l"(dy));
+                else if constexpr (OP == DFMA_) asm volatile("{.reg .f64 t, s, q; mov.b64 t, %0; mov.b64 s, %1; mov.b64 q, %2; fma.rn.f64 t, t, s, q; mov.b64 %0, t;}" : "+l"(d[c]) : "l"(dy), "l"(dz));
+                else if constexpr (OP == F2F_64_32) asm volatile("{.reg .f64 t; cvt.f64.f32 t, %0; cvt.rn.f32.f64 %0, t;}" : "+f"(x[c]));
+                else if constexpr (OP == F2F_32_64) asm volatile("{.reg .f64 t; mov.b64 t, %1; cvt.rn.f32.f64 %0, t;}" : "+f"(x[c]) : "l"(d[c]));
+                else if constexpr (OP == FMNMX3_) asm volatile("{.reg .f32 t; max.f32 t, %0, %1; max.f32 %0, t, %2;}" : "+f"(x[c]) : "f"(y), "f"(z));
+                else if constexpr (OP == IMAD_LO) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(u[c]) : "r"(uy), "r"(uz));
+                else if constexpr (OP == IMAD_HI) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(u[c]) : "r"(uy));
+                else if constexpr (OP == SHF_) asm volatile("shf.r.wrap.b32 %0, %0, %1, 7;" : "+r"(u[c]) : "r"(uy));
+                else if constexpr (OP == LDS128_) { float4 v = *reinterpret_cast<const float4*>(&smem[(u[c] & 0x1ffu) * 4]); u[c] = __float_as_uint(v.x) + __float_as_uint(v.w); }
+                else if constexpr (OP == SHFL_) u[c] = __shfl_sync(0xffffffffu, u[c], (int)(u[c] & 31u));
+                else if constexpr (OP == MIX_DFMA_FMUL) {
+                    asm volatile("{.reg .f64 t, s, q; mov.b64 t, %0; mov.b64 s, %1; mov.b64 q, %2; fma.rn.f64 t, t, s, q; mov.b64 %0, t;}" : "+l"(d[c]) : "l"(dy), "l"(dz));
+                    asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(x[c]) : "f"(y));
+                } else if constexpr (OP == MIX_F2F_FMUL) {
+                    asm volatile("{.reg .f64 t; cvt.f64.f32 t, %0; cvt.rn.f32.f64 %0, t;}" : "+f"(x[c]));
+                    asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(y2[c]) : "f"(y));
+                    asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(y2[c]) : "f"(z));
+                }
                 else if constexpr (OP == MIX_FMUL_LOP3) {
                     asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(x[c]) : "f"(y));
                     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[c]) : "r"(uy), "r"(uz));
@@ -105,7 +128,7 @@ __global__ void __launch_bounds__(1024, 1) probe(float* out, long long* cyc, int
     const long long t1 = clock64();
     float acc = (float)pacc;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) acc += x[c] + (float)u[c] + (float)(d[c] & 0xffff) + (float)(d[c] >> 48);
+    for (int c = 0; c < CH; ++c) acc += x[c] + y2[c] + (float)u[c] + (float)(d[c] & 0xffff) + (float)(d[c] >> 48);
     if (acc == 123.456f) out[0] = acc;
     if ((threadIdx.x & 31) == 0) cyc[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = t1 - t0;
 }
@@ -151,11 +174,13 @@ int main(int argc, char** argv)
     CK(cudaGetDeviceProperties(&pr, dev));
     const int sms = pr.multiProcessorCount;
     int iters = argc > 1 ? atoi(argv[1]) : 2000;
+    const bool only_new = argc > 2;
     printf("device %s, %d SMs, clock %d kHz; iters %d\n", pr.name, sms, pr.clockRate, iters);
     float* out; long long* cyc_d;
     CK(cudaMalloc(&out, 4));
     CK(cudaMalloc(&cyc_d, sms * 32 * sizeof(long long)));
     std::vector<long long> cyc_h(sms * 32);
+    if (!only_new) {
     suite<FADD_IMM>(sms, iters, out, cyc_d, cyc_h);
     suite<FADD_RR>(sms, iters, out, cyc_d, cyc_h);
     suite<FMUL_RR>(sms, iters, out, cyc_d, cyc_h);
@@ -181,5 +206,19 @@ int main(int argc, char** argv)
     suite<MIX_IMADW_LOP3>(sms, iters, out, cyc_d, cyc_h);
     suite<MIX_FADD2_FMNMX_LOP3>(sms, iters, out, cyc_d, cyc_h);
     suite<MIX_FMUL_IMADW>(sms, iters, out, cyc_d, cyc_h);
+    }
+    suite<DADD_>(sms, iters, out, cyc_d, cyc_h);
+    suite<DMUL_>(sms, iters, out, cyc_d, cyc_h);
+    suite<DFMA_>(sms, iters, out, cyc_d, cyc_h);
+    suite<F2F_64_32>(sms, iters, out, cyc_d, cyc_h);
+    suite<F2F_32_64>(sms, iters, out, cyc_d, cyc_h);
+    suite<FMNMX3_>(sms, iters, out, cyc_d, cyc_h);
+    suite<IMAD_LO>(sms, iters, out, cyc_d, cyc_h);
+    suite<IMAD_HI>(sms, iters, out, cyc_d, cyc_h);
+    suite<SHF_>(sms, iters, out, cyc_d, cyc_h);
+    suite<LDS128_>(sms, iters, out, cyc_d, cyc_h);
+    suite<SHFL_>(sms, iters, out, cyc_d, cyc_h);
+    suite<MIX_DFMA_FMUL>(sms, iters, out, cyc_d, cyc_h);
+    suite<MIX_F2F_FMUL>(sms, iters, out, cyc_d, cyc_h);
     return 0;
 }
