@@ -1574,6 +1574,7 @@ __device__ __forceinline__ void rng_normals4_rep8(const Rng& key, const float4* 
 // stores its four raw values with one STS.128 into row `rank` of the warp's buffer (rows padded to 36 floats: the owners'
 // LDS.128 of different rows fall into different banks), the owners rebuild their state from their row.
 constexpr int kGridResetRow = 36;
+constexpr int kGridResetRanks = 8;                 // rows of a warp's buffer: the resetting lanes are served eight ranks at a time
 __device__ __forceinline__ void grid_coop_reset(const Rng& key, const float4* tab8l, uint32_t env, uint32_t tick, uint32_t epoch, bool need,
                                                 float (&s)[Grid::S], float* wbuf, uint32_t* list)
 {
@@ -1586,29 +1587,32 @@ __device__ __forceinline__ void grid_coop_reset(const Rng& key, const float4* ta
     const uint32_t j = lane & 7u;
     const uint32_t env_w = env - lane;                               // env id of lane 0
     const bool uni = (j == 4u) || (j == 5u);
-    for (int r0 = 0; r0 < cnt; r0 += 4) {
-        const int r = r0 + (int)(lane >> 3);
-        const bool live = r < cnt;
-        const uint32_t src = list[live ? r : 0];
-        const uint4 w = rng_words(key, env_w + src, tick, STREAM_RESET, (epoch << 8) | j);
-        float4 v;
-        v.x = uni ? u_sym(w.x) : spec_normal_rep8(tab8l, w.x);
-        v.y = uni ? u_sym(w.y) : spec_normal_rep8(tab8l, w.y);
-        v.z = uni ? u_sym(w.z) : spec_normal_rep8(tab8l, w.z);
-        v.w = uni ? u_sym(w.w) : spec_normal_rep8(tab8l, w.w);
-        if (live) *reinterpret_cast<float4*>(wbuf + r * kGridResetRow + (int)j * 4) = v;
-    }
-    __syncwarp();
-    if (need) {
-        float v[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 x = *reinterpret_cast<const float4*>(wbuf + rk * kGridResetRow + q * 4);
-            v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    for (int c0 = 0; c0 < cnt; c0 += kGridResetRanks) {              // (8 or fewer resetting lanes: one pass)
+#pragma unroll 1
+        for (int r0 = c0; r0 < cnt && r0 < c0 + kGridResetRanks; r0 += 4) {
+            const int r = r0 + (int)(lane >> 3);
+            const bool live = r < cnt;
+            const uint32_t src = list[live ? r : 0];
+            const uint4 w = rng_words(key, env_w + src, tick, STREAM_RESET, (epoch << 8) | j);
+            float4 v;
+            v.x = uni ? u_sym(w.x) : spec_normal_rep8(tab8l, w.x);
+            v.y = uni ? u_sym(w.y) : spec_normal_rep8(tab8l, w.y);
+            v.z = uni ? u_sym(w.z) : spec_normal_rep8(tab8l, w.z);
+            v.w = uni ? u_sym(w.w) : spec_normal_rep8(tab8l, w.w);
+            if (live) *reinterpret_cast<float4*>(wbuf + (r - c0) * kGridResetRow + (int)j * 4) = v;
         }
-        Grid::reset_from_values(v, s);
+        __syncwarp();
+        if (need && rk >= c0 && rk < c0 + kGridResetRanks) {
+            float v[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 x = *reinterpret_cast<const float4*>(wbuf + (rk - c0) * kGridResetRow + q * 4);
+                v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+            }
+            Grid::reset_from_values(v, s);
+        }
+        __syncwarp();
     }
-    __syncwarp();
 }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
@@ -2264,9 +2268,9 @@ __global__ void __launch_bounds__(kWsThreads, 7) rollout_reactor_ws_kernel(const
 // CTAS x (65.7 KB table + 4.6 KB of reset buffer per warp) of dynamic shared memory. Warps whose envs do not all satisfy
 // the loop invariants (and warps whose division guard failed) step through the generic path (global-memory table).
 // ================================================================================================
-template <int THREADS> constexpr size_t grid_rollout_smem()
+template <int THREADS> __host__ __device__ constexpr size_t grid_rollout_smem()
 {
-    return (size_t)NIG_NORMAL_TAB_N * kTabRep * sizeof(float4) + (size_t)(THREADS / 32) * (32 * kGridResetRow * sizeof(float) + 32 * sizeof(uint32_t));
+    return (size_t)NIG_NORMAL_TAB_N * kTabRep * sizeof(float4) + (size_t)(THREADS / 32) * (kGridResetRanks * kGridResetRow * sizeof(float) + 32 * sizeof(uint32_t));
 }
 template <bool EXTREMA, int THREADS, int MAXREG>
 __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) rollout_grid_kernel(const __grid_constant__ RolloutArgs p)
@@ -2279,7 +2283,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) rollout_grid_kern
     extern __shared__ __align__(128) float4 dyn_smem4[];
     float4* tab8 = dyn_smem4;
     float* wbuf_all = reinterpret_cast<float*>(tab8 + NIG_NORMAL_TAB_N * kTabRep);
-    uint32_t* list_all = reinterpret_cast<uint32_t*>(wbuf_all + (THREADS / 32) * 32 * kGridResetRow);
+    uint32_t* list_all = reinterpret_cast<uint32_t*>(wbuf_all + (THREADS / 32) * kGridResetRanks * kGridResetRow);
     BlockStats bs;
     if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
     if constexpr (EXTREMA) { if (threadIdx.x < 2) sext[threadIdx.x] = 0ull; }
@@ -2312,13 +2316,247 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) rollout_grid_kern
         if (__all_sync(0xffffffffu, inv)) {
             const int warp = threadIdx.x >> 5;
             t_begin = grid_fast_steps<EXTREMA>(key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi,
-                                               tab8 + (threadIdx.x & 7), wbuf_all + warp * 32 * kGridResetRow, list_all + warp * 32);
+                                               tab8 + (threadIdx.x & 7), wbuf_all + warp * kGridResetRanks * kGridResetRow, list_all + warp * 32);
         }
     }
 #pragma unroll 1
     for (int t = t_begin; t < p.n_steps; ++t)
         rollout_generic_uniform_step<Env, CONS_DEFAULT, EXTREMA>(p, key, env, tick0 + (uint32_t)t, epoch, valid, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
     rollout_epilogue<Env, EXTREMA>(p, bs, sfl, sext, valid, i, s, ep_st, ep_vi, latched, ep_ret, rsum, acc, r_lo, r_hi);
+}
+
+// ================================================================================================
+// PowerGrid-v0 single step, dedicated persistent kernel (plain SoA step, default constraints): the lean step of the fused
+// rollout above applied to ONE step per launch. gridDim = resident CTAs; each CTA copies the 8 x replicated normal table
+// once and walks tiles of THREADS envs. The state is updated in place in registers; instead of entry invariants (there is no
+// previous step to establish them) every step carries its own guards, all evaluated before anything is stored:
+//   * bits(gen + a) <= bits(100.0f) for the eight generators: gen + a is in [+0, 100] (no generation_limits violation, the
+//     np.clip is the identity, not NaN, not -0.0) -- so the lean path has no clamp and no third constraint at all;
+//   * |f_dot numerator| in [2^-120, 2^100]: the fast division is exact; a NaN / inf frequency, generation or load ends up here;
+//   * the voltage reward term is not NaN (a NaN voltage would be dropped by the FMNMX trees);
+//   * 0 * a stays 0 for the raw actions (a NaN action would be hidden by the min / max clip; an infinite one only costs the
+//     fallback).
+// A warp in which any lane fails a guard (or is inactive: padding, done latch) reloads its inputs and takes step_core, the
+// generic path. Same outputs, flags, counters and episode statistics as step_kernel<Grid, 1, CONS_DEFAULT, PLAIN>.
+// The inputs of the NEXT tile (32 state rows, 8 action rows, the episode words, the episode returns: 42 contiguous row
+// segments) are fetched by cp.async.bulk into one shared-memory stage while the current tile, already in registers, is
+// stepped: with few warps per scheduler the loads of a tile (2 us under load) would otherwise serialise with its arithmetic
+// (measured, 384-thread CTAs, 1M envs: 103 us per step without the stage -- no better than the one-tile kernel --, 90 us with
+// it; a per-warp stage fed by 128-byte copies: 102 us).
+// ================================================================================================
+template <int THREADS> __host__ __device__ constexpr size_t grid_step_stage_bytes() { return (size_t)(Grid::S + Grid::A + 1) * THREADS * sizeof(float) + (size_t)THREADS * sizeof(double); }
+template <int THREADS> __host__ __device__ constexpr size_t grid_step_smem() { return grid_rollout_smem<THREADS>() + grid_step_stage_bytes<THREADS>(); }
+
+template <int THREADS, int MAXREG>
+__global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) step_grid_kernel(const __grid_constant__ StepArgs p)
+{
+    using Env = Grid;
+    constexpr int S = Env::S, A = Env::A, NZ = Env::NZ;
+    constexpr float kE90 = (float)((double)0.9f - 1.0), kE95 = (float)((double)0.95f - 1.0);
+    constexpr float kE105 = (float)((double)1.05f - 1.0), kE110 = (float)((double)1.1f - 1.0);
+    __shared__ unsigned int sstat[NIG_STATS_SLOTS];
+    __shared__ EpisodeStaging estage;
+    __shared__ alignas(8) uint64_t full_bar;
+    extern __shared__ __align__(128) float4 dyn_smem4[];
+    float4* tab8 = dyn_smem4;
+    float* wbuf = reinterpret_cast<float*>(tab8 + NIG_NORMAL_TAB_N * kTabRep) + (threadIdx.x >> 5) * kGridResetRanks * kGridResetRow;
+    uint32_t* list = reinterpret_cast<uint32_t*>(reinterpret_cast<float*>(tab8 + NIG_NORMAL_TAB_N * kTabRep) + (THREADS / 32) * kGridResetRanks * kGridResetRow) + (threadIdx.x >> 5) * 32;
+    const float4* tab8l = tab8 + (threadIdx.x & 7);
+    float* stage = reinterpret_cast<float*>(reinterpret_cast<char*>(dyn_smem4) + grid_rollout_smem<THREADS>());   // [S + A + 1][THREADS] floats
+    double* stage_er = reinterpret_cast<double*>(stage + (S + A + 1) * THREADS);                                   // [THREADS]
+    BlockStats bs;
+    episode_staging_init(&estage);
+    normal_table_to_smem_rep8(tab8);
+    if (threadIdx.x == 0) {
+        mbar_init(&full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    bs.init(sstat);                              // (synchronises the CTA)
+    const Rng key(p.key, g_normal_tab);          // (the generic fallback reads the global table)
+    // programmatic dependent launch: everything above overlaps the tail of the previous step (see step_kernel)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t tick0 = load_tick(p.tick_dev, p.tick) + base_tick(p.tick_base);
+    const uint32_t epoch = p.epoch;
+    const int64_t n_tiles = (p.pitch + THREADS - 1) / THREADS;
+    // one elected thread issues the 42 row copies of a tile
+    auto fetch = [&](int64_t tile) {
+        const int64_t e0 = tile * THREADS;
+        const uint32_t cnt = (uint32_t)((p.pitch - e0 < THREADS) ? (p.pitch - e0) : THREADS);        // (a multiple of 128)
+        const bool with_er = p.ep_return != nullptr;
+        mbar_expect_tx(&full_bar, cnt * (uint32_t)sizeof(float) * (S + A + 1) + (with_er ? cnt * (uint32_t)sizeof(double) : 0u));
+        for (int k = 0; k < S; ++k) bulk_load(stage + k * THREADS, p.state + k * p.pitch + e0, cnt * (uint32_t)sizeof(float), &full_bar);
+        for (int k = 0; k < A; ++k) bulk_load(stage + (S + k) * THREADS, p.actions + k * p.pitch + e0, cnt * (uint32_t)sizeof(float), &full_bar);
+        bulk_load(stage + (S + A) * THREADS, p.ep_word + e0, cnt * (uint32_t)sizeof(float), &full_bar);
+        if (with_er) bulk_load(stage_er, p.ep_return + e0, cnt * (uint32_t)sizeof(double), &full_bar);
+    };
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
+    uint32_t phase = 0u;
+
+    unsigned int c_steps = 0, c_ep = 0, c_term = 0, c_trunc = 0, c_crit = 0, c_viol = 0, c_con0 = 0, c_con1 = 0, c_con2 = 0;
+    StepEpisodeStats eps;
+#pragma unroll 1
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t i = tile * THREADS + threadIdx.x;
+        const bool in_pitch = i < p.pitch, valid = i < p.n;
+        const int64_t ic = in_pitch ? i : 0;            // lanes past the pitch shadow another env and store nothing
+        const uint32_t env = p.env0 + (uint32_t)i;
+        float s[S], a_raw[A];
+        mbar_wait(&full_bar, phase);
+        phase ^= 1u;
+        const int tl = in_pitch ? (int)threadIdx.x : 0;
+#pragma unroll
+        for (int k = 0; k < S; ++k) s[k] = stage[k * THREADS + tl];
+#pragma unroll
+        for (int k = 0; k < A; ++k) a_raw[k] = stage[(S + k) * THREADS + tl];
+        uint32_t w = __float_as_uint(stage[(S + A) * THREADS + tl]);
+        const bool active = valid && !(w >> 31);
+        double er = 0.0;
+        if (p.ep_return && active) er = stage_er[tl];
+        __syncthreads();                                 // everyone has its tile in registers: the stage is free
+        if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fetch(tile + gridDim.x);
+        }
+
+        double r = 0.0;
+        uint32_t f = NIG_F_INACTIVE, vm = 0u;
+        bool lean = false;
+        if (__all_sync(0xffffffffu, active)) {
+            // ---- the lean step (see grid_fast_steps for the derivation) ----
+            float a[A], poison = 0.0f, ap;
+            bool ok = true;
+            float gsum;
+            {
+                float a2[A], g[A];
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    poison = __fmaf_rn(0.0f, a_raw[k], poison);
+                    a[k] = fmaxf(fminf(a_raw[k], 1.0f), -1.0f);                   // base.py:167 (finite or infinite a; NaN -> poison)
+                    a2[k] = mul(a[k], a[k]);
+                    g[k] = add(s[9 + k], a[k]);
+                    ok = ok && __float_as_uint(g[k]) <= 0x42c80000u;
+                }
+                ap = mul(-5.0f, pairwise8(a2));
+                gsum = pairwise8(g);
+#pragma unroll
+                for (int k = 0; k < A; ++k) s[9 + k] = g[k];                      // np.clip(gen + a, 0, 100) == gen + a here
+            }
+            float lsum;
+            {
+                const float ld[8] = {s[17], s[18], s[19], s[20], s[21], s[22], s[23], s[24]};
+                lsum = pairwise8(ld);
+            }
+            const float x = add(-s[0], sub(gsum, lsum));
+            ok = ok && fabsf(x) >= 0x1.0p-120f && fabsf(x) <= 0x1.0p+100f && poison == 0.0f;
+            const bool f_bad = !(fabsf(s[0]) < 0.5f);
+            bool v_bad;
+            {
+                float e[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) e[k] = sub(s[1 + k], 1.0f);
+                const float emax = fmax3(fmax3(e[0], e[1], e[2]), fmax3(e[3], e[4], e[5]), fmaxf(e[6], e[7]));
+                const float emin = fmin3(fmin3(e[0], e[1], e[2]), fmin3(e[3], e[4], e[5]), fminf(e[6], e[7]));
+                v_bad = emin < kE95 || emax > kE105;
+            }
+            s[0] = add(s[0], mul(NIG_CDIV_NG(x, 5.0f), 0.1f));
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                float z[4];
+                rng_normals4_rep8(key, tab8l, env, tick0, STREAM_NOISE, (uint32_t)j, z);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = 4 * j + q;
+                    if (k < 8) s[1 + k] = add(s[1 + k], mul(0.005f, z[q]));
+                    else if (k < 16) s[9 + k] = fmaxf(add(s[9 + k], z[q]), 0.0f);
+                    else if (k < 23) s[9 + k] = add(s[9 + k], mul(2.0f, z[q]));
+                }
+            }
+            const float fr = mul(-100.0f, mul(s[0], s[0]));
+            float vr;
+            bool term;
+            {
+                float e[8], d2[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { e[k] = sub(s[1 + k], 1.0f); d2[k] = mul(e[k], e[k]); }
+                vr = mul(-50.0f, pairwise8(d2));
+                const float emax = fmax3(fmax3(e[0], e[1], e[2]), fmax3(e[3], e[4], e[5]), fmaxf(e[6], e[7]));
+                const float emin = fmin3(fmin3(e[0], e[1], e[2]), fmin3(e[3], e[4], e[5]), fminf(e[6], e[7]));
+                term = fabsf(s[0]) > 1.0f || emin < kE90 || emax > kE110;
+            }
+            ok = ok && vr == vr;
+            double cg[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cg[k] = dmul(Grid::gen_cost(k), (double)s[9 + k]);
+            const double ec = ddiv_const(-pairwise8d(cg), 1000.0, 1.0 / 1000.0);
+            r = dadd(dadd((double)add(fr, vr), ec), (double)ap);
+            if (f_bad) r = r + (double)Grid::penalty(0);
+            if (v_bad) r = r + (double)Grid::penalty(1);
+            const bool crit = f_bad || v_bad;
+            if (crit) r = r - 1000.0;
+            lean = __all_sync(0xffffffffu, ok);
+            if (lean) {
+                const uint32_t step = epw_step(w) + 1u;
+                vm = (f_bad ? 1u : 0u) | (v_bad ? 2u : 0u);
+                f = (crit ? (uint32_t)NIG_F_CRITICAL : 0u) | ((term || crit) ? (uint32_t)NIG_F_TERMINATED : 0u) |
+                    (step >= (uint32_t)p.max_steps ? (uint32_t)NIG_F_TRUNCATED : 0u);
+                w = epw_make(step, epw_viol(w) + (uint32_t)__popc(vm), 0u);
+            } else {                                     // (uniform) reload: the lean path has updated s in place
+#pragma unroll
+                for (int k = 0; k < S; ++k) s[k] = p.state[k * p.pitch + ic];
+            }
+        }
+        if (!lean && active) {
+            float nz[NZ], ns[S];
+            Env::NoiseGen::get_single(key, env, tick0, nz);
+            step_core<Env, CONS_DEFAULT>(p.cons, p.max_steps, s, a_raw, nz, 0u, w, ns, r, f, vm);
+#pragma unroll
+            for (int k = 0; k < S; ++k) s[k] = ns[k];
+        }
+        // (an inactive env keeps its state and episode word: r = 0, f = NIG_F_INACTIVE, vm = 0)
+        const bool done = active && (f & (NIG_F_TERMINATED | NIG_F_TRUNCATED));
+        if (p.ep_return && active) {
+            er = er + r;
+            if (done) eps.episode(er, (unsigned long long)epw_step(w));
+            p.ep_return[i] = (done && p.auto_reset) ? 0.0 : er;
+        }
+        bool need_reset = false;
+        if (done) {
+            if (p.auto_reset) { need_reset = true; w = 0u; f |= NIG_F_RESET; }
+            else w |= 0x80000000u;
+        }
+        if (__any_sync(0xffffffffu, need_reset)) grid_coop_reset(key, tab8l, env, tick0 + 1u, epoch, need_reset, s, wbuf, list);
+        if (in_pitch) {
+#pragma unroll
+            for (int k = 0; k < S; ++k) p.state[k * p.pitch + i] = s[k];
+            p.ep_word[i] = w;
+        }
+        if (valid) {
+            if (p.reward) p.reward[i] = (float)r;
+            if (p.flags) p.flags[i] = (uint8_t)f;
+            if (p.viol_mask) p.viol_mask[i] = (uint8_t)vm;
+        }
+        if (active) {
+            c_steps += 1; c_viol += __popc(vm);
+            c_crit += (f & NIG_F_CRITICAL) ? 1u : 0u;
+            if (done) { c_ep += 1; c_term += (f & NIG_F_TERMINATED) ? 1u : 0u; c_trunc += (f & NIG_F_TRUNCATED) ? 1u : 0u; }
+            c_con0 += vm & 1u; c_con1 += (vm >> 1) & 1u; c_con2 += (vm >> 2) & 1u;
+        }
+    }
+    bs.warp_add(NIG_ST_STEPS, c_steps);
+    if (__any_sync(0xffffffffu, (c_ep | c_viol | c_crit) != 0u)) {
+        bs.warp_add(NIG_ST_EPISODES, c_ep);
+        bs.warp_add(NIG_ST_TERMINATED, c_term);
+        bs.warp_add(NIG_ST_TRUNCATED, c_trunc);
+        bs.warp_add(NIG_ST_CRITICAL, c_crit);
+        bs.warp_add(NIG_ST_VIOLATIONS, c_viol);
+        bs.warp_add(NIG_ST_CON0, c_con0); bs.warp_add(NIG_ST_CON0 + 1, c_con1); bs.warp_add(NIG_ST_CON0 + 2, c_con2);
+        if (p.ep_return && __any_sync(0xffffffffu, c_ep != 0u)) stage_episode_stats(bs, &estage, eps);
+    }
+    unsigned long long* const stats_out = p.stats_shards ? p.stats_shards + (blockIdx.x % kStatsShards) * NIG_STATS_SLOTS : p.stats;
+    bs.flush(stats_out);
+    if (p.ep_return) flush_episode_staging(stats_out, &estage);
+    advance_device_tick(p.tick_dev, 1u);
 }
 
 // ================================================================================================

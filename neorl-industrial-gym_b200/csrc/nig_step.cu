@@ -63,6 +63,44 @@ cudaError_t go_pipe_t(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* u
     return cudaGetLastError();
 }
 
+// PowerGrid-v0: the dedicated persistent single-step kernel (NIG_GRID_STEP = 0: off, 1: 192-thread CTAs, two per SM, 2: one
+// 384-thread CTA per SM); gridDim = the CTAs resident on the device
+template <int THREADS, int REGS>
+cudaError_t go_grid_t(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
+{
+    static const bool pdl = [] { const char* v = getenv("NIG_STEP_PDL"); return v ? atoi(v) != 0 : true; }();
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    auto kern = step_grid_kernel<THREADS, REGS>;
+    constexpr size_t smem = grid_step_smem<THREADS>();
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if (!cache[dev]) {
+        int per_sm = 0, sms = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        cache[dev] = (per_sm > 0 ? per_sm : 1) * sms;
+    }
+    const int64_t tiles = (pitch + THREADS - 1) / THREADS;
+    if (tiles < 2 * (int64_t)cache[dev]) return cudaSuccess;     // small population: the table copy would not pay
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)cache[dev]); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    *used = true;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+}
+cudaError_t go_grid(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
+{
+    static const int mode = [] { const char* v = getenv("NIG_GRID_STEP"); return v ? atoi(v) : 1; }();
+    if (mode == 0) return cudaSuccess;
+    return mode == 2 ? go_grid_t<384, 168>(pitch, a, st, used) : go_grid_t<192, 168>(pitch, a, st, used);
+}
+
 template <class Env, int VEC>
 cudaError_t go_pipe(int cons, int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
 {
@@ -94,8 +132,10 @@ cudaError_t launch_step_pipelined(int kind, int cons, int64_t pitch, const StepA
         return go_pipe<Robot, 1>(cons, pitch, a, st, used);
     default:
         // PowerGrid (23 Gaussian draws per step, block-cooperative reset buffer) is latency-bound at the pipeline's two
-        // resident CTAs per SM: 115 -> 136 us at 1M envs. It keeps step_kernel.
+        // resident CTAs per SM (115 -> 136 us at 1M envs): with the env's default constraints it takes its own persistent
+        // kernel (lean in-place step, 8 x replicated normal table), otherwise step_kernel.
         *used = false;
+        if (cons == CONS_DEFAULT) return go_grid(pitch, a, st, used);
         return cudaSuccess;
     }
 }
