@@ -1585,28 +1585,34 @@ __device__ __forceinline__ void grid_coop_reset(const Rng& key, const float4* ta
     if (need) list[rk] = lane;
     __syncwarp();
     const uint32_t j = lane & 7u;
+    const int q4 = (int)(lane >> 3);                                 // this lane's rank within a round of four
     const uint32_t env_w = env - lane;                               // env id of lane 0
     const bool uni = (j == 4u) || (j == 5u);
-    for (int c0 = 0; c0 < cnt; c0 += kGridResetRanks) {              // (8 or fewer resetting lanes: one pass)
+    float4* const slot = reinterpret_cast<float4*>(wbuf + q4 * kGridResetRow + (int)j * 4);
+    // one round: ranks r0 .. r0 + 3, one Philox block (4 raw values) per lane, stored at row (r0 - c0) + q4 of the buffer
+    auto round = [&](int r0, int row0) {
+        const int r = r0 + q4;
+        const bool live = r < cnt;
+        const uint32_t src = list[live ? r : 0];
+        const uint4 w = rng_words(key, env_w + src, tick, STREAM_RESET, (epoch << 8) | j);
+        float4 v;
+        v.x = uni ? u_sym(w.x) : spec_normal_rep8(tab8l, w.x);
+        v.y = uni ? u_sym(w.y) : spec_normal_rep8(tab8l, w.y);
+        v.z = uni ? u_sym(w.z) : spec_normal_rep8(tab8l, w.z);
+        v.w = uni ? u_sym(w.w) : spec_normal_rep8(tab8l, w.w);
+        if (live) slot[row0 * (kGridResetRow / 4)] = v;
+    };
 #pragma unroll 1
-        for (int r0 = c0; r0 < cnt && r0 < c0 + kGridResetRanks; r0 += 4) {
-            const int r = r0 + (int)(lane >> 3);
-            const bool live = r < cnt;
-            const uint32_t src = list[live ? r : 0];
-            const uint4 w = rng_words(key, env_w + src, tick, STREAM_RESET, (epoch << 8) | j);
-            float4 v;
-            v.x = uni ? u_sym(w.x) : spec_normal_rep8(tab8l, w.x);
-            v.y = uni ? u_sym(w.y) : spec_normal_rep8(tab8l, w.y);
-            v.z = uni ? u_sym(w.z) : spec_normal_rep8(tab8l, w.z);
-            v.w = uni ? u_sym(w.w) : spec_normal_rep8(tab8l, w.w);
-            if (live) *reinterpret_cast<float4*>(wbuf + (r - c0) * kGridResetRow + (int)j * 4) = v;
-        }
+    for (int c0 = 0; c0 < cnt; c0 += kGridResetRanks) {              // (8 or fewer resetting lanes: one pass)
+        round(c0, 0);
+        if (cnt - c0 > 4) round(c0 + 4, 4);                          // (uniform)
         __syncwarp();
-        if (need && rk >= c0 && rk < c0 + kGridResetRanks) {
+        const int row = rk - c0;
+        if (need && row >= 0 && row < kGridResetRanks) {
             float v[32];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const float4 x = *reinterpret_cast<const float4*>(wbuf + (rk - c0) * kGridResetRow + q * 4);
+                const float4 x = *reinterpret_cast<const float4*>(wbuf + row * kGridResetRow + q * 4);
                 v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
             }
             Grid::reset_from_values(v, s);
@@ -2414,6 +2420,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) step_grid_kernel(
         double er = 0.0;
         if (p.ep_return && active) er = stage_er[tl];
         __syncthreads();                                 // everyone has its tile in registers: the stage is free
+        // (letting the last warp to arrive -- a shared counter instead of the barrier -- issue the refill: 92 instead of 87 us)
         if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             fetch(tile + gridDim.x);

@@ -128,7 +128,7 @@ def test_grid_persistent_step_kernel_from_adversarial_states_and_actions(mods, m
     step; and to the one-tile kernel (NIG_GRID_STEP=0) through the same oracle."""
     ni, N, O, torch = mods
     rng = np.random.default_rng(17)
-    n, T = 130_007, 7
+    n, T = 180_011, 7      # (>= 3 tiles of 192 envs per resident CTA: the dedicated kernel)
     env = ni.NativeEnv(N.ENV_POWER_GRID, n, device=0, seed=5, env_id_offset=3, auto_reset=auto_reset)
     orc = O.OracleEnv(O.GRID, n, seed=5, env_id0=3, exp_mode=1, auto_reset=auto_reset, threads=8)
     s0 = env.reset_host()
