@@ -1049,6 +1049,16 @@ static __global__ void __launch_bounds__(kThreads) state_io_kernel(const __grid_
 // ================================================================================================
 constexpr int kTmaChunk = 16;   // steps of actions staged per TMA box
 
+// Programmatic dependent launch of the fused rollout kernels (the launchers set cudaLaunchAttributeProgrammaticStreamSerialization):
+// the K-step launches of an env slice follow each other on one stream; the CTAs of launch c + 1 are scheduled while launch c
+// drains, copy the normal table and zero their shared counters, and wait HERE -- before the first read of anything launch c
+// writes (device tick words, state, episode words, per-env sums, statistics). A no-op when launched without the attribute.
+__device__ __forceinline__ void rollout_pdl_sync()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 struct RolloutArgs {
     float* state; uint32_t* ep_word; double* ep_return;
     int64_t n, pitch;
@@ -1871,6 +1881,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     if constexpr (Env::ROLLOUT_TAB_SMEM) normal_table_to_smem(s_tab);
     const Rng key(p.key, Env::ROLLOUT_TAB_SMEM ? s_tab : g_normal_tab);
     bs.init(sstat);                              // (synchronises the CTA)
+    rollout_pdl_sync();
 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < p.n;
@@ -2296,6 +2307,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) rollout_grid_kern
     normal_table_to_smem_rep8(tab8);
     const Rng key(p.key, g_normal_tab);          // (the generic fallback and nothing else reads the table through `key`)
     bs.init(sstat);                              // (synchronises the CTA)
+    rollout_pdl_sync();
 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < p.n;
@@ -2587,6 +2599,7 @@ __global__ void __launch_bounds__(kThreads, 1) rollout_reactor_pair_kernel(const
     normal_table_to_smem(s_tab);
     const Rng key(p.key, s_tab);
     bs.init(sstat);                              // (synchronises the CTA)
+    rollout_pdl_sync();
 
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t i0 = 2 * j;

@@ -1,6 +1,7 @@
 // nig_launch.h -- kernel launchers, one translation unit per kernel family so the library builds in parallel
 // (nig_step.cu, nig_rollout_{reactor,grid,robot}.cu, nig_dataset.cu, nig_misc.cu). nig_api.cu holds no kernels.
 #pragma once
+#include <cstdlib>
 #include "nig_kernels.cuh"
 
 namespace nig {
@@ -35,5 +36,20 @@ cudaError_t launch_selftest_policy(int kind, const PolicyTestArgs& a, cudaStream
 cudaError_t launch_selftest_division(RngKey key, int iters, int blocks, unsigned long long* out, cudaStream_t st);
 
 inline unsigned grid_for(int64_t items, int block = kThreads) { return (unsigned)((items + block - 1) / block); }
+
+// launch of a kernel that executes griddepcontrol.wait before its first dependent read (rollout_pdl_sync): programmatic
+// stream serialisation lets its prologue overlap the tail of the previous launch on the stream (NIG_ROLLOUT_PDL=0: off)
+template <class Kern, class... Args>
+cudaError_t launch_pdl(Kern kern, unsigned grid, unsigned block, size_t smem, cudaStream_t st, const Args&... args)
+{
+    static const bool pdl = [] { const char* v = getenv("NIG_ROLLOUT_PDL"); return v ? atoi(v) != 0 : true; }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 
 } // namespace nig

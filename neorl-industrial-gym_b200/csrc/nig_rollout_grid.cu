@@ -9,8 +9,7 @@ static cudaError_t grid_fast_go(int64_t pitch, const RolloutArgs& a, cudaStream_
     constexpr size_t smem = grid_rollout_smem<THREADS>();
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // (per device: set on every launch)
     if (e != cudaSuccess) return e;
-    kern<<<grid_for(pitch, THREADS), THREADS, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(kern, grid_for(pitch, THREADS), (unsigned)THREADS, smem, st, a);
 }
 template <bool EXTREMA>
 static cudaError_t grid_fast(int shape, int64_t pitch, const RolloutArgs& a, cudaStream_t st)

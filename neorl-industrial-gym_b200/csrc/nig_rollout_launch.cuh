@@ -14,8 +14,7 @@ cudaError_t rollout_go(const RolloutLaunch& cfg, int64_t pitch, const RolloutArg
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    kern<<<grid_for(pitch, block), block, smem, st>>>(a, map);
-    return cudaGetLastError();
+    return launch_pdl(kern, grid_for(pitch, block), (unsigned)block, smem, st, a, map);
 }
 
 template <class Env, int CONS>

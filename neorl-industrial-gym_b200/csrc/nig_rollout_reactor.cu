@@ -5,9 +5,8 @@ cudaError_t launch_rollout_reactor(const RolloutLaunch& cfg, int64_t pitch, cons
 {
     if (cfg.pair && cfg.policy == NIG_POLICY_UNIFORM && cfg.cons == CONS_DEFAULT && !cfg.tma && !cfg.tf_noise) {
         const unsigned grid = grid_for(pitch / 2, cfg.block);
-        if (cfg.extrema) rollout_reactor_pair_kernel<true><<<grid, cfg.block, 0, st>>>(a);
-        else rollout_reactor_pair_kernel<false><<<grid, cfg.block, 0, st>>>(a);
-        return cudaGetLastError();
+        return cfg.extrema ? launch_pdl(rollout_reactor_pair_kernel<true>, grid, (unsigned)cfg.block, 0, st, a)
+                           : launch_pdl(rollout_reactor_pair_kernel<false>, grid, (unsigned)cfg.block, 0, st, a);
     }
     if (cfg.ws && cfg.policy == NIG_POLICY_UNIFORM && cfg.cons == CONS_DEFAULT && !cfg.tma && !cfg.tf_noise) {
         const unsigned grid = (unsigned)((pitch + kWsEnvs - 1) / kWsEnvs);
