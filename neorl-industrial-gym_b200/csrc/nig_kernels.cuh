@@ -1557,25 +1557,31 @@ __device__ __forceinline__ bool grid_fast_invariants(const float (&s)[Grid::S])
 // at 1.8e10 env-steps/s; it would saturate at 2.9e10. The dedicated PowerGrid kernel therefore keeps EIGHT interleaved copies of
 // the table, row r of copy c at float4 index 8 r + c, and lane l reads copy l mod 8: the eight lanes of a quarter-warp always
 // touch eight different bank groups -> exactly 4 wavefronts per LDS.128, whatever the rows. 65.7 KB per CTA (dynamic).
-constexpr int kTabRep = 8;
-__device__ __forceinline__ void normal_table_to_smem_rep8(float4* dst)
+constexpr int kTabRep = 8;                     // the fused rollout kernel; the single-step kernel also runs with 4 (two lanes per copy)
+template <int REP>
+__device__ __forceinline__ void normal_table_to_smem_rep(float4* dst)
 {
-    for (int i = threadIdx.x; i < NIG_NORMAL_TAB_N * kTabRep; i += blockDim.x) dst[i] = g_normal_tab[i >> 3];
+    static_assert(REP == 8 || REP == 4, "copies per bank-group set");
+    for (int i = threadIdx.x; i < NIG_NORMAL_TAB_N * REP; i += blockDim.x) dst[i] = g_normal_tab[i / REP];
 }
-// spec_normal with the replicated table; tab8l = table base + (lane & 7)
-__device__ __forceinline__ float spec_normal_rep8(const float4* tab8l, uint32_t w)
+// spec_normal with the replicated table; tabl = table base + (lane & (REP - 1))
+template <int REP>
+__device__ __forceinline__ float spec_normal_rep(const float4* tabl, uint32_t w)
 {
+    constexpr int SH = REP == 8 ? 16 : 17;
+    constexpr uint32_t MASK = REP == 8 ? 0xfff8u : 0x7ffcu;
     const uint32_t v = w * 2u + 1u;
     const float f = __uint2float_rn(v);
-    const float4 c = tab8l[((__float_as_uint(f) >> 16) & 0xfff8u) - 2032u * kTabRep];
+    const float4 c = tabl[((__float_as_uint(f) >> SH) & MASK) - 2032u * REP];
     const float z = __fmaf_rn(__fmaf_rn(__fmaf_rn(c.w, f, c.z), f, c.y), f, c.x);
     return __uint_as_float(__float_as_uint(z) ^ (w & 0x80000000u));
 }
-__device__ __forceinline__ void rng_normals4_rep8(const Rng& key, const float4* tab8l, uint32_t env, uint32_t tick, uint32_t stream, uint32_t j, float (&z)[4])
+template <int REP>
+__device__ __forceinline__ void rng_normals4_rep(const Rng& key, const float4* tabl, uint32_t env, uint32_t tick, uint32_t stream, uint32_t j, float (&z)[4])
 {
     const uint4 w = rng_words(key, env, tick, stream, j);
-    z[0] = spec_normal_rep8(tab8l, w.x); z[1] = spec_normal_rep8(tab8l, w.y);
-    z[2] = spec_normal_rep8(tab8l, w.z); z[3] = spec_normal_rep8(tab8l, w.w);
+    z[0] = spec_normal_rep<REP>(tabl, w.x); z[1] = spec_normal_rep<REP>(tabl, w.y);
+    z[2] = spec_normal_rep<REP>(tabl, w.z); z[3] = spec_normal_rep<REP>(tabl, w.w);
 }
 
 // ---- block-granular cooperative reset of the dedicated PowerGrid kernel (same draws as coop_reset_blocks / Grid::reset) ----
@@ -1585,6 +1591,7 @@ __device__ __forceinline__ void rng_normals4_rep8(const Rng& key, const float4* 
 // LDS.128 of different rows fall into different banks), the owners rebuild their state from their row.
 constexpr int kGridResetRow = 36;
 constexpr int kGridResetRanks = 8;                 // rows of a warp's buffer: the resetting lanes are served eight ranks at a time
+template <int REP>
 __device__ __forceinline__ void grid_coop_reset(const Rng& key, const float4* tab8l, uint32_t env, uint32_t tick, uint32_t epoch, bool need,
                                                 float (&s)[Grid::S], float* wbuf, uint32_t* list)
 {
@@ -1606,10 +1613,10 @@ __device__ __forceinline__ void grid_coop_reset(const Rng& key, const float4* ta
         const uint32_t src = list[live ? r : 0];
         const uint4 w = rng_words(key, env_w + src, tick, STREAM_RESET, (epoch << 8) | j);
         float4 v;
-        v.x = uni ? u_sym(w.x) : spec_normal_rep8(tab8l, w.x);
-        v.y = uni ? u_sym(w.y) : spec_normal_rep8(tab8l, w.y);
-        v.z = uni ? u_sym(w.z) : spec_normal_rep8(tab8l, w.z);
-        v.w = uni ? u_sym(w.w) : spec_normal_rep8(tab8l, w.w);
+        v.x = uni ? u_sym(w.x) : spec_normal_rep<REP>(tab8l, w.x);
+        v.y = uni ? u_sym(w.y) : spec_normal_rep<REP>(tab8l, w.y);
+        v.z = uni ? u_sym(w.z) : spec_normal_rep<REP>(tab8l, w.z);
+        v.w = uni ? u_sym(w.w) : spec_normal_rep<REP>(tab8l, w.w);
         if (live) slot[row0 * (kGridResetRow / 4)] = v;
     };
 #pragma unroll 1
@@ -1694,7 +1701,7 @@ __device__ __forceinline__ int grid_fast_steps(const Rng& key, uint32_t env, uin
 #pragma unroll
         for (int j = 0; j < 6; ++j) {                                             // V(8) sigma .005, load(8) sigma 1, flow(7) sigma 2
             float z[4];
-            rng_normals4_rep8(key, tab8l, env, tick, STREAM_NOISE, (uint32_t)j, z);
+            rng_normals4_rep<kTabRep>(key, tab8l, env, tick, STREAM_NOISE, (uint32_t)j, z);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int k = 4 * j + q;
@@ -1748,7 +1755,7 @@ __device__ __forceinline__ int grid_fast_steps(const Rng& key, uint32_t env, uin
                 ep_ret = 0.0; vi = 0u;
                 t_trunc = t + max_steps;
             }
-            grid_coop_reset(key, tab8l, env, tick + 1u, epoch, fin, s, wbuf, list);
+            grid_coop_reset<kTabRep>(key, tab8l, env, tick + 1u, epoch, fin, s, wbuf, list);
         }
     }
     // every step belongs to an episode: the lengths of the episodes finished here add up to the steps taken, plus the part of
@@ -2285,9 +2292,9 @@ __global__ void __launch_bounds__(kWsThreads, 7) rollout_reactor_ws_kernel(const
 // CTAS x (65.7 KB table + 4.6 KB of reset buffer per warp) of dynamic shared memory. Warps whose envs do not all satisfy
 // the loop invariants (and warps whose division guard failed) step through the generic path (global-memory table).
 // ================================================================================================
-template <int THREADS> __host__ __device__ constexpr size_t grid_rollout_smem()
+template <int THREADS, int REP = kTabRep> __host__ __device__ constexpr size_t grid_rollout_smem()
 {
-    return (size_t)NIG_NORMAL_TAB_N * kTabRep * sizeof(float4) + (size_t)(THREADS / 32) * (kGridResetRanks * kGridResetRow * sizeof(float) + 32 * sizeof(uint32_t));
+    return (size_t)NIG_NORMAL_TAB_N * REP * sizeof(float4) + (size_t)(THREADS / 32) * (kGridResetRanks * kGridResetRow * sizeof(float) + 32 * sizeof(uint32_t));
 }
 template <bool EXTREMA, int THREADS, int MAXREG>
 __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) rollout_grid_kernel(const __grid_constant__ RolloutArgs p)
@@ -2304,7 +2311,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) rollout_grid_kern
     BlockStats bs;
     if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
     if constexpr (EXTREMA) { if (threadIdx.x < 2) sext[threadIdx.x] = 0ull; }
-    normal_table_to_smem_rep8(tab8);
+    normal_table_to_smem_rep<kTabRep>(tab8);
     const Rng key(p.key, g_normal_tab);          // (the generic fallback and nothing else reads the table through `key`)
     bs.init(sstat);                              // (synchronises the CTA)
     rollout_pdl_sync();
@@ -2363,9 +2370,9 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) rollout_grid_kern
 // it; a per-warp stage fed by 128-byte copies: 102 us).
 // ================================================================================================
 template <int THREADS> __host__ __device__ constexpr size_t grid_step_stage_bytes() { return (size_t)(Grid::S + Grid::A + 1) * THREADS * sizeof(float) + (size_t)THREADS * sizeof(double); }
-template <int THREADS> __host__ __device__ constexpr size_t grid_step_smem() { return grid_rollout_smem<THREADS>() + grid_step_stage_bytes<THREADS>(); }
+template <int THREADS, int REP> __host__ __device__ constexpr size_t grid_step_smem() { return grid_rollout_smem<THREADS, REP>() + grid_step_stage_bytes<THREADS>(); }
 
-template <int THREADS, int MAXREG>
+template <int THREADS, int MAXREG, int REP>
 __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) step_grid_kernel(const __grid_constant__ StepArgs p)
 {
     using Env = Grid;
@@ -2377,14 +2384,14 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) step_grid_kernel(
     __shared__ alignas(8) uint64_t full_bar;
     extern __shared__ __align__(128) float4 dyn_smem4[];
     float4* tab8 = dyn_smem4;
-    float* wbuf = reinterpret_cast<float*>(tab8 + NIG_NORMAL_TAB_N * kTabRep) + (threadIdx.x >> 5) * kGridResetRanks * kGridResetRow;
-    uint32_t* list = reinterpret_cast<uint32_t*>(reinterpret_cast<float*>(tab8 + NIG_NORMAL_TAB_N * kTabRep) + (THREADS / 32) * kGridResetRanks * kGridResetRow) + (threadIdx.x >> 5) * 32;
-    const float4* tab8l = tab8 + (threadIdx.x & 7);
-    float* stage = reinterpret_cast<float*>(reinterpret_cast<char*>(dyn_smem4) + grid_rollout_smem<THREADS>());   // [S + A + 1][THREADS] floats
+    float* wbuf = reinterpret_cast<float*>(tab8 + NIG_NORMAL_TAB_N * REP) + (threadIdx.x >> 5) * kGridResetRanks * kGridResetRow;
+    uint32_t* list = reinterpret_cast<uint32_t*>(reinterpret_cast<float*>(tab8 + NIG_NORMAL_TAB_N * REP) + (THREADS / 32) * kGridResetRanks * kGridResetRow) + (threadIdx.x >> 5) * 32;
+    const float4* tab8l = tab8 + (threadIdx.x & (REP - 1));
+    float* stage = reinterpret_cast<float*>(reinterpret_cast<char*>(dyn_smem4) + grid_rollout_smem<THREADS, REP>());   // [S + A + 1][THREADS] floats
     double* stage_er = reinterpret_cast<double*>(stage + (S + A + 1) * THREADS);                                   // [THREADS]
     BlockStats bs;
     episode_staging_init(&estage);
-    normal_table_to_smem_rep8(tab8);
+    normal_table_to_smem_rep<REP>(tab8);
     if (threadIdx.x == 0) {
         mbar_init(&full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -2482,7 +2489,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) step_grid_kernel(
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
                 float z[4];
-                rng_normals4_rep8(key, tab8l, env, tick0, STREAM_NOISE, (uint32_t)j, z);
+                rng_normals4_rep<REP>(key, tab8l, env, tick0, STREAM_NOISE, (uint32_t)j, z);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int k = 4 * j + q;
@@ -2544,7 +2551,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) step_grid_kernel(
             if (p.auto_reset) { need_reset = true; w = 0u; f |= NIG_F_RESET; }
             else w |= 0x80000000u;
         }
-        if (__any_sync(0xffffffffu, need_reset)) grid_coop_reset(key, tab8l, env, tick0 + 1u, epoch, need_reset, s, wbuf, list);
+        if (__any_sync(0xffffffffu, need_reset)) grid_coop_reset<REP>(key, tab8l, env, tick0 + 1u, epoch, need_reset, s, wbuf, list);
         if (in_pitch) {
 #pragma unroll
             for (int k = 0; k < S; ++k) p.state[k * p.pitch + i] = s[k];

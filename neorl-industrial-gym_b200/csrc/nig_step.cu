@@ -63,9 +63,9 @@ cudaError_t go_pipe_t(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* u
     return cudaGetLastError();
 }
 
-// PowerGrid-v0: the dedicated persistent single-step kernel (NIG_GRID_STEP = 0: off, 1: 192-thread CTAs, two per SM, 2: one
-// 384-thread CTA per SM); gridDim = the CTAs resident on the device
-template <int THREADS, int REGS>
+// PowerGrid-v0: the dedicated persistent single-step kernel (NIG_GRID_STEP = 0: off, 1 / unset: the default shape, 2.. other
+// CTA shapes / table replications, see go_grid); gridDim = the CTAs resident on the device
+template <int THREADS, int REGS, int REP>
 cudaError_t go_grid_t(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
 {
     static const bool pdl = [] { const char* v = getenv("NIG_STEP_PDL"); return v ? atoi(v) != 0 : true; }();
@@ -74,8 +74,8 @@ cudaError_t go_grid_t(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* u
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-    auto kern = step_grid_kernel<THREADS, REGS>;
-    constexpr size_t smem = grid_step_smem<THREADS>();
+    auto kern = step_grid_kernel<THREADS, REGS, REP>;
+    constexpr size_t smem = grid_step_smem<THREADS, REP>();
     if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if (!cache[dev]) {
         int per_sm = 0, sms = 0;
@@ -96,9 +96,16 @@ cudaError_t go_grid_t(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* u
 }
 cudaError_t go_grid(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* used)
 {
-    static const int mode = [] { const char* v = getenv("NIG_GRID_STEP"); return v ? atoi(v) : 1; }();
+    const char* const v = getenv("NIG_GRID_STEP");         // (read per launch: the tests switch shapes inside one process)
+    const int mode = v ? atoi(v) : 1;
     if (mode == 0) return cudaSuccess;
-    return mode == 2 ? go_grid_t<384, 168>(pitch, a, st, used) : go_grid_t<192, 168>(pitch, a, st, used);
+    switch (mode) {                   // measured at 1M / 4M envs (profiles/r02_f_grid_step_ab.txt): us per launch
+    case 2: return go_grid_t<384, 168, 8>(pitch, a, st, used);      // 93.2 / 313   one CTA per SM, 12 warps
+    case 3: return go_grid_t<128, 168, 4>(pitch, a, st, used);      // 87.0 / 308   three CTAs per SM, 12 warps, table copies shared by lane pairs
+    case 4: return go_grid_t<192, 168, 4>(pitch, a, st, used);      // 89.1
+    case 6: return go_grid_t<192, 168, 8>(pitch, a, st, used);      // 89.1 / 304   two CTAs per SM, 12 warps
+    default: return go_grid_t<256, 128, 4>(pitch, a, st, used);     // 82.9 / 280   two CTAs per SM, 16 warps (8 B of spills)
+    }
 }
 
 template <class Env, int VEC>

@@ -119,14 +119,15 @@ def test_grid_fast_loop_from_adversarial_entry_states(mods, monkeypatch, shape):
     env.close()
 
 
-@pytest.mark.parametrize("auto_reset", [True, False])
-def test_grid_persistent_step_kernel_from_adversarial_states_and_actions(mods, monkeypatch, auto_reset):
+@pytest.mark.parametrize("auto_reset,mode", [(True, "1"), (False, "1"), (True, "2"), (True, "3"), (False, "6"), (True, "6")])
+def test_grid_persistent_step_kernel_from_adversarial_states_and_actions(mods, monkeypatch, auto_reset, mode):
     """PowerGrid-v0 single step at a population large enough for the dedicated persistent kernel (lean in-place step with
     per-step guards, generic step_core as the per-warp fallback): out-of-range / non-finite / signed-zero states, NaN /
     infinite / over-range actions, generation-limit violations, envs on the brink of truncation, done latches (auto_reset
     off): rewards, flags, violation masks, states, episode words and counters equal to the oracle's, bit for bit, step after
     step; and to the one-tile kernel (NIG_GRID_STEP=0) through the same oracle."""
     ni, N, O, torch = mods
+    monkeypatch.setenv("NIG_GRID_STEP", mode)          # CTA shape / table replication of the dedicated kernel
     rng = np.random.default_rng(17)
     n, T = 180_011, 7      # (>= 3 tiles of 192 envs per resident CTA: the dedicated kernel)
     env = ni.NativeEnv(N.ENV_POWER_GRID, n, device=0, seed=5, env_id_offset=3, auto_reset=auto_reset)
