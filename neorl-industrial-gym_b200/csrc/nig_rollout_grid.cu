@@ -7,8 +7,15 @@ static cudaError_t grid_fast_go(int64_t pitch, const RolloutArgs& a, cudaStream_
 {
     auto kern = rollout_grid_kernel<EXTREMA, THREADS, MAXREG>;
     constexpr size_t smem = grid_rollout_smem<THREADS>();
-    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // (per device: set on every launch)
+    static bool attr_set[64] = {false};           // the attribute is per function and per device: set once for each
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!attr_set[dev]) {
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        attr_set[dev] = true;
+    }
     return launch_pdl(kern, grid_for(pitch, THREADS), (unsigned)THREADS, smem, st, a);
 }
 template <bool EXTREMA>

@@ -76,9 +76,9 @@ cudaError_t go_grid_t(int64_t pitch, const StepArgs& a, cudaStream_t st, bool* u
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
     auto kern = step_grid_kernel<THREADS, REGS, REP>;
     constexpr size_t smem = grid_step_smem<THREADS, REP>();
-    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if (!cache[dev]) {
         int per_sm = 0, sms = 0;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         cache[dev] = (per_sm > 0 ? per_sm : 1) * sms;
