@@ -97,6 +97,7 @@ struct Reactor {
     // (0.86 -> 0.92 of the HBM peak), the fused rollout loses 2 % (one extra ballot per step) and keeps Env::reset()
     static constexpr bool COOP_RESET = true;
     static constexpr int COOP_BLOCKS = 0;
+    static constexpr bool COOP_FK = false;
     static constexpr int RESET_NORMALS = 8;
     // resident CTAs per SM the fused rollout is compiled for (register cap): measured, more resident warps LOSE for
     // the reactor (7.0 -> 6.8 -> 6.3e10 env-steps/s at 1M envs for 4 / 6 / 8 CTAs)
@@ -291,6 +292,7 @@ struct Grid {
     static constexpr bool ROLLOUT_TAB_SMEM = true;
     static constexpr int STEP_MIN_CTAS = 4;          // single step: 146 -> 128 registers, 3 -> 4 CTAs per SM, +11 % (5, 6: worse)
     static constexpr int COOP_BLOCKS = 8;
+    static constexpr bool COOP_FK = false;
     __device__ static __forceinline__ void reset_block(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, uint32_t j, float (&v)[4])
     {
         if (j == 4u || j == 5u) {
@@ -413,6 +415,10 @@ struct Robot {
     static constexpr bool FAST_DIV = false;          // fp64 divisions only
     static constexpr bool COOP_RESET = false;
     static constexpr int COOP_BLOCKS = 0;
+#ifndef NIG_ROBOT_COOP_FK
+#define NIG_ROBOT_COOP_FK 1
+#endif
+    static constexpr bool COOP_FK = NIG_ROBOT_COOP_FK != 0;   // warp-cooperative forward kinematics of the reset (coop_reset_fk)
     static constexpr bool TAB_SMEM = false;          // normals only in reset / policy draws
     static constexpr bool ROLLOUT_TAB_SMEM = false;
     static constexpr int ROLLOUT_MIN_CTAS = 4;       // 177 -> 128 registers: 1.76 -> 2.05e10 env-steps/s at 1M envs

@@ -265,8 +265,72 @@ __device__ __forceinline__ void coop_reset(const Rng& key, uint32_t env, uint32_
 // Gaussians + 8 uniforms per reset, ~18 % of the envs reset every step under random actions, i.e. ~6 lanes of every
 // warp): the work items (resetting lane, block) of the whole warp are dealt round-robin to the 32 lanes, the raw values
 // go through a per-warp shared-memory buffer [32 resetting lanes][COOP_BLOCKS * 4], the owners rebuild their state.
+constexpr int kFkRanks = 8, kFkWarpFloats = kFkRanks * 8 * 3 * 2 + 32;       // coop_reset_fk: 8 ranks x 8 slots x {q, sin, cos} fp64 + the rank list
 template <class Env>
-struct CoopSmem { static constexpr int floats = Env::COOP_BLOCKS > 0 ? (kThreads / 32) * 32 * Env::COOP_BLOCKS * 4 : 1; };
+struct CoopSmem {
+    static constexpr int floats = Env::COOP_BLOCKS > 0 ? (kThreads / 32) * 32 * Env::COOP_BLOCKS * 4
+                                : (Env::COOP_FK ? (kThreads / 32) * kFkWarpFloats : 1);
+};
+
+// RobotAssembly-v0: a fresh state is seven uniform joint angles and the forward kinematics of them -- seven binary64
+// sin / cos pairs, ~430 instructions that the whole warp walks for the 2 - 3 lanes that finished (episodes are short under
+// random actions: 58 % of the warp-steps have a resetting lane). Here the (resetting lane, joint) items are dealt to the
+// lanes -- four ranks per round, lane l takes joint l mod 8 (slot 7 idles) --, each producer draws the joint's angle from the
+// reset stream, evaluates ONE sin / cos pair and leaves {q, sin q, cos q} in the warp's shared-memory buffer; the owners sum the
+// link contributions in the reference's order (:94-111). Same counters, same bits as Env::reset(). Must be called convergently.
+template <class Env>
+__device__ __forceinline__ void coop_reset_fk(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, bool need,
+                                              float (&s)[Env::S], float* cta_buf)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m == 0u) return;                                        // warp-uniform
+    const uint32_t lane = threadIdx.x & 31u;
+    double* const buf = reinterpret_cast<double*>(cta_buf + (threadIdx.x >> 5) * kFkWarpFloats);       // [kFkRanks][8][3]
+    uint32_t* const list = reinterpret_cast<uint32_t*>(buf + kFkRanks * 8 * 3);
+    const int cnt = __popc(m);
+    const int rk = __popc(m & ((1u << lane) - 1u));
+    if (need) list[rk] = lane;
+    __syncwarp();
+    const uint32_t j = lane & 7u;
+    const int q4 = (int)(lane >> 3);
+#pragma unroll 1
+    for (int c0 = 0; c0 < cnt; c0 += kFkRanks) {
+#pragma unroll 1
+        for (int r0 = c0; r0 < cnt && r0 < c0 + kFkRanks; r0 += 4) {
+            const int r = r0 + q4;
+            const bool live = r < cnt && j < 7u;
+            const int src = (int)list[r < cnt ? r : 0];
+            const uint32_t e_src = __shfl_sync(0xffffffffu, env, src);
+            const uint4 w = rng_words(key, e_src, tick, STREAM_RESET, (epoch << 8) | (j >> 2));
+            const uint32_t word = (j & 2u) ? ((j & 1u) ? w.w : w.z) : ((j & 1u) ? w.y : w.x);
+            const double q = (double)mul(0x1.921fb6p+0f, u_sym(word));
+            double sn, cs;
+            spec_sincos_f64(q, sn, cs);
+            if (live) {
+                double* d = buf + ((r - c0) * 8 + (int)j) * 3;
+                d[0] = q; d[1] = sn; d[2] = cs;
+            }
+        }
+        __syncwarp();
+        const int row = rk - c0;
+        if (need && row >= 0 && row < kFkRanks) {
+            const double* d = buf + row * 8 * 3;
+            double x = 0.0, y = 0.0, z = 0.0;
+#pragma unroll
+            for (int i = 0; i < Env::S; ++i) s[i] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const double q = d[i * 3], sn = d[i * 3 + 1], cs = d[i * 3 + 2];
+                if ((i & 1) == 0) { x = dadd(x, dmul(Env::link(i), cs)); z = dadd(z, dmul(Env::link(i), sn)); }
+                else y = dadd(y, dmul(Env::link(i), sn));
+                s[7 + i] = (float)q;
+            }
+            s[0] = (float)x; s[1] = (float)y; s[2] = (float)z;
+            s[6] = 1.0f;
+        }
+        __syncwarp();
+    }
+}
 
 template <class Env>
 __device__ __forceinline__ void coop_reset_blocks(const Rng& key, uint32_t env, uint32_t tick, uint32_t epoch, bool need,
@@ -549,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
     using acc_t = typename Env::acc_t;
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
     __shared__ EpisodeStaging estage;
-    __shared__ float coop_buf[CoopSmem<Env>::floats];
+    __shared__ alignas(16) float coop_buf[CoopSmem<Env>::floats];
     __shared__ float aos_tile[(VEC == 1 && !PLAIN) ? (kThreads / 32) * 32 * (S + 1) : 1];      // AoS transposes (VEC == 1 only)
     float* my_tile = aos_tile + ((VEC == 1 && !PLAIN) ? (threadIdx.x >> 5) * 32 * (S + 1) : 0);
     BlockStats bs;
@@ -643,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
 #pragma unroll
                         for (int k = 0; k < S; ++k) s[k] = rs[k][e];
                     } else {
-                        if constexpr (Env::COOP_RESET || Env::COOP_BLOCKS > 0) need_reset = true;
+                        if constexpr (Env::COOP_RESET || Env::COOP_BLOCKS > 0 || Env::COOP_FK) need_reset = true;
                         else Env::reset(key, env, tick0 + 1u, p.epoch, s);
                     }
                     w = 0u; f |= NIG_F_RESET;
@@ -658,6 +722,7 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             }
             if constexpr (Env::COOP_RESET) coop_reset<Env>(key, env, tick0 + 1u, p.epoch, need_reset, s);
             else if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(key, env, tick0 + 1u, p.epoch, need_reset, s, coop_buf);
+            else if constexpr (Env::COOP_FK) coop_reset_fk<Env>(key, env, tick0 + 1u, p.epoch, need_reset, s, coop_buf);
 #pragma unroll
             for (int k = 0; k < S; ++k) sv[k][e] = s[k];
             wv[e] = __uint_as_float(w);
@@ -800,7 +865,7 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];
     __shared__ EpisodeStaging estage;
     __shared__ alignas(8) uint64_t full[kStepStages];
-    __shared__ float coop_buf[CoopSmem<Env>::floats];
+    __shared__ alignas(16) float coop_buf[CoopSmem<Env>::floats];
     // persistent CTAs amortise a shared copy of the normal table where the env draws many normals per step (PowerGrid);
     // for the reactor it would cost the fourth resident CTA its stage ring (measured: 0.90 -> 0.85 of the HBM peak)
     __shared__ float4 s_tab[Env::TAB_SMEM ? NIG_NORMAL_TAB_N : 1];
@@ -900,13 +965,14 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             }
             if (done) {
                 if (p.auto_reset) {
-                    if constexpr (Env::COOP_RESET || Env::COOP_BLOCKS > 0) need_reset = true;
+                    if constexpr (Env::COOP_RESET || Env::COOP_BLOCKS > 0 || Env::COOP_FK) need_reset = true;
                     else Env::reset(key, env, tick0 + 1u, p.epoch, ns);
                     w = 0u; f |= NIG_F_RESET;
                 } else w |= 0x80000000u;
             }
             if constexpr (Env::COOP_RESET) coop_reset<Env>(key, env, tick0 + 1u, p.epoch, need_reset, ns);
             else if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(key, env, tick0 + 1u, p.epoch, need_reset, ns, coop_buf);
+            else if constexpr (Env::COOP_FK) coop_reset_fk<Env>(key, env, tick0 + 1u, p.epoch, need_reset, ns, coop_buf);
 #pragma unroll
             for (int k = 0; k < S; ++k) sv[k][e] = ns[k];
             wv[e] = __uint_as_float(w);
@@ -1880,7 +1946,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     __shared__ unsigned long long sext[2];       // extremum keys of the episodes this CTA finished
     __shared__ float4 s_tab[Env::ROLLOUT_TAB_SMEM ? NIG_NORMAL_TAB_N : 1];   // this CTA's copy of the normal table (8 KB, read K * draws times)
     __shared__ alignas(8) uint64_t bars[2];
-    __shared__ float coop_buf[CoopSmem<Env>::floats];
+    __shared__ alignas(16) float coop_buf[CoopSmem<Env>::floats];
     extern __shared__ __align__(128) float act_smem[];     // [2][kTmaChunk][A][kThreads] when TMA
     BlockStats bs;
     if (threadIdx.x < 4) sfl[threadIdx.x] = 0.0;
@@ -2048,7 +2114,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
                 acc.ret_sum += (double)ep_ret; acc.ret_sq += (double)ep_ret * (double)ep_ret;
                 if constexpr (EXTREMA) { r_lo = ep_ret < r_lo ? ep_ret : r_lo; r_hi = ep_ret > r_hi ? ep_ret : r_hi; }
                 if (p.auto_reset) {
-                    if constexpr (Env::COOP_BLOCKS > 0) need_reset = true;
+                    if constexpr (Env::COOP_BLOCKS > 0 || Env::COOP_FK) need_reset = true;
                     else Env::reset(key, env, tick + 1u, epoch, s);
                     ep_st = 0u; ep_vi = 0u; ep_ret = (acc_t)0;
                 } else {
@@ -2062,6 +2128,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
             }
         }
         if constexpr (Env::COOP_BLOCKS > 0) coop_reset_blocks<Env>(key, env, tick + 1u, epoch, need_reset, s, coop_buf);
+        else if constexpr (Env::COOP_FK) coop_reset_fk<Env>(key, env, tick + 1u, epoch, need_reset, s, coop_buf);
     }
 
     if (valid) {
