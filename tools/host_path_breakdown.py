@@ -24,7 +24,7 @@ def run(graph, slices, with_init, want_obs, n=65536, T=1000, K=64, reps=30):
 if __name__ == "__main__":
     for graph in (0, 1):
         for slices in (4, 8):
-            for with_init, want_obs in ((True, True), (False, False)):
+            for with_init, want_obs in ((True, True), (True, False), (False, True), (False, False)):
                 med, best, lc = run(graph, slices, with_init, want_obs)
                 print(f"graph={graph} slices={slices} init_h2d={with_init} obs_d2h={want_obs}: median {med:.3f} ms  best {best:.3f} ms  "
                       f"-> {65536 * 1000 / (med * 1e-3):.4g} env-steps/s  (launches {lc})", flush=True)
