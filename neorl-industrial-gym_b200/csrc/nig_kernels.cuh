@@ -1421,15 +1421,38 @@ __device__ __forceinline__ V spec_expf_v(V x)
 }
 
 // returns the number of steps committed (== n_steps unless a guard failed). V = float: one env (env[0]); V = F2: two envs.
-template <class V, bool EXTREMA, class Src>
+// NX appended SafetyWrapper bounds (CONS_BOUNDS1 / 2: non-critical lo <= T <= hi or lo <= P <= hi on the PRE-step state, the
+// temperature / pressure bands of BASELINE config 4) ride along as straight-line code: one select of the bounded value, two
+// compares, a selected penalty add after the built-ins' penalties (base.py:179-183 walks the constraints in order), counters.
+struct FastBounds { float lo[2], hi[2], pen[2]; bool use_p[2]; };
+
+// the appended bounds of p.cons the fast loop can carry (warp-uniform): pure, non-critical, on state component 0 (T) or 1 (P)
+template <int NX>
+__device__ __forceinline__ bool fast_bounds_from(const ConsParams& cp, FastBounds& fb)
+{
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        const nig_constraint_t& c = cp.c[Reactor::NB + j];
+        ok = ok && c.kind == NIG_CON_BOUND && c.ai < 0 && c.critical == 0 && (c.si == 0 || c.si == 1);
+        fb.lo[j] = c.lo; fb.hi[j] = c.hi; fb.pen[j] = c.penalty; fb.use_p[j] = c.si == 1;
+    }
+    return ok;
+}
+
+template <class V, bool EXTREMA, class Src, int NX = 0>
 __device__ __forceinline__ int reactor_fast_steps_v(Src& src, const Rng& key, const uint32_t (&env)[VT<V>::N], uint32_t tick0, uint32_t epoch,
                                                     int n_steps, int max_steps, float (&s)[VT<V>::N][Reactor::S],
                                                     uint32_t (&ep_st)[VT<V>::N], uint32_t (&ep_vi)[VT<V>::N], float (&ep_ret_)[VT<V>::N],
-                                                    float (&rsum_)[VT<V>::N], RolloutAcc (&acc)[VT<V>::N], float& r_lo, float& r_hi)
+                                                    float (&rsum_)[VT<V>::N], RolloutAcc (&acc)[VT<V>::N], float& r_lo, float& r_hi,
+                                                    const FastBounds& fb = FastBounds{})
 {
     using T_ = VT<V>;
     using M = typename T_::M;
     constexpr int N = T_::N;
+    static_assert(NX == 0 || N == 1, "appended bounds: one env per thread only");
+    unsigned int c_x[NX > 0 ? NX : 1] = {0u};
+    bool xbad[NX > 0 ? NX : 1] = {false};
     V T, P, cool, feed, conc, cat, hx, rv, level, bt, catd, ep_ret, rsum;
     M alarm;
     int t_trunc[N];
@@ -1526,6 +1549,15 @@ __device__ __forceinline__ int reactor_fast_steps_v(Src& src, const Rng& key, co
         r = vsel(trip, sub(r, T_::bc(200.0f)), r);
         r = sub(r, apen);
         r = vsel(lvl_bad, add(r, T_::bc(-25.0f)), r);
+        if constexpr (NX > 0) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                const float v = fb.use_p[j] ? T_::get(P, 0) : T_::get(T, 0);           // pre-step value (committed below)
+                xbad[j] = !((fb.lo[j] <= v) && (v <= fb.hi[j]));
+                const float rp = add(T_::get(r, 0), fb.pen[j]);
+                T_::set(r, 0, xbad[j] ? rp : T_::get(r, 0));
+            }
+        }
         if (__builtin_expect(!__all_sync(0xffffffffu, mall(ok)), 0)) break;     // (uniform) redo this step in the generic loop
         src.done(t, n_steps);
         rsum = add(rsum, r);
@@ -1538,6 +1570,10 @@ __device__ __forceinline__ int reactor_fast_steps_v(Src& src, const Rng& key, co
         for (int k = 0; k < N; ++k) {
             const unsigned int bad = T_::getm(lvl_bad, k) ? 1u : 0u;
             c_lvl[k] += bad; ep_vi[k] += bad;
+            if constexpr (NX > 0) {
+#pragma unroll
+                for (int j = 0; j < NX; ++j) { const unsigned int b = xbad[j] ? 1u : 0u; c_x[j] += b; ep_vi[k] += b; }
+            }
             T_::setm(fin, k, T_::getm(term, k) || t >= t_trunc[k]);
         }
         if (__any_sync(0xffffffffu, many(fin))) {
@@ -1580,15 +1616,19 @@ __device__ __forceinline__ int reactor_fast_steps_v(Src& src, const Rng& key, co
         acc[k].c_steps += (unsigned int)t;
         acc[k].c_viol += c_lvl[k];
         acc[k].c_con[2] += c_lvl[k];
+        if constexpr (NX > 0) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) { acc[k].c_viol += c_x[j]; acc[k].c_con[Reactor::NB + j] += c_x[j]; }
+        }
     }
     return t;
 }
 
 // one env per thread: the scalar instantiation behind the interface the one-env kernels use
-template <bool EXTREMA, class Src>
+template <bool EXTREMA, class Src, int NX = 0>
 __device__ __forceinline__ int reactor_fast_steps(Src& src, const Rng& key, uint32_t env, uint32_t tick0, uint32_t epoch, int n_steps, int max_steps,
                                                   float (&s)[Reactor::S], uint32_t& ep_st, uint32_t& ep_vi, float& ep_ret, float& rsum,
-                                                  RolloutAcc& acc, float& r_lo, float& r_hi)
+                                                  RolloutAcc& acc, float& r_lo, float& r_hi, const FastBounds& fb = FastBounds{})
 {
     const uint32_t envs[1] = {env};
     auto& s1 = reinterpret_cast<float (&)[1][Reactor::S]>(s);
@@ -1597,7 +1637,7 @@ __device__ __forceinline__ int reactor_fast_steps(Src& src, const Rng& key, uint
     auto& er1 = reinterpret_cast<float (&)[1]>(ep_ret);
     auto& rs1 = reinterpret_cast<float (&)[1]>(rsum);
     auto& ac1 = reinterpret_cast<RolloutAcc (&)[1]>(acc);
-    return reactor_fast_steps_v<float, EXTREMA>(src, key, envs, tick0, epoch, n_steps, max_steps, s1, st1, vi1, er1, rs1, ac1, r_lo, r_hi);
+    return reactor_fast_steps_v<float, EXTREMA, Src, NX>(src, key, envs, tick0, epoch, n_steps, max_steps, s1, st1, vi1, er1, rs1, ac1, r_lo, r_hi, fb);
 }
 
 // ================================================================================================
@@ -2037,15 +2077,20 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     // auto-reset): warps whose envs all satisfy the loop invariants of reactor_fast_steps run the specialised loop; whatever
     // it does not commit (nothing, normally) is left to the generic loop below
     int t_begin = 0;
-    if constexpr (Env::KIND == NIG_ENV_CHEMICAL_REACTOR && CONS == CONS_DEFAULT && POLICY == NIG_POLICY_UNIFORM && !TMA && !TFNOISE) {
-        const bool inv = valid && !latched && p.auto_reset != 0 && __float_as_uint(s[8]) == 0u &&
+    if constexpr (Env::KIND == NIG_ENV_CHEMICAL_REACTOR && (CONS == CONS_DEFAULT || cons_fast_extras(CONS) > 0) && POLICY == NIG_POLICY_UNIFORM &&
+                  !TMA && !TFNOISE) {
+        constexpr int NX = cons_fast_extras(CONS);
+        FastBounds fb;
+        const bool fb_ok = fast_bounds_from<NX>(p.cons, fb);       // else (critical / other components): the generic loop
+        const bool inv = fb_ok && valid && !latched && p.auto_reset != 0 && __float_as_uint(s[8]) == 0u &&
                          (__float_as_uint(s[9]) == 0u || __float_as_uint(s[9]) == 0x3f800000u) &&
                          s[0] >= 200.0f && s[0] <= 350.0f && s[1] <= 506625.0f && s[5] >= 1e-30f && s[5] <= 1e30f &&
                          ep_st < (uint32_t)p.max_steps;
         if (__all_sync(0xffffffffu, inv))
         {
             DrawInKernel src{key, env, tick0};
-            t_begin = reactor_fast_steps<EXTREMA>(src, key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc, r_lo, r_hi);
+            t_begin = reactor_fast_steps<EXTREMA, DrawInKernel, NX>(src, key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc,
+                                                                    r_lo, r_hi, fb);
         }
     }
 

@@ -464,3 +464,54 @@ def test_host_evaluated_constraints_vectorised_or_bounded(mods):
     _, _, _, _, info = small.step(np.zeros((64, 3), np.float32))
     assert np.array_equal((info["violation_mask"] >> 3) & 1, (o[:, 0] > 321.0).astype(np.uint8))
     small.close()
+
+
+@pytest.mark.parametrize("bands", ["T", "P", "TP", "PT", "T_nan_hi"])
+@pytest.mark.parametrize("extrema", [False, True])
+def test_reactor_fast_loop_with_wrapper_bands(mods, bands, extrema):
+    """BASELINE config 4: ChemicalReactor-v0 + SafetyWrapper temperature / pressure bands (non-critical, penalty on the
+    PRE-step value, applied after the built-ins' penalties in constraint order). Such bounds ride along in the
+    invariant-specialised loop (FastBounds); the population also holds warps that leave it (tripped e-stop, over-limit
+    temperature, imminent truncation). 600 steps through nig_rollout_steps (env slices, K = 64) == the oracle bit for bit:
+    states, episode words, per-constraint counters, per-env reward sums."""
+    ni, N, O, torch = mods
+    from neorl_industrial.vector import make_constraint
+    f32 = lambda x: float(np.float32(x))
+    spec = N.env_spec(N.ENV_CHEMICAL_REACTOR)
+    builtins = [make_constraint(N.CON_BUILTIN, cid=k, penalty=spec.constraints[k].penalty, critical=bool(spec.constraints[k].critical))
+                for k in range(3)]
+    bT = make_constraint(N.CON_BOUND, si=0, lo=f32(305.0), hi=f32(325.0), penalty=-100.0)
+    bP = make_constraint(N.CON_BOUND, si=1, lo=f32(101325.0), hi=f32(2.6e5), penalty=-37.5)
+    bTn = make_constraint(N.CON_BOUND, si=0, lo=f32(305.0), hi=float("nan"), penalty=-3.0)       # always violated (a NaN bound compares false)
+    cons = builtins + {"T": [bT], "P": [bP], "TP": [bT, bP], "PT": [bP, bT], "T_nan_hi": [bTn]}[bands]
+    n = 6000 + 17
+    env = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=77, constraints=cons)
+    ocons = [O.Con(c.kind, c.id, c.si, c.ai, c.coef, c.lo, c.hi, c.penalty, c.critical) for c in cons]
+    orc = O.OracleEnv(O.REACTOR, n, auto_reset=True, seed=77, exp_mode=1, builtin=False, extra_cons=ocons)
+    s0 = env.reset_host()
+    assert_bits_equal(s0, orc.reset(), "reset")
+    rng = np.random.default_rng(8)
+    st = s0.copy()
+    ep_step = np.zeros(n, np.int32)
+    st[rng.choice(n, 30, replace=False), 8] = 1.0
+    st[rng.choice(n, 30, replace=False), 0] = rng.uniform(349.0, 353.0, 30).astype(np.float32)
+    ep_step[rng.choice(n, 300, replace=False)] = rng.integers(380, 500, 300)
+    env.set_state_host(st, ep_step, np.zeros(n, np.int32), np.zeros(n, np.uint8))
+    orc.state[:] = st
+    orc.ep_step[:] = ep_step
+    env.track_extrema(extrema)
+    rsum = env.empty()
+    env.rollout_device(70, N.POLICY_UNIFORM, reward_sum=rsum)
+    o_rs = O.rollout(orc, 70, O.POLICY_UNIFORM, want_reward_sum=True)
+    torch.cuda.synchronize()
+    assert_bits_equal(rsum[:n].cpu().numpy(), o_rs, "reward sum with band penalties")
+    env.rollout_steps_device(530, 64, N.POLICY_UNIFORM)
+    O.rollout(orc, 530, O.POLICY_UNIFORM)
+    torch.cuda.synchronize()
+    st1, es, ev, dn = env.get_state_host()
+    assert_bits_equal(st1, orc.state, "state"); assert_bits_equal(es, orc.ep_step, "ep_step"); assert_bits_equal(ev, orc.ep_viol, "ep_viol")
+    c, _ = env.read_stats()
+    assert c[:6].tolist() == orc.stats[:6].tolist()
+    assert c[8:8 + len(cons)].tolist() == orc.stats[8:8 + len(cons)].tolist()
+    assert c[8 + 3] > 0 and c[1] > 0                     # the first band fired; episodes ended (auto-resets inside the loop)
+    env.close()
