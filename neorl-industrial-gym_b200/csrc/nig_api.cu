@@ -113,6 +113,15 @@ struct nig_env {
         const void* ptr[5]; int32_t T, K, policy, reset, slices; int64_t launches; uint64_t config; nig_policy_params_t pp;
     } host_graph_key;
     uint32_t *d_tickbase, *h_tickbase;
+    // nig_rollout_steps (device-resident): its sliced launch sequence (fork, slices x ceil(T / K) launches, join) captured once
+    // on the internal stream and replayed on the caller's stream -- 2 driver calls per call instead of ~150, so the host
+    // thread no longer paces the first steps of a short run. Tick / epoch reach the replay through d_tickbase, written by a
+    // one-thread kernel launched (arguments by value) right before the graph.
+    cudaGraphExec_t steps_graph;
+    struct StepsGraphKey {
+        const void* ptr[3]; int32_t T, K, policy, flags, slices; int64_t launches; uint64_t config; nig_policy_params_t pp;
+    } steps_graph_key;
+    int steps_graph_enable;     // NIG_STEPS_GRAPH (default 1)
     bool graph_mode;            // set while a pipeline is being captured: rollout_range / reset_range emit base-relative counters
     uint32_t graph_tick0;       // tick at the start of the call being captured
     uint64_t config_version;    // bumped by every setter whose value is baked into kernel arguments (invalidates host_graph)
@@ -607,6 +616,8 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     if (const char* v = getenv("NIG_GRID_FAST")) e->grid_fast = atoi(v);
     e->host_graph_enable = 1;
     if (const char* v = getenv("NIG_HOST_GRAPH")) e->host_graph_enable = atoi(v);
+    e->steps_graph_enable = 1;
+    if (const char* v = getenv("NIG_STEPS_GRAPH")) e->steps_graph_enable = atoi(v);
     e->step_pipe = 1;
     if (const char* v = getenv("NIG_STEP_PIPE")) e->step_pipe = atoi(v);
     e->zero_copy = 1;
@@ -642,6 +653,7 @@ int nig_destroy(nig_env_t* e)
     if (!e) return NIG_OK;
     DeviceGuard guard(e->cfg.device);
     if (e->host_graph) cudaGraphExecDestroy(e->host_graph);
+    if (e->steps_graph) cudaGraphExecDestroy(e->steps_graph);
     if (e->h_tickbase) cudaFreeHost(e->h_tickbase);
     cudaFree(e->d_tickbase);
     cudaFree(e->state); cudaFree(e->ep_word); cudaFree(e->ep_return); cudaFree(e->stats); cudaFree(e->stats_shards);
@@ -857,6 +869,51 @@ int nig_rollout_steps(nig_env_t* e, const nig_rollout_t* r, int32_t total_steps,
         }
         return NIG_OK;
     }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+    if (e->steps_graph_enable != 0 && cap == cudaStreamCaptureStatusNone) {
+        // ---- replay of the captured launch sequence (captured on first use and whenever an argument that is baked into the
+        // kernel parameters changes: horizon, K, policy, output pointers, constraint set, seed, tracking switches)
+        nig_env::StepsGraphKey key;
+        memset(&key, 0, sizeof key);
+        key.ptr[0] = r->reward_sum; key.ptr[1] = r->viol_count; key.ptr[2] = r->done_count;
+        key.T = total_steps; key.K = r->n_steps; key.policy = r->policy; key.flags = (int32_t)r->flags; key.slices = slices;
+        key.config = e->config_version; key.pp = r->pp;
+        if (!e->d_tickbase) NIG_CUDA(cudaMalloc((void**)&e->d_tickbase, 2 * sizeof(uint32_t)));
+        key.launches = e->steps_graph ? e->steps_graph_key.launches : 0;
+        if (!e->steps_graph || memcmp(&key, &e->steps_graph_key, sizeof key) != 0) {
+            if (e->steps_graph) { cudaGraphExecDestroy(e->steps_graph); e->steps_graph = nullptr; }
+            if (int rc = prepare_slices(e, slices)) return rc;
+            {   // argument checks and lazy allocations (PID controller state) happen before the capture starts
+                nig_rollout_t probe = *r;
+                probe.n_steps = total_steps < r->n_steps ? total_steps : r->n_steps;
+                if (int rc = rollout_checks(e, &probe)) return rc;
+            }
+            const uint32_t tick0 = e->tick;
+            const int64_t launches0 = e->launches;
+            cudaGraph_t graph = nullptr;
+            NIG_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeRelaxed));
+            e->graph_mode = true; e->graph_tick0 = tick0;
+            int rc = fork_slices(e, slices, e->stream);
+            if (rc == NIG_OK) rc = sliced_launches(e, *r, total_steps, r->n_steps, slices, slice_size(e->n, slices));
+            const int jrc = join_slices(e, slices, e->stream);
+            e->graph_mode = false;
+            const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+            key.launches = e->launches - launches0;
+            e->tick = tick0; e->launches = launches0;
+            if (rc != NIG_OK || jrc != NIG_OK) { if (graph) cudaGraphDestroy(graph); return rc ? rc : jrc; }
+            if (ce != cudaSuccess) return fail(NIG_ERR_CUDA, "nig_rollout_steps: cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+            const cudaError_t ci = cudaGraphInstantiate(&e->steps_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ci != cudaSuccess) { e->steps_graph = nullptr; return fail(NIG_ERR_CUDA, "nig_rollout_steps: cudaGraphInstantiate failed: %s", cudaGetErrorString(ci)); }
+            e->steps_graph_key = key;
+        }
+        NIG_CUDA(nig::launch_set_ticks(e->d_tickbase, e->tick, e->epoch, st));
+        NIG_CUDA(cudaGraphLaunch(e->steps_graph, st));
+        e->tick += (uint32_t)total_steps;
+        e->launches += e->steps_graph_key.launches + 1;
+        return NIG_OK;
+    }
     if (int rc = fork_slices(e, slices, st)) return rc;
     const int rc = sliced_launches(e, *r, total_steps, r->n_steps, slices, slice_size(e->n, slices));
     const int jrc = join_slices(e, slices, st);
@@ -933,10 +990,8 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
             key.ptr[0] = r->init_states; key.ptr[1] = r->reward_sum; key.ptr[2] = r->viol_count; key.ptr[3] = r->done_count; key.ptr[4] = r->final_obs;
             key.T = T; key.K = K; key.policy = r->policy; key.reset = reset ? 1 : 0; key.slices = slices;
             key.config = e->config_version; key.pp = r->pp;
-            if (!e->h_tickbase) {
-                NIG_CUDA(cudaHostAlloc((void**)&e->h_tickbase, 2 * sizeof(uint32_t), cudaHostAllocPortable));
-                NIG_CUDA(cudaMalloc((void**)&e->d_tickbase, 2 * sizeof(uint32_t)));
-            }
+            if (!e->h_tickbase) NIG_CUDA(cudaHostAlloc((void**)&e->h_tickbase, 2 * sizeof(uint32_t), cudaHostAllocPortable));
+            if (!e->d_tickbase) NIG_CUDA(cudaMalloc((void**)&e->d_tickbase, 2 * sizeof(uint32_t)));
             key.launches = e->host_graph ? e->host_graph_key.launches : 0;
             if (!e->host_graph || memcmp(&key, &e->host_graph_key, sizeof key) != 0) {
                 if (e->host_graph) { cudaGraphExecDestroy(e->host_graph); e->host_graph = nullptr; }

@@ -1075,6 +1075,7 @@ static __global__ void __launch_bounds__(32) fold_stats_kernel(unsigned long lon
 // sequence-tick mode: the launches of a captured sequence carry tick offsets 0 .. n-1 from tick_base[0]; this one-thread
 // kernel, captured at the end of the sequence, moves the base on by n so that the next replay draws fresh noise
 static __global__ void commit_ticks_kernel(uint32_t* tick_base, uint32_t by) { tick_base[0] += by; }
+static __global__ void set_ticks_kernel(uint32_t* tick_base, uint32_t tick, uint32_t epoch) { tick_base[0] = tick; tick_base[1] = epoch; }
 
 // SoA <-> AoS / ep_word <-> (step, viol, done) conversion for get/set_state
 struct StateIoArgs {
@@ -1297,15 +1298,90 @@ __device__ __forceinline__ StepDraw reactor_step_draw(const Rng& key, uint32_t e
 // where the fast loop gets a step's draw from: computed in place ...
 struct DrawInKernel {
     static constexpr bool kPure = true;        // get(t) is a pure function of t: may be called one step ahead
+    static constexpr bool kUserActions = false;
     const Rng& key; uint32_t env, tick0;
     __device__ __forceinline__ StepDraw get(int t, int) const { return reactor_step_draw(key, env, tick0 + (uint32_t)t); }
     __device__ __forceinline__ void done(int, int) const {}
 };
 struct DrawInKernel2 {         // two envs per thread: lane 0 / 1 of the value type
-    static constexpr bool kPure = true;
+    static constexpr bool kPure = true, kUserActions = false;
     const Rng& key; uint32_t env[2], tick0;
     __device__ __forceinline__ StepDraw get(int t, int lane) const { return reactor_step_draw(key, env[lane], tick0 + (uint32_t)t); }
     __device__ __forceinline__ void done(int, int) const {}
+};
+
+// ... or built from caller-supplied actions (NIG_POLICY_ACTIONS): np.clip(action, -1, 1) (base.py:167), then the same derived
+// values; the process noise still comes from words x, y of the step's Philox block (Reactor::NoiseGen)
+__device__ __forceinline__ StepDraw reactor_draw_from_actions(const Rng& key, uint32_t env, uint32_t tick, const float (&a_raw)[Reactor::A])
+{
+    float a[Reactor::A];
+#pragma unroll
+    for (int j = 0; j < Reactor::A; ++j) {
+        float v = a_raw[j];
+        v = v < -1.0f ? -1.0f : v;
+        v = v > 1.0f ? 1.0f : v;
+        a[j] = v;
+    }
+    const uint4 w = rng_words(key, env, tick, STREAM_NOISE, 0u);
+    float za, zb;
+    normal_pair(key.tab, w.x, w.y, za, zb);
+    StepDraw d;
+    d.nz0 = mul(0.1f, za); d.nz1 = mul(500.0f, zb);
+    d.hp = mul(a[0], 50000.0f); d.cadj = mul(a[1], 0.1f); d.fadj = mul(a[2], 0.1f);
+    d.apen = mul(add(add(fabsf(a[0]), fabsf(a[1])), fabsf(a[2])), 0.1f);
+    return d;
+}
+// action rows [K][A][pitch] read one step ahead into registers (the LDG flavour of rollout_kernel; a_pf holds step t's
+// actions whenever get(t) is called and step t + 1's afterwards)
+struct DrawActionsLdg {
+    static constexpr bool kPure = false, kUserActions = true;
+    const Rng& key; uint32_t env, tick0; const float* actions; int64_t pitch, ic; int n_steps; float (&a_pf)[Reactor::A];
+    __device__ __forceinline__ StepDraw get(int t, int)
+    {
+        float a[Reactor::A];
+#pragma unroll
+        for (int k = 0; k < Reactor::A; ++k) a[k] = a_pf[k];
+        const int tn = t + 1 < n_steps ? t + 1 : t;
+#pragma unroll
+        for (int k = 0; k < Reactor::A; ++k) a_pf[k] = __ldcs(actions + ((int64_t)tn * Reactor::A + k) * pitch + ic);
+        return reactor_draw_from_actions(key, env, tick0 + (uint32_t)t, a);
+    }
+    __device__ __forceinline__ void done(int, int) const {}
+    __device__ __forceinline__ void rewind(int t)           // the loop left at step t without committing it: a_pf = step t again
+    {
+#pragma unroll
+        for (int k = 0; k < Reactor::A; ++k) a_pf[k] = __ldcs(actions + ((int64_t)t * Reactor::A + k) * pitch + ic);
+    }
+};
+
+// action boxes [kTmaChunk][A][kThreads] staged in shared memory by cp.async.bulk.tensor.3d (the TMA flavour): the same
+// double-buffer protocol as the generic loop of rollout_kernel -- wait for the box at its first step, one CTA barrier and a
+// refill at its last -- so warps of one CTA may run either loop (and change over on a failed guard) without losing count
+struct DrawActionsTma {
+    static constexpr bool kPure = false, kUserActions = true;
+    const Rng& key; uint32_t env, tick0; float* act_smem; uint64_t* bars; const CUtensorMap* amap; int n_chunks;
+    __device__ __forceinline__ StepDraw get(int t, int) const
+    {
+        const int c = t / kTmaChunk, tt = t % kTmaChunk, b = c & 1;
+        if (tt == 0) mbar_wait(&bars[b], (uint32_t)((c >> 1) & 1));
+        const float* src = act_smem + ((size_t)b * kTmaChunk + tt) * Reactor::A * kThreads;
+        float a[Reactor::A];
+#pragma unroll
+        for (int k = 0; k < Reactor::A; ++k) a[k] = src[k * kThreads + threadIdx.x];
+        return reactor_draw_from_actions(key, env, tick0 + (uint32_t)t, a);
+    }
+    __device__ __forceinline__ void done(int t, int n_steps) const
+    {
+        const int c = t / kTmaChunk, tt = t % kTmaChunk, b = c & 1;
+        if (tt == kTmaChunk - 1 || t == n_steps - 1) {
+            __syncthreads();                       // everyone finished reading buffer b
+            if (threadIdx.x == 0 && c + 2 < n_chunks) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&bars[b], kTmaChunk * Reactor::A * kThreads * (uint32_t)sizeof(float));
+                tma_load_3d(act_smem + (size_t)b * kTmaChunk * Reactor::A * kThreads, amap, (int)(blockIdx.x * kThreads), 0, (c + 2) * kTmaChunk, &bars[b]);
+            }
+        }
+    }
 };
 
 // ---- one or two envs per thread -------------------------------------------------------------------------------------
@@ -1502,6 +1578,8 @@ __device__ __forceinline__ int reactor_fast_steps_v(Src& src, const Rng& key, co
         const V ch = mul(mul(mul(cool, T_::bc(100.0f)), sub(T, hx)), T_::bc(0.1f));
         const V num = sub(add(hp, rh), ch);
         M ok = vge(vabs(num), 0x1.0p-120f);
+        // caller-supplied actions may be NaN (np.clip keeps it): |a0| + |a1| + |a2| <= 3 fails then and the step is the generic loop's
+        if constexpr (Src::kUserActions) ok = mand(ok, vle(apen, 1.0f));
         const V dT = add(NIG_CDIV_V(num, 418000.0f), nz0);
         const V nT = add(T, mul(dT, T_::bc(0.1f)));
         const V d = sub(nT, T_::bc(320.0f));
@@ -2077,8 +2155,8 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
     // auto-reset): warps whose envs all satisfy the loop invariants of reactor_fast_steps run the specialised loop; whatever
     // it does not commit (nothing, normally) is left to the generic loop below
     int t_begin = 0;
-    if constexpr (Env::KIND == NIG_ENV_CHEMICAL_REACTOR && (CONS == CONS_DEFAULT || cons_fast_extras(CONS) > 0) && POLICY == NIG_POLICY_UNIFORM &&
-                  !TMA && !TFNOISE) {
+    if constexpr (Env::KIND == NIG_ENV_CHEMICAL_REACTOR && (CONS == CONS_DEFAULT || cons_fast_extras(CONS) > 0) && !TFNOISE &&
+                  ((POLICY == NIG_POLICY_UNIFORM && !TMA) || POLICY == NIG_POLICY_ACTIONS)) {
         constexpr int NX = cons_fast_extras(CONS);
         FastBounds fb;
         const bool fb_ok = fast_bounds_from<NX>(p.cons, fb);       // else (critical / other components): the generic loop
@@ -2088,9 +2166,20 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
                          ep_st < (uint32_t)p.max_steps;
         if (__all_sync(0xffffffffu, inv))
         {
-            DrawInKernel src{key, env, tick0};
-            t_begin = reactor_fast_steps<EXTREMA, DrawInKernel, NX>(src, key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum, acc,
-                                                                    r_lo, r_hi, fb);
+            if constexpr (POLICY == NIG_POLICY_UNIFORM) {
+                DrawInKernel src{key, env, tick0};
+                t_begin = reactor_fast_steps<EXTREMA, DrawInKernel, NX>(src, key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum,
+                                                                        acc, r_lo, r_hi, fb);
+            } else if constexpr (TMA) {
+                DrawActionsTma src{key, env, tick0, act_smem, bars, &amap, n_chunks};
+                t_begin = reactor_fast_steps<EXTREMA, DrawActionsTma, NX>(src, key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum,
+                                                                          acc, r_lo, r_hi, fb);
+            } else {
+                DrawActionsLdg src{key, env, tick0, p.actions, p.pitch, ic, p.n_steps, a_pf};
+                t_begin = reactor_fast_steps<EXTREMA, DrawActionsLdg, NX>(src, key, env, tick0, epoch, p.n_steps, p.max_steps, s, ep_st, ep_vi, ep_ret, rsum,
+                                                                          acc, r_lo, r_hi, fb);
+                if (t_begin < p.n_steps) src.rewind(t_begin);
+            }
         }
     }
 
@@ -2229,7 +2318,7 @@ constexpr int kWsEnvs = 64;        // envs per CTA
 constexpr int kWsThreads = 96;     // producer warp + two consumer warps
 
 struct DrawFromRing {
-    static constexpr bool kPure = false;
+    static constexpr bool kPure = false, kUserActions = false;
     const float2* lane_base;       // ring + this consumer lane's env index within the CTA; layout [slot][g][3][kWsEnvs]
     uint64_t* full; uint64_t* empty;
     __device__ __forceinline__ void wait_full(int t) const

@@ -30,6 +30,7 @@ cudaError_t launch_state_io(const StateIoArgs& a, cudaStream_t st);
 cudaError_t launch_scan_lengths(const int64_t* len, int64_t* off, int64_t n, int64_t* total, cudaStream_t st);
 cudaError_t launch_fp32_probe(float* sink, int iters, int blocks, cudaStream_t st);
 cudaError_t launch_commit_ticks(uint32_t* tick_base, uint32_t by, cudaStream_t st);
+cudaError_t launch_set_ticks(uint32_t* tick_base, uint32_t tick, uint32_t epoch, cudaStream_t st);
 cudaError_t launch_fold_stats(unsigned long long* shards, unsigned long long* stats, cudaStream_t st);
 cudaError_t launch_selftest_normal(uint32_t first, uint32_t stride, unsigned long long count, unsigned long long* out, cudaStream_t st);
 cudaError_t launch_selftest_policy(int kind, const PolicyTestArgs& a, cudaStream_t st);

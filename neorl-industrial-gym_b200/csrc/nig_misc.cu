@@ -26,6 +26,11 @@ cudaError_t launch_commit_ticks(uint32_t* tick_base, uint32_t by, cudaStream_t s
     commit_ticks_kernel<<<1, 1, 0, st>>>(tick_base, by);
     return cudaGetLastError();
 }
+cudaError_t launch_set_ticks(uint32_t* tick_base, uint32_t tick, uint32_t epoch, cudaStream_t st)
+{
+    set_ticks_kernel<<<1, 1, 0, st>>>(tick_base, tick, epoch);
+    return cudaGetLastError();
+}
 cudaError_t launch_fp32_probe(float* sink, int iters, int blocks, cudaStream_t st)
 {
     fp32_probe_kernel<<<blocks, 256, 0, st>>>(sink, iters);

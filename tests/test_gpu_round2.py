@@ -515,3 +515,52 @@ def test_reactor_fast_loop_with_wrapper_bands(mods, bands, extrema):
     assert c[8:8 + len(cons)].tolist() == orc.stats[8:8 + len(cons)].tolist()
     assert c[8 + 3] > 0 and c[1] > 0                     # the first band fired; episodes ended (auto-resets inside the loop)
     env.close()
+
+
+@pytest.mark.parametrize("use_tma", [True, False])
+@pytest.mark.parametrize("extrema", [False, True])
+def test_reactor_fast_loop_with_supplied_actions(mods, use_tma, extrema):
+    """NIG_POLICY_ACTIONS takes the invariant-specialised loop too (actions staged by TMA boxes or read one step ahead into
+    registers, np.clip in the draw, noise from the step's Philox block). Adversarial action tensors -- out of [-1, 1], NaN,
+    +-inf, -0.0 -- and a population mixing warps inside / outside the invariants, several launches with horizons that are not
+    multiples of the 16-step TMA box: everything == the oracle bit for bit (a NaN action fails the loop's guard and the step
+    is redone by the generic loop, including the box hand-over of a CTA whose warps run different loops)."""
+    ni, N, O, torch = mods
+    n = 2048 + 300
+    env = ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=13)
+    orc = O.OracleEnv(O.REACTOR, n, seed=13, exp_mode=1)
+    s0 = env.reset_host()
+    assert_bits_equal(s0, orc.reset(), "reset")
+    rng = np.random.default_rng(3)
+    st = s0.copy()
+    ep_step = np.zeros(n, np.int32)
+    st[rng.choice(n, 20, replace=False), 8] = 1.0
+    st[rng.choice(n, 20, replace=False), 0] = rng.uniform(349.0, 353.0, 20).astype(np.float32)
+    st[32 * 7:32 * 8, 9] = 0.5                  # one whole warp outside the invariant
+    ep_step[rng.choice(n, 150, replace=False)] = rng.integers(400, 500, 150)
+    env.set_state_host(st, ep_step, np.zeros(n, np.int32), np.zeros(n, np.uint8))
+    orc.state[:] = st
+    orc.ep_step[:] = ep_step
+    env.track_extrema(extrema)
+    dev = env.torch_device()
+    for K in (70, 16, 33, 1, 64):
+        acts = rng.uniform(-1.4, 1.4, (K, n, env.A)).astype(np.float32)
+        flat = acts.reshape(-1)
+        k = flat.size
+        flat[rng.choice(k, k // 400, replace=False)] = np.nan
+        flat[rng.choice(k, k // 400, replace=False)] = np.inf
+        flat[rng.choice(k, k // 400, replace=False)] = -np.inf
+        flat[rng.choice(k, k // 200, replace=False)] = -0.0
+        flat[rng.choice(k, k // 200, replace=False)] = 1.0
+        d_act = torch.zeros((K, env.A, env.pitch), dtype=torch.float32, device=dev)
+        d_act[:, :, :n] = torch.from_numpy(np.ascontiguousarray(acts.transpose(0, 2, 1))).to(dev)
+        rsum = env.empty()
+        env.rollout_device(K, N.POLICY_ACTIONS, actions=d_act, use_tma=use_tma, reward_sum=rsum)
+        o_rs = np.zeros(n, np.float32)
+        for t in range(K):
+            _, r, _, _ = orc.step(acts[t], want_next_obs=False)
+            o_rs = (o_rs + r).astype(np.float32)
+        torch.cuda.synchronize()
+        _compare(env, orc, N, f"after a {K}-step launch of supplied actions")
+        assert_bits_equal(rsum[:n].cpu().numpy(), o_rs, "per-env reward sum")
+    env.close()
