@@ -604,14 +604,14 @@ def other_configs(torch, ni, N, local, rank, world, dist, seed):
     nat = wrapped.native
     nat.reset_device()
     nat.clear_stats()
-    ms = timed(lambda: nat.rollout_steps_device(256, 64, N.POLICY_UNIFORM), 5)
+    ms = timed(lambda: nat.rollout_steps_device(HORIZON, K, N.POLICY_UNIFORM), 5)       # the headline's 15 x 64 + 40 launch sequence
     allreduce_device_stats(nat)
     torch.cuda.synchronize()
     st = nat.stats_dict()
     out["reactor_safety_wrapper"] = {
         "workload": f"ChemicalReactor-v0 + SafetyWrapper(temperature 280..330 K, pressure 101325..400000 Pa, penalty -100), "
-                    f"{n} envs per GPU x {world}, fused K=64, counters all-reduced over NCCL",
-        "value": world * n * 256 / (ms * 1e-3), "unit": UNIT,
+                    f"{n} envs per GPU x {world} x {HORIZON} steps, fused K=64, counters all-reduced over NCCL",
+        "value": world * n * HORIZON / (ms * 1e-3), "unit": UNIT,
         "violations_per_constraint": st["violations_per_constraint"], "episodes": st["episodes"],
         "critical_shutdowns": st["critical_shutdowns"], "return_mean": st["return_sum"] / max(st["episodes"], 1)}
     renv.close()

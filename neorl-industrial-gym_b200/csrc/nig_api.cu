@@ -122,6 +122,8 @@ struct nig_env {
         const void* ptr[3]; int32_t T, K, policy, flags, slices; int64_t launches; uint64_t config; nig_policy_params_t pp;
     } steps_graph_key;
     int steps_graph_enable;     // NIG_STEPS_GRAPH (default 1)
+    unsigned long long* h_stats_pinned;   // nig_rollout_host: page-locked landing block of the statistics copy
+    int host_direct;            // NIG_HOST_DIRECT (default 1): nig_rollout_host's slices read / write mapped host arrays in-kernel
     bool graph_mode;            // set while a pipeline is being captured: rollout_range / reset_range emit base-relative counters
     uint32_t graph_tick0;       // tick at the start of the call being captured
     uint64_t config_version;    // bumped by every setter whose value is baked into kernel arguments (invalidates host_graph)
@@ -254,10 +256,10 @@ int make_action_map(nig_env* e, const float* actions, int n_steps, CUtensorMap* 
         e->encode_tiled = (PFN_encodeTiled)fn;
     }
     // actions[K][A][pitch] fp32 as a 3-D tensor (x = env, y = action component, z = step); one box = the
-    // kTmaChunk x A x 128 tile a CTA consumes over kTmaChunk steps
+    // tma_chunk(A) x A x 128 tile a CTA consumes over tma_chunk(A) steps
     const cuuint64_t gdim[3] = {(cuuint64_t)e->pitch, (cuuint64_t)e->A, (cuuint64_t)n_steps};
     const cuuint64_t gstr[2] = {(cuuint64_t)e->pitch * sizeof(float), (cuuint64_t)e->pitch * e->A * sizeof(float)};
-    const cuuint32_t box[3] = {(cuuint32_t)kThreads, (cuuint32_t)e->A, (cuuint32_t)kTmaChunk};
+    const cuuint32_t box[3] = {(cuuint32_t)kThreads, (cuuint32_t)e->A, (cuuint32_t)tma_chunk(e->A)};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = e->encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)actions, gdim, gstr, box, estr,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -505,15 +507,50 @@ bool host_buffers_pinned(const nig_rollout_host_t* r)
 // initial states in, resets, runs its ceil(T / K) fused launches and copies its results out independently of the others, so
 // the PCIe copies overlap the stepping and a slice's next launch fills the SMs another slice's tail leaves idle. Trajectories
 // do not depend on the slicing (random streams are keyed by global env id and tick). Capturable (no synchronisation inside).
+// device-side alias of a page-locked host array a kernel may read / write directly (16-byte aligned), or null
+template <class T>
+T* mapped_alias(T* host)
+{
+    if (!host || ((uintptr_t)host & 15u) != 0) return nullptr;
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, (void*)host, 0) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return ((uintptr_t)d & 15u) == 0 ? (T*)d : nullptr;
+}
+
+bool host_direct_ok(const nig_env* e, const nig_rollout_host_t* r)
+{
+    return e->host_direct != 0 && e->S % 4 == 0 && (!r->init_states || mapped_alias(r->init_states)) && (!r->final_obs || mapped_alias(r->final_obs)) &&
+           (!r->reward_sum || mapped_alias(r->reward_sum)) && (!r->viol_count || mapped_alias(r->viol_count)) &&
+           (!r->done_count || mapped_alias(r->done_count));
+}
+
 int enqueue_sliced_host(nig_env* e, const nig_rollout_host_t* r, int slices, int64_t per, int32_t T, int32_t K, bool reset, cudaStream_t st)
 {
     const int64_t n = e->n;
     int rc;
+    // direct mode (NIG_HOST_DIRECT, default on): no staging copies -- the ingest / export kernels of a slice touch the caller's
+    // page-locked arrays themselves. Needs every supplied array mapped into the device's address space; else the copy path.
+    const float* m_init = mapped_alias(r->init_states);
+    float* m_obs = mapped_alias(r->final_obs);
+    float* m_rew = mapped_alias(r->reward_sum);
+    int32_t* m_vi = mapped_alias(r->viol_count);
+    int32_t* m_dn = mapped_alias(r->done_count);
+    const bool direct = host_direct_ok(e, r);
     if ((rc = fork_slices(e, slices, st)) != NIG_OK) return rc;
     for (int k = 0; k < slices; ++k) {
         const int64_t i0 = k * per, ns = std::min<int64_t>(per, n - i0);
         if (ns <= 0) continue;
         cudaStream_t ss = e->slice_stream[k];
+        if (direct && r->init_states) {
+            HostIoArgs a;
+            memset(&a, 0, sizeof a);
+            a.state = e->state + i0; a.ep_word = e->ep_word + i0; a.ep_return = e->ep_return + i0; a.n = ns; a.pitch = e->pitch; a.S = e->S;
+            a.in_aos = m_init + i0 * e->S;
+            e->launches++;
+            const cudaError_t ce = nig::launch_host_ingest(a, ss);
+            if (ce != cudaSuccess) { join_slices(e, slices, st); return fail(NIG_ERR_CUDA, "host_ingest_kernel: %s", cudaGetErrorString(ce)); }
+            continue;
+        }
         if (r->init_states)
             NIG_CUDA(cudaMemcpyAsync(e->h_reset + i0 * e->S, r->init_states + i0 * e->S, (size_t)ns * e->S * sizeof(float), cudaMemcpyHostToDevice, ss));
         if (reset && (rc = reset_range(e, r->init_states ? e->h_reset : nullptr, i0, ns, e->epoch, ss)) != NIG_OK) { join_slices(e, slices, st); return rc; }
@@ -529,6 +566,20 @@ int enqueue_sliced_host(nig_env* e, const nig_rollout_host_t* r, int slices, int
         const int64_t i0 = k * per, ns = std::min<int64_t>(per, n - i0);
         if (ns <= 0) continue;
         cudaStream_t ss = e->slice_stream[k];
+        if (direct) {
+            if (!r->final_obs && !r->reward_sum && !r->viol_count && !r->done_count) continue;
+            HostIoArgs a;
+            memset(&a, 0, sizeof a);
+            a.state = e->state + i0; a.ep_word = e->ep_word + i0; a.ep_return = e->ep_return + i0; a.n = ns; a.pitch = e->pitch; a.S = e->S;
+            a.out_aos = m_obs ? m_obs + i0 * e->S : nullptr;
+            if (m_rew) { a.d_reward = e->h_reward + i0; a.h_reward = m_rew + i0; }
+            if (m_vi) { a.d_viol = e->h_i32a + i0; a.h_viol = m_vi + i0; }
+            if (m_dn) { a.d_done = e->h_i32b + i0; a.h_done = m_dn + i0; }
+            e->launches++;
+            const cudaError_t ce = nig::launch_host_export(a, ss);
+            if (ce != cudaSuccess) { join_slices(e, slices, st); return fail(NIG_ERR_CUDA, "host_export_kernel: %s", cudaGetErrorString(ce)); }
+            continue;
+        }
         if (r->final_obs) {
             if ((rc = state_to_aos_range(e, e->h_obs, i0, ns, ss)) != NIG_OK) { join_slices(e, slices, st); return rc; }
             NIG_CUDA(cudaMemcpyAsync(r->final_obs + i0 * e->S, e->h_obs + i0 * e->S, (size_t)ns * e->S * sizeof(float), cudaMemcpyDeviceToHost, ss));
@@ -616,6 +667,8 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     if (const char* v = getenv("NIG_GRID_FAST")) e->grid_fast = atoi(v);
     e->host_graph_enable = 1;
     if (const char* v = getenv("NIG_HOST_GRAPH")) e->host_graph_enable = atoi(v);
+    e->host_direct = 1;
+    if (const char* v = getenv("NIG_HOST_DIRECT")) e->host_direct = atoi(v);
     e->steps_graph_enable = 1;
     if (const char* v = getenv("NIG_STEPS_GRAPH")) e->steps_graph_enable = atoi(v);
     e->step_pipe = 1;
@@ -655,6 +708,7 @@ int nig_destroy(nig_env_t* e)
     if (e->host_graph) cudaGraphExecDestroy(e->host_graph);
     if (e->steps_graph) cudaGraphExecDestroy(e->steps_graph);
     if (e->h_tickbase) cudaFreeHost(e->h_tickbase);
+    if (e->h_stats_pinned) cudaFreeHost(e->h_stats_pinned);
     cudaFree(e->d_tickbase);
     cudaFree(e->state); cudaFree(e->ep_word); cudaFree(e->ep_return); cudaFree(e->stats); cudaFree(e->stats_shards);
     cudaFree(e->h_actions); cudaFree(e->h_noise); cudaFree(e->h_reset); cudaFree(e->h_obs); cudaFree(e->h_next_obs);
@@ -977,7 +1031,10 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
     // copies overlap the stepping, and a slice's next launch fills the SMs another slice's tail leaves idle. Trajectories
     // do not depend on the slicing (random streams are keyed by global env id and tick).
     const bool use_graph = e->host_graph_enable != 0 && !forced && !e->tick_dev && host_buffers_pinned(r);
-    const int slices = host_slices(e, forced, 4);      // (8 measured slower than 4 with and without the graph: tools/host_path_breakdown.py)
+    // copy path: 4 slices (8 measured slower, with and without the graph); direct path (the slices' kernels read / write the
+    // mapped host arrays, no copy nodes): 8 slices -- 0.730 ms per 65,536 x 1,000 call against 0.762 with 4 and 0.835 for the
+    // copy path (tools/host_path_breakdown.py, profiles/r02_h_host_direct_ab.txt)
+    const int slices = host_slices(e, forced, host_direct_ok(e, r) ? 8 : 4);
     if (slices > 1) {
         const int64_t per = slice_size((int64_t)n, slices);
         const bool reset = r->reset_first || r->init_states;
@@ -1027,10 +1084,12 @@ int nig_rollout_host(nig_env_t* e, const nig_rollout_host_t* r)
         } else {
             if ((rc = enqueue_sliced_host(e, r, slices, per, T, K, reset, st)) != NIG_OK) return rc;
         }
-        unsigned long long hs[NIG_STATS_SLOTS];
+        // the statistics block lands in a page-locked word block of the handle (a copy into pageable memory is staged by the driver)
+        if (!e->h_stats_pinned) NIG_CUDA(cudaHostAlloc((void**)&e->h_stats_pinned, NIG_STATS_SLOTS * sizeof(unsigned long long), cudaHostAllocPortable));
+        unsigned long long* hs = e->h_stats_pinned;
         if (r->counters24 || r->sums8) {
             if ((rc = fold_stats(e, st)) != NIG_OK) return rc;
-            NIG_CUDA(cudaMemcpyAsync(hs, e->stats, sizeof hs, cudaMemcpyDeviceToHost, st));
+            NIG_CUDA(cudaMemcpyAsync(hs, e->stats, NIG_STATS_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         }
         NIG_CUDA(cudaStreamSynchronize(st));
         if (r->counters24) for (int k = 0; k < 24; ++k) r->counters24[k] = (int64_t)hs[k];

@@ -1111,10 +1111,63 @@ static __global__ void __launch_bounds__(kThreads) state_io_kernel(const __grid_
     }
 }
 
+// ---- nig_rollout_host without staging copies: the slice's kernels read / write the caller's page-locked arrays themselves ----
+// ingest: IndustrialEnv.reset(options = initial states) of one env slice straight from the mapped host array [n][S]
+// (every warp instruction reads 512 contiguous bytes over PCIe; the AoS -> SoA transposition goes through shared memory);
+// export: final observations [n][S] + per-env reward sums / violation counts / episode counts straight into the mapped host
+// arrays (posted 512-byte writes). One kernel per slice replaces a copy node + a kernel on the way in and a kernel + four
+// copy nodes on the way out. Requires 16-byte aligned rows (S % 4 == 0, slices start at multiples of 128 envs).
+struct HostIoArgs {
+    float* state; uint32_t* ep_word; double* ep_return;
+    int64_t n, pitch;
+    int32_t S;
+    const float* in_aos;                          // ingest: mapped host [n][S]
+    float* out_aos;                               // export (each may be null)
+    const float* d_reward; const int32_t* d_viol; const int32_t* d_done;
+    float* h_reward; int32_t* h_viol; int32_t* h_done;
+};
+static __global__ void __launch_bounds__(kThreads) host_ingest_kernel(const __grid_constant__ HostIoArgs p)
+{
+    __shared__ alignas(16) float tile[kThreads * NIG_MAX_STATE_DIM];
+    const int64_t i0 = (int64_t)blockIdx.x * kThreads;
+    const int64_t cnt = p.n - i0 < kThreads ? p.n - i0 : kThreads;          // envs of this CTA
+    const int nvec = (int)(cnt * p.S / 4);
+    const float4* src = reinterpret_cast<const float4*>(p.in_aos + i0 * p.S);
+    for (int j = threadIdx.x; j < nvec; j += kThreads) reinterpret_cast<float4*>(tile)[j] = src[j];
+    __syncthreads();
+    const int64_t i = i0 + threadIdx.x;
+    if (i >= p.n) return;
+    for (int k = 0; k < p.S; ++k) p.state[(int64_t)k * p.pitch + i] = tile[threadIdx.x * p.S + k];
+    p.ep_word[i] = 0u;
+    p.ep_return[i] = 0.0;
+}
+static __global__ void __launch_bounds__(kThreads) host_export_kernel(const __grid_constant__ HostIoArgs p)
+{
+    __shared__ alignas(16) float tile[kThreads * NIG_MAX_STATE_DIM];
+    const int64_t i0 = (int64_t)blockIdx.x * kThreads;
+    const int64_t i = i0 + threadIdx.x;
+    const bool valid = i < p.n;
+    if (valid) {
+        if (p.h_reward) p.h_reward[i] = p.d_reward[i];
+        if (p.h_viol) p.h_viol[i] = p.d_viol[i];
+        if (p.h_done) p.h_done[i] = p.d_done[i];
+    }
+    if (!p.out_aos) return;
+    if (valid)
+        for (int k = 0; k < p.S; ++k) tile[threadIdx.x * p.S + k] = p.state[(int64_t)k * p.pitch + i];
+    __syncthreads();
+    const int64_t cnt = p.n - i0 < kThreads ? p.n - i0 : kThreads;
+    const int nvec = (int)(cnt * p.S / 4);
+    float4* dst = reinterpret_cast<float4*>(p.out_aos + i0 * p.S);
+    for (int j = threadIdx.x; j < nvec; j += kThreads) dst[j] = reinterpret_cast<const float4*>(tile)[j];
+}
+
 // ================================================================================================
 // fused K-step rollout kernel
 // ================================================================================================
-constexpr int kTmaChunk = 16;   // steps of actions staged per TMA box
+// steps of actions staged per TMA box. Two boxes of [chunk][A][128] floats per CTA: with 16 steps the reactor kernel needed 48 KB
+// + 9.5 KB static = 3 resident CTAs per SM, i.e. a second wave for the 512 CTAs of 65,536 envs (PowerGrid: 131 KB, one CTA per SM)
+__host__ __device__ constexpr int tma_chunk(int action_dim) { return action_dim <= 4 ? 8 : 4; }
 
 // Programmatic dependent launch of the fused rollout kernels (the launchers set cudaLaunchAttributeProgrammaticStreamSerialization):
 // the K-step launches of an env slice follow each other on one stream; the CTAs of launch c + 1 are scheduled while launch c
@@ -1359,6 +1412,7 @@ struct DrawActionsLdg {
 // refill at its last -- so warps of one CTA may run either loop (and change over on a failed guard) without losing count
 struct DrawActionsTma {
     static constexpr bool kPure = false, kUserActions = true;
+    static constexpr int kTmaChunk = tma_chunk(Reactor::A);
     const Rng& key; uint32_t env, tick0; float* act_smem; uint64_t* bars; const CUtensorMap* amap; int n_chunks;
     __device__ __forceinline__ StepDraw get(int t, int) const
     {
@@ -2075,6 +2129,7 @@ __global__ void __launch_bounds__(kThreads, Env::ROLLOUT_MIN_CTAS) rollout_kerne
 {
     static_assert(!TFNOISE || POLICY == NIG_POLICY_ACTIONS, "teacher-forced noise comes with teacher-forced actions");
     constexpr int S = Env::S, A = Env::A, NZ = Env::NZ, NZA = NZ > 0 ? NZ : 1;
+    constexpr int kTmaChunk = tma_chunk(A);
     constexpr bool PREFETCH = (POLICY == NIG_POLICY_ACTIONS) && !TMA;
     using acc_t = typename Env::acc_t;
     __shared__ unsigned int sstat[NIG_STATS_SLOTS];

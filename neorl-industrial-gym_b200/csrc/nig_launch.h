@@ -27,6 +27,8 @@ cudaError_t launch_rollout_robot(const RolloutLaunch& cfg, int64_t pitch, const 
 cudaError_t launch_dataset(int kind, int cons, bool write, const DatasetArgs& a, cudaStream_t st);
 cudaError_t launch_reset(int kind, const ResetArgs& a, cudaStream_t st);
 cudaError_t launch_state_io(const StateIoArgs& a, cudaStream_t st);
+cudaError_t launch_host_ingest(const HostIoArgs& a, cudaStream_t st);
+cudaError_t launch_host_export(const HostIoArgs& a, cudaStream_t st);
 cudaError_t launch_scan_lengths(const int64_t* len, int64_t* off, int64_t n, int64_t* total, cudaStream_t st);
 cudaError_t launch_fp32_probe(float* sink, int iters, int blocks, cudaStream_t st);
 cudaError_t launch_commit_ticks(uint32_t* tick_base, uint32_t by, cudaStream_t st);

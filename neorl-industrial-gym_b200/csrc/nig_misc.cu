@@ -31,6 +31,16 @@ cudaError_t launch_set_ticks(uint32_t* tick_base, uint32_t tick, uint32_t epoch,
     set_ticks_kernel<<<1, 1, 0, st>>>(tick_base, tick, epoch);
     return cudaGetLastError();
 }
+cudaError_t launch_host_ingest(const HostIoArgs& a, cudaStream_t st)
+{
+    host_ingest_kernel<<<(unsigned)((a.n + kThreads - 1) / kThreads), kThreads, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_host_export(const HostIoArgs& a, cudaStream_t st)
+{
+    host_export_kernel<<<(unsigned)((a.n + kThreads - 1) / kThreads), kThreads, 0, st>>>(a);
+    return cudaGetLastError();
+}
 cudaError_t launch_fp32_probe(float* sink, int iters, int blocks, cudaStream_t st)
 {
     fp32_probe_kernel<<<blocks, 256, 0, st>>>(sink, iters);

@@ -9,7 +9,7 @@ cudaError_t rollout_go(const RolloutLaunch& cfg, int64_t pitch, const RolloutArg
 {
     auto kern = rollout_kernel<Env, CONS, POLICY, TMA, TFNOISE, EXTREMA>;
     const int block = TMA ? kThreads : cfg.block;
-    const size_t smem = TMA ? (size_t)2 * kTmaChunk * Env::A * kThreads * sizeof(float) : 0;
+    const size_t smem = TMA ? (size_t)2 * tma_chunk(Env::A) * Env::A * kThreads * sizeof(float) : 0;
     if (TMA) {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
