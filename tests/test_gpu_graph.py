@@ -9,7 +9,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-def test_graph_replay_matches_eager_stepping(mode):
+@pytest.mark.parametrize("kind", ["reactor", "grid", "robot"])
+def test_graph_replay_matches_eager_stepping(mode, kind):
     """mode 1: the device tick is advanced by every launch; mode 2: base + per-launch sequence offsets, the captured
     sequence ends with commit_ticks() (and the single-step kernel draws its noise before the previous launch has finished)."""
     import torch
@@ -17,11 +18,12 @@ def test_graph_replay_matches_eager_stepping(mode):
     from neorl_industrial import _native as N
     n = 20_000
     dev = torch.device("cuda", 0)
-    envs = [ni.NativeEnv(N.ENV_CHEMICAL_REACTOR, n, device=0, seed=31) for _ in range(2)]
+    ek = {"reactor": N.ENV_CHEMICAL_REACTOR, "grid": N.ENV_POWER_GRID, "robot": N.ENV_ROBOT_ASSEMBLY}[kind]
+    envs = [ni.NativeEnv(ek, n, device=0, seed=31) for _ in range(2)]
     graph_env, eager_env = envs
     for e in envs:
         e.reset_device()
-    acts = torch.rand((3, graph_env.pitch), device=dev) * 2 - 1
+    acts = torch.rand((graph_env.A, graph_env.pitch), device=dev) * 2 - 1
     bufs = [(e.empty(), e.empty(dtype=torch.uint8), e.empty(dtype=torch.uint8)) for e in envs]
 
     def body(e, b):
