@@ -170,3 +170,59 @@ def test_rollout_host_argument_errors(mods):
     with pytest.raises(ValueError):
         env.rollout(4, "actions")
     env.close()
+
+
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+def test_rollout_host_direct_mode_equals_copy_path(name, monkeypatch):
+    """nig_rollout_host has two data paths for the caller's host arrays: direct (the slices' ingest / export kernels read and
+    write the page-locked arrays over PCIe themselves) and staged (cudaMemcpyAsync through device buffers). Which one runs
+    depends on NIG_HOST_DIRECT and on every supplied array being page-locked and 16-byte aligned; the results may not.
+    Four calls through the raw C ABI -- pinned + aligned (direct), NIG_HOST_DIRECT=0, pageable numpy arrays, pinned arrays
+    shifted by 4 bytes -- from the same initial states: bit-identical outputs. n is not a multiple of 128 (ragged last slice)."""
+    import ctypes as C
+    import neorl_industrial as ni
+    from neorl_industrial import _native as N
+    kind = KINDS[name]
+    n, T, K = 33_000 + 77, 150, 64
+    rng = np.random.default_rng(4)
+
+    def call(direct, how):
+        monkeypatch.setenv("NIG_HOST_DIRECT", "1" if direct else "0")
+        env = ni.NativeEnv(kind, n, device=0, seed=91)
+        S = env.S
+        init0 = env.reset_host().copy()
+        keep = []
+
+        def host(shape, dtype):
+            cnt = int(np.prod(shape))
+            if how == "pageable":
+                a = np.zeros(cnt + 4, dtype)[:cnt]
+            else:
+                p = N.PinnedArray((cnt + 4,), dtype)
+                keep.append(p)
+                a = p.array[1:cnt + 1] if how == "shifted" else p.array[:cnt]
+            return a.reshape(shape)
+        init, obs = host((n, S), np.float32), host((n, S), np.float32)
+        rew, vi, dn = host((n,), np.float32), host((n,), np.int32), host((n,), np.int32)
+        init[:] = init0
+        counters, sums = np.zeros(24, np.int64), np.zeros(8, np.float64)
+        r = N.RolloutHost()
+        r.n_steps, r.steps_per_launch, r.policy, r.reset_first = T, K, N.POLICY_UNIFORM, 0
+        r.init_states, r.final_obs = N.ptr_of(init), N.ptr_of(obs)
+        r.reward_sum, r.viol_count, r.done_count = N.ptr_of(rew), N.ptr_of(vi), N.ptr_of(dn)
+        r.counters24, r.sums8 = N.ptr_of(counters), N.ptr_of(sums)
+        for _ in range(2):                                   # second call = graph replay where a graph is used
+            N.check(N.lib().nig_rollout_host(env._h, C.byref(r)))
+        res = (obs.copy(), rew.copy(), vi.copy(), dn.copy(), counters.copy(), sums.copy())
+        env.close()
+        return res
+
+    ref = call(True, "pinned")
+    assert ref[4][0] == 2 * n * T
+    for direct, how in ((False, "pinned"), (True, "pageable"), (True, "shifted")):
+        got = call(direct, how)
+        assert_bits_equal(got[0], ref[0], f"{how} direct={direct}: observations")
+        assert_bits_equal(got[1], ref[1], f"{how} direct={direct}: reward sums")
+        assert np.array_equal(got[2], ref[2]) and np.array_equal(got[3], ref[3])
+        assert got[4].tolist() == ref[4].tolist()
+        np.testing.assert_allclose(got[5], ref[5], rtol=1e-12)      # fp64 sums: the order of the CTAs' atomic adds is not fixed
