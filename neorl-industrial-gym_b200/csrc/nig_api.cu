@@ -120,7 +120,7 @@ struct nig_env {
     cudaGraphExec_t steps_graph;
     struct StepsGraphKey {
         const void* ptr[3]; int32_t T, K, policy, flags, slices; int64_t launches; uint64_t config; nig_policy_params_t pp;
-    } steps_graph_key;
+    } steps_graph_key, steps_graph_candidate;
     int steps_graph_enable;     // NIG_STEPS_GRAPH (default 1)
     unsigned long long* h_stats_pinned;   // nig_rollout_host: page-locked landing block of the statistics copy
     int host_direct;            // NIG_HOST_DIRECT (default 1): nig_rollout_host's slices read / write mapped host arrays in-kernel
@@ -935,7 +935,18 @@ int nig_rollout_steps(nig_env_t* e, const nig_rollout_t* r, int32_t total_steps,
         key.config = e->config_version; key.pp = r->pp;
         if (!e->d_tickbase) NIG_CUDA(cudaMalloc((void**)&e->d_tickbase, 2 * sizeof(uint32_t)));
         key.launches = e->steps_graph ? e->steps_graph_key.launches : 0;
-        if (!e->steps_graph || memcmp(&key, &e->steps_graph_key, sizeof key) != 0) {
+        const bool hit = e->steps_graph && memcmp(&key, &e->steps_graph_key, sizeof key) == 0;
+        if (!hit) {
+            // capture only a call pattern that repeats: the first call with a new argument set is enqueued launch by launch and
+            // remembered, the second one captures (a one-off horizon or a caller that rotates its output buffers never pays
+            // ~1 ms of capture + instantiation per call)
+            nig_env::StepsGraphKey cand = key;
+            cand.launches = 0;
+            const bool repeat = memcmp(&cand, &e->steps_graph_candidate, sizeof cand) == 0;
+            e->steps_graph_candidate = cand;
+            if (!repeat) goto plain_enqueue;
+        }
+        if (!hit) {
             if (e->steps_graph) { cudaGraphExecDestroy(e->steps_graph); e->steps_graph = nullptr; }
             if (int rc = prepare_slices(e, slices)) return rc;
             {   // argument checks and lazy allocations (PID controller state) happen before the capture starts
@@ -968,6 +979,7 @@ int nig_rollout_steps(nig_env_t* e, const nig_rollout_t* r, int32_t total_steps,
         e->launches += e->steps_graph_key.launches + 1;
         return NIG_OK;
     }
+plain_enqueue:
     if (int rc = fork_slices(e, slices, st)) return rc;
     const int rc = sliced_launches(e, *r, total_steps, r->n_steps, slices, slice_size(e->n, slices));
     const int jrc = join_slices(e, slices, st);

@@ -564,3 +564,33 @@ def test_reactor_fast_loop_with_supplied_actions(mods, use_tma, extrema):
         _compare(env, orc, N, f"after a {K}-step launch of supplied actions")
         assert_bits_equal(rsum[:n].cpu().numpy(), o_rs, "per-env reward sum")
     env.close()
+
+
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+def test_rollout_steps_graph_replay_equals_plain_enqueue(mods, monkeypatch, name):
+    """nig_rollout_steps replays its sliced launch sequence from a captured CUDA graph once a call pattern repeats (first call:
+    plain enqueue, second: capture + replay, later: replay; a different horizon in between re-arms the capture). Same calls on
+    a handle created with NIG_STEPS_GRAPH=0: bit-identical states, episode words, per-env sums and counters."""
+    ni, N, O, torch = mods
+    kind = KINDS[name]
+    n = 40_000 + 5
+    res = []
+    for graph in ("1", "0"):
+        monkeypatch.setenv("NIG_STEPS_GRAPH", graph)
+        env = ni.NativeEnv(kind, n, device=0, seed=17)
+        env.reset_device()
+        rsum = env.empty()
+        launches0 = env.launch_count
+        for horizon in (150, 150, 150, 150, 70, 150, 150):
+            env.rollout_steps_device(horizon, 64, N.POLICY_UNIFORM, reward_sum=rsum)
+        torch.cuda.synchronize()
+        st, es, ev, dn = env.get_state_host()
+        c, _ = env.read_stats()
+        res.append((st, es, ev, dn, rsum[:n].cpu().numpy(), c.copy(), env.tick, env.launch_count - launches0))
+        env.close()
+    g, p = res
+    assert_bits_equal(g[0], p[0], "state"); assert_bits_equal(g[1], p[1], "ep_step"); assert_bits_equal(g[2], p[2], "ep_viol")
+    assert_bits_equal(g[4], p[4], "per-env reward sum of the last call")
+    assert g[5].tolist() == p[5].tolist()
+    assert g[6] == p[6] == 5 * 150 + 70 + 150
+    assert g[7] == p[7] + 5            # calls 2, 3, 4, 6, 7 are replays, each with its tick-setting kernel
