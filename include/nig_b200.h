@@ -257,17 +257,24 @@ NIG_API int nig_step_host(nig_env_t* env, const nig_step_io_t* io);
 NIG_API int nig_rollout(nig_env_t* env, const nig_rollout_t* r, void* stream);
 /* total_steps steps of every env as ceil(total_steps / r->n_steps) fused launches (in-kernel policies only). On a large
  * population the envs are split into slices that advance on internal streams forked from and joined back to `stream`
- * (NIG_HOST_SLICES, default 8 here and 4 in nig_rollout_host, >= 8,192 envs per slice): a slice's next launch fills the SMs another slice's tail leaves
+ * (NIG_HOST_SLICES, default 8, >= 8,192 envs per slice): a slice's next launch fills the SMs another slice's tail leaves
  * idle, which a single sequence of whole-population launches cannot do. Results do not depend on the slicing. Per-env
- * outputs cover the whole call (or add to the arrays with NIG_ROLLOUT_ACCUMULATE). Asynchronous like nig_rollout. */
+ * outputs cover the whole call (or add to the arrays with NIG_ROLLOUT_ACCUMULATE). Asynchronous like nig_rollout.
+ * A call pattern that repeats (same horizon, K, policy, output pointers, settings) is captured once as a CUDA graph on an
+ * internal stream and replayed on `stream` from then on (2 driver calls per call instead of one per launch; NIG_STEPS_GRAPH=0
+ * disables it; a caller that is itself capturing `stream` always gets the plain launch sequence). */
 NIG_API int nig_rollout_steps(nig_env_t* env, const nig_rollout_t* r, int32_t total_steps, void* stream);
 
 /* The same loops with HOST buffers: what performance_benchmark.py:106-133 / utils.evaluate_with_safety do per env in
- * Python, for every env of the handle in one call. Host arrays are exact-size ([n] or [n][dim]); the call stages
- * them through device buffers (cudaMemcpyAsync, true DMA when the host arrays are page-locked, see nig_host_alloc),
- * runs ceil(n_steps / steps_per_launch) fused launches and returns synchronised. With an in-kernel policy and at least
- * 16,384 envs the population is split into env slices (NIG_HOST_SLICES, default 4) that each copy in, step and copy out on
- * their own stream, so the PCIe copies of one slice overlap the stepping of the others; results do not depend on it.
+ * Python, for every env of the handle in one call. Host arrays are exact-size ([n] or [n][dim]); the call runs
+ * ceil(n_steps / steps_per_launch) fused launches and returns synchronised. With an in-kernel policy and at least
+ * 16,384 envs the population is split into env slices (NIG_HOST_SLICES) that each take their states in, step and put their
+ * results out on their own stream, so the PCIe traffic of one slice overlaps the stepping of the others; results do not
+ * depend on it. Two data paths, chosen per call: DIRECT (every supplied array page-locked -- nig_host_alloc /
+ * cudaHostAlloc / cudaHostRegister -- and 16-byte aligned; NIG_HOST_DIRECT=0 disables): the slices' own kernels read the
+ * initial states from and write the results into the caller's arrays over PCIe, no staging, 8 slices; STAGED (anything else):
+ * cudaMemcpyAsync through device buffers (true DMA when page-locked), 4 slices. With page-locked arrays the whole sliced
+ * pipeline is one captured CUDA graph replayed per call (NIG_HOST_GRAPH=0 disables). Identical results either way.
  * Teacher-forced inputs (optional): init_states [n][S]; actions [T][A][n] with policy == NIG_POLICY_ACTIONS and
  * noise [T][NZ][n] (time-major, SoA per step -- the layout the kernel consumes; copied chunk by chunk,
  * double-buffered so the copy of chunk c+1 overlaps the launch of chunk c). */
