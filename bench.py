@@ -546,7 +546,8 @@ def other_configs(torch, ni, N, local, rank, world, dist, seed):
     out = {}
 
     def timed(fn, reps):
-        fn()
+        for _ in range(3):                 # warm-up (nig_rollout_steps captures its launch sequence on the second identical call)
+            fn()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
