@@ -123,6 +123,7 @@ struct nig_env {
     } steps_graph_key, steps_graph_candidate;
     int steps_graph_enable;     // NIG_STEPS_GRAPH (default 1)
     unsigned long long* h_stats_pinned;   // nig_rollout_host: page-locked landing block of the statistics copy
+    double host_direct_max_mb[2];  // NIG_HOST_DIRECT_MAX_MB: ingest, export
     int host_direct;            // NIG_HOST_DIRECT (default 1): nig_rollout_host's slices read / write mapped host arrays in-kernel
     bool graph_mode;            // set while a pipeline is being captured: rollout_range / reset_range emit base-relative counters
     uint32_t graph_tick0;       // tick at the start of the call being captured
@@ -536,12 +537,21 @@ int enqueue_sliced_host(nig_env* e, const nig_rollout_host_t* r, int slices, int
     int32_t* m_vi = mapped_alias(r->viol_count);
     int32_t* m_dn = mapped_alias(r->done_count);
     const bool direct = host_direct_ok(e, r);
+    // which side goes direct: bit 0 of NIG_HOST_DIRECT = ingest, bit 1 = export, each up to a size (megabytes per call) above
+    // which the copy engines' DMA wins: SM-issued PCIe READS are 32..128-byte requests with a bounded number in flight
+    // (measured: direct ingest wins at 3 MB, loses from 6 MB up), posted WRITES stay level with DMA up to ~32 MB
+    // (tools/host_direct_check.py, profiles/r02_h_host_direct_ab.txt). NIG_HOST_DIRECT_MAX_MB="in,out" overrides.
+    const double mb_in = r->init_states ? (double)n * e->S * 4 / 1e6 : 0.0;
+    const double mb_out = ((r->final_obs ? (double)n * e->S * 4 : 0.0) + (r->reward_sum ? n * 4.0 : 0.0) + (r->viol_count ? n * 4.0 : 0.0) +
+                           (r->done_count ? n * 4.0 : 0.0)) / 1e6;
+    const bool direct_in = direct && (e->host_direct & 1) && mb_in <= e->host_direct_max_mb[0];
+    const bool direct_out = direct && (e->host_direct & 2) && mb_out <= e->host_direct_max_mb[1];
     if ((rc = fork_slices(e, slices, st)) != NIG_OK) return rc;
     for (int k = 0; k < slices; ++k) {
         const int64_t i0 = k * per, ns = std::min<int64_t>(per, n - i0);
         if (ns <= 0) continue;
         cudaStream_t ss = e->slice_stream[k];
-        if (direct && r->init_states) {
+        if (direct_in && r->init_states) {
             HostIoArgs a;
             memset(&a, 0, sizeof a);
             a.state = e->state + i0; a.ep_word = e->ep_word + i0; a.ep_return = e->ep_return + i0; a.n = ns; a.pitch = e->pitch; a.S = e->S;
@@ -566,7 +576,7 @@ int enqueue_sliced_host(nig_env* e, const nig_rollout_host_t* r, int slices, int
         const int64_t i0 = k * per, ns = std::min<int64_t>(per, n - i0);
         if (ns <= 0) continue;
         cudaStream_t ss = e->slice_stream[k];
-        if (direct) {
+        if (direct_out) {
             if (!r->final_obs && !r->reward_sum && !r->viol_count && !r->done_count) continue;
             HostIoArgs a;
             memset(&a, 0, sizeof a);
@@ -667,8 +677,15 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     if (const char* v = getenv("NIG_GRID_FAST")) e->grid_fast = atoi(v);
     e->host_graph_enable = 1;
     if (const char* v = getenv("NIG_HOST_GRAPH")) e->host_graph_enable = atoi(v);
-    e->host_direct = 1;
+    e->host_direct = 3;
     if (const char* v = getenv("NIG_HOST_DIRECT")) e->host_direct = atoi(v);
+    e->host_direct_max_mb[0] = 4.0; e->host_direct_max_mb[1] = 48.0;
+    if (const char* v = getenv("NIG_HOST_DIRECT_MAX_MB")) {
+        double a = 0, b = 0;
+        const int got = sscanf(v, "%lf,%lf", &a, &b);
+        if (got >= 1) e->host_direct_max_mb[0] = e->host_direct_max_mb[1] = a;
+        if (got == 2) e->host_direct_max_mb[1] = b;
+    }
     e->steps_graph_enable = 1;
     if (const char* v = getenv("NIG_STEPS_GRAPH")) e->steps_graph_enable = atoi(v);
     e->step_pipe = 1;

@@ -187,7 +187,8 @@ def test_rollout_host_direct_mode_equals_copy_path(name, monkeypatch):
     rng = np.random.default_rng(4)
 
     def call(direct, how):
-        monkeypatch.setenv("NIG_HOST_DIRECT", "1" if direct else "0")
+        monkeypatch.setenv("NIG_HOST_DIRECT", "3" if direct else "0")          # bit 0: ingest, bit 1: export
+        monkeypatch.setenv("NIG_HOST_DIRECT_MAX_MB", "1e9")                      # no size thresholds: both sides direct
         env = ni.NativeEnv(kind, n, device=0, seed=91)
         S = env.S
         init0 = env.reset_host().copy()
