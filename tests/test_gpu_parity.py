@@ -135,12 +135,17 @@ def test_trace_replay_gym_api(mods, golden_dir, name):
 
 
 @pytest.mark.parametrize("name,vec", [("reactor", 1), ("reactor", 2), ("reactor", 4), ("grid", 1), ("robot", 1)])
-@pytest.mark.parametrize("layout", ["host_aos", "device_soa"])
+@pytest.mark.parametrize("layout", ["host_aos", "host_aos_staged", "device_soa"])
 def test_step_bitexact_vs_oracle(mods, name, vec, layout, monkeypatch):
-    """Teacher-forced single step, every vector width and both layouts, N not a multiple of anything."""
+    """Teacher-forced single step, every vector width and both layouts, N not a multiple of anything. host_aos: nig_step_host
+    runs the kernel in place on the page-locked host arrays (zero-copy, populations up to 131,072 envs); host_aos_staged:
+    the same call through device staging buffers and copies (NIG_ZERO_COPY=0, what larger populations get)."""
     ni, N, O, torch = mods
-    if layout == "host_aos" and vec != 1:
+    if layout.startswith("host_aos") and vec != 1:
         pytest.skip("AoS layouts always use VEC=1")
+    monkeypatch.setenv("NIG_ZERO_COPY", "0" if layout == "host_aos_staged" else "1")
+    if layout == "host_aos_staged":
+        layout = "host_aos"
     kind = KINDS[name]
     n = 5003
     rng = np.random.default_rng(10 + kind)
