@@ -1,0 +1,78 @@
+// Floor of a dependent kernel chain on this GPU: 100 launches captured in a CUDA graph and replayed, each launch reading what the
+// previous one wrote (the structure of IndustrialEnv.step called in a loop). Variants: empty kernel / 12-row load-modify-store
+// per thread (the reactor step's memory shape, ~no arithmetic); grid = 512 x 128 (65,536 envs) or 128 x 128; with / without
+// programmatic dependent launch.    nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/launch_probe_bin tools/launch_probe.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); return 1; } } while (0)
+
+__global__ void k_empty(float* s, int pitch, int pdl)
+{
+    if (pdl) { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); }
+}
+__global__ void k_rows(float* s, int pitch, int pdl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pdl) { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); }
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = s[k * pitch + i];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s[k * pitch + i] = v[k] * 1.0001f + v[(k + 1) % 12] * 1e-6f;
+}
+// ~250 dependent FP32 operations per thread between the loads and the stores (the step's arithmetic chain)
+__global__ void k_chain(float* s, int pitch, int pdl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pdl) { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); }
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = s[k * pitch + i];
+    float a = v[0];
+#pragma unroll 1
+    for (int t = 0; t < 60; ++t) { a = a * 1.0001f + v[1]; a = a * 0.9999f + v[2]; a = a + v[3]; a = a * v[4]; }
+    v[0] = a;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s[k * pitch + i] = v[k];
+}
+
+template <class K>
+int run(const char* name, K kern, int grid, int pdl, float* d, int pitch)
+{
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaGraph_t g; cudaGraphExec_t ge;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    for (int l = 0; l < 100; ++l) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = pdl;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, kern, d, pitch, pdl));
+    }
+    CK(cudaStreamEndCapture(st, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    CK(cudaGraphLaunch(ge, st)); CK(cudaStreamSynchronize(st));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, st));
+    for (int r = 0; r < 20; ++r) CK(cudaGraphLaunch(ge, st));
+    CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("%-28s grid %4d x 128  pdl %d: %.3f us per launch\n", name, grid, pdl, ms * 1e3 / 2000);
+    cudaGraphExecDestroy(ge); cudaGraphDestroy(g); cudaStreamDestroy(st);
+    return 0;
+}
+
+int main()
+{
+    const int pitch = 65536;
+    float* d; CK(cudaMalloc(&d, (size_t)12 * pitch * sizeof(float))); CK(cudaMemset(d, 0, (size_t)12 * pitch * sizeof(float)));
+    for (int pdl = 0; pdl < 2; ++pdl)
+        for (int grid : {128, 512}) {
+            if (run("empty kernel", k_empty, grid, pdl, d, pitch)) return 1;
+            if (run("12-row load / store", k_rows, grid, pdl, d, pitch)) return 1;
+            if (run("load, 240-op chain, store", k_chain, grid, pdl, d, pitch)) return 1;
+        }
+    return 0;
+}
