@@ -194,15 +194,20 @@ def test_rollout_host_direct_mode_equals_copy_path(name, monkeypatch):
         init0 = env.reset_host().copy()
         keep = []
 
+        guards = []
+
         def host(shape, dtype):
             cnt = int(np.prod(shape))
             if how == "pageable":
-                a = np.zeros(cnt + 4, dtype)[:cnt]
+                full = np.zeros(cnt + 4, dtype)
             else:
                 p = N.PinnedArray((cnt + 4,), dtype)
                 keep.append(p)
-                a = p.array[1:cnt + 1] if how == "shifted" else p.array[:cnt]
-            return a.reshape(shape)
+                full = p.array
+            lo = 1 if how == "shifted" else 0
+            full.view(np.uint32)[:] = 0xA5A5A5A5                   # canaries around the exact-size window the library may touch
+            guards.append((full, lo, cnt))
+            return full[lo:lo + cnt].reshape(shape)
         init, obs = host((n, S), np.float32), host((n, S), np.float32)
         rew, vi, dn = host((n,), np.float32), host((n,), np.int32), host((n,), np.int32)
         init[:] = init0
@@ -215,6 +220,9 @@ def test_rollout_host_direct_mode_equals_copy_path(name, monkeypatch):
         for _ in range(2):                                   # second call = graph replay where a graph is used
             N.check(N.lib().nig_rollout_host(env._h, C.byref(r)))
         res = (obs.copy(), rew.copy(), vi.copy(), dn.copy(), counters.copy(), sums.copy())
+        for full, lo, cnt in guards:
+            w = full.view(np.uint32)
+            assert (w[:lo] == 0xA5A5A5A5).all() and (w[lo + cnt:] == 0xA5A5A5A5).all(), "bytes outside a host array were overwritten"
         env.close()
         return res
 
