@@ -1938,7 +1938,6 @@ __device__ __forceinline__ int grid_fast_steps(const Rng& key, uint32_t env, uin
         const float imb = sub(pairwise8(gen), sum_load);                          // :127-129
         const float x = add(-s[0], imb);                                          // mul(-1.0f, f) == -f
         const bool ok = fabsf(x) >= 0x1.0p-120f && fabsf(x) <= 0x1.0p+100f;
-        if (__builtin_expect(!__all_sync(0xffffffffu, ok), 0)) break;             // (uniform) nothing committed yet
         // frequency_stability (:10-14), voltage_limits (:17-21) on the pre-step state
         const bool f_bad = !(fabsf(s[0]) < 0.5f);
         bool v_bad;
@@ -1951,7 +1950,12 @@ __device__ __forceinline__ int grid_fast_steps(const Rng& key, uint32_t env, uin
             v_bad = emin < kE95 || emax > kE105;
         }
         // _dynamics (:112-153), in place
-        s[0] = add(s[0], mul(NIG_CDIV_NG(x, 5.0f), 0.1f));                        // :132-133
+        {   // outside the proven domain of the constant division (a zero / denormal / huge / NaN imbalance): the IEEE division,
+            // for that lane only -- no warp vote, no way out of the loop (+1 % over the vote + break)
+            float q5 = NIG_CDIV_NG(x, 5.0f);
+            if (__builtin_expect(!ok, 0)) q5 = __fdiv_rn(x, 5.0f);
+            s[0] = add(s[0], mul(q5, 0.1f));                                      // :132-133
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[9 + i] = gen[i];
 #pragma unroll
