@@ -8,12 +8,12 @@
 
 __global__ void k_empty(float* s, int pitch, int pdl)
 {
-    if (pdl) { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); }
+    if (pdl) { asm volatile("griddepcontrol.wait;" ::: "memory"); asm volatile("griddepcontrol.launch_dependents;"); }
 }
 __global__ void k_rows(float* s, int pitch, int pdl)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pdl) { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); }
+    if (pdl) { asm volatile("griddepcontrol.wait;" ::: "memory"); asm volatile("griddepcontrol.launch_dependents;"); }
     float v[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) v[k] = s[k * pitch + i];
@@ -24,7 +24,7 @@ __global__ void k_rows(float* s, int pitch, int pdl)
 __global__ void k_chain(float* s, int pitch, int pdl)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pdl) { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); }
+    if (pdl) { asm volatile("griddepcontrol.wait;" ::: "memory"); asm volatile("griddepcontrol.launch_dependents;"); }
     float v[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) v[k] = s[k * pitch + i];
@@ -34,6 +34,30 @@ __global__ void k_chain(float* s, int pitch, int pdl)
     v[0] = a;
 #pragma unroll
     for (int k = 0; k < 12; ++k) s[k * pitch + i] = v[k];
+}
+
+// the same plus what a step's bookkeeping adds: a CTA-wide reduction of a counter through shared memory and one global atomic
+// per CTA (into 64 shards)
+__global__ void k_chain_stats(float* s, int pitch, int pdl)
+{
+    __shared__ unsigned int cnt;
+    if (threadIdx.x == 0) cnt = 0u;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pdl) { asm volatile("griddepcontrol.wait;" ::: "memory"); asm volatile("griddepcontrol.launch_dependents;"); }
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = s[k * pitch + i];
+    float a = v[0];
+#pragma unroll 1
+    for (int t = 0; t < 60; ++t) { a = a * 1.0001f + v[1]; a = a * 0.9999f + v[2]; a = a + v[3]; a = a * v[4]; }
+    v[0] = a;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s[k * pitch + i] = v[k];
+    const unsigned int w = __reduce_add_sync(0xffffffffu, a > 0.5f ? 1u : 0u);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&cnt, w);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned int*>(s) + 12 * pitch + (blockIdx.x & 63) * 32, cnt);
 }
 
 template <class K>
@@ -67,12 +91,13 @@ int run(const char* name, K kern, int grid, int pdl, float* d, int pitch)
 int main()
 {
     const int pitch = 65536;
-    float* d; CK(cudaMalloc(&d, (size_t)12 * pitch * sizeof(float))); CK(cudaMemset(d, 0, (size_t)12 * pitch * sizeof(float)));
+    float* d; CK(cudaMalloc(&d, (size_t)13 * pitch * sizeof(float))); CK(cudaMemset(d, 0, (size_t)13 * pitch * sizeof(float)));
     for (int pdl = 0; pdl < 2; ++pdl)
         for (int grid : {128, 512}) {
             if (run("empty kernel", k_empty, grid, pdl, d, pitch)) return 1;
             if (run("12-row load / store", k_rows, grid, pdl, d, pitch)) return 1;
             if (run("load, 240-op chain, store", k_chain, grid, pdl, d, pitch)) return 1;
+            if (run("... + CTA reduce + atomic", k_chain_stats, grid, pdl, d, pitch)) return 1;
         }
     return 0;
 }
