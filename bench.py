@@ -455,6 +455,27 @@ def single_step_section(torch, ni, N, local, dev, flush, hbm_peak, peak_src, arg
         out["envs_64k_cuda_graph"] = {"value": ENVS_PER_GPU * HORIZON / (msg * 1e-3), "unit": UNIT, "us_per_launch": msg * 1e3 / HORIZON,
                                       "hbm_frac": frac64(msg * 1e3 / HORIZON),
                                       "note": "10 replays of a 100-launch CUDA graph (nig_use_device_tick mode 2 + nig_commit_ticks; programmatic dependent launch)"}
+        # the same replay without the device counter block (nig_track_step_stats(env, 0): IndustrialEnv.step has no global counters;
+        # its per-env outputs are complete) and without the return accumulator: what the plain gym loop needs
+        env.track_step_stats(False)
+        env.track_returns(False)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            for _ in range(100):
+                env.step_device(acts, reward=rew, flags=fl, viol_mask=vm)
+            env.commit_ticks()
+        g2.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(HORIZON // 100):
+            g2.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        msq = e0.elapsed_time(e1)
+        out["envs_64k_cuda_graph_no_counters"] = {"value": ENVS_PER_GPU * HORIZON / (msq * 1e-3), "unit": UNIT, "us_per_launch": msq * 1e3 / HORIZON,
+                                                  "hbm_frac": frac64(msq * 1e3 / HORIZON),
+                                                  "note": "as above with nig_track_step_stats(env, 0) and nig_track_returns(env, 0): no warp reductions / "
+                                                          "atomics at the tail of the launch, no 16 B of accumulator traffic"}
     except Exception as ex:                                   # graph capture is an optimisation, never a requirement
         out["envs_64k_cuda_graph"] = {"error": repr(ex)}
     env.close()

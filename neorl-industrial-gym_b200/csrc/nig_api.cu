@@ -100,6 +100,7 @@ struct nig_env {
     bool shards_dirty;
     unsigned long long* extrema; // [2] min / max finished-episode return keys (outside the summable stats block)
     bool track_extrema;          // nig_track_extrema: rollouts run the EXTREMA kernel flavour
+    bool track_step_stats;       // nig_track_step_stats (default on): the single-step kernels add to the device counter block
     bool track_returns;          // nig_track_returns (default on, set in nig_create): the single-step kernels keep the episode-return accumulator too
     // nig_rollout_host over env slices: slice s runs H2D -> reset -> K-step launches -> D2H on its own stream, so the
     // copies of one slice overlap the stepping of the others (and the slices' launches fill each other's tails)
@@ -660,6 +661,7 @@ int nig_create(const nig_config_t* cfg, nig_env_t** out)
     if (!e) return fail(NIG_ERR_INVALID, "out of host memory");
     memset(e, 0, sizeof *e);
     e->track_returns = true;
+    e->track_step_stats = true;
     e->cfg = *cfg;
     e->kind = cfg->env_kind;
     e->S = kS[e->kind]; e->A = kA[e->kind]; e->NZ = kNZ[e->kind];
@@ -818,7 +820,7 @@ int nig_step(nig_env_t* e, const nig_step_io_t* io, void* stream)
     a.obs = io->obs; a.next_obs = io->next_obs; a.reward = io->reward; a.flags = io->flags; a.viol_mask = io->viol_mask;
     a.terminated = io->terminated; a.truncated = io->truncated;
     a.action_aos = io->action_layout == NIG_LAYOUT_AOS; a.aux_aos = io->aux_layout == NIG_LAYOUT_AOS;
-    a.stats = e->stats; a.stats_shards = e->stats_shards; a.cons = e->cons;
+    a.stats = e->track_step_stats ? e->stats : nullptr; a.stats_shards = e->track_step_stats ? e->stats_shards : nullptr; a.cons = e->cons;
     e->shards_dirty = true;
     fill_tick(e, a, e->tick);
     const int rc = launch_step(e, a, (cudaStream_t)stream);
@@ -1570,6 +1572,14 @@ int nig_track_returns(nig_env_t* e, int32_t on)
     if (e) e->config_version++;
     NIG_CHECK_ENV(e);
     e->track_returns = on != 0;
+    return NIG_OK;
+}
+
+int nig_track_step_stats(nig_env_t* e, int32_t on)
+{
+    if (e) e->config_version++;
+    NIG_CHECK_ENV(e);
+    e->track_step_stats = on != 0;
     return NIG_OK;
 }
 

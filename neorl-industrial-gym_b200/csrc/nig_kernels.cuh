@@ -782,6 +782,10 @@ __global__ void __launch_bounds__(kThreads, VEC == 1 ? Env::STEP_MIN_CTAS : 1) s
             }
         }
     }
+    if (p.stats == nullptr) {             // nig_track_step_stats(env, 0): no device counters for single steps (the per-env outputs are complete)
+        advance_device_tick(p.tick_dev, 1u);
+        return;
+    }
     if constexpr (PLAIN) {
         if (p.stats_shards) {
             // per-WARP flush straight into a shard copy of the stats block: no CTA barrier and no shared staging, so the
@@ -1015,8 +1019,10 @@ __global__ void __launch_bounds__(kThreads, 4) step_pipe_kernel(const __grid_con
             if (k < p.cons.n) bs.warp_add(NIG_ST_CON0 + k, c_con[k]);
         if (p.ep_return && __any_sync(0xffffffffu, c_ep != 0u)) stage_episode_stats(bs, &estage, eps);
     }
-    bs.flush(p.stats);
-    if (p.ep_return) flush_episode_staging(p.stats, &estage);
+    if (p.stats != nullptr) {
+        bs.flush(p.stats);
+        if (p.ep_return) flush_episode_staging(p.stats, &estage);
+    }
     advance_device_tick(p.tick_dev, 1u);
 }
 
@@ -2858,9 +2864,11 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(MAXREG) step_grid_kernel(
         bs.warp_add(NIG_ST_CON0, c_con0); bs.warp_add(NIG_ST_CON0 + 1, c_con1); bs.warp_add(NIG_ST_CON0 + 2, c_con2);
         if (p.ep_return && __any_sync(0xffffffffu, c_ep != 0u)) stage_episode_stats(bs, &estage, eps);
     }
-    unsigned long long* const stats_out = p.stats_shards ? p.stats_shards + (blockIdx.x % kStatsShards) * NIG_STATS_SLOTS : p.stats;
-    bs.flush(stats_out);
-    if (p.ep_return) flush_episode_staging(stats_out, &estage);
+    if (p.stats != nullptr) {
+        unsigned long long* const stats_out = p.stats_shards ? p.stats_shards + (blockIdx.x % kStatsShards) * NIG_STATS_SLOTS : p.stats;
+        bs.flush(stats_out);
+        if (p.ep_return) flush_episode_staging(stats_out, &estage);
+    }
     advance_device_tick(p.tick_dev, 1u);
 }
 

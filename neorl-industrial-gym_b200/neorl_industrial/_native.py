@@ -134,6 +134,7 @@ SYMBOLS = {
     "nig_nccl_comm_destroy": (C.c_int, [_VP]),
     "nig_track_extrema": (C.c_int, [_VP, C.c_int32]),
     "nig_track_returns": (C.c_int, [_VP, C.c_int32]),
+    "nig_track_step_stats": (C.c_int, [_VP, C.c_int32]),
     "nig_extrema_ptr": (C.c_int, [_VP, C.POINTER(_VP)]),
     "nig_read_extrema": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I32)]),
     "nig_decode_extrema": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I32)]),

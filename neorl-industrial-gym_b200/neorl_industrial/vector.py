@@ -266,6 +266,11 @@ class NativeEnv:
         env-step; the statistics then cover only episodes that ran entirely inside rollout calls."""
         N.check(N.lib().nig_track_returns(self._h, int(bool(on))))
 
+    def track_step_stats(self, on: bool = True):
+        """Whether single steps add to the device counter block (``stats_dict``); off saves ~1 us per launch at 65,536 envs.
+        The per-env outputs of ``step`` and the fused rollouts' counters are not affected."""
+        N.check(N.lib().nig_track_step_stats(self._h, int(bool(on))))
+
     def track_extrema(self, on: bool = True):
         """Rollouts of this handle also keep the smallest / largest finished-episode return (a 2 % slower kernel flavour)."""
         N.check(N.lib().nig_track_extrema(self._h, int(bool(on))))

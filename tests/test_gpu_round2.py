@@ -594,3 +594,42 @@ def test_rollout_steps_graph_replay_equals_plain_enqueue(mods, monkeypatch, name
     assert g[5].tolist() == p[5].tolist()
     assert g[6] == p[6] == 5 * 150 + 70 + 150
     assert g[7] == p[7] + 5            # calls 2, 3, 4, 6, 7 are replays, each with its tick-setting kernel
+
+
+@pytest.mark.parametrize("name", ["reactor", "grid", "robot"])
+def test_step_without_device_counters(mods, name):
+    """nig_track_step_stats(env, 0): single steps skip the device counter block (IndustrialEnv.step has none) -- states, rewards,
+    flags, violation masks and episode words are those of a counting handle bit for bit, the counters stay where they were,
+    and the fused rollout keeps counting."""
+    ni, N, O, torch = mods
+    kind = KINDS[name]
+    n = 70_000 + 3                                     # above the persistent-pipeline threshold of none, below for all: both kernels appear across envs
+    envs = [ni.NativeEnv(kind, n, device=0, seed=23) for _ in range(2)]
+    quiet, counting = envs
+    quiet.track_step_stats(False)
+    for e in envs:
+        e.reset_device()
+    dev = quiet.torch_device()
+    torch.manual_seed(0)
+    outs = []
+    for e in envs:
+        rew, fl, vm = e.empty(), e.empty(dtype=torch.uint8), e.empty(dtype=torch.uint8)
+        g = torch.Generator(device=dev); g.manual_seed(5)
+        for _ in range(40):
+            acts = torch.rand((e.A, e.pitch), device=dev, generator=g) * 2.6 - 1.3
+            e.step_device(acts, reward=rew, flags=fl, viol_mask=vm)
+        torch.cuda.synchronize()
+        outs.append((rew[:n].cpu().numpy(), fl[:n].cpu().numpy(), vm[:n].cpu().numpy()))
+    sq, sc = quiet.get_state_host(), counting.get_state_host()
+    assert_bits_equal(sq[0], sc[0], "state"); assert_bits_equal(sq[1], sc[1], "ep_step"); assert_bits_equal(sq[2], sc[2], "ep_viol")
+    assert_bits_equal(outs[0][0], outs[1][0], "reward of the last step")
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    cq, _ = quiet.read_stats()
+    cc, _ = counting.read_stats()
+    assert cq[N.ST_STEPS] == 0 and cc[N.ST_STEPS] == 40 * n
+    quiet.rollout_device(16, N.POLICY_UNIFORM)
+    torch.cuda.synchronize()
+    cq, _ = quiet.read_stats()
+    assert cq[N.ST_STEPS] == 16 * n
+    for e in envs:
+        e.close()
