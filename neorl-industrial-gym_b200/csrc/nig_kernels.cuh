@@ -2084,6 +2084,54 @@ __device__ __forceinline__ void rollout_stats_flush(const RolloutArgs& p, BlockS
                                                     typename Env::acc_t r_lo, typename Env::acc_t r_hi)
 {
     using acc_t = typename Env::acc_t;
+    if (blockDim.x == 32) {
+        // one-warp CTA (the env slices of a small population): no shared staging, no CTA barrier -- lane l ends up holding the warp
+        // total of statistics slot l and ONE atomic-add instruction per warp sends the non-zero ones to the global block
+        const int lane = threadIdx.x;
+        unsigned long long mine = 0ull;
+        double dmine = 0.0;
+        auto put = [&](int slot, unsigned int v) {
+            const unsigned int t = __reduce_add_sync(0xffffffffu, v);
+            if (lane == slot) mine = t;
+        };
+        put(NIG_ST_STEPS, acc.c_steps);
+        put(NIG_ST_VIOLATIONS, acc.c_viol);
+        put(NIG_ST_CRITICAL, acc.c_crit);
+#pragma unroll
+        for (int k = 0; k < NIG_MAX_CONSTRAINTS; ++k)
+            if (k < p.cons.n) put(NIG_ST_CON0 + k, acc.c_con[k]);
+        if (__any_sync(0xffffffffu, acc.c_ep != 0u)) {
+            put(NIG_ST_EPISODES, acc.c_ep);
+            put(NIG_ST_TERMINATED, acc.c_term);
+            put(NIG_ST_TRUNCATED, acc.c_trunc);
+            put(NIG_ST_SUCCESSES, acc.c_succ);
+            const unsigned long long ls = warp_sum(acc.len_sum), lq = warp_sum(acc.len_sq);
+            const double rs_ = warp_sum(acc.ret_sum), rq = warp_sum(acc.ret_sq);
+            if (lane == NIG_ST_EP_LEN_SUM) mine = ls;
+            if (lane == NIG_ST_EP_LEN_SQ) mine = lq;
+            if (lane == NIG_ST_F_RETURN_SUM) dmine = rs_;
+            if (lane == NIG_ST_F_RETURN_SQ) dmine = rq;
+            if constexpr (EXTREMA) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const acc_t a_ = __shfl_xor_sync(0xffffffffu, r_lo, o), b_ = __shfl_xor_sync(0xffffffffu, r_hi, o);
+                    r_lo = a_ < r_lo ? a_ : r_lo; r_hi = b_ > r_hi ? b_ : r_hi;
+                }
+                if (lane == 0) {
+                    atomicMax(&p.extrema[0], extremum_key(-(double)r_lo));
+                    atomicMax(&p.extrema[1], extremum_key((double)r_hi));
+                }
+            }
+        }
+        {
+            const double rw_ = warp_sum(acc.rew_sum);
+            if (lane == NIG_ST_F_REWARD_SUM) dmine = rw_;
+        }
+        if (lane < 24) { if (mine != 0ull) atomicAdd(&p.stats[lane], mine); }
+        else if (lane <= NIG_ST_F_REWARD_SUM && dmine != 0.0) atomicAdd(reinterpret_cast<double*>(p.stats) + lane, dmine);
+        advance_device_tick(p.tick_dev, (uint32_t)p.n_steps);
+        return;
+    }
     bs.warp_add(NIG_ST_STEPS, acc.c_steps);
     bs.warp_add(NIG_ST_VIOLATIONS, acc.c_viol);
     bs.warp_add(NIG_ST_CRITICAL, acc.c_crit);
